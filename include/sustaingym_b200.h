@@ -1,0 +1,205 @@
+/*
+ * sustaingym_b200 — C ABI of the B200-native batched step() engine.
+ *
+ * The reference (chrisyeh96/sustaingym @ eac2a4d) is pure Python and has no FFI layer; its
+ * boundary is the Gymnasium `Env.step()/reset()` and PettingZoo `ParallelEnv` API.  The Python
+ * package `sustaingym_b200` mirrors that API and calls the entry points below through ctypes.
+ * Every entry point cites the reference function whose per-step work it replaces.
+ *
+ * Conventions
+ *   - All `const T*` / `T*` arguments marked [device] are CUDA device pointers owned by the
+ *     caller (torch tensors in the Python host code); the library never allocates or frees.
+ *     Arguments marked [host] are host pointers (pinned memory recommended).
+ *   - Batched arrays are env-major, C-contiguous: `action[B, n]`, `obs[B, obs_dim]`.
+ *   - `stream` is a `cudaStream_t` passed as `void*` (0 = legacy default stream).  Calls are
+ *     asynchronous on that stream unless the name ends in `_host` (those synchronise the stream
+ *     before returning because they write host memory).
+ *   - Return value: 0 on success, non-zero on error; `sg_last_error()` returns a message
+ *     (thread-local).  Numerical non-convergence is NEVER an error: it is reported per env in a
+ *     status array (this replaces `pdb.set_trace()` in sustaingym/envs/utils.py:21-24).
+ *   - The library is re-entrant per stream; it keeps no global mutable state.
+ */
+#ifndef SUSTAINGYM_B200_H
+#define SUSTAINGYM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SG_ABI_VERSION 1
+
+int         sg_abi_version(void);
+const char* sg_last_error(void);
+/* Number of SMs of the current device (grid sizing helper for callers / tests). */
+int         sg_device_sm_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * BuildingEnv  —  replaces sustaingym/envs/building/env.py:205-312 (step), :314-386 (reset),
+ *                 :411-434 (_calc_occupower); constants from :196-203 (A_d, BD_d).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct sg_building_model {
+    int32_t n;             /* zones                                                         */
+    int32_t T;             /* rows of the weather tables (env.py:141 length_of_weather)      */
+    int32_t episode_len;   /* env.py:138                                                     */
+    int32_t discrete;      /* 0: action is f32 [B,n] in [-ac,ac]; 1: int64 MultiDiscrete     */
+    double  q_rate;        /* (1-beta)*24, env.py:179                                        */
+    double  error_rate;    /* beta, env.py:180                                               */
+    double  pnorm;         /* reward_pnorm (2 = Euclidean fast path)                         */
+    const double* A_d;     /* [device] [n, n]    env.py:202                                  */
+    const double* BD_d;    /* [device] [n, n+4]  env.py:203, columns [occ|ground,out,a..,ghi]*/
+    const double* target;  /* [device] [n]                                                   */
+    const double* ac_map;  /* [device] [n]                                                   */
+    const double* weather; /* [device] [T, 4]: out_temp, ground_temp, ghi, metabolism per row */
+} sg_building_model;
+
+/* on done: runs <- 0, zone temperatures <- target, weather cursor keeps running (equivalent to
+ * reset(seed) with the seed that maps to the current cursor, env.py:339-378).  The observation
+ * returned for a finished env is then the first observation of its next episode. */
+#define SG_BUILDING_FLAG_AUTORESET 16
+
+/* reset(): env.py:346-378 with the weather cursor already resolved by the host
+ * (seed -> epoch mapping env.py:339-345 is host logic).  `T_initial` may be NULL (= target). */
+int sg_building_reset(const sg_building_model* m, int64_t num_envs,
+                      const int32_t* epoch_in /* [device] [B] */,
+                      const double* T_initial /* [device] [B,n] or NULL */,
+                      float* state /* [device] [B,n+4] out */,
+                      int32_t* epoch /* [device] [B] out */, int32_t* runs /* [device] [B] out */,
+                      void* stream);
+
+/* One step() of B independent envs.  `state` is the previous observation and is overwritten
+ * with the new one (the reference's state IS its f32 observation, env.py:286-296). */
+int sg_building_step(const sg_building_model* m, int64_t num_envs,
+                     const void* action /* [device] [B,n] f32 or i64 */,
+                     float* state /* [device] [B,n+4] in/out */,
+                     int32_t* epoch /* [device] [B] in/out */, int32_t* runs /* [device] [B] in/out */,
+                     double* reward /* [device] [B] out */, uint8_t* done /* [device] [B] out */,
+                     int32_t flags /* SG_BUILDING_FLAG_* */, double* stats /* [device] [16] or NULL */,
+                     void* stream);
+
+/* `steps` consecutive step() calls fused in one launch (state stays in registers between
+ * steps).  action: [steps, B, n]; obs_out: [steps, B, n+4] or NULL (only final state kept);
+ * reward: [steps, B]; done: [steps, B]. */
+int sg_building_rollout(const sg_building_model* m, int64_t num_envs, int32_t steps,
+                        const void* action, float* state, int32_t* epoch, int32_t* runs,
+                        float* obs_out, double* reward, uint8_t* done,
+                        int32_t flags, double* stats, void* stream);
+
+/* Host-buffer variant of sg_building_step: copies `h_action` to `d_action`, steps, copies
+ * state/reward/done back, synchronises. d_* are caller-owned device scratch of the same shapes. */
+int sg_building_step_host(const sg_building_model* m, int64_t num_envs,
+                          const void* h_action, float* h_obs, double* h_reward, uint8_t* h_done,
+                          void* d_action, float* d_state, int32_t* d_epoch, int32_t* d_runs,
+                          double* d_reward, uint8_t* d_done, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * EVChargingEnv  —  replaces sustaingym/envs/evcharging/env.py:229-291 (step), :200-221 +
+ *   :178-198 + :473-500 + envs/utils.py:6-24 (action projection, cvxpy+MOSEK), :340-379
+ *   (_to_schedule), :381-394 (_get_observation), :431-464 (_get_reward), and the un-vendored
+ *   acnportal.acnsim Simulator.step / ChargingNetwork / Linear2StageBattery inner loop
+ *   (call sites env.py:283-284, 385, 445, 450-451).
+ * ---------------------------------------------------------------------------------------- */
+#define SG_EV_MAX_STATIONS    64
+#define SG_EV_MAX_CLASSES     8
+#define SG_EV_MAX_CONSTRAINTS 16
+#define SG_EV_MOER_COLS       37   /* load_moer.py:364-377: col 0 historical + 36 forecasts  */
+#define SG_EV_MOER_ROWS       289
+#define SG_EV_EPISODE_STEPS   288
+
+/* One charging session = one row of the events DataFrame (event_generation.py:125-147) after
+ * the requested-energy cap (:169-170).  Slot k of station i on day d lives at
+ * sessions[(d*K + k)*n + i]; slots of a station are ordered by arrival; unused slots have
+ * arrival = departure = 32767. */
+typedef struct sg_ev_session {
+    int16_t arrival;        /* period index 0..287                                            */
+    int16_t departure;
+    int16_t est_departure;
+    int16_t reserved;
+    double  energy;         /* requested kWh                                                   */
+} sg_ev_session;
+
+typedef struct sg_ev_model {
+    int32_t n_stations;      /* 54 (Caltech)                                                 */
+    int32_t n_classes;       /* distinct columns of A~ (env.py:485-486); 5 for Caltech        */
+    int32_t n_constraints;   /* rows of constraint_matrix; 8 for Caltech                      */
+    int32_t moer_steps;      /* k = moer_forecast_steps (env.py:117), 1..36                   */
+    int32_t max_sessions;    /* K: session slots per station per day in the trace tables      */
+    int32_t n_days;          /* D: day traces resident on the device                          */
+    int32_t n_moer_days;     /* Dm: MOER day tables resident on the device                    */
+    int32_t project;         /* project_action_in_env (env.py:118)                            */
+    const uint8_t* station_class; /* [device] [n] class id of each station                    */
+    const uint8_t* station_type;  /* [device] [n] 0: {0,6..32} A (min_pilot 6), 1: {0,8,..,32}*/
+    const double*  con_re;        /* [device] [J, C] Re of per-class constraint coefficient   */
+    const double*  con_im;        /* [device] [J, C] Im                                       */
+    const double*  magnitudes;    /* [device] [J] limits in A                                 */
+    const void*    sessions;      /* [device] [D, K, n] 16-byte records (sg_ev_session)        */
+    const float*   moer;          /* [device] [Dm, 289, 37]                                   */
+} sg_ev_model;
+
+typedef struct sg_ev_state {
+    double*  delivered;   /* [device] [B, n] kWh delivered to the session now at the station  */
+    uint8_t* sess_idx;    /* [device] [B, n] slot of the station's current-or-next session    */
+    int32_t* t;           /* [device] [B] timestep 0..288 (env.py:168)                        */
+    int32_t* day;         /* [device] [B] trace index in [0, D)                               */
+    int32_t* moer_day;    /* [device] [B] MOER table index in [0, Dm)                         */
+    double*  breakdown;   /* [device] [B, 3] cumulative profit, carbon_cost, excess_charge    */
+} sg_ev_state;
+
+/* status bits written per env by sg_ev_step */
+#define SG_EV_STATUS_PROJECTED   1  /* clipped action violated the network -> solver ran      */
+#define SG_EV_STATUS_MAXITER     2  /* solver hit its iteration cap (result still feasible)   */
+
+/* flags */
+#define SG_EV_ACTION_F32      0
+#define SG_EV_ACTION_I64      1   /* DiscreteActionWrapper input (wrappers.py:43-45)          */
+#define SG_EV_FLAG_AUTORESET  16  /* on done: advance day (mod D), reset state, obs = reset obs */
+
+/* reset(): env.py:293-338 for envs whose `reset_mask` byte is non-zero (NULL = all).
+ * `day_in`/`moer_day_in` pick the trace/MOER table (the seed->day map is host logic,
+ * event_generation.py:273-282).  Writes the reset observation. */
+int sg_ev_reset(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs,
+                const uint8_t* reset_mask, const int32_t* day_in, const int32_t* moer_day_in,
+                float* obs /* [device] [B, 2n+k+2] */, void* stream);
+
+/* One step() of B independent envs.
+ *   action : [B, n] f32 in [0,1] (or i64 in [0,bins) with SG_EV_ACTION_I64)
+ *   obs    : [B, 2n+k+2] f32, gymnasium flatten order (sorted keys):
+ *            demands[n] | est_departures[n] | forecasted_moer[k] | prev_moer[1] | timestep[1]
+ *   reward : [B] f64;  done: [B] u8 (terminated; truncated is always False, env.py:291)
+ *   pilots : [B, n] u8 amps actually sent (schedule of env.py:368-378) or NULL
+ *   final_obs: with AUTORESET, receives the terminal observation of envs that finished, or NULL
+ *   status : [B] u8 or NULL;  stats: [16] f64 accumulators or NULL (see sg_stats_*)
+ *   todo   : [B+1] i32 device scratch used when m->project != 0 (deferred-solve work list)
+ */
+int sg_ev_step(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs,
+               const void* action, int32_t flags, int32_t discrete_bins,
+               float* obs, double* reward, uint8_t* done, uint8_t* pilots, float* final_obs,
+               uint8_t* status, double* stats, int32_t* todo, void* stream);
+
+/* Host-buffer variant: H2D(action) -> step -> D2H(obs, reward, done) -> sync. */
+int sg_ev_step_host(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs,
+                    const void* h_action, int32_t flags, int32_t discrete_bins,
+                    float* h_obs, double* h_reward, uint8_t* h_done,
+                    void* d_action, float* d_obs, double* d_reward, uint8_t* d_done,
+                    uint8_t* d_status, double* d_stats, int32_t* d_todo, void* stream);
+
+/* The projection alone (env.py:200-221): x = argmin ||x-a||_2 s.t. 0<=x<=min(1,d/(c*32)),
+ * 32*|A~ x| <= magnitudes.  a: [B,n] f32, demands: [B,n] f32, x out: [B,n] f64. */
+int sg_ev_project(const sg_ev_model* m, int64_t num_envs, const float* action,
+                  const float* demands, double* x_out, uint8_t* status, int32_t* iters,
+                  void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Aggregate reward statistics (the one collective of the multi-GPU path):
+ * kernels accumulate into a 16-double vector; the host all-reduces it (NCCL SUM / MIN / MAX).
+ *   [0] count  [1] sum r  [2] sum r^2  [3] min r  [4] max r  [5] n_done  [6] n_projected
+ *   [7] n_maxiter  [8..10] sum of reward components  [11..15] reserved
+ * ---------------------------------------------------------------------------------------- */
+#define SG_STATS_LEN 16
+int sg_stats_reset(double* stats /* [device] [16] */, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SUSTAINGYM_B200_H */

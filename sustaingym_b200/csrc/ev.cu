@@ -1,0 +1,776 @@
+// EVChargingEnv batched step()/reset() and action projection for sm_100a.
+//
+// Replaces, per env and per step, the reference's
+//   EVChargingEnv.step            sustaingym/envs/evcharging/env.py:229-291
+//   _project_action (cvxpy+MOSEK) env.py:178-221, 473-500, sustaingym/envs/utils.py:6-24
+//   _to_schedule                  env.py:340-379
+//   acnsim Simulator.step -> ChargingNetwork.update_pilots -> EV.charge ->
+//   Linear2StageBattery._charge_stepwise, event queue (Unplug < Plugin)   [acnportal 0.3.x]
+//   _get_observation              env.py:381-394
+//   _get_reward                   env.py:431-464
+//   DiscreteActionWrapper.action  sustaingym/envs/wrappers.py:43-45
+//
+// Mapping: one warp advances one env; lane l owns stations 2l and 2l+1 (54 stations -> 27
+// lanes), so the env-major rows action[B,n] (f32), delivered[B,n] (f64), sess_idx[B,n] (u8) and
+// obs[B,2n+k+2] (f32) are read/written as 8/16/2-byte vectors that are contiguous across the
+// warp and across consecutive warps (fully coalesced, each byte touched once).  Per-station
+// feasibility / reward reductions are warp-shuffle butterflies over the <= 8 class sums the
+// network constraints depend on; the small constraint tables are staged in
+// shared memory once per CTA.  Trace (16-byte session records) and MOER tables are shared by
+// all envs of a day and stay L2-resident.
+//
+// The projection has a fast path (box-clipped action already satisfies the network: it IS the
+// projection) executed inline, and a slow path (primal-dual interior point on the QCQP, Newton
+// systems reduced to n_classes x n_classes by Woodbury) executed by a second, register-heavy
+// kernel over a device-side work list — so the common path keeps a small register footprint.
+//
+// Bound: HBM.  Algorithmic bytes per env-step: SURVEY.md 8d (1709 B at n=54, k=36).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace sg {
+namespace {
+
+// ---- env.py:99-114 (evaluated in IEEE double exactly like the Python class attributes) --------
+constexpr double kVoltage = 208.0;
+constexpr double kPeriod = 5.0;                                   // minutes
+constexpr double kPeriodH = kPeriod / 60.0;                       // hours
+constexpr double kActionScale = 32.0;
+constexpr double kMarginalProfit = 0.15 * 0.20;
+constexpr double kAMinsToKwh = (1.0 / 60.0) * (kVoltage / 1000.0);
+constexpr double kAPersToKwh = kAMinsToKwh * 5.0;
+constexpr double kProfitFactor = kAPersToKwh * kMarginalProfit;
+constexpr double kViolationFactor = kAPersToKwh * 0.001;
+constexpr double kCarbonFactor = kAPersToKwh * (30.85 / 1000.0);
+// event_generation.py:60-62 and acnportal defaults
+constexpr double kCapacity = 100.0, kMaxPower = 100.0, kTransitionSoc = 0.8, kFullEps = 1e-3;
+constexpr int kEmpty = 32767;
+constexpr int kEpisode = SG_EV_EPISODE_STEPS;
+
+constexpr int kWarpsPerBlock = 8;
+constexpr int kThreads = kWarpsPerBlock * 32;
+
+struct EvShared {
+    double con_re[SG_EV_MAX_CONSTRAINTS * SG_EV_MAX_CLASSES];
+    double con_im[SG_EV_MAX_CONSTRAINTS * SG_EV_MAX_CLASSES];
+    double lim[SG_EV_MAX_CONSTRAINTS];     // magnitudes in A
+    uint8_t cls[SG_EV_MAX_STATIONS];
+    uint8_t type[SG_EV_MAX_STATIONS];
+    double stat[11 * kWarpsPerBlock];
+};
+
+__device__ __forceinline__ void load_shared(const sg_ev_model& m, EvShared& sh) {
+    const int C = m.n_classes, J = m.n_constraints;
+    for (int i = threadIdx.x; i < SG_EV_MAX_CONSTRAINTS * SG_EV_MAX_CLASSES; i += blockDim.x) {
+        sh.con_re[i] = 0.0; sh.con_im[i] = 0.0;      // padding classes/constraints contribute nothing
+    }
+    for (int i = threadIdx.x; i < SG_EV_MAX_CONSTRAINTS; i += blockDim.x) sh.lim[i] = 0.0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < J * C; i += blockDim.x) {
+        const int j = i / C, c = i % C;
+        sh.con_re[j * SG_EV_MAX_CLASSES + c] = m.con_re[i];
+        sh.con_im[j * SG_EV_MAX_CLASSES + c] = m.con_im[i];
+    }
+    for (int i = threadIdx.x; i < J; i += blockDim.x) sh.lim[i] = m.magnitudes[i];
+    for (int i = threadIdx.x; i < m.n_stations; i += blockDim.x) {
+        sh.cls[i] = m.station_class[i];
+        sh.type[i] = m.station_type[i];
+    }
+    __syncthreads();
+}
+
+struct Session { int arr, dep, est; double energy; };
+
+__device__ __forceinline__ Session load_session(const sg_ev_model& m, int day, int k, int i) {
+    Session s;
+    if (k >= m.max_sessions) { s.arr = s.dep = s.est = kEmpty; s.energy = 0.0; return s; }
+    const uint4* recs = reinterpret_cast<const uint4*>(m.sessions);
+    const uint4 r = __ldg(recs + ((long long)day * m.max_sessions + k) * m.n_stations + i);
+    s.arr = (int)(short)(r.x & 0xffffu);
+    s.dep = (int)(short)(r.x >> 16);
+    s.est = (int)(short)(r.y & 0xffffu);
+    s.energy = __longlong_as_double((long long)(((unsigned long long)r.w << 32) | r.z));
+    return s;
+}
+
+// class sums of a per-station value (two stations per lane) -> every lane gets all C sums
+template <int MAXC>
+__device__ __forceinline__ void class_sums(const double (&v)[2], const int (&cls)[2], int C, double (&S)[MAXC]) {
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) {
+        if (c < C) S[c] = warp_sum((cls[0] == c ? v[0] : 0.0) + (cls[1] == c ? v[1] : 0.0));
+        else S[c] = 0.0;
+    }
+}
+
+// env.py:373-378: pilot in A from the normalised action
+__device__ __forceinline__ double to_pilot(double x, int type) {
+    const double amps = x * kActionScale;
+    if (type == 0) return amps >= 6.0 ? rint(amps) : 0.0;     // np.round = half-to-even = rint
+    return rint(amps / 8.0) * 8.0;
+}
+
+// env.py:188-189
+__device__ __forceinline__ double upper_bound(float demand_f32) {
+    return fmin(1.0, (double)demand_f32 / kAPersToKwh / kActionScale);
+}
+
+// =================================================================================================
+// Interior-point projection (slow path).  Same iteration as oracle/ev.py::_ipm, but the Newton
+// system (D + M^T K M) dx = rho is solved through the C x C system (I + H K H) v = H^-1 g.
+// Returns iteration count; *maxiter set when the cap was hit.
+// =================================================================================================
+template <int MAXC, int MAXJ>
+__device__ __noinline__ int ipm_project(const EvShared& sh, const int C, const int J, const double (&a)[2],
+                                         const double (&u)[2], const int (&cls)[2], const bool (&valid)[2],
+                                         double (&x)[2], bool* hit_cap) {
+    const double tol = 1e-13, tau = 0.995;
+    const int max_iter = 60;
+    bool fr[2];
+    double uf[2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) { fr[p] = valid[p] && u[p] > 0.0; uf[p] = fr[p] ? u[p] : 1.0; }
+    const int nfree = __popc(__ballot_sync(kFull, fr[0])) + __popc(__ballot_sync(kFull, fr[1]));
+    const double ncomp = 2.0 * nfree + J;
+    double r2[MAXJ];
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) { const double r = (j < J) ? sh.lim[j] / kActionScale : 1.0; r2[j] = r * r; }
+
+    double S[MAXC];
+    // strictly interior start: x = theta*u with every |A~ x| <= r/2
+    {
+        double uu[2] = {fr[0] ? u[0] : 0.0, fr[1] ? u[1] : 0.0};
+        class_sums<MAXC>(uu, cls, C, S);
+        double theta = 0.5;
+#pragma unroll
+        for (int j = 0; j < MAXJ; ++j) {
+            if (j < J) {
+                double wr = 0, wi = 0;
+#pragma unroll
+                for (int c = 0; c < MAXC; ++c) { wr = fma(sh.con_re[j * 8 + c], S[c], wr); wi = fma(sh.con_im[j * 8 + c], S[c], wi); }
+                const double mag = sqrt(wr * wr + wi * wi);
+                theta = fmin(theta, 0.5 * sqrt(r2[j]) / fmax(mag, 1e-300));
+            }
+        }
+        x[0] = fr[0] ? theta * uf[0] : 0.0;
+        x[1] = fr[1] ? theta * uf[1] : 0.0;
+    }
+    double mu = 0.1;
+    double zl[2], zu[2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) { zl[p] = fr[p] ? mu / x[p] : 0.0; zu[p] = fr[p] ? mu / (uf[p] - x[p]) : 0.0; }
+    double lam[MAXJ], wre[MAXJ], wim[MAXJ], q[MAXJ];
+    class_sums<MAXC>(x, cls, C, S);
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) {
+        double wr = 0, wi = 0;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) { wr = fma(sh.con_re[j * 8 + c], S[c], wr); wi = fma(sh.con_im[j * 8 + c], S[c], wi); }
+        lam[j] = (j < J) ? mu / (r2[j] - (wr * wr + wi * wi)) : 0.0;
+    }
+
+    int it = 0;
+    *hit_cap = true;
+    for (; it < max_iter; ++it) {
+        class_sums<MAXC>(x, cls, C, S);
+        double nu[MAXC];
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) nu[c] = 0.0;
+        double lamq = 0.0;
+#pragma unroll
+        for (int j = 0; j < MAXJ; ++j) {
+            if (j < J) {
+                double wr = 0, wi = 0;
+#pragma unroll
+                for (int c = 0; c < MAXC; ++c) { wr = fma(sh.con_re[j * 8 + c], S[c], wr); wi = fma(sh.con_im[j * 8 + c], S[c], wi); }
+                wre[j] = wr; wim[j] = wi;
+                q[j] = r2[j] - (wr * wr + wi * wi);
+                lamq = fma(lam[j], q[j], lamq);
+#pragma unroll
+                for (int c = 0; c < MAXC; ++c)
+                    nu[c] = fma(2.0 * lam[j], wr * sh.con_re[j * 8 + c] + wi * sh.con_im[j * 8 + c], nu[c]);
+            } else { wre[j] = wim[j] = 0.0; q[j] = 1.0; }
+        }
+        double xs[2], us[2], rd[2], part = 0.0, rmax = 0.0;
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            xs[p] = fr[p] ? x[p] : 1.0;
+            us[p] = fr[p] ? uf[p] - x[p] : 1.0;
+            double nuc = 0.0;
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c) nuc = (cls[p] == c) ? nu[c] : nuc;
+            rd[p] = fr[p] ? (x[p] - a[p]) - zl[p] + zu[p] + nuc : 0.0;
+            part += fr[p] ? zl[p] * xs[p] + zu[p] * us[p] : 0.0;
+            rmax = fmax(rmax, fabs(rd[p]));
+        }
+        const double gap = (warp_sum(part) + lamq) / ncomp;
+        const double resid = warp_max(rmax);
+        if (gap < tol && resid < 100.0 * tol) { *hit_cap = false; break; }
+        mu = 0.1 * gap;
+        // ---- reduced Newton system ---------------------------------------------------------
+        double kap[MAXC], Kmat[MAXC][MAXC];
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+            kap[c] = 0.0;
+#pragma unroll
+            for (int d = 0; d < MAXC; ++d) Kmat[c][d] = 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < MAXJ; ++j) {
+            if (j < J) {
+                double G[MAXC];
+#pragma unroll
+                for (int c = 0; c < MAXC; ++c) G[c] = wre[j] * sh.con_re[j * 8 + c] + wim[j] * sh.con_im[j * 8 + c];
+                const double mq = 2.0 * mu / q[j], l2 = 2.0 * lam[j], l4 = 4.0 * lam[j] / q[j];
+#pragma unroll
+                for (int c = 0; c < MAXC; ++c) {
+                    kap[c] = fma(mq, G[c], kap[c]);
+#pragma unroll
+                    for (int d = 0; d <= c; ++d) {
+                        const double Q = sh.con_re[j * 8 + c] * sh.con_re[j * 8 + d] + sh.con_im[j * 8 + c] * sh.con_im[j * 8 + d];
+                        Kmat[c][d] = fma(l2, Q, fma(l4 * G[c], G[d], Kmat[c][d]));
+                    }
+                }
+            }
+        }
+        double Dd[2], rho[2], inv[2], rhoD[2];
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            Dd[p] = fr[p] ? 1.0 + zl[p] / xs[p] + zu[p] / us[p] : 1.0;
+            double kc = 0.0;
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c) kc = (cls[p] == c) ? kap[c] : kc;
+            rho[p] = fr[p] ? -(x[p] - a[p]) + mu / xs[p] - mu / us[p] - kc : 0.0;
+            inv[p] = fr[p] ? 1.0 / Dd[p] : 0.0;
+            rhoD[p] = rho[p] * inv[p];
+        }
+        double E[MAXC], g[MAXC];
+        class_sums<MAXC>(inv, cls, C, E);
+        class_sums<MAXC>(rhoD, cls, C, g);
+        // (I + H K H) v = g / h,  ds = H v   (SPD; classes without free stations drop out)
+        double h[MAXC], L[MAXC][MAXC], v[MAXC];
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) h[c] = (c < C && E[c] > 0.0) ? sqrt(E[c]) : 0.0;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+#pragma unroll
+            for (int d = 0; d <= c; ++d) L[c][d] = h[c] * Kmat[c][d] * h[d] + (c == d ? 1.0 : 0.0);
+            v[c] = h[c] > 0.0 ? g[c] / h[c] : 0.0;
+        }
+        // Cholesky L L^T in place (lower), then two triangular solves
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+#pragma unroll
+            for (int d = 0; d <= c; ++d) {
+                double sum = L[c][d];
+#pragma unroll
+                for (int e = 0; e < d; ++e) sum -= L[c][e] * L[d][e];
+                L[c][d] = (c == d) ? sqrt(sum) : sum / L[d][d];
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+            double sum = v[c];
+#pragma unroll
+            for (int e = 0; e < c; ++e) sum -= L[c][e] * v[e];
+            v[c] = sum / L[c][c];
+        }
+#pragma unroll
+        for (int c = MAXC - 1; c >= 0; --c) {
+            double sum = v[c];
+#pragma unroll
+            for (int e = c + 1; e < MAXC; ++e) sum -= L[e][c] * v[e];
+            v[c] = sum / L[c][c];
+        }
+        double ds[MAXC], y[MAXC];
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) ds[c] = h[c] * v[c];
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+            double sum = 0.0;
+#pragma unroll
+            for (int d = 0; d < MAXC; ++d) sum = fma(d <= c ? Kmat[c][d] : Kmat[d][c], ds[d], sum);
+            y[c] = sum;
+        }
+        // ---- directions and fraction-to-boundary step -----------------------------------------
+        double dx[2], dzl[2], dzu[2], amin = 1.0;
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            double yc = 0.0;
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c) yc = (cls[p] == c) ? y[c] : yc;
+            dx[p] = fr[p] ? (rho[p] - yc) * inv[p] : 0.0;
+            dzl[p] = fr[p] ? mu / xs[p] - zl[p] - zl[p] / xs[p] * dx[p] : 0.0;
+            dzu[p] = fr[p] ? mu / us[p] - zu[p] + zu[p] / us[p] * dx[p] : 0.0;
+            if (fr[p]) {
+                if (dx[p] < 0.0) amin = fmin(amin, -tau * xs[p] / dx[p]);
+                if (dx[p] > 0.0) amin = fmin(amin, tau * us[p] / dx[p]);
+                if (dzl[p] < 0.0) amin = fmin(amin, -tau * zl[p] / dzl[p]);
+                if (dzu[p] < 0.0) amin = fmin(amin, -tau * zu[p] / dzu[p]);
+            }
+        }
+        double dlam[MAXJ];
+#pragma unroll
+        for (int j = 0; j < MAXJ; ++j) {
+            if (j < J) {
+                double dwr = 0, dwi = 0, Gds = 0;
+#pragma unroll
+                for (int c = 0; c < MAXC; ++c) {
+                    dwr = fma(sh.con_re[j * 8 + c], ds[c], dwr);
+                    dwi = fma(sh.con_im[j * 8 + c], ds[c], dwi);
+                    Gds = fma(wre[j] * sh.con_re[j * 8 + c] + wim[j] * sh.con_im[j * 8 + c], ds[c], Gds);
+                }
+                dlam[j] = mu / q[j] - lam[j] + 2.0 * lam[j] / q[j] * Gds;
+                const double bq = wre[j] * dwr + wim[j] * dwi;
+                const double c2 = dwr * dwr + dwi * dwi;
+                const double den = bq + sqrt(bq * bq + c2 * tau * q[j]);
+                if (den > 0.0) amin = fmin(amin, tau * q[j] / den);
+                if (dlam[j] < 0.0) amin = fmin(amin, -tau * lam[j] / dlam[j]);
+            } else dlam[j] = 0.0;
+        }
+        const double alpha = warp_min(amin);
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            x[p] = fma(alpha, dx[p], x[p]);
+            zl[p] = fma(alpha, dzl[p], zl[p]);
+            zu[p] = fma(alpha, dzu[p], zu[p]);
+        }
+#pragma unroll
+        for (int j = 0; j < MAXJ; ++j) lam[j] = fma(alpha, dlam[j], lam[j]);
+    }
+    return it;
+}
+
+__device__ __forceinline__ int ipm_dispatch(const EvShared& sh, int C, int J, const double (&a)[2],
+                                            const double (&u)[2], const int (&cls)[2], const bool (&valid)[2],
+                                            double (&x)[2], bool* hit_cap) {
+    if (C <= 5 && J <= 8) return ipm_project<5, 8>(sh, C, J, a, u, cls, valid, x, hit_cap);
+    return ipm_project<SG_EV_MAX_CLASSES, SG_EV_MAX_CONSTRAINTS>(sh, C, J, a, u, cls, valid, x, hit_cap);
+}
+
+// Is the (box-clipped) action inside every network constraint?  x in normalised units.
+__device__ __forceinline__ bool network_feasible(const EvShared& sh, int C, int J, const double (&x)[2],
+                                                 const int (&cls)[2]) {
+    double S[SG_EV_MAX_CLASSES];
+    class_sums<SG_EV_MAX_CLASSES>(x, cls, C, S);
+    bool ok = true;
+    for (int j = 0; j < J; ++j) {
+        double wr = 0, wi = 0;
+#pragma unroll
+        for (int c = 0; c < SG_EV_MAX_CLASSES; ++c) { wr = fma(sh.con_re[j * 8 + c], S[c], wr); wi = fma(sh.con_im[j * 8 + c], S[c], wi); }
+        const double r = sh.lim[j] / kActionScale;
+        ok = ok && !(sqrt(wr * wr + wi * wi) > r);
+    }
+    return ok;
+}
+
+// =================================================================================================
+// One env, one step.  MODE 0: no projection.  MODE 1: projection, fast path inline, otherwise
+// defer to the work list.  MODE 2: projection with the solver inline (work-list kernel).
+// =================================================================================================
+template <int MODE>
+__device__ __forceinline__ void ev_env_step(const sg_ev_model& m, const sg_ev_state& s, const EvShared& sh,
+                                            const long long b, const int lane, const void* __restrict__ action,
+                                            const int flags, const int bins, float* __restrict__ obs,
+                                            double* __restrict__ reward, uint8_t* __restrict__ done,
+                                            uint8_t* __restrict__ pilots, float* __restrict__ final_obs,
+                                            uint8_t* __restrict__ status, int32_t* __restrict__ todo,
+                                            StatsAcc& acc) {
+    const int n = m.n_stations, kf = m.moer_steps, OBS = 2 * n + kf + 2;
+    const int C = m.n_classes, J = m.n_constraints;
+    const int t = s.t[b];
+    if (t >= kEpisode) {            // finished episode that was not reset: no-op, stays terminal
+        if (lane == 0) { reward[b] = 0.0; done[b] = 1; if (status) status[b] = 0; }
+        return;
+    }
+    int day = s.day[b], md = s.moer_day[b];
+    const int i0 = 2 * lane;
+    const bool valid[2] = {i0 < n, i0 + 1 < n};
+    const bool vec = ((n & 1) == 0);     // rows are 8/16-byte aligned when n is even
+
+    // ---- coalesced row loads -------------------------------------------------------------------
+    float af[2] = {0.f, 0.f};
+    if ((flags & 1) == SG_EV_ACTION_I64) {
+        const long long* ap = reinterpret_cast<const long long*>(action) + b * n;
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+            if (valid[p]) af[p] = __fdiv_rn((float)ap[i0 + p], (float)(bins - 1));   // wrappers.py:45
+    } else {
+        const float* ap = reinterpret_cast<const float*>(action) + b * n;
+        if (vec) {
+            if (valid[0]) { const float2 v = ldg_stream_f2(reinterpret_cast<const float2*>(ap + i0)); af[0] = v.x; af[1] = v.y; }
+        } else {
+#pragma unroll
+            for (int p = 0; p < 2; ++p) if (valid[p]) af[p] = __ldg(ap + i0 + p);
+        }
+    }
+    double del[2] = {0.0, 0.0};
+    int k[2] = {0, 0};
+    {
+        const double* dp = s.delivered + b * n;
+        const uint8_t* kp = s.sess_idx + b * n;
+        if (vec) {
+            if (valid[0]) {
+                const double2 v = *reinterpret_cast<const double2*>(dp + i0);
+                del[0] = v.x; del[1] = v.y;
+                const uchar2 kk = *reinterpret_cast<const uchar2*>(kp + i0);
+                k[0] = kk.x; k[1] = kk.y;
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < 2; ++p) if (valid[p]) { del[p] = dp[i0 + p]; k[p] = kp[i0 + p]; }
+        }
+    }
+    int cls[2], type[2];
+    Session ses[2];
+    bool plugged[2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        cls[p] = valid[p] ? sh.cls[i0 + p] : 255;
+        type[p] = valid[p] ? sh.type[i0 + p] : 0;
+        if (valid[p]) ses[p] = load_session(m, day, k[p], i0 + p);
+        else { ses[p].arr = ses[p].dep = ses[p].est = kEmpty; ses[p].energy = 0.0; }
+        // plugged in during period t: its Plugin event (timestamp <= t) has been processed (events
+        // are only drained after the first charge, so nothing is plugged at t = 0) and its Unplug
+        // event (timestamp = departure) has not.
+        plugged[p] = valid[p] && t >= 1 && ses[p].arr <= t && t < ses[p].dep;
+    }
+
+    // ---- action -> normalised pilot x (env.py:363-366) -------------------------------------------
+    double x[2];
+    int st = 0;
+    if constexpr (MODE == 0) {
+        x[0] = (double)af[0]; x[1] = (double)af[1];
+    } else {
+        double a[2], u[2];
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const double rem = ses[p].energy - del[p];
+            const float dem = (plugged[p] && rem > kFullEps) ? (float)rem : 0.f;     // obs 'demands', env.py:388
+            a[p] = (double)af[p];
+            u[p] = upper_bound(dem);
+            x[p] = valid[p] ? fmin(fmax(a[p], 0.0), u[p]) : 0.0;
+        }
+        if (!network_feasible(sh, C, J, x, cls)) {
+            if constexpr (MODE == 1) {
+                if (lane == 0) todo[1 + atomicAdd(todo, 1)] = (int)b;
+                return;                                     // the work-list kernel redoes this env
+            } else {
+                bool cap = false;
+                ipm_dispatch(sh, C, J, a, u, cls, valid, x, &cap);
+                st = SG_EV_STATUS_PROJECTED | (cap ? SG_EV_STATUS_MAXITER : 0);
+            }
+        }
+    }
+
+    // ---- schedule (env.py:368-378), charging (acnsim update_pilots), rates ------------------------
+    double pilot[2], rate_sum = 0.0;
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        pilot[p] = valid[p] ? to_pilot(x[p], type[p]) : 0.0;
+        if (plugged[p]) {
+            const double charge = fmax(0.0, kCapacity - ses[p].energy) + del[p];
+            const double rate_to_full = (kCapacity - charge) / kPeriodH;
+            const double soc = charge / kCapacity;
+            const double p_pilot = pilot[p] * kVoltage / 1000.0;
+            double power;
+            if (soc < kTransitionSoc) power = fmin(fmin(p_pilot, kMaxPower), rate_to_full);
+            else power = fmin(fmin(p_pilot, (1.0 - soc) / (1.0 - kTransitionSoc) * kMaxPower), rate_to_full);
+            const double rate = power * 1000.0 / kVoltage;
+            del[p] += rate * kVoltage / 1000.0 * kPeriodH;
+            rate_sum += rate;
+        }
+    }
+    const double total_rate = warp_sum(rate_sum);
+
+    // ---- excess current from the rounded schedule (env.py:449-452) ---------------------------------
+    double excess;
+    {
+        double S[SG_EV_MAX_CLASSES];
+        class_sums<SG_EV_MAX_CLASSES>(pilot, cls, C, S);
+        double ex = 0.0;
+        if (lane < J) {
+            double wr = 0, wi = 0;
+#pragma unroll
+            for (int c = 0; c < SG_EV_MAX_CLASSES; ++c) { wr = fma(sh.con_re[lane * 8 + c], S[c], wr); wi = fma(sh.con_im[lane * 8 + c], S[c], wi); }
+            ex = fmax(0.0, sqrt(wr * wr + wi * wi) - sh.lim[lane]);
+        }
+        excess = warp_sum(ex);
+    }
+
+    // ---- advance time, drain events with timestamp <= t+1: Unplug (0) before Plugin (10) ------------
+    const int tn = t + 1;
+    float dem_o[2], est_o[2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        while (valid[p] && ses[p].dep <= tn && ses[p].arr != kEmpty) {   // session over (or zero-length)
+            k[p] += 1; del[p] = 0.0;
+            ses[p] = load_session(m, day, k[p], i0 + p);
+        }
+        const bool pl = valid[p] && ses[p].arr <= tn && tn < ses[p].dep;
+        const double rem = ses[p].energy - del[p];
+        const bool active = pl && rem > kFullEps;                         // Interface.active_sessions()
+        dem_o[p] = active ? (float)rem : 0.f;
+        est_o[p] = active ? (float)(ses[p].est - tn) : 0.f;
+    }
+    const bool dn = tn >= kEpisode;
+
+    // ---- reward (env.py:444-462) ---------------------------------------------------------------------
+    const float* mrow = m.moer + ((long long)md * SG_EV_MOER_ROWS + tn) * SG_EV_MOER_COLS;
+    const double moer0 = (double)__ldg(mrow);
+    const double profit = kProfitFactor * total_rate;
+    const double excess_charge = excess * kViolationFactor;
+    const double carbon = kCarbonFactor * total_rate * moer0;
+    const double rew = profit - carbon - excess_charge;
+
+    const bool autoreset = dn && (flags & SG_EV_FLAG_AUTORESET);
+
+    // ---- observation row: demands | est_departures | forecasted_moer | prev_moer | timestep ----------
+    auto write_obs = [&](float* orow, const float* row, const int tstep) {
+        if (vec) {
+            if (valid[0]) {
+                stg_stream_f2(reinterpret_cast<float2*>(orow + i0), make_float2(dem_o[0], dem_o[1]));
+                stg_stream_f2(reinterpret_cast<float2*>(orow + n + i0), make_float2(est_o[0], est_o[1]));
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < 2; ++p) if (valid[p]) { orow[i0 + p] = dem_o[p]; orow[n + i0 + p] = est_o[p]; }
+        }
+        for (int e = lane; e < kf + 2; e += 32) {
+            float v;
+            if (e < kf) v = __ldg(row + 1 + e);
+            else if (e == kf) v = __ldg(row);
+            else v = (float)((double)tstep / (double)kEpisode);     // env.py:392
+            orow[2 * n + e] = v;
+        }
+    };
+    if (!autoreset) {
+        write_obs(obs + b * OBS, mrow, tn);
+    } else {
+        if (final_obs != nullptr) write_obs(final_obs + b * OBS, mrow, tn);   // terminal observation
+        // reset observation of the next episode (env.py:293-338): next day, empty garage, t = 0
+        day = (day + 1) % m.n_days;                      // sequential days, event_generation.py:284-291
+        md = (md + 1) % m.n_moer_days;
+        dem_o[0] = dem_o[1] = est_o[0] = est_o[1] = 0.f;
+        k[0] = k[1] = 0; del[0] = del[1] = 0.0;
+        write_obs(obs + b * OBS, m.moer + ((long long)md * SG_EV_MOER_ROWS) * SG_EV_MOER_COLS, 0);
+    }
+
+    // ---- state write-back ------------------------------------------------------------------------------
+    {
+        double* dp = s.delivered + b * n;
+        uint8_t* kp = s.sess_idx + b * n;
+        if (vec) {
+            if (valid[0]) {
+                *reinterpret_cast<double2*>(dp + i0) = make_double2(del[0], del[1]);
+                *reinterpret_cast<uchar2*>(kp + i0) = make_uchar2((unsigned char)k[0], (unsigned char)k[1]);
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < 2; ++p) if (valid[p]) { dp[i0 + p] = del[p]; kp[i0 + p] = (uint8_t)k[p]; }
+        }
+        if (pilots != nullptr) {
+#pragma unroll
+            for (int p = 0; p < 2; ++p) if (valid[p]) pilots[b * n + i0 + p] = (uint8_t)pilot[p];
+        }
+    }
+    if (lane == 0) {
+        // cumulative reward breakdown (env.py:460-462); cleared on the first step of an episode so
+        // that after an auto-reset the finished episode's totals stay readable until the next step
+        double* bd = s.breakdown + b * 3;
+        if (t == 0) { bd[0] = profit; bd[1] = carbon; bd[2] = excess_charge; }
+        else { bd[0] += profit; bd[1] += carbon; bd[2] += excess_charge; }
+        s.t[b] = autoreset ? 0 : tn;
+        if (autoreset) { s.day[b] = day; s.moer_day[b] = md; }
+        reward[b] = rew;
+        done[b] = dn ? 1 : 0;
+        if (status != nullptr) status[b] = (uint8_t)st;
+        acc.add(rew, dn, profit, carbon, excess_charge);
+        acc.n_proj += (st & SG_EV_STATUS_PROJECTED) ? 1.0 : 0.0;
+        acc.n_maxiter += (st & SG_EV_STATUS_MAXITER) ? 1.0 : 0.0;
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+ev_step_kernel(const sg_ev_model m, const sg_ev_state s, const long long B, const void* __restrict__ action,
+               const int flags, const int bins, float* __restrict__ obs, double* __restrict__ reward,
+               uint8_t* __restrict__ done, uint8_t* __restrict__ pilots, float* __restrict__ final_obs,
+               uint8_t* __restrict__ status, double* __restrict__ stats, int32_t* __restrict__ todo) {
+    __shared__ EvShared sh;
+    load_shared(m, sh);
+    const int lane = threadIdx.x & 31;
+    const long long b = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    StatsAcc acc;
+    if (b < B) ev_env_step<MODE>(m, s, sh, b, lane, action, flags, bins, obs, reward, done, pilots, final_obs, status, todo, acc);
+    if (stats != nullptr) {
+        __syncthreads();
+        stats_flush_block(acc, stats, sh.stat);
+    }
+}
+
+// Work-list kernel: envs whose clipped action violated the network (MODE 1 deferred them).
+__global__ void __launch_bounds__(128)
+ev_step_solve_kernel(const sg_ev_model m, const sg_ev_state s, const void* __restrict__ action, const int flags,
+                     const int bins, float* __restrict__ obs, double* __restrict__ reward,
+                     uint8_t* __restrict__ done, uint8_t* __restrict__ pilots, float* __restrict__ final_obs,
+                     uint8_t* __restrict__ status, double* __restrict__ stats, int32_t* __restrict__ todo) {
+    __shared__ EvShared sh;
+    load_shared(m, sh);
+    const int lane = threadIdx.x & 31;
+    const int count = todo[0];
+    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    StatsAcc acc;
+    for (int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < count; w += nwarps) {
+        const long long b = todo[1 + w];
+        ev_env_step<2>(m, s, sh, b, lane, action, flags, bins, obs, reward, done, pilots, final_obs, status, nullptr, acc);
+    }
+    if (stats != nullptr) {
+        __syncthreads();
+        stats_flush_block(acc, stats, sh.stat);
+    }
+}
+
+__global__ void ev_reset_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
+                                const uint8_t* __restrict__ mask, const int32_t* __restrict__ day_in,
+                                const int32_t* __restrict__ moer_day_in, float* __restrict__ obs) {
+    const long long b = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (b >= B) return;
+    if (mask != nullptr && mask[b] == 0) return;
+    const int n = m.n_stations, kf = m.moer_steps, OBS = 2 * n + kf + 2;
+    int day = day_in ? day_in[b] : s.day[b];
+    int md = moer_day_in ? moer_day_in[b] : s.moer_day[b];
+    day = ((day % m.n_days) + m.n_days) % m.n_days;
+    md = ((md % m.n_moer_days) + m.n_moer_days) % m.n_moer_days;
+    for (int i = lane; i < n; i += 32) { s.delivered[b * n + i] = 0.0; s.sess_idx[b * n + i] = 0; }
+    float* orow = obs + b * OBS;
+    for (int i = lane; i < 2 * n; i += 32) orow[i] = 0.f;
+    const float* mrow = m.moer + ((long long)md * SG_EV_MOER_ROWS) * SG_EV_MOER_COLS;
+    for (int e = lane; e < kf + 2; e += 32) orow[2 * n + e] = e < kf ? mrow[1 + e] : (e == kf ? mrow[0] : 0.f);
+    if (lane == 0) {
+        s.t[b] = 0; s.day[b] = day; s.moer_day[b] = md;
+        s.breakdown[b * 3] = s.breakdown[b * 3 + 1] = s.breakdown[b * 3 + 2] = 0.0;
+    }
+}
+
+// Stand-alone projection operator (env.py:200-221): one warp per problem.
+__global__ void __launch_bounds__(128)
+ev_project_kernel(const sg_ev_model m, const long long B, const float* __restrict__ action,
+                  const float* __restrict__ demands, double* __restrict__ x_out, uint8_t* __restrict__ status,
+                  int32_t* __restrict__ iters) {
+    __shared__ EvShared sh;
+    load_shared(m, sh);
+    const int lane = threadIdx.x & 31;
+    const long long b = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (b >= B) return;
+    const int n = m.n_stations, i0 = 2 * lane;
+    const bool valid[2] = {i0 < n, i0 + 1 < n};
+    double a[2], u[2], x[2];
+    int cls[2];
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        a[p] = valid[p] ? (double)action[b * n + i0 + p] : 0.0;
+        u[p] = valid[p] ? upper_bound(demands[b * n + i0 + p]) : 0.0;
+        cls[p] = valid[p] ? sh.cls[i0 + p] : 255;
+        x[p] = valid[p] ? fmin(fmax(a[p], 0.0), u[p]) : 0.0;
+    }
+    int st = 0, it = 0;
+    if (!network_feasible(sh, m.n_classes, m.n_constraints, x, cls)) {
+        bool cap = false;
+        it = ipm_dispatch(sh, m.n_classes, m.n_constraints, a, u, cls, valid, x, &cap);
+        st = SG_EV_STATUS_PROJECTED | (cap ? SG_EV_STATUS_MAXITER : 0);
+    }
+#pragma unroll
+    for (int p = 0; p < 2; ++p) if (valid[p]) x_out[b * n + i0 + p] = x[p];
+    if (lane == 0) { if (status) status[b] = (uint8_t)st; if (iters) iters[b] = it; }
+}
+
+int check_model(const sg_ev_model* m) {
+    SG_CHECK_ARG(m != nullptr, "ev: model is NULL");
+    SG_CHECK_ARG(m->n_stations >= 1 && m->n_stations <= SG_EV_MAX_STATIONS, "ev: n_stations=%d outside [1,64]", m->n_stations);
+    SG_CHECK_ARG(m->n_classes >= 1 && m->n_classes <= SG_EV_MAX_CLASSES, "ev: n_classes=%d outside [1,8]", m->n_classes);
+    SG_CHECK_ARG(m->n_constraints >= 0 && m->n_constraints <= SG_EV_MAX_CONSTRAINTS, "ev: n_constraints=%d outside [0,16]", m->n_constraints);
+    SG_CHECK_ARG(m->moer_steps >= 1 && m->moer_steps <= 36, "ev: moer_forecast_steps=%d outside [1,36]", m->moer_steps);
+    SG_CHECK_ARG(m->station_class && m->station_type && m->con_re && m->con_im && m->magnitudes, "ev: NULL network table");
+    return 0;
+}
+
+}  // namespace
+}  // namespace sg
+
+extern "C" {
+
+int sg_ev_reset(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, const uint8_t* reset_mask,
+                const int32_t* day_in, const int32_t* moer_day_in, float* obs, void* stream) {
+    if (int rc = sg::check_model(m)) return rc;
+    SG_CHECK_ARG(s && obs && m->moer, "ev_reset: NULL argument");
+    SG_CHECK_ARG(m->n_days >= 1 && m->n_moer_days >= 1, "ev_reset: empty trace/MOER pool");
+    if (num_envs <= 0) return 0;
+    const unsigned grid = (unsigned)((num_envs + 3) / 4);
+    sg::ev_reset_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*m, *s, num_envs, reset_mask,
+                                                                                day_in, moer_day_in, obs);
+    return sg::launch_status("ev_reset_kernel");
+}
+
+int sg_ev_step(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, const void* action, int32_t flags,
+               int32_t discrete_bins, float* obs, double* reward, uint8_t* done, uint8_t* pilots,
+               float* final_obs, uint8_t* status, double* stats, int32_t* todo, void* stream) {
+    if (int rc = sg::check_model(m)) return rc;
+    SG_CHECK_ARG(s && action && obs && reward && done, "ev_step: NULL argument");
+    SG_CHECK_ARG(m->sessions && m->moer && m->n_days >= 1 && m->n_moer_days >= 1 && m->max_sessions >= 1,
+                 "ev_step: empty trace/MOER pool");
+    SG_CHECK_ARG(!((flags & 1) == SG_EV_ACTION_I64) || discrete_bins >= 2, "ev_step: discrete_bins must be >= 2");
+    SG_CHECK_ARG(!m->project || todo != nullptr, "ev_step: projection needs the todo scratch buffer");
+    if (num_envs <= 0) return 0;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const unsigned grid = (unsigned)((num_envs + sg::kWarpsPerBlock - 1) / sg::kWarpsPerBlock);
+    if (!m->project) {
+        sg::ev_step_kernel<0><<<grid, sg::kThreads, 0, st>>>(*m, *s, num_envs, action, flags, discrete_bins, obs,
+                                                           reward, done, pilots, final_obs, status, stats, todo);
+        return sg::launch_status("ev_step_kernel<0>");
+    }
+    SG_CUDA(cudaMemsetAsync(todo, 0, sizeof(int32_t), st));
+    sg::ev_step_kernel<1><<<grid, sg::kThreads, 0, st>>>(*m, *s, num_envs, action, flags, discrete_bins, obs, reward,
+                                                       done, pilots, final_obs, status, stats, todo);
+    if (int rc = sg::launch_status("ev_step_kernel<1>")) return rc;
+    int sms = sg_device_sm_count();
+    if (sms <= 0) sms = 148;
+    const unsigned sgrid = (unsigned)std::min<long long>((num_envs + 3) / 4, (long long)sms * 4);
+    sg::ev_step_solve_kernel<<<sgrid, 128, 0, st>>>(*m, *s, action, flags, discrete_bins, obs, reward, done, pilots,
+                                                  final_obs, status, stats, todo);
+    return sg::launch_status("ev_step_solve_kernel");
+}
+
+int sg_ev_step_host(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, const void* h_action,
+                    int32_t flags, int32_t discrete_bins, float* h_obs, double* h_reward, uint8_t* h_done,
+                    void* d_action, float* d_obs, double* d_reward, uint8_t* d_done, uint8_t* d_status,
+                    double* d_stats, int32_t* d_todo, void* stream) {
+    SG_CHECK_ARG(m && h_action && h_obs && h_reward && h_done && d_action && d_obs && d_reward && d_done,
+                 "ev_step_host: NULL argument");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t B = (size_t)num_envs, n = (size_t)m->n_stations, OBS = 2 * n + m->moer_steps + 2;
+    const size_t abytes = B * n * (((flags & 1) == SG_EV_ACTION_I64) ? 8 : 4);
+    SG_CUDA(cudaMemcpyAsync(d_action, h_action, abytes, cudaMemcpyHostToDevice, st));
+    if (int rc = sg_ev_step(m, s, num_envs, d_action, flags, discrete_bins, d_obs, d_reward, d_done, nullptr,
+                            nullptr, d_status, d_stats, d_todo, stream)) return rc;
+    SG_CUDA(cudaMemcpyAsync(h_obs, d_obs, B * OBS * 4, cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaMemcpyAsync(h_reward, d_reward, B * 8, cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaMemcpyAsync(h_done, d_done, B, cudaMemcpyDeviceToHost, st));
+    SG_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int sg_ev_project(const sg_ev_model* m, int64_t num_envs, const float* action, const float* demands,
+                  double* x_out, uint8_t* status, int32_t* iters, void* stream) {
+    if (int rc = sg::check_model(m)) return rc;
+    SG_CHECK_ARG(action && demands && x_out, "ev_project: NULL argument");
+    if (num_envs <= 0) return 0;
+    const unsigned grid = (unsigned)((num_envs + 3) / 4);
+    sg::ev_project_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*m, num_envs, action, demands,
+                                                                                  x_out, status, iters);
+    return sg::launch_status("ev_project_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,310 @@
+"""Batched EVChargingEnv on the B200 engine.
+
+``BatchedEVChargingEnv`` advances ``num_envs`` independent copies of the reference's
+``EVChargingEnv`` (``sustaingym/envs/evcharging/env.py``) in lock-step with one kernel launch per
+``step()``; ``EVChargingEnv`` is the ``num_envs = 1`` view with the reference's exact Gymnasium
+signature (``reset(*, seed, options) -> (obs, info)``, ``step(action) -> 5-tuple``).
+
+All compute happens in ``libsustaingym_b200.so`` (``sg_ev_step`` / ``sg_ev_reset``); this module is
+host plumbing: it owns the device tensors and mirrors the reference API.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any
+
+import numpy as np
+import torch
+
+from ... import _lib, spaces
+from .event_generation import AbstractTraceGenerator
+from .network import ChargingNetworkSpec
+
+OBS_KEYS = ("demands", "est_departures", "forecasted_moer", "prev_moer", "timestep")  # sorted (flatten order)
+
+
+class BatchedEVChargingEnv:
+    """See module docstring.  Mirrors the constructor of the reference (env.py:116-119) plus
+    ``num_envs``/``device``/``auto_reset``.
+
+    Observations are returned flat, ``[num_envs, 2n+k+2]`` f32 in gymnasium's flatten order
+    (``demands | est_departures | forecasted_moer | prev_moer | timestep``); ``obs_dict()`` gives
+    the Dict view (slices of the same storage).
+    """
+
+    # env.py:99-114
+    TIMESTEP_DURATION = 5
+    ACTION_SCALE_FACTOR = 32
+    VOLTAGE = 208
+    MARGINAL_REVENUE_PER_KWH = 0.15
+    OPERATING_MARGIN = 0.20
+    MARGINAL_PROFIT_PER_KWH = MARGINAL_REVENUE_PER_KWH * OPERATING_MARGIN
+    CO2_COST_PER_METRIC_TON = 30.85
+    A_MINS_TO_KWH = (1 / 60) * (VOLTAGE / 1000)
+    VIOLATION_WEIGHT = 0.001
+    A_PERS_TO_KWH = A_MINS_TO_KWH * TIMESTEP_DURATION
+    PROFIT_FACTOR = A_PERS_TO_KWH * MARGINAL_PROFIT_PER_KWH
+    VIOLATION_FACTOR = A_PERS_TO_KWH * VIOLATION_WEIGHT
+    CARBON_COST_FACTOR = A_PERS_TO_KWH * (CO2_COST_PER_METRIC_TON / 1000)
+
+    def __init__(self, data_generator: AbstractTraceGenerator, num_envs: int = 1,
+                 moer_forecast_steps: int = 36, project_action_in_env: bool = True, verbose: int = 0,
+                 device: str | torch.device | None = None, auto_reset: bool = False,
+                 discrete_bins: int = -1, collect_stats: bool = False):
+        assert 1 <= moer_forecast_steps <= 36                                   # env.py:120
+        self.lib = _lib.load()                                                  # fails loudly if not built
+        if not torch.cuda.is_available():
+            raise RuntimeError("BatchedEVChargingEnv needs a CUDA device (no CPU fallback)")
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.data_generator = data_generator
+        self.num_envs = int(num_envs)
+        self.max_timestep = 288
+        self.moer_forecast_steps = moer_forecast_steps
+        self.project_action_in_env = project_action_in_env
+        self.verbose = verbose
+        self.auto_reset = auto_reset
+        self.discrete_bins = discrete_bins
+        self.cn: ChargingNetworkSpec = data_generator.network
+        self.num_stations = n = self.cn.num_stations
+        self.obs_dim = 2 * n + moer_forecast_steps + 2
+
+        # ---- spaces (env.py:143-150, 171-172; wrappers.py:36-41 for the discrete variant) ---------
+        k = moer_forecast_steps
+        self.single_observation_space = spaces.Dict({
+            "timestep": spaces.Box(0, 1, shape=(1,), dtype=np.float32),
+            "est_departures": spaces.Box(-288, 288, shape=(n,), dtype=np.float32),
+            "demands": spaces.Box(0, data_generator.requested_energy_cap, shape=(n,), dtype=np.float32),
+            "prev_moer": spaces.Box(0, 1, shape=(1,), dtype=np.float32),
+            "forecasted_moer": spaces.Box(0, 1, shape=(k,), dtype=np.float32),
+        })
+        if discrete_bins > 0:
+            self.single_action_space = spaces.MultiDiscrete(np.ones(n, dtype=np.int64) * discrete_bins)
+        else:
+            self.single_action_space = spaces.Box(low=0, high=1.0, shape=(n,), dtype=np.float32)
+        self.obs_slices = {"demands": slice(0, n), "est_departures": slice(n, 2 * n),
+                           "forecasted_moer": slice(2 * n, 2 * n + k),
+                           "prev_moer": slice(2 * n + k, 2 * n + k + 1),
+                           "timestep": slice(2 * n + k + 1, 2 * n + k + 2)}
+
+        # ---- device-resident constants ----------------------------------------------------------
+        dev = self.device
+        cls, coef = self.cn.class_reduce()
+        if coef.shape[1] > _lib.SG_EV_MAX_CLASSES or coef.shape[0] > _lib.SG_EV_MAX_CONSTRAINTS:
+            raise ValueError("network has more station classes/constraints than the kernels support")
+        t = data_generator.tables
+        rec = np.zeros(t.arrival.shape, dtype=np.dtype([("arr", "<i2"), ("dep", "<i2"), ("est", "<i2"),
+                                                         ("res", "<i2"), ("energy", "<f8")]))
+        rec["arr"], rec["dep"], rec["est"], rec["energy"] = t.arrival, t.departure, t.est_departure, t.energy
+        self._c = {
+            "cls": torch.from_numpy(cls.astype(np.uint8)).to(dev),
+            "type": torch.from_numpy(self.cn.evse_type.astype(np.uint8)).to(dev),
+            "re": torch.from_numpy(np.ascontiguousarray(coef.real)).to(dev),
+            "im": torch.from_numpy(np.ascontiguousarray(coef.imag)).to(dev),
+            "mag": torch.from_numpy(self.cn.magnitudes.astype(np.float64)).to(dev),
+            "sessions": torch.from_numpy(rec.view(np.uint8).reshape(-1)).to(dev),
+            "moer": torch.from_numpy(data_generator.moer).to(dev),
+        }
+        self._max_profit_per_day = t.max_profit(self.MARGINAL_PROFIT_PER_KWH, self.A_PERS_TO_KWH, self.ACTION_SCALE_FACTOR)
+        self._model = _lib.EVModel(
+            n, coef.shape[1], coef.shape[0], k, t.max_sessions, t.num_days, data_generator.moer.shape[0],
+            int(project_action_in_env), self._c["cls"].data_ptr(), self._c["type"].data_ptr(),
+            self._c["re"].data_ptr(), self._c["im"].data_ptr(), self._c["mag"].data_ptr(),
+            self._c["sessions"].data_ptr(), self._c["moer"].data_ptr())
+
+        # ---- per-env state and outputs ---------------------------------------------------------------
+        B = self.num_envs
+        z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)  # noqa: E731
+        self.delivered = z(B, n, dtype=torch.float64)
+        self.sess_idx = z(B, n, dtype=torch.uint8)
+        self.t = z(B, dtype=torch.int32)
+        self.day = z(B, dtype=torch.int32)
+        self.moer_day = z(B, dtype=torch.int32)
+        self.breakdown = z(B, 3, dtype=torch.float64)
+        self._state = _lib.EVState(self.delivered.data_ptr(), self.sess_idx.data_ptr(), self.t.data_ptr(),
+                                   self.day.data_ptr(), self.moer_day.data_ptr(), self.breakdown.data_ptr())
+        self.obs = z(B, self.obs_dim, dtype=torch.float32)
+        self.final_obs = z(B, self.obs_dim, dtype=torch.float32) if auto_reset else None
+        self.reward = z(B, dtype=torch.float64)
+        self.done = z(B, dtype=torch.uint8)
+        self.status = z(B, dtype=torch.uint8)
+        self.pilots = z(B, n, dtype=torch.uint8)
+        self.todo = z(B + 1, dtype=torch.int32)
+        self.stats = z(_lib.SG_STATS_LEN, dtype=torch.float64) if collect_stats else None
+        if self.stats is not None:
+            self.reset_stats()
+        self._action_dtype = torch.int64 if discrete_bins > 0 else torch.float32
+        self._d_action = z(B, n, dtype=self._action_dtype)
+        # pinned host staging for the host-buffer path
+        self._h_action = torch.zeros(B, n, dtype=self._action_dtype).pin_memory()
+        self._h_obs = torch.zeros(B, self.obs_dim, dtype=torch.float32).pin_memory()
+        self._h_reward = torch.zeros(B, dtype=torch.float64).pin_memory()
+        self._h_done = torch.zeros(B, dtype=torch.uint8).pin_memory()
+        self._flags = (_lib.SG_EV_ACTION_I64 if discrete_bins > 0 else _lib.SG_EV_ACTION_F32) | \
+            (_lib.SG_EV_FLAG_AUTORESET if auto_reset else 0)
+        self.kernel_launches = 0
+        self._needs_reset = True
+
+    # ------------------------------------------------------------------------------------------
+    def __repr__(self) -> str:
+        return (f"EVChargingGym (action projection = {self.project_action_in_env}, "
+                f"moer forecast steps = {self.moer_forecast_steps}) using {self.data_generator!r} "
+                f"x {self.num_envs} envs on {self.device}")
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def reset_stats(self) -> None:
+        _lib.check(self.lib.sg_stats_reset(self.stats.data_ptr(), self._stream()), "sg_stats_reset")
+
+    def obs_dict(self, obs=None) -> dict:
+        obs = self.obs if obs is None else obs
+        return {k: obs[..., s] for k, s in self.obs_slices.items()}
+
+    def reset(self, *, seed: int | np.ndarray | None = None, options: dict | None = None,
+              mask: torch.Tensor | np.ndarray | None = None):
+        """env.py:293-338 for every env (or those in ``mask``).  ``seed`` may be one int (env i gets
+        ``seed + i``) or an array of per-env seeds; it selects the day exactly as the reference's
+        sequential ``RealTraceGenerator`` does."""
+        if options is not None and "verbose" in options:
+            self.verbose = options["verbose"]
+        B = self.num_envs
+        if seed is None:
+            seeds = None
+        elif np.isscalar(seed):
+            seeds = int(seed) + np.arange(B)
+        else:
+            seeds = np.asarray(seed)
+        self.data_generator.set_seed(None if seeds is None else int(seeds[0]))
+        days = self.data_generator.first_days(seeds, B)
+        mdays = self.data_generator.moer_days(days)
+        d_days = torch.from_numpy(days).to(self.device)
+        d_mdays = torch.from_numpy(mdays).to(self.device)
+        d_mask = None
+        if mask is not None:
+            d_mask = torch.as_tensor(mask, device=self.device).to(torch.uint8).contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sg_ev_reset(C.byref(self._model), C.byref(self._state), B,
+                                            _lib.ptr(d_mask), d_days.data_ptr(), d_mdays.data_ptr(),
+                                            self.obs.data_ptr(), self._stream()), "sg_ev_reset")
+        self.kernel_launches += 1
+        self._needs_reset = False
+        return self.obs, self._infos()
+
+    def step(self, actions):
+        """env.py:229-291 for every env.  ``actions``: ``[num_envs, n]`` CUDA tensor (device path,
+        returns CUDA tensors, asynchronous) or NumPy array (host path: pinned H2D copy, step, D2H
+        copy of obs/reward/done, synchronised; returns NumPy arrays)."""
+        if self._needs_reset:
+            raise RuntimeError("call reset() before step()")      # env.py:283 NOTE
+        B, n = self.num_envs, self.num_stations
+        if isinstance(actions, np.ndarray):
+            if actions.shape != (B, n):
+                raise ValueError(f"actions must have shape {(B, n)}, got {actions.shape}")
+            self._h_action.numpy()[...] = actions
+            with torch.cuda.device(self.device):
+                _lib.check(self.lib.sg_ev_step_host(
+                    C.byref(self._model), C.byref(self._state), B, self._h_action.data_ptr(), self._flags,
+                    max(self.discrete_bins, 0), self._h_obs.data_ptr(), self._h_reward.data_ptr(),
+                    self._h_done.data_ptr(), self._d_action.data_ptr(), self.obs.data_ptr(),
+                    self.reward.data_ptr(), self.done.data_ptr(), self.status.data_ptr(),
+                    _lib.ptr(self.stats), self.todo.data_ptr(), self._stream()), "sg_ev_step_host")
+            self.kernel_launches += 2 if self.project_action_in_env else 1
+            done = self._h_done.numpy().astype(bool)
+            return (self._h_obs.numpy().copy(), self._h_reward.numpy().copy(), done,
+                    np.zeros(B, bool), self._infos())
+        if actions.device != self.device or actions.dtype != self._action_dtype or tuple(actions.shape) != (B, n):
+            raise ValueError(f"actions must be a {self._action_dtype} tensor of shape {(B, n)} on {self.device}")
+        actions = actions.contiguous()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sg_ev_step(
+                C.byref(self._model), C.byref(self._state), B, actions.data_ptr(), self._flags,
+                max(self.discrete_bins, 0), self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
+                self.pilots.data_ptr(), _lib.ptr(self.final_obs), self.status.data_ptr(), _lib.ptr(self.stats),
+                self.todo.data_ptr(), self._stream()), "sg_ev_step")
+        self.kernel_launches += 2 if self.project_action_in_env else 1
+        return self.obs, self.reward, self.done.bool(), torch.zeros_like(self.done, dtype=torch.bool), self._infos()
+
+    def project(self, actions: torch.Tensor, demands: torch.Tensor):
+        """The action projection alone (env.py:200-221): returns (x f64 [B,n], status u8 [B], iters i32 [B])."""
+        B = actions.shape[0]
+        x = torch.empty(B, self.num_stations, dtype=torch.float64, device=self.device)
+        st = torch.empty(B, dtype=torch.uint8, device=self.device)
+        it = torch.empty(B, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sg_ev_project(C.byref(self._model), B, actions.contiguous().data_ptr(),
+                                              demands.contiguous().data_ptr(), x.data_ptr(), st.data_ptr(),
+                                              it.data_ptr(), self._stream()), "sg_ev_project")
+        return x, st, it
+
+    def _infos(self) -> dict:
+        """Lazy batched info (env.py:403-406): tensors, not per-env dicts — no sync on the hot path."""
+        return {"reward_breakdown": self.breakdown, "day": self.day, "status": self.status,
+                "max_profit_per_day": self._max_profit_per_day}
+
+    def close(self) -> None:
+        pass
+
+
+class EVChargingEnv:
+    """The reference's single-env Gymnasium interface (env.py:20-470) on top of a 1-env batch.
+
+    ``reset(*, seed, options) -> (obs dict, info)``; ``step(action) -> (obs dict, float reward,
+    bool terminated, False, info)``.  NumPy in, NumPy out.  Unlike the reference, the caller's
+    action array is not scaled in place (env.py:366 mutates it when projection is off)."""
+
+    metadata: dict = {}
+    render_mode = None
+    spec = None
+
+    def __init__(self, data_generator: AbstractTraceGenerator, moer_forecast_steps: int = 36,
+                 project_action_in_env: bool = True, verbose: int = 0, device=None, discrete_bins: int = -1):
+        self._b = BatchedEVChargingEnv(data_generator, 1, moer_forecast_steps, project_action_in_env, verbose,
+                                       device, auto_reset=False, discrete_bins=discrete_bins)
+        self.data_generator = data_generator
+        self.max_timestep = 288
+        self.moer_forecast_steps = moer_forecast_steps
+        self.project_action_in_env = project_action_in_env
+        self.verbose = verbose
+        self.cn = self._b.cn
+        self.num_stations = self._b.num_stations
+        self.observation_space = self._b.single_observation_space
+        self.action_space = self._b.single_action_space
+        self.t = 0
+        self._episodes = 0
+        self._seed0 = 0
+
+    def __repr__(self) -> str:
+        return (f"EVChargingGym (action projection = {self.project_action_in_env}, "
+                f"moer forecast steps = {self.moer_forecast_steps}) using {self.data_generator!r}")
+
+    def _obs(self, flat: np.ndarray) -> dict:
+        return {k: flat[0, s].copy() for k, s in self._b.obs_slices.items()}
+
+    def _info(self) -> dict[str, Any]:
+        bd = self._b.breakdown[0].cpu().numpy()
+        day = int(self._b.day[0])
+        return {"max_profit": float(self._b._max_profit_per_day[day]),
+                "reward_breakdown": {"profit": float(bd[0]), "carbon_cost": float(bd[1]),
+                                     "excess_charge": float(bd[2])}}
+
+    def reset(self, *, seed: int | None = None, options: dict | None = None):
+        if seed is None:
+            # the reference's sequential generator simply moves on to the next day (event_generation.py:284-291)
+            seed_eff = self._seed0 + self._episodes
+        else:
+            self._seed0, self._episodes, seed_eff = int(seed), 0, int(seed)
+        self._episodes += 1
+        self.action_space.seed(seed)
+        obs, _ = self._b.reset(seed=seed_eff, options=options)
+        self.t = 0
+        return self._obs(obs.cpu().numpy()), self._info()
+
+    def step(self, action):
+        a = np.asarray(action).reshape(1, self.num_stations)
+        a = a.astype(np.int64 if self._b.discrete_bins > 0 else np.float32)
+        obs, rew, done, trunc, _ = self._b.step(a)
+        self.t += 1
+        return self._obs(obs), float(rew[0]), bool(done[0]), False, self._info()
+
+    def close(self) -> None:
+        self._b.close()
