@@ -170,12 +170,21 @@ int sg_ev_reset(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs,
  *   pilots : [B, n] u8 amps actually sent (schedule of env.py:368-378) or NULL
  *   final_obs: with AUTORESET, receives the terminal observation of envs that finished, or NULL
  *   status : [B] u8 or NULL;  stats: [16] f64 accumulators or NULL (see sg_stats_*)
- *   todo   : [B+1] i32 device scratch used when m->project != 0 (deferred-solve work list)
+ *   todo   : [B+2] i32 zero-initialised device scratch (work list of envs whose clipped action
+ *            violates the network); required when m->project != 0
+ * With m->project != 0 a step is two launches: sg_ev_step advances every env whose box-clipped
+ * action is already feasible (then it is the exact projection) and queues the others;
+ * sg_ev_step_finish (same arguments) runs the interior-point projection for the queued envs and
+ * advances them, then re-arms the work list.  Call both, in order, on the same stream.
  */
 int sg_ev_step(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs,
                const void* action, int32_t flags, int32_t discrete_bins,
                float* obs, double* reward, uint8_t* done, uint8_t* pilots, float* final_obs,
                uint8_t* status, double* stats, int32_t* todo, void* stream);
+int sg_ev_step_finish(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs,
+                      const void* action, int32_t flags, int32_t discrete_bins,
+                      float* obs, double* reward, uint8_t* done, uint8_t* pilots, float* final_obs,
+                      uint8_t* status, double* stats, int32_t* todo, void* stream);
 
 /* Host-buffer variant: H2D(action) -> step -> D2H(obs, reward, done) -> sync. */
 int sg_ev_step_host(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs,

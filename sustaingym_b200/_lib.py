@@ -70,6 +70,8 @@ SIGNATURES = {
     "sg_ev_reset": (C.c_int, [C.POINTER(EVModel), C.POINTER(EVState), _i64, _vp, _vp, _vp, _vp, _vp]),
     "sg_ev_step": (C.c_int, [C.POINTER(EVModel), C.POINTER(EVState), _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp,
                              _vp, _vp, _vp, _vp, _vp]),
+    "sg_ev_step_finish": (C.c_int, [C.POINTER(EVModel), C.POINTER(EVState), _i64, _vp, _i32, _i32, _vp, _vp, _vp,
+                                    _vp, _vp, _vp, _vp, _vp, _vp]),
     "sg_ev_step_host": (C.c_int, [C.POINTER(EVModel), C.POINTER(EVState), _i64, _vp, _i32, _i32, _vp, _vp, _vp,
                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sg_ev_project": (C.c_int, [C.POINTER(EVModel), _i64, _vp, _vp, _vp, _vp, _vp, _vp]),

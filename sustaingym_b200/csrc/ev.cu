@@ -454,7 +454,7 @@ __device__ __forceinline__ void ev_env_step(const sg_ev_model& m, const sg_ev_st
         }
         if (!network_feasible(sh, C, J, x, cls)) {
             if constexpr (MODE == 1) {
-                if (lane == 0) todo[1 + atomicAdd(todo, 1)] = (int)b;
+                if (lane == 0) todo[2 + atomicAdd(todo, 1)] = (int)b;
                 return;                                     // the work-list kernel redoes this env
             } else {
                 bool cap = false;
@@ -623,12 +623,18 @@ ev_step_solve_kernel(const sg_ev_model m, const sg_ev_state s, const void* __res
     const int nwarps = gridDim.x * (blockDim.x >> 5);
     StatsAcc acc;
     for (int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < count; w += nwarps) {
-        const long long b = todo[1 + w];
+        const long long b = todo[2 + w];
         ev_env_step<2>(m, s, sh, b, lane, action, flags, bins, obs, reward, done, pilots, final_obs, status, nullptr, acc);
     }
     if (stats != nullptr) {
         __syncthreads();
         stats_flush_block(acc, stats, sh.stat);
+    }
+    // last CTA to finish re-arms the work list for the next step (no memset node needed)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(todo + 1, 1) == (int)gridDim.x - 1) { todo[0] = 0; todo[1] = 0; __threadfence(); }
     }
 }
 
@@ -731,10 +737,19 @@ int sg_ev_step(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, con
                                                            reward, done, pilots, final_obs, status, stats, todo);
         return sg::launch_status("ev_step_kernel<0>");
     }
-    SG_CUDA(cudaMemsetAsync(todo, 0, sizeof(int32_t), st));
     sg::ev_step_kernel<1><<<grid, sg::kThreads, 0, st>>>(*m, *s, num_envs, action, flags, discrete_bins, obs, reward,
                                                        done, pilots, final_obs, status, stats, todo);
-    if (int rc = sg::launch_status("ev_step_kernel<1>")) return rc;
+    return sg::launch_status("ev_step_kernel<1>");
+}
+
+int sg_ev_step_finish(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, const void* action,
+                      int32_t flags, int32_t discrete_bins, float* obs, double* reward, uint8_t* done,
+                      uint8_t* pilots, float* final_obs, uint8_t* status, double* stats, int32_t* todo,
+                      void* stream) {
+    if (int rc = sg::check_model(m)) return rc;
+    if (!m->project || num_envs <= 0) return 0;          // nothing is ever deferred without projection
+    SG_CHECK_ARG(s && action && obs && reward && done && todo, "ev_step_finish: NULL argument");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     int sms = sg_device_sm_count();
     if (sms <= 0) sms = 148;
     const unsigned sgrid = (unsigned)std::min<long long>((num_envs + 3) / 4, (long long)sms * 4);
@@ -755,6 +770,8 @@ int sg_ev_step_host(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs
     SG_CUDA(cudaMemcpyAsync(d_action, h_action, abytes, cudaMemcpyHostToDevice, st));
     if (int rc = sg_ev_step(m, s, num_envs, d_action, flags, discrete_bins, d_obs, d_reward, d_done, nullptr,
                             nullptr, d_status, d_stats, d_todo, stream)) return rc;
+    if (int rc = sg_ev_step_finish(m, s, num_envs, d_action, flags, discrete_bins, d_obs, d_reward, d_done, nullptr,
+                                   nullptr, d_status, d_stats, d_todo, stream)) return rc;
     SG_CUDA(cudaMemcpyAsync(h_obs, d_obs, B * OBS * 4, cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaMemcpyAsync(h_reward, d_reward, B * 8, cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaMemcpyAsync(h_done, d_done, B, cudaMemcpyDeviceToHost, st));

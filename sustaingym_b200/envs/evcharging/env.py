@@ -128,7 +128,7 @@ class BatchedEVChargingEnv:
         self.done = z(B, dtype=torch.uint8)
         self.status = z(B, dtype=torch.uint8)
         self.pilots = z(B, n, dtype=torch.uint8)
-        self.todo = z(B + 1, dtype=torch.int32)
+        self.todo = z(B + 2, dtype=torch.int32)
         self.stats = z(_lib.SG_STATS_LEN, dtype=torch.float64) if collect_stats else None
         if self.stats is not None:
             self.reset_stats()
@@ -197,32 +197,65 @@ class BatchedEVChargingEnv:
         if self._needs_reset:
             raise RuntimeError("call reset() before step()")      # env.py:283 NOTE
         B, n = self.num_envs, self.num_stations
-        if isinstance(actions, np.ndarray):
-            if actions.shape != (B, n):
-                raise ValueError(f"actions must have shape {(B, n)}, got {actions.shape}")
-            self._h_action.numpy()[...] = actions
+        host_np = isinstance(actions, np.ndarray)
+        if host_np or actions.device.type == "cpu":
+            if tuple(actions.shape) != (B, n):
+                raise ValueError(f"actions must have shape {(B, n)}, got {tuple(actions.shape)}")
+            if host_np:
+                self._h_action.numpy()[...] = actions
+                h_act = self._h_action
+            elif actions.is_pinned() and actions.dtype == self._action_dtype and actions.is_contiguous():
+                h_act = actions                                   # zero-copy: DMA straight from the caller's buffer
+            else:
+                self._h_action.copy_(actions)
+                h_act = self._h_action
             with torch.cuda.device(self.device):
                 _lib.check(self.lib.sg_ev_step_host(
-                    C.byref(self._model), C.byref(self._state), B, self._h_action.data_ptr(), self._flags,
+                    C.byref(self._model), C.byref(self._state), B, h_act.data_ptr(), self._flags,
                     max(self.discrete_bins, 0), self._h_obs.data_ptr(), self._h_reward.data_ptr(),
                     self._h_done.data_ptr(), self._d_action.data_ptr(), self.obs.data_ptr(),
                     self.reward.data_ptr(), self.done.data_ptr(), self.status.data_ptr(),
                     _lib.ptr(self.stats), self.todo.data_ptr(), self._stream()), "sg_ev_step_host")
             self.kernel_launches += 2 if self.project_action_in_env else 1
-            done = self._h_done.numpy().astype(bool)
-            return (self._h_obs.numpy().copy(), self._h_reward.numpy().copy(), done,
-                    np.zeros(B, bool), self._infos())
+            if host_np:
+                done = self._h_done.numpy().astype(bool)
+                return (self._h_obs.numpy().copy(), self._h_reward.numpy().copy(), done,
+                        np.zeros(B, bool), self._infos())
+            # torch host path: views of the pinned result buffers (valid until the next step)
+            return self._h_obs, self._h_reward, self._h_done.bool(), torch.zeros(B, dtype=torch.bool), self._infos()
         if actions.device != self.device or actions.dtype != self._action_dtype or tuple(actions.shape) != (B, n):
             raise ValueError(f"actions must be a {self._action_dtype} tensor of shape {(B, n)} on {self.device}")
         actions = actions.contiguous()
-        with torch.cuda.device(self.device):
-            _lib.check(self.lib.sg_ev_step(
-                C.byref(self._model), C.byref(self._state), B, actions.data_ptr(), self._flags,
+        self.launch_step(actions)
+        return self.obs, self.reward, self.done.bool(), torch.zeros_like(self.done, dtype=torch.bool), self._infos()
+
+    def launch_step(self, actions: torch.Tensor, phase: int = 0) -> None:
+        """Enqueues the step kernels on the current stream without building return values (used by
+        ``step``, CUDA-graph capture and the benchmark).  ``phase``: 0 both, 1 only the main kernel,
+        2 only the work-list (projection solver) kernel."""
+        args = (C.byref(self._model), C.byref(self._state), self.num_envs, actions.data_ptr(), self._flags,
                 max(self.discrete_bins, 0), self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
                 self.pilots.data_ptr(), _lib.ptr(self.final_obs), self.status.data_ptr(), _lib.ptr(self.stats),
-                self.todo.data_ptr(), self._stream()), "sg_ev_step")
-        self.kernel_launches += 2 if self.project_action_in_env else 1
-        return self.obs, self.reward, self.done.bool(), torch.zeros_like(self.done, dtype=torch.bool), self._infos()
+                self.todo.data_ptr(), self._stream())
+        with torch.cuda.device(self.device):
+            if phase in (0, 1):
+                _lib.check(self.lib.sg_ev_step(*args), "sg_ev_step")
+                self.kernel_launches += 1
+            if phase in (0, 2) and self.project_action_in_env:
+                _lib.check(self.lib.sg_ev_step_finish(*args), "sg_ev_step_finish")
+                self.kernel_launches += 1
+
+    def capture_graph(self, actions: torch.Tensor) -> "torch.cuda.CUDAGraph":
+        """Captures one step (reading ``actions`` in place) into a CUDA graph; ``graph.replay()``
+        then advances all envs with a single graph launch."""
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream(self.device)
+        s.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(s):
+            with torch.cuda.graph(g, stream=s):
+                self.launch_step(actions)
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        return g
 
     def project(self, actions: torch.Tensor, demands: torch.Tensor):
         """The action projection alone (env.py:200-221): returns (x f64 [B,n], status u8 [B], iters i32 [B])."""

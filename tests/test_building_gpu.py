@@ -1,0 +1,106 @@
+"""GPU: BuildingEnv kernels vs (a) the reference's own trajectories (golden fixtures) and (b) the
+NumPy oracle on seeded random batches.  Tolerances: observations (f32 state) 1e-5 relative as the
+north star states (we assert 1e-6); cursor / counters / done bit-exact; reward 1e-6 relative."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import building_fixtures, load_building_fixture, oracle_building_params, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("path", building_fixtures(), ids=lambda p: p.split("building_")[-1][:-4])
+def test_kernel_matches_reference_trajectory(native_lib, path):
+    from sustaingym_b200.envs.building.env import BuildingEnv
+    g, params = load_building_fixture(path)
+    env = BuildingEnv(params)
+    obs0, _ = env.reset(seed=int(g["seed"]))
+    assert env.epoch == int(g["epoch0"])
+    np.testing.assert_array_equal(obs0, g["obs0"])
+    exact = 0
+    for t in range(len(g["actions"])):
+        ob, r, term, trunc, info = env.step(g["actions"][t])
+        exact += np.array_equal(ob, g["obs"][t])
+        assert rel_err(ob, g["obs"][t]) < 1e-6, t
+        assert abs(r - g["rewards"][t]) <= 1e-6 * abs(g["rewards"][t]), t
+        assert term == trunc == bool(g["dones"][t])
+    assert exact >= len(g["actions"]) - 3
+
+
+@pytest.mark.parametrize("name,B", [("retail_s5", 1000), ("officesmall_occ", 777), ("officemedium_s9", 300),
+                                    ("retail_discrete", 513)])
+def test_kernel_matches_oracle_random_batch(native_lib, name, B):
+    from oracle.building import BuildingOracle
+    from sustaingym_b200.envs.building.env import BatchedBuildingEnv
+    path = [p for p in building_fixtures() if name in p][0]
+    g, params = load_building_fixture(path)
+    env = BatchedBuildingEnv(params, B)
+    orc = BuildingOracle(oracle_building_params(g), B)
+    rng = np.random.default_rng(7)
+    T = len(g["out_temp"])
+    epochs = rng.integers(0, T, B)
+    epochs[:4] = [T - 1, T - 2, 0, T - 100]
+    T0 = rng.uniform(15, 30, (B, env.n))
+    obs, _ = env.reset(epochs=epochs, options={"T_initial": T0})
+    o_obs = orc.reset(epochs, T0)
+    np.testing.assert_array_equal(obs.cpu().numpy(), o_obs)
+    n_exact = 0
+    for t in range(60):
+        if env.is_continuous_action:
+            a = (rng.uniform(-1, 1, (B, env.n)) * env.ac_map).astype(np.float32)
+        else:
+            a = rng.integers(0, 200, (B, env.n)).astype(np.int64)
+        ob, r, term, trunc, _ = env.step(torch.from_numpy(a).cuda())
+        o_ob, o_r, o_d, _ = orc.step(a)
+        ob = ob.cpu().numpy()
+        n_exact += np.array_equal(ob, o_ob)
+        assert rel_err(ob, o_ob) < 1e-6
+        np.testing.assert_allclose(r.cpu().numpy(), o_r, rtol=1e-6)
+        np.testing.assert_array_equal(term.cpu().numpy(), o_d)
+        np.testing.assert_array_equal(env.epoch.cpu().numpy(), orc.epoch)
+        np.testing.assert_array_equal(env.runs.cpu().numpy(), orc.runs)
+        # keep the two in lock-step on the exact same f32 state
+        orc.state = ob.copy()
+    assert n_exact >= 50
+
+
+def test_rollout_equals_repeated_step_and_host_path(native_lib):
+    from sustaingym_b200.envs.building.env import BatchedBuildingEnv
+    g, params = load_building_fixture([p for p in building_fixtures() if "retail_s5" in p][0])
+    B, T = 300, 40
+    rng = np.random.default_rng(3)
+    acts = rng.uniform(-1, 1, (T, B, 5)).astype(np.float32)
+    epochs = rng.integers(0, 1900, B)
+    e1, e2, e3 = (BatchedBuildingEnv(params, B) for _ in range(3))
+    for e in (e1, e2, e3):
+        e.reset(epochs=epochs)
+    obs_r, rew_r, done_r = e1.rollout(torch.from_numpy(acts).cuda())
+    for t in range(T):
+        ob, r, d, _, _ = e2.step(torch.from_numpy(acts[t]).cuda())
+        assert torch.equal(ob, obs_r[t]) and torch.equal(r, rew_r[t]) and torch.equal(d, done_r[t].bool())
+        ob_h, r_h, d_h, _, _ = e3.step(acts[t])
+        np.testing.assert_array_equal(ob_h, ob.cpu().numpy())
+        np.testing.assert_array_equal(r_h, r.cpu().numpy())
+    assert torch.equal(e1.state, e2.state) and torch.equal(e1.epoch, e2.epoch)
+
+
+def test_autoreset_and_stats(native_lib):
+    from sustaingym_b200.envs.building.env import BatchedBuildingEnv
+    g, params = load_building_fixture([p for p in building_fixtures() if "officesmall_s5" in p][0])
+    params = dict(params, episode_len=10)
+    B = 257
+    env = BatchedBuildingEnv(params, B, auto_reset=True, collect_stats=True)
+    env.reset(epochs=np.arange(B) % 1900)
+    rng = np.random.default_rng(0)
+    tot = 0.0
+    for t in range(25):
+        a = torch.from_numpy(rng.uniform(-1, 1, (B, 6)).astype(np.float32)).cuda()
+        ob, r, d, _, _ = env.step(a)
+        tot += float(r.sum())
+        assert bool(d.all()) == (t % 10 == 9)
+        if t % 10 == 9:
+            assert torch.all(env.runs == 0) and torch.all(ob[:, :6] == 22.0)
+    st = env.stats.cpu().numpy()
+    assert st[0] == 25 * B and st[5] == 2 * B
+    assert abs(st[1] - tot) < 1e-6 * abs(tot)

@@ -1,0 +1,153 @@
+"""GPU: EVChargingEnv kernels vs the CPU oracle (oracle/ev.py) on the same seeded inputs.
+
+Bars: schedule (integer amps), est_departures, done, day cursor: bit-exact; demands / MOER /
+reward: <= 1e-5 relative (asserted tighter).  With the projection on, a pilot may legitimately
+differ when the exact projected current sits within 1e-6 A of a rounding tie (both solvers are
+only accurate to ~1e-10); such envs are excluded from that step on and counted."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_err, tie_distance
+from oracle import ev as O
+
+pytestmark = pytest.mark.gpu
+
+
+def make(num_days, mean_sessions, seed, B, project, **kw):
+    from sustaingym_b200.envs.evcharging.env import BatchedEVChargingEnv
+    from sustaingym_b200.envs.evcharging.event_generation import SyntheticTraceGenerator
+    gen = SyntheticTraceGenerator("caltech", num_days=num_days, mean_sessions=mean_sessions, seed=seed)
+    env = BatchedEVChargingEnv(gen, B, project_action_in_env=project, **kw)
+    net = O.caltech_acn()
+    sess = [[O.Session(*x) for x in d] for d in gen.days]
+    orc = O.EVOracle(net, sess, gen.moer.astype(np.float64), B, moer_forecast_steps=env.moer_forecast_steps,
+                     project_action_in_env=project)
+    return gen, env, net, orc
+
+
+def run_parity(env, orc, net, gen, B, steps, seed, action_fn, project):
+    obs, _ = env.reset(seed=seed)
+    days = gen.first_days(seed + np.arange(B), B)
+    o_obs = orc.reset(days, gen.moer_days(days))
+    np.testing.assert_array_equal(obs.cpu().numpy(), O.flatten_obs(o_obs))
+    rng = np.random.default_rng(seed)
+    clean = np.ones(B, bool)
+    n_sched_exact = n_obs_exact = n_slow = 0
+    for t in range(steps):
+        a = action_fn(rng, t)
+        ob, r, d, tr, info = env.step(torch.from_numpy(a).cuda())
+        o_ob, o_r, o_d, _, o_info = orc.step(a if a.dtype == np.float32 else O.discrete_to_continuous(a, env.discrete_bins))
+        n_slow += len(o_info["slow"])
+        if project:
+            clean &= tie_distance(net, o_info["x"]).min(axis=1) > 1e-6
+        ob, r = ob.cpu().numpy(), r.cpu().numpy()
+        f = O.flatten_obs(o_ob)
+        sched = env.pilots.cpu().numpy().astype(np.float64)
+        c = clean
+        np.testing.assert_array_equal(sched[c], o_info["schedule"][c])
+        n = net.n
+        np.testing.assert_array_equal(ob[c, n:2 * n], f[c, n:2 * n])            # est_departures: integers
+        np.testing.assert_array_equal(ob[c, 2 * n:], f[c, 2 * n:])              # MOER row + timestep
+        assert rel_err(ob[c, :n], f[c, :n], floor=1e-3) < 1e-6                  # demands (kWh)
+        np.testing.assert_allclose(r[c], o_r[c], rtol=1e-6, atol=1e-12)
+        np.testing.assert_array_equal(d.cpu().numpy(), o_d)
+        n_obs_exact += int(np.array_equal(ob[c], f[c]))
+    bd = env.breakdown.cpu().numpy()
+    np.testing.assert_allclose(bd[clean], orc.breakdown[clean], rtol=1e-6, atol=1e-12)
+    return clean, n_obs_exact, n_slow
+
+
+@pytest.mark.parametrize("B,mean", [(64, 25.0), (257, 70.0)])
+def test_step_no_projection(native_lib, B, mean):
+    gen, env, net, orc = make(7, mean, 11, B, False)
+    clean, n_exact, _ = run_parity(env, orc, net, gen, B, 288, 3,
+                                   lambda rng, t: rng.uniform(0, 1, (B, 54)).astype(np.float32), False)
+    assert clean.all() and n_exact >= 280
+    assert bool(env.done.all()) and int(env.t[0]) == 288
+
+
+@pytest.mark.parametrize("B,mean", [(64, 25.0), (200, 80.0)])
+def test_step_with_projection(native_lib, B, mean):
+    gen, env, net, orc = make(5, mean, 5, B, True)
+    clean, n_exact, n_slow = run_parity(env, orc, net, gen, B, 288, 9,
+                                        lambda rng, t: rng.uniform(0, 1, (B, 54)).astype(np.float32), True)
+    assert clean.mean() > 0.97
+    if mean > 50:
+        assert n_slow > 100            # the interior-point path was really exercised
+    st = env.status.cpu().numpy()
+    assert not (st & 2).any()          # no iteration-cap hits
+
+
+def test_discrete_actions_config1(native_lib):
+    """BASELINE config 1: discrete actions {0..4} -> a/4 (wrappers.py:43-45)."""
+    B = 33
+    gen, env, net, orc = make(3, 40.0, 2, B, True, discrete_bins=5)
+    clean, _, _ = run_parity(env, orc, net, gen, B, 288, 1,
+                             lambda rng, t: rng.integers(0, 5, (B, 54)).astype(np.int64), True)
+    assert clean.mean() > 0.9
+
+
+def test_projection_operator_matches_oracle(native_lib):
+    from sustaingym_b200.envs.evcharging.env import BatchedEVChargingEnv
+    from sustaingym_b200.envs.evcharging.event_generation import SyntheticTraceGenerator
+    env = BatchedEVChargingEnv(SyntheticTraceGenerator(num_days=1), 1)
+    net = O.caltech_acn()
+    rng = np.random.default_rng(0)
+    M = 2000
+    a = rng.uniform(0, 1, (M, 54)).astype(np.float32)
+    occ = rng.uniform(0, 1, (M, 54)) < rng.uniform(0.05, 1.0, (M, 1))
+    dem = np.where(occ, np.clip(rng.lognormal(1.5, 1.2, (M, 54)), 0.002, 100), 0).astype(np.float32)
+    a[0] = 0; dem[1] = 0; a[2] = 1; dem[2] = 100          # edge cases: zero action, empty garage, all-max
+    x, st, it = env.project(torch.from_numpy(a).cuda(), torch.from_numpy(dem).cuda())
+    xo, info = O.project_action(net, a, dem)
+    x, st, it = x.cpu().numpy(), st.cpu().numpy(), it.cpu().numpy()
+    slow = np.zeros(M, bool); slow[info["slow"]] = True
+    np.testing.assert_array_equal((st & 1).astype(bool), slow)
+    assert not (st & 2).any() and it.max() < 40
+    np.testing.assert_array_equal(x[~slow], xo[~slow])     # fast path: exact clip
+    assert np.abs(x - xo).max() < 1e-9                     # solver path: both converge to the projection
+    assert slow.sum() > 500
+
+
+def test_autoreset_sequential_days_and_host_path(native_lib):
+    B = 40
+    gen, env, net, orc = make(4, 30.0, 8, B, False, auto_reset=True)
+    _, env2, _, _ = make(4, 30.0, 8, B, False, auto_reset=True)
+    env.reset(seed=0); env2.reset(seed=0)
+    day0 = env.day.cpu().numpy().copy()
+    rng = np.random.default_rng(0)
+    for t in range(288 * 2 + 5):
+        a = rng.uniform(0, 1, (B, 54)).astype(np.float32)
+        ob, r, d, _, _ = env.step(torch.from_numpy(a).cuda())
+        ob2, r2, d2, _, _ = env2.step(a)                                   # host-buffer path
+        np.testing.assert_array_equal(ob.cpu().numpy(), ob2)
+        np.testing.assert_array_equal(r.cpu().numpy(), r2)
+        if t % 288 == 287:
+            assert bool(d.all())
+            assert torch.all(env.t == 0) and torch.all(ob[:, :108] == 0) and torch.all(ob[:, -1] == 0)
+            assert env.final_obs[0, -1].item() == 1.0
+        else:
+            assert not bool(d.any())
+    np.testing.assert_array_equal(env.day.cpu().numpy(), (day0 + 2) % 4)
+
+
+def test_single_env_gymnasium_view(native_lib):
+    from sustaingym_b200.envs.evcharging.env import EVChargingEnv
+    from sustaingym_b200.envs.evcharging.event_generation import SyntheticTraceGenerator
+    env = EVChargingEnv(SyntheticTraceGenerator(num_days=3, seed=4), project_action_in_env=True)
+    obs, info = env.reset(seed=1)
+    assert set(obs) == {"timestep", "est_departures", "demands", "prev_moer", "forecasted_moer"}
+    assert env.observation_space.contains(obs)
+    tot, done, steps = 0.0, False, 0
+    while not done:
+        obs, r, done, trunc, info = env.step(env.action_space.sample())
+        assert isinstance(r, float) and trunc is False and env.observation_space.contains(obs)
+        tot += r; steps += 1
+    assert steps == 288
+    bd = info["reward_breakdown"]
+    assert abs(tot - (bd["profit"] - bd["carbon_cost"] - bd["excess_charge"])) < 1e-9
+    obs_a, _ = env.reset(seed=1)
+    obs_b, _ = env.reset(seed=1)
+    for k in obs_a:
+        np.testing.assert_array_equal(obs_a[k], obs_b[k])
