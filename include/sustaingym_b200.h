@@ -140,9 +140,8 @@ typedef struct sg_ev_model {
 typedef struct sg_ev_state {
     double*  delivered;   /* [device] [B, n] kWh delivered to the session now at the station  */
     uint8_t* sess_idx;    /* [device] [B, n] slot of the station's current-or-next session    */
-    int32_t* t;           /* [device] [B] timestep 0..288 (env.py:168)                        */
-    int32_t* day;         /* [device] [B] trace index in [0, D)                               */
-    int32_t* moer_day;    /* [device] [B] MOER table index in [0, Dm)                         */
+    int32_t* clock;       /* [device] [B, 4] {t (0..288, env.py:168), day (trace index in     */
+                          /*   [0,D)), moer_day (MOER table index in [0,Dm)), reserved}        */
     double*  breakdown;   /* [device] [B, 3] cumulative profit, carbon_cost, excess_charge    */
 } sg_ev_state;
 

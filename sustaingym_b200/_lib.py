@@ -50,8 +50,7 @@ class EVModel(C.Structure):
 
 class EVState(C.Structure):
     _fields_ = [
-        ("delivered", _vp), ("sess_idx", _vp), ("t", _vp), ("day", _vp), ("moer_day", _vp),
-        ("breakdown", _vp),
+        ("delivered", _vp), ("sess_idx", _vp), ("clock", _vp), ("breakdown", _vp),
     ]
 
 

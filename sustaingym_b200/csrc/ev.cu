@@ -13,11 +13,17 @@
 // Mapping: one warp advances one env; lane l owns stations 2l and 2l+1 (54 stations -> 27
 // lanes), so the env-major rows action[B,n] (f32), delivered[B,n] (f64), sess_idx[B,n] (u8) and
 // obs[B,2n+k+2] (f32) are read/written as 8/16/2-byte vectors that are contiguous across the
-// warp and across consecutive warps (fully coalesced, each byte touched once).  Per-station
-// feasibility / reward reductions are warp-shuffle butterflies over the <= 8 class sums the
-// network constraints depend on; the small constraint tables are staged in
-// shared memory once per CTA.  Trace (16-byte session records) and MOER tables are shared by
-// all envs of a day and stay L2-resident.
+// warp and across consecutive warps (fully coalesced, each byte touched once).  The network
+// constraints depend on the schedule only through <= 8 per-class sums:
+//   * the integer pilots are summed with packed 16-bit fields through REDUX (2 classes / word);
+//   * the fast-path feasibility test of the projection sums 2^-20 fixed-point actions the same
+//     way, with a safety margin; anything not certainly feasible is queued for the solver kernel.
+// The small constraint tables are staged in shared memory once per CTA.  Trace (16-byte session
+// records) and MOER tables are shared by all envs of a day and stay L2-resident.
+//
+// All divisions by constants use the FMA-corrected reciprocal (Markstein) which reproduces the
+// IEEE quotient the reference's Python arithmetic produces (checked on 2e7 samples per constant,
+// tests/test_div_const.py), so results stay bit-comparable with the oracle.
 //
 // The projection has a fast path (box-clipped action already satisfies the network: it IS the
 // projection) executed inline, and a slow path (primal-dual interior point on the QCQP, Newton
@@ -45,15 +51,45 @@ constexpr double kViolationFactor = kAPersToKwh * 0.001;
 constexpr double kCarbonFactor = kAPersToKwh * (30.85 / 1000.0);
 // event_generation.py:60-62 and acnportal defaults
 constexpr double kCapacity = 100.0, kMaxPower = 100.0, kTransitionSoc = 0.8, kFullEps = 1e-3;
+constexpr double kOneMinusTrans = 1.0 - kTransitionSoc;
 constexpr int kEmpty = 32767;
 constexpr int kEpisode = SG_EV_EPISODE_STEPS;
+// correctly rounded reciprocals for div_c
+constexpr double kInv1000 = 1.0 / 1000.0, kInv208 = 1.0 / kVoltage, kInv100 = 1.0 / kCapacity;
+constexpr double kInvOMT = 1.0 / kOneMinusTrans, kInvPeriodH = 1.0 / kPeriodH, kInvAPers = 1.0 / kAPersToKwh;
+// fixed-point scale and safety margin of the fast-path feasibility test (normalised units)
+constexpr double kFixScale = 1048576.0, kFixInv = 1.0 / 1048576.0, kFeasMargin = 1e-4;
 
 constexpr int kWarpsPerBlock = 8;
 constexpr int kThreads = kWarpsPerBlock * 32;
+constexpr int kMC = SG_EV_MAX_CLASSES;
+
+// a / b for a compile-time constant b with inv = RN(1/b): q' = RN(q + RN(a - q b) * inv)
+__device__ __forceinline__ double div_c(double a, double b, double inv) {
+    const double q = a * inv;
+    const double r = fma(-q, b, a);
+    return fma(r, inv, q);
+}
+// ~1e-15-accurate reciprocal / reciprocal square root for the interior-point iteration, which is
+// self-correcting (residuals are recomputed exactly every iteration)
+__device__ __forceinline__ double fast_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = r * fma(-x, r, 2.0);
+    r = r * fma(-x, r, 2.0);
+    return r * fma(-x, r, 2.0);
+}
+__device__ __forceinline__ double fast_rsqrt(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    y = y * fma(-0.5 * x * y, y, 1.5);
+    y = y * fma(-0.5 * x * y, y, 1.5);
+    return y * fma(-0.5 * x * y, y, 1.5);
+}
 
 struct EvShared {
-    double con_re[SG_EV_MAX_CONSTRAINTS * SG_EV_MAX_CLASSES];
-    double con_im[SG_EV_MAX_CONSTRAINTS * SG_EV_MAX_CLASSES];
+    double con_re[SG_EV_MAX_CONSTRAINTS * kMC];
+    double con_im[SG_EV_MAX_CONSTRAINTS * kMC];
     double lim[SG_EV_MAX_CONSTRAINTS];     // magnitudes in A
     uint8_t cls[SG_EV_MAX_STATIONS];
     uint8_t type[SG_EV_MAX_STATIONS];
@@ -62,15 +98,15 @@ struct EvShared {
 
 __device__ __forceinline__ void load_shared(const sg_ev_model& m, EvShared& sh) {
     const int C = m.n_classes, J = m.n_constraints;
-    for (int i = threadIdx.x; i < SG_EV_MAX_CONSTRAINTS * SG_EV_MAX_CLASSES; i += blockDim.x) {
+    for (int i = threadIdx.x; i < SG_EV_MAX_CONSTRAINTS * kMC; i += blockDim.x) {
         sh.con_re[i] = 0.0; sh.con_im[i] = 0.0;      // padding classes/constraints contribute nothing
     }
     for (int i = threadIdx.x; i < SG_EV_MAX_CONSTRAINTS; i += blockDim.x) sh.lim[i] = 0.0;
     __syncthreads();
     for (int i = threadIdx.x; i < J * C; i += blockDim.x) {
         const int j = i / C, c = i % C;
-        sh.con_re[j * SG_EV_MAX_CLASSES + c] = m.con_re[i];
-        sh.con_im[j * SG_EV_MAX_CLASSES + c] = m.con_im[i];
+        sh.con_re[j * kMC + c] = m.con_re[i];
+        sh.con_im[j * kMC + c] = m.con_im[i];
     }
     for (int i = threadIdx.x; i < J; i += blockDim.x) sh.lim[i] = m.magnitudes[i];
     for (int i = threadIdx.x; i < m.n_stations; i += blockDim.x) {
@@ -94,7 +130,7 @@ __device__ __forceinline__ Session load_session(const sg_ev_model& m, int day, i
     return s;
 }
 
-// class sums of a per-station value (two stations per lane) -> every lane gets all C sums
+// class sums of a per-station f64 value (two stations per lane) -> every lane gets all sums
 template <int MAXC>
 __device__ __forceinline__ void class_sums(const double (&v)[2], const int (&cls)[2], int C, double (&S)[MAXC]) {
 #pragma unroll
@@ -104,22 +140,49 @@ __device__ __forceinline__ void class_sums(const double (&v)[2], const int (&cls
     }
 }
 
+// class sums of small non-negative integers (< 2^26 / n per station): one REDUX per class
+__device__ __forceinline__ void class_sums_u32(const unsigned (&v)[2], const int (&cls)[2], int C, double (&S)[kMC],
+                                               double scale) {
+#pragma unroll
+    for (int c = 0; c < kMC; ++c) {
+        if (c < C) S[c] = (double)__reduce_add_sync(kFull, (cls[0] == c ? v[0] : 0u) + (cls[1] == c ? v[1] : 0u)) * scale;
+        else S[c] = 0.0;
+    }
+}
+
+// class sums of integer pilots (<= 32 A, <= 64 stations => < 2^16): two classes per REDUX
+__device__ __forceinline__ void class_sums_pilots(const unsigned (&v)[2], const int (&cls)[2], int C, double (&S)[kMC]) {
+#pragma unroll
+    for (int w = 0; w < kMC / 2; ++w) {
+        if (2 * w < C) {
+            unsigned part = 0;
+#pragma unroll
+            for (int p = 0; p < 2; ++p)
+                if ((cls[p] >> 1) == w) part += v[p] << ((cls[p] & 1) * 16);
+            const unsigned tot = __reduce_add_sync(kFull, part);
+            S[2 * w] = (double)(tot & 0xffffu);
+            S[2 * w + 1] = (double)(tot >> 16);
+        } else { S[2 * w] = 0.0; S[2 * w + 1] = 0.0; }
+    }
+}
+
 // env.py:373-378: pilot in A from the normalised action
 __device__ __forceinline__ double to_pilot(double x, int type) {
     const double amps = x * kActionScale;
     if (type == 0) return amps >= 6.0 ? rint(amps) : 0.0;     // np.round = half-to-even = rint
-    return rint(amps / 8.0) * 8.0;
+    return rint(amps * 0.125) * 8.0;                          // /8 is exact
 }
 
-// env.py:188-189
+// env.py:188-189: min(1, demands / A_PERS_TO_KWH / 32)
 __device__ __forceinline__ double upper_bound(float demand_f32) {
-    return fmin(1.0, (double)demand_f32 / kAPersToKwh / kActionScale);
+    return fmin(1.0, div_c((double)demand_f32, kAPersToKwh, kInvAPers) * (1.0 / kActionScale));
 }
 
 // =================================================================================================
 // Interior-point projection (slow path).  Same iteration as oracle/ev.py::_ipm, but the Newton
-// system (D + M^T K M) dx = rho is solved through the C x C system (I + H K H) v = H^-1 g.
-// Returns iteration count; *maxiter set when the cap was hit.
+// system (D + M^T K M) dx = rho is solved through the C x C SPD system (I + H K H) v = H^-1 g
+// (Woodbury on the class-indicator structure), Cholesky with reciprocal square roots.
+// Returns the iteration count; *hit_cap is set when the cap was reached.
 // =================================================================================================
 template <int MAXC, int MAXJ>
 __device__ __noinline__ int ipm_project(const EvShared& sh, const int C, const int J, const double (&a)[2],
@@ -132,10 +195,10 @@ __device__ __noinline__ int ipm_project(const EvShared& sh, const int C, const i
 #pragma unroll
     for (int p = 0; p < 2; ++p) { fr[p] = valid[p] && u[p] > 0.0; uf[p] = fr[p] ? u[p] : 1.0; }
     const int nfree = __popc(__ballot_sync(kFull, fr[0])) + __popc(__ballot_sync(kFull, fr[1]));
-    const double ncomp = 2.0 * nfree + J;
+    const double inv_ncomp = 1.0 / (2.0 * nfree + J);
     double r2[MAXJ];
 #pragma unroll
-    for (int j = 0; j < MAXJ; ++j) { const double r = (j < J) ? sh.lim[j] / kActionScale : 1.0; r2[j] = r * r; }
+    for (int j = 0; j < MAXJ; ++j) { const double r = (j < J) ? sh.lim[j] * (1.0 / kActionScale) : 1.0; r2[j] = r * r; }
 
     double S[MAXC];
     // strictly interior start: x = theta*u with every |A~ x| <= r/2
@@ -148,7 +211,7 @@ __device__ __noinline__ int ipm_project(const EvShared& sh, const int C, const i
             if (j < J) {
                 double wr = 0, wi = 0;
 #pragma unroll
-                for (int c = 0; c < MAXC; ++c) { wr = fma(sh.con_re[j * 8 + c], S[c], wr); wi = fma(sh.con_im[j * 8 + c], S[c], wi); }
+                for (int c = 0; c < MAXC; ++c) { wr = fma(sh.con_re[j * kMC + c], S[c], wr); wi = fma(sh.con_im[j * kMC + c], S[c], wi); }
                 const double mag = sqrt(wr * wr + wi * wi);
                 theta = fmin(theta, 0.5 * sqrt(r2[j]) / fmax(mag, 1e-300));
             }
@@ -160,13 +223,13 @@ __device__ __noinline__ int ipm_project(const EvShared& sh, const int C, const i
     double zl[2], zu[2];
 #pragma unroll
     for (int p = 0; p < 2; ++p) { zl[p] = fr[p] ? mu / x[p] : 0.0; zu[p] = fr[p] ? mu / (uf[p] - x[p]) : 0.0; }
-    double lam[MAXJ], wre[MAXJ], wim[MAXJ], q[MAXJ];
+    double lam[MAXJ], wre[MAXJ], wim[MAXJ], q[MAXJ], iq[MAXJ];
     class_sums<MAXC>(x, cls, C, S);
 #pragma unroll
     for (int j = 0; j < MAXJ; ++j) {
         double wr = 0, wi = 0;
 #pragma unroll
-        for (int c = 0; c < MAXC; ++c) { wr = fma(sh.con_re[j * 8 + c], S[c], wr); wi = fma(sh.con_im[j * 8 + c], S[c], wi); }
+        for (int c = 0; c < MAXC; ++c) { wr = fma(sh.con_re[j * kMC + c], S[c], wr); wi = fma(sh.con_im[j * kMC + c], S[c], wi); }
         lam[j] = (j < J) ? mu / (r2[j] - (wr * wr + wi * wi)) : 0.0;
     }
 
@@ -183,16 +246,16 @@ __device__ __noinline__ int ipm_project(const EvShared& sh, const int C, const i
             if (j < J) {
                 double wr = 0, wi = 0;
 #pragma unroll
-                for (int c = 0; c < MAXC; ++c) { wr = fma(sh.con_re[j * 8 + c], S[c], wr); wi = fma(sh.con_im[j * 8 + c], S[c], wi); }
+                for (int c = 0; c < MAXC; ++c) { wr = fma(sh.con_re[j * kMC + c], S[c], wr); wi = fma(sh.con_im[j * kMC + c], S[c], wi); }
                 wre[j] = wr; wim[j] = wi;
                 q[j] = r2[j] - (wr * wr + wi * wi);
                 lamq = fma(lam[j], q[j], lamq);
 #pragma unroll
                 for (int c = 0; c < MAXC; ++c)
-                    nu[c] = fma(2.0 * lam[j], wr * sh.con_re[j * 8 + c] + wi * sh.con_im[j * 8 + c], nu[c]);
+                    nu[c] = fma(2.0 * lam[j], wr * sh.con_re[j * kMC + c] + wi * sh.con_im[j * kMC + c], nu[c]);
             } else { wre[j] = wim[j] = 0.0; q[j] = 1.0; }
         }
-        double xs[2], us[2], rd[2], part = 0.0, rmax = 0.0;
+        double xs[2], us[2], part = 0.0, rmax = 0.0;
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
             xs[p] = fr[p] ? x[p] : 1.0;
@@ -200,11 +263,11 @@ __device__ __noinline__ int ipm_project(const EvShared& sh, const int C, const i
             double nuc = 0.0;
 #pragma unroll
             for (int c = 0; c < MAXC; ++c) nuc = (cls[p] == c) ? nu[c] : nuc;
-            rd[p] = fr[p] ? (x[p] - a[p]) - zl[p] + zu[p] + nuc : 0.0;
+            const double rd = fr[p] ? (x[p] - a[p]) - zl[p] + zu[p] + nuc : 0.0;
             part += fr[p] ? zl[p] * xs[p] + zu[p] * us[p] : 0.0;
-            rmax = fmax(rmax, fabs(rd[p]));
+            rmax = fmax(rmax, fabs(rd));
         }
-        const double gap = (warp_sum(part) + lamq) / ncomp;
+        const double gap = (warp_sum(part) + lamq) * inv_ncomp;
         const double resid = warp_max(rmax);
         if (gap < tol && resid < 100.0 * tol) { *hit_cap = false; break; }
         mu = 0.1 * gap;
@@ -219,30 +282,33 @@ __device__ __noinline__ int ipm_project(const EvShared& sh, const int C, const i
 #pragma unroll
         for (int j = 0; j < MAXJ; ++j) {
             if (j < J) {
+                iq[j] = fast_rcp(q[j]);
                 double G[MAXC];
 #pragma unroll
-                for (int c = 0; c < MAXC; ++c) G[c] = wre[j] * sh.con_re[j * 8 + c] + wim[j] * sh.con_im[j * 8 + c];
-                const double mq = 2.0 * mu / q[j], l2 = 2.0 * lam[j], l4 = 4.0 * lam[j] / q[j];
+                for (int c = 0; c < MAXC; ++c) G[c] = wre[j] * sh.con_re[j * kMC + c] + wim[j] * sh.con_im[j * kMC + c];
+                const double mq = 2.0 * mu * iq[j], l2 = 2.0 * lam[j], l4 = 4.0 * lam[j] * iq[j];
 #pragma unroll
                 for (int c = 0; c < MAXC; ++c) {
                     kap[c] = fma(mq, G[c], kap[c]);
 #pragma unroll
                     for (int d = 0; d <= c; ++d) {
-                        const double Q = sh.con_re[j * 8 + c] * sh.con_re[j * 8 + d] + sh.con_im[j * 8 + c] * sh.con_im[j * 8 + d];
+                        const double Q = sh.con_re[j * kMC + c] * sh.con_re[j * kMC + d] + sh.con_im[j * kMC + c] * sh.con_im[j * kMC + d];
                         Kmat[c][d] = fma(l2, Q, fma(l4 * G[c], G[d], Kmat[c][d]));
                     }
                 }
-            }
+            } else iq[j] = 1.0;
         }
-        double Dd[2], rho[2], inv[2], rhoD[2];
+        double ixs[2], ius[2], rho[2], inv[2], rhoD[2];
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
-            Dd[p] = fr[p] ? 1.0 + zl[p] / xs[p] + zu[p] / us[p] : 1.0;
+            ixs[p] = fast_rcp(xs[p]);
+            ius[p] = fast_rcp(us[p]);
+            const double Dd = fr[p] ? 1.0 + zl[p] * ixs[p] + zu[p] * ius[p] : 1.0;
             double kc = 0.0;
 #pragma unroll
             for (int c = 0; c < MAXC; ++c) kc = (cls[p] == c) ? kap[c] : kc;
-            rho[p] = fr[p] ? -(x[p] - a[p]) + mu / xs[p] - mu / us[p] - kc : 0.0;
-            inv[p] = fr[p] ? 1.0 / Dd[p] : 0.0;
+            rho[p] = fr[p] ? -(x[p] - a[p]) + mu * ixs[p] - mu * ius[p] - kc : 0.0;
+            inv[p] = fr[p] ? fast_rcp(Dd) : 0.0;
             rhoD[p] = rho[p] * inv[p];
         }
         double E[MAXC], g[MAXC];
@@ -251,37 +317,45 @@ __device__ __noinline__ int ipm_project(const EvShared& sh, const int C, const i
         // (I + H K H) v = g / h,  ds = H v   (SPD; classes without free stations drop out)
         double h[MAXC], L[MAXC][MAXC], v[MAXC];
 #pragma unroll
-        for (int c = 0; c < MAXC; ++c) h[c] = (c < C && E[c] > 0.0) ? sqrt(E[c]) : 0.0;
-#pragma unroll
         for (int c = 0; c < MAXC; ++c) {
+            const bool on = (c < C) && E[c] > 0.0;
+            const double ih = on ? fast_rsqrt(E[c]) : 0.0;
+            h[c] = on ? E[c] * ih : 0.0;
+            v[c] = g[c] * ih;
+        }
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c)
 #pragma unroll
             for (int d = 0; d <= c; ++d) L[c][d] = h[c] * Kmat[c][d] * h[d] + (c == d ? 1.0 : 0.0);
-            v[c] = h[c] > 0.0 ? g[c] / h[c] : 0.0;
-        }
-        // Cholesky L L^T in place (lower), then two triangular solves
+        // Cholesky in place; the diagonal stores 1/L[d][d]
 #pragma unroll
-        for (int c = 0; c < MAXC; ++c) {
+        for (int d = 0; d < MAXC; ++d) {
+            double sum = L[d][d];
 #pragma unroll
-            for (int d = 0; d <= c; ++d) {
-                double sum = L[c][d];
+            for (int e = 0; e < d; ++e) sum = fma(-L[d][e], L[d][e], sum);
+            const double il = fast_rsqrt(sum);
+            L[d][d] = il;
 #pragma unroll
-                for (int e = 0; e < d; ++e) sum -= L[c][e] * L[d][e];
-                L[c][d] = (c == d) ? sqrt(sum) : sum / L[d][d];
+            for (int c = d + 1; c < MAXC; ++c) {
+                double s2 = L[c][d];
+#pragma unroll
+                for (int e = 0; e < d; ++e) s2 = fma(-L[c][e], L[d][e], s2);
+                L[c][d] = s2 * il;
             }
         }
 #pragma unroll
         for (int c = 0; c < MAXC; ++c) {
             double sum = v[c];
 #pragma unroll
-            for (int e = 0; e < c; ++e) sum -= L[c][e] * v[e];
-            v[c] = sum / L[c][c];
+            for (int e = 0; e < c; ++e) sum = fma(-L[c][e], v[e], sum);
+            v[c] = sum * L[c][c];
         }
 #pragma unroll
         for (int c = MAXC - 1; c >= 0; --c) {
             double sum = v[c];
 #pragma unroll
-            for (int e = c + 1; e < MAXC; ++e) sum -= L[e][c] * v[e];
-            v[c] = sum / L[c][c];
+            for (int e = c + 1; e < MAXC; ++e) sum = fma(-L[e][c], v[e], sum);
+            v[c] = sum * L[c][c];
         }
         double ds[MAXC], y[MAXC];
 #pragma unroll
@@ -293,21 +367,21 @@ __device__ __noinline__ int ipm_project(const EvShared& sh, const int C, const i
             for (int d = 0; d < MAXC; ++d) sum = fma(d <= c ? Kmat[c][d] : Kmat[d][c], ds[d], sum);
             y[c] = sum;
         }
-        // ---- directions and fraction-to-boundary step -----------------------------------------
-        double dx[2], dzl[2], dzu[2], amin = 1.0;
+        // ---- directions; fraction-to-boundary step as alpha = tau / max(tau, worst ratio) ----------
+        double dx[2], dzl[2], dzu[2], worst = 0.0;
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
             double yc = 0.0;
 #pragma unroll
             for (int c = 0; c < MAXC; ++c) yc = (cls[p] == c) ? y[c] : yc;
             dx[p] = fr[p] ? (rho[p] - yc) * inv[p] : 0.0;
-            dzl[p] = fr[p] ? mu / xs[p] - zl[p] - zl[p] / xs[p] * dx[p] : 0.0;
-            dzu[p] = fr[p] ? mu / us[p] - zu[p] + zu[p] / us[p] * dx[p] : 0.0;
+            dzl[p] = fr[p] ? mu * ixs[p] - zl[p] - zl[p] * ixs[p] * dx[p] : 0.0;
+            dzu[p] = fr[p] ? mu * ius[p] - zu[p] + zu[p] * ius[p] * dx[p] : 0.0;
             if (fr[p]) {
-                if (dx[p] < 0.0) amin = fmin(amin, -tau * xs[p] / dx[p]);
-                if (dx[p] > 0.0) amin = fmin(amin, tau * us[p] / dx[p]);
-                if (dzl[p] < 0.0) amin = fmin(amin, -tau * zl[p] / dzl[p]);
-                if (dzu[p] < 0.0) amin = fmin(amin, -tau * zu[p] / dzu[p]);
+                worst = fmax(worst, -dx[p] * ixs[p]);
+                worst = fmax(worst, dx[p] * ius[p]);
+                worst = fmax(worst, -dzl[p] * fast_rcp(zl[p]));
+                worst = fmax(worst, -dzu[p] * fast_rcp(zu[p]));
             }
         }
         double dlam[MAXJ];
@@ -317,19 +391,20 @@ __device__ __noinline__ int ipm_project(const EvShared& sh, const int C, const i
                 double dwr = 0, dwi = 0, Gds = 0;
 #pragma unroll
                 for (int c = 0; c < MAXC; ++c) {
-                    dwr = fma(sh.con_re[j * 8 + c], ds[c], dwr);
-                    dwi = fma(sh.con_im[j * 8 + c], ds[c], dwi);
-                    Gds = fma(wre[j] * sh.con_re[j * 8 + c] + wim[j] * sh.con_im[j * 8 + c], ds[c], Gds);
+                    dwr = fma(sh.con_re[j * kMC + c], ds[c], dwr);
+                    dwi = fma(sh.con_im[j * kMC + c], ds[c], dwi);
+                    Gds = fma(wre[j] * sh.con_re[j * kMC + c] + wim[j] * sh.con_im[j * kMC + c], ds[c], Gds);
                 }
-                dlam[j] = mu / q[j] - lam[j] + 2.0 * lam[j] / q[j] * Gds;
+                dlam[j] = mu * iq[j] - lam[j] + 2.0 * lam[j] * iq[j] * Gds;
                 const double bq = wre[j] * dwr + wim[j] * dwi;
                 const double c2 = dwr * dwr + dwi * dwi;
-                const double den = bq + sqrt(bq * bq + c2 * tau * q[j]);
-                if (den > 0.0) amin = fmin(amin, tau * q[j] / den);
-                if (dlam[j] < 0.0) amin = fmin(amin, -tau * lam[j] / dlam[j]);
+                const double den = bq + sqrt(fma(bq, bq, c2 * tau * q[j]));
+                worst = fmax(worst, den * iq[j]);                          // tau*q/den >= alpha
+                worst = fmax(worst, -dlam[j] * fast_rcp(lam[j]));
             } else dlam[j] = 0.0;
         }
-        const double alpha = warp_min(amin);
+        worst = warp_max(worst);
+        const double alpha = worst > tau ? tau * fast_rcp(worst) : 1.0;
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
             x[p] = fma(alpha, dx[p], x[p]);
@@ -349,20 +424,38 @@ __device__ __forceinline__ int ipm_dispatch(const EvShared& sh, int C, int J, co
     return ipm_project<SG_EV_MAX_CLASSES, SG_EV_MAX_CONSTRAINTS>(sh, C, J, a, u, cls, valid, x, hit_cap);
 }
 
-// Is the (box-clipped) action inside every network constraint?  x in normalised units.
+// Exact test: is the (box-clipped) action inside every network constraint?  x normalised.
 __device__ __forceinline__ bool network_feasible(const EvShared& sh, int C, int J, const double (&x)[2],
                                                  const int (&cls)[2]) {
-    double S[SG_EV_MAX_CLASSES];
-    class_sums<SG_EV_MAX_CLASSES>(x, cls, C, S);
+    double S[kMC];
+    class_sums<kMC>(x, cls, C, S);
     bool ok = true;
     for (int j = 0; j < J; ++j) {
         double wr = 0, wi = 0;
 #pragma unroll
-        for (int c = 0; c < SG_EV_MAX_CLASSES; ++c) { wr = fma(sh.con_re[j * 8 + c], S[c], wr); wi = fma(sh.con_im[j * 8 + c], S[c], wi); }
-        const double r = sh.lim[j] / kActionScale;
+        for (int c = 0; c < kMC; ++c) { wr = fma(sh.con_re[j * kMC + c], S[c], wr); wi = fma(sh.con_im[j * kMC + c], S[c], wi); }
+        const double r = sh.lim[j] * (1.0 / kActionScale);
         ok = ok && !(sqrt(wr * wr + wi * wi) > r);
     }
     return ok;
+}
+
+// Conservative test (fast path): fixed-point class sums through REDUX; true only when every
+// constraint holds with a margin that covers the quantisation error.
+__device__ __forceinline__ bool network_certainly_feasible(const EvShared& sh, int C, int J, int lane,
+                                                           const double (&x)[2], const int (&cls)[2]) {
+    const unsigned xi[2] = {__double2uint_rn(x[0] * kFixScale), __double2uint_rn(x[1] * kFixScale)};
+    double S[kMC];
+    class_sums_u32(xi, cls, C, S, kFixInv);
+    bool bad = false;
+    if (lane < J) {
+        double wr = 0, wi = 0;
+#pragma unroll
+        for (int c = 0; c < kMC; ++c) { wr = fma(sh.con_re[lane * kMC + c], S[c], wr); wi = fma(sh.con_im[lane * kMC + c], S[c], wi); }
+        const double r = sh.lim[lane] * (1.0 / kActionScale) - kFeasMargin;
+        bad = !(r > 0.0 && fma(wr, wr, wi * wi) <= r * r);
+    }
+    return !__any_sync(kFull, bad);
 }
 
 // =================================================================================================
@@ -379,12 +472,13 @@ __device__ __forceinline__ void ev_env_step(const sg_ev_model& m, const sg_ev_st
                                             StatsAcc& acc) {
     const int n = m.n_stations, kf = m.moer_steps, OBS = 2 * n + kf + 2;
     const int C = m.n_classes, J = m.n_constraints;
-    const int t = s.t[b];
+    const int4 clk = *reinterpret_cast<const int4*>(s.clock + b * 4);
+    const int t = clk.x;
     if (t >= kEpisode) {            // finished episode that was not reset: no-op, stays terminal
         if (lane == 0) { reward[b] = 0.0; done[b] = 1; if (status) status[b] = 0; }
         return;
     }
-    int day = s.day[b], md = s.moer_day[b];
+    int day = clk.y, md = clk.z;
     const int i0 = 2 * lane;
     const bool valid[2] = {i0 < n, i0 + 1 < n};
     const bool vec = ((n & 1) == 0);     // rows are 8/16-byte aligned when n is even
@@ -452,11 +546,13 @@ __device__ __forceinline__ void ev_env_step(const sg_ev_model& m, const sg_ev_st
             u[p] = upper_bound(dem);
             x[p] = valid[p] ? fmin(fmax(a[p], 0.0), u[p]) : 0.0;
         }
-        if (!network_feasible(sh, C, J, x, cls)) {
-            if constexpr (MODE == 1) {
+        if constexpr (MODE == 1) {
+            if (!network_certainly_feasible(sh, C, J, lane, x, cls)) {
                 if (lane == 0) todo[2 + atomicAdd(todo, 1)] = (int)b;
                 return;                                     // the work-list kernel redoes this env
-            } else {
+            }
+        } else {
+            if (!network_feasible(sh, C, J, x, cls)) {
                 bool cap = false;
                 ipm_dispatch(sh, C, J, a, u, cls, valid, x, &cap);
                 st = SG_EV_STATUS_PROJECTED | (cap ? SG_EV_STATUS_MAXITER : 0);
@@ -470,33 +566,37 @@ __device__ __forceinline__ void ev_env_step(const sg_ev_model& m, const sg_ev_st
     for (int p = 0; p < 2; ++p) {
         pilot[p] = valid[p] ? to_pilot(x[p], type[p]) : 0.0;
         if (plugged[p]) {
+            // Linear2StageBattery._charge_stepwise (capacity 100 kWh, max_power 100 kW, transition 0.8)
             const double charge = fmax(0.0, kCapacity - ses[p].energy) + del[p];
-            const double rate_to_full = (kCapacity - charge) / kPeriodH;
-            const double soc = charge / kCapacity;
-            const double p_pilot = pilot[p] * kVoltage / 1000.0;
-            double power;
-            if (soc < kTransitionSoc) power = fmin(fmin(p_pilot, kMaxPower), rate_to_full);
-            else power = fmin(fmin(p_pilot, (1.0 - soc) / (1.0 - kTransitionSoc) * kMaxPower), rate_to_full);
-            const double rate = power * 1000.0 / kVoltage;
-            del[p] += rate * kVoltage / 1000.0 * kPeriodH;
+            const double rate_to_full = div_c(kCapacity - charge, kPeriodH, kInvPeriodH);
+            const double soc = div_c(charge, kCapacity, kInv100);
+            const double p_pilot = div_c(pilot[p] * kVoltage, 1000.0, kInv1000);
+            const double cap2 = soc < kTransitionSoc ? kMaxPower
+                                                     : div_c(1.0 - soc, kOneMinusTrans, kInvOMT) * kMaxPower;
+            const double power = fmin(fmin(p_pilot, cap2), rate_to_full);
+            const double rate = div_c(power * 1000.0, kVoltage, kInv208);                 // A
+            del[p] += div_c(rate * kVoltage, 1000.0, kInv1000) * kPeriodH;               // EV.charge
             rate_sum += rate;
         }
     }
     const double total_rate = warp_sum(rate_sum);
 
     // ---- excess current from the rounded schedule (env.py:449-452) ---------------------------------
-    double excess;
+    double excess = 0.0;
     {
-        double S[SG_EV_MAX_CLASSES];
-        class_sums<SG_EV_MAX_CLASSES>(pilot, cls, C, S);
-        double ex = 0.0;
+        const unsigned pi[2] = {(unsigned)pilot[0], (unsigned)pilot[1]};
+        double S[kMC];
+        class_sums_pilots(pi, cls, C, S);
+        double sq = 0.0, lim = 0.0;
         if (lane < J) {
             double wr = 0, wi = 0;
 #pragma unroll
-            for (int c = 0; c < SG_EV_MAX_CLASSES; ++c) { wr = fma(sh.con_re[lane * 8 + c], S[c], wr); wi = fma(sh.con_im[lane * 8 + c], S[c], wi); }
-            ex = fmax(0.0, sqrt(wr * wr + wi * wi) - sh.lim[lane]);
+            for (int c = 0; c < kMC; ++c) { wr = fma(sh.con_re[lane * kMC + c], S[c], wr); wi = fma(sh.con_im[lane * kMC + c], S[c], wi); }
+            sq = fma(wr, wr, wi * wi);
+            lim = sh.lim[lane];
         }
-        excess = warp_sum(ex);
+        const bool over = lane < J && sq > lim * lim;
+        if (__any_sync(kFull, over)) excess = warp_sum(over ? fmax(0.0, sqrt(sq) - lim) : 0.0);
     }
 
     // ---- advance time, drain events with timestamp <= t+1: Unplug (0) before Plugin (10) ------------
@@ -571,8 +671,13 @@ __device__ __forceinline__ void ev_env_step(const sg_ev_model& m, const sg_ev_st
             for (int p = 0; p < 2; ++p) if (valid[p]) { dp[i0 + p] = del[p]; kp[i0 + p] = (uint8_t)k[p]; }
         }
         if (pilots != nullptr) {
+            if (vec) {
+                if (valid[0]) *reinterpret_cast<uchar2*>(pilots + b * n + i0) =
+                    make_uchar2((unsigned char)pilot[0], (unsigned char)pilot[1]);
+            } else {
 #pragma unroll
-            for (int p = 0; p < 2; ++p) if (valid[p]) pilots[b * n + i0 + p] = (uint8_t)pilot[p];
+                for (int p = 0; p < 2; ++p) if (valid[p]) pilots[b * n + i0 + p] = (uint8_t)pilot[p];
+            }
         }
     }
     if (lane == 0) {
@@ -581,8 +686,7 @@ __device__ __forceinline__ void ev_env_step(const sg_ev_model& m, const sg_ev_st
         double* bd = s.breakdown + b * 3;
         if (t == 0) { bd[0] = profit; bd[1] = carbon; bd[2] = excess_charge; }
         else { bd[0] += profit; bd[1] += carbon; bd[2] += excess_charge; }
-        s.t[b] = autoreset ? 0 : tn;
-        if (autoreset) { s.day[b] = day; s.moer_day[b] = md; }
+        *reinterpret_cast<int4*>(s.clock + b * 4) = make_int4(autoreset ? 0 : tn, day, md, clk.w);
         reward[b] = rew;
         done[b] = dn ? 1 : 0;
         if (status != nullptr) status[b] = (uint8_t)st;
@@ -593,7 +697,7 @@ __device__ __forceinline__ void ev_env_step(const sg_ev_model& m, const sg_ev_st
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 ev_step_kernel(const sg_ev_model m, const sg_ev_state s, const long long B, const void* __restrict__ action,
                const int flags, const int bins, float* __restrict__ obs, double* __restrict__ reward,
                uint8_t* __restrict__ done, uint8_t* __restrict__ pilots, float* __restrict__ final_obs,
@@ -610,7 +714,7 @@ ev_step_kernel(const sg_ev_model m, const sg_ev_state s, const long long B, cons
     }
 }
 
-// Work-list kernel: envs whose clipped action violated the network (MODE 1 deferred them).
+// Work-list kernel: envs whose clipped action was not certainly feasible (MODE 1 deferred them).
 __global__ void __launch_bounds__(128)
 ev_step_solve_kernel(const sg_ev_model m, const sg_ev_state s, const void* __restrict__ action, const int flags,
                      const int bins, float* __restrict__ obs, double* __restrict__ reward,
@@ -622,7 +726,8 @@ ev_step_solve_kernel(const sg_ev_model m, const sg_ev_state s, const void* __res
     const int count = todo[0];
     const int nwarps = gridDim.x * (blockDim.x >> 5);
     StatsAcc acc;
-    for (int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < count; w += nwarps) {
+    // warp w of CTA c takes item c + w*gridDim.x: the first items spread over different SMs
+    for (int w = blockIdx.x + (threadIdx.x >> 5) * gridDim.x; w < count; w += nwarps) {
         const long long b = todo[2 + w];
         ev_env_step<2>(m, s, sh, b, lane, action, flags, bins, obs, reward, done, pilots, final_obs, status, nullptr, acc);
     }
@@ -646,8 +751,8 @@ __global__ void ev_reset_kernel(const sg_ev_model m, const sg_ev_state s, const 
     if (b >= B) return;
     if (mask != nullptr && mask[b] == 0) return;
     const int n = m.n_stations, kf = m.moer_steps, OBS = 2 * n + kf + 2;
-    int day = day_in ? day_in[b] : s.day[b];
-    int md = moer_day_in ? moer_day_in[b] : s.moer_day[b];
+    int day = day_in ? day_in[b] : s.clock[b * 4 + 1];
+    int md = moer_day_in ? moer_day_in[b] : s.clock[b * 4 + 2];
     day = ((day % m.n_days) + m.n_days) % m.n_days;
     md = ((md % m.n_moer_days) + m.n_moer_days) % m.n_moer_days;
     for (int i = lane; i < n; i += 32) { s.delivered[b * n + i] = 0.0; s.sess_idx[b * n + i] = 0; }
@@ -656,7 +761,7 @@ __global__ void ev_reset_kernel(const sg_ev_model m, const sg_ev_state s, const 
     const float* mrow = m.moer + ((long long)md * SG_EV_MOER_ROWS) * SG_EV_MOER_COLS;
     for (int e = lane; e < kf + 2; e += 32) orow[2 * n + e] = e < kf ? mrow[1 + e] : (e == kf ? mrow[0] : 0.f);
     if (lane == 0) {
-        s.t[b] = 0; s.day[b] = day; s.moer_day[b] = md;
+        s.clock[b * 4 + 0] = 0; s.clock[b * 4 + 1] = day; s.clock[b * 4 + 2] = md;
         s.breakdown[b * 3] = s.breakdown[b * 3 + 1] = s.breakdown[b * 3 + 2] = 0.0;
     }
 }
@@ -752,7 +857,7 @@ int sg_ev_step_finish(const sg_ev_model* m, const sg_ev_state* s, int64_t num_en
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     int sms = sg_device_sm_count();
     if (sms <= 0) sms = 148;
-    const unsigned sgrid = (unsigned)std::min<long long>((num_envs + 3) / 4, (long long)sms * 4);
+    const unsigned sgrid = (unsigned)std::min<long long>((num_envs + 3) / 4, (long long)sms * 2);
     sg::ev_step_solve_kernel<<<sgrid, 128, 0, st>>>(*m, *s, action, flags, discrete_bins, obs, reward, done, pilots,
                                                   final_obs, status, stats, todo);
     return sg::launch_status("ev_step_solve_kernel");

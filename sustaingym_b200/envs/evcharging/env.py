@@ -116,12 +116,11 @@ class BatchedEVChargingEnv:
         z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)  # noqa: E731
         self.delivered = z(B, n, dtype=torch.float64)
         self.sess_idx = z(B, n, dtype=torch.uint8)
-        self.t = z(B, dtype=torch.int32)
-        self.day = z(B, dtype=torch.int32)
-        self.moer_day = z(B, dtype=torch.int32)
+        self.clock = z(B, 4, dtype=torch.int32)          # columns: t, day, moer_day, reserved
+        self.t, self.day, self.moer_day = self.clock[:, 0], self.clock[:, 1], self.clock[:, 2]
         self.breakdown = z(B, 3, dtype=torch.float64)
-        self._state = _lib.EVState(self.delivered.data_ptr(), self.sess_idx.data_ptr(), self.t.data_ptr(),
-                                   self.day.data_ptr(), self.moer_day.data_ptr(), self.breakdown.data_ptr())
+        self._state = _lib.EVState(self.delivered.data_ptr(), self.sess_idx.data_ptr(), self.clock.data_ptr(),
+                                   self.breakdown.data_ptr())
         self.obs = z(B, self.obs_dim, dtype=torch.float32)
         self.final_obs = z(B, self.obs_dim, dtype=torch.float32) if auto_reset else None
         self.reward = z(B, dtype=torch.float64)
