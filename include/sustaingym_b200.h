@@ -130,9 +130,10 @@ typedef struct sg_ev_model {
     int32_t project;         /* project_action_in_env (env.py:118)                            */
     const uint8_t* station_class; /* [device] [n] class id of each station                    */
     const uint8_t* station_type;  /* [device] [n] 0: {0,6..32} A (min_pilot 6), 1: {0,8,..,32}*/
-    const double*  con_re;        /* [device] [J, C] Re of per-class constraint coefficient   */
-    const double*  con_im;        /* [device] [J, C] Im                                       */
-    const double*  magnitudes;    /* [device] [J] limits in A                                 */
+    const double*  con_re;        /* [device] [16, 8] Re of the per-class constraint coefficient,
+                                     zero-padded to [SG_EV_MAX_CONSTRAINTS, SG_EV_MAX_CLASSES]  */
+    const double*  con_im;        /* [device] [16, 8] Im, same layout                          */
+    const double*  magnitudes;    /* [device] [16] limits in A, zero-padded                    */
     const void*    sessions;      /* [device] [D, K, n] 16-byte records (sg_ev_session)        */
     const float*   moer;          /* [device] [Dm, 289, 37]                                   */
 } sg_ev_model;

@@ -96,22 +96,18 @@ struct EvShared {
     double stat[11 * kWarpsPerBlock];
 };
 
+// The host pads con_re / con_im to [SG_EV_MAX_CONSTRAINTS][SG_EV_MAX_CLASSES] and magnitudes to
+// [SG_EV_MAX_CONSTRAINTS] with zeros, so staging is a straight copy (no index arithmetic).
 __device__ __forceinline__ void load_shared(const sg_ev_model& m, EvShared& sh) {
-    const int C = m.n_classes, J = m.n_constraints;
     for (int i = threadIdx.x; i < SG_EV_MAX_CONSTRAINTS * kMC; i += blockDim.x) {
-        sh.con_re[i] = 0.0; sh.con_im[i] = 0.0;      // padding classes/constraints contribute nothing
+        sh.con_re[i] = m.con_re[i];
+        sh.con_im[i] = m.con_im[i];
     }
-    for (int i = threadIdx.x; i < SG_EV_MAX_CONSTRAINTS; i += blockDim.x) sh.lim[i] = 0.0;
-    __syncthreads();
-    for (int i = threadIdx.x; i < J * C; i += blockDim.x) {
-        const int j = i / C, c = i % C;
-        sh.con_re[j * kMC + c] = m.con_re[i];
-        sh.con_im[j * kMC + c] = m.con_im[i];
-    }
-    for (int i = threadIdx.x; i < J; i += blockDim.x) sh.lim[i] = m.magnitudes[i];
-    for (int i = threadIdx.x; i < m.n_stations; i += blockDim.x) {
-        sh.cls[i] = m.station_class[i];
-        sh.type[i] = m.station_type[i];
+    if (threadIdx.x < SG_EV_MAX_CONSTRAINTS) sh.lim[threadIdx.x] = m.magnitudes[threadIdx.x];
+    if (threadIdx.x < SG_EV_MAX_STATIONS) {
+        const bool in = (int)threadIdx.x < m.n_stations;
+        sh.cls[threadIdx.x] = in ? m.station_class[threadIdx.x] : 255;
+        sh.type[threadIdx.x] = in ? m.station_type[threadIdx.x] : 0;
     }
     __syncthreads();
 }
@@ -424,6 +420,72 @@ __device__ __forceinline__ int ipm_dispatch(const EvShared& sh, int C, int J, co
     return ipm_project<SG_EV_MAX_CLASSES, SG_EV_MAX_CONSTRAINTS>(sh, C, J, a, u, cls, valid, x, hit_cap);
 }
 
+// Exact projection when only "simple" constraints (a single class with a non-zero coefficient,
+// e.g. the 80 A pods) are violated: x_i = clip(a_i - nu, 0, u_i) on that class with nu >= 0 such
+// that the class sum meets the limit (KKT of the QCQP with every other multiplier zero).  nu is
+// the root of a decreasing piecewise-linear function: safeguarded Newton, which terminates on
+// the exact linear piece.  The caller re-checks all constraints afterwards and falls back to the
+// interior-point solver if another constraint is (or became) violated.
+__device__ __forceinline__ bool simple_project(const EvShared& sh, const int C, const int J, const double (&a)[2],
+                                               const double (&u)[2], const int (&cls)[2], const bool (&valid)[2],
+                                               double (&x)[2]) {
+    double S[kMC];
+    class_sums<kMC>(x, cls, C, S);
+    bool any_fixed = false;
+    for (int j = 0; j < J; ++j) {
+        int cstar = -1, nz = 0;
+        double wr = 0, wi = 0;
+#pragma unroll
+        for (int c = 0; c < kMC; ++c) {
+            const double re = sh.con_re[j * kMC + c], im = sh.con_im[j * kMC + c];
+            if (re != 0.0 || im != 0.0) { nz++; cstar = c; }
+            wr = fma(re, S[c], wr); wi = fma(im, S[c], wi);
+        }
+        const double r = sh.lim[j] * (1.0 / kActionScale);
+        if (!(sqrt(wr * wr + wi * wi) > r)) continue;        // satisfied
+        if (nz != 1) return false;                           // a coupled constraint is violated -> IPM
+        const double kappa = sqrt(sh.con_re[j * kMC + cstar] * sh.con_re[j * kMC + cstar] +
+                                  sh.con_im[j * kMC + cstar] * sh.con_im[j * kMC + cstar]);
+        const double R = r / kappa;                           // limit on the class sum
+        bool in[2];
+        double amax = 0.0;
+#pragma unroll
+        for (int p = 0; p < 2; ++p) { in[p] = valid[p] && cls[p] == cstar && u[p] > 0.0; if (in[p]) amax = fmax(amax, a[p]); }
+        double lo = 0.0, hi = warp_max(amax), nu = 0.0;
+        unsigned sig_prev = 0xffffffffu;
+        for (int it = 0; it < 100; ++it) {
+            double s_mid = 0.0, s_up = 0.0;
+            unsigned code = 0;
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                if (in[p]) {
+                    const double v = a[p] - nu;
+                    if (v >= u[p]) { s_up += u[p]; code |= 2u << (2 * p); }
+                    else if (v > 0.0) { s_mid += a[p]; code |= 1u << (2 * p); }
+                }
+            }
+            const int n_mid = __popc(__ballot_sync(kFull, code & 1u)) + __popc(__ballot_sync(kFull, code & 4u));
+            // classification signature (order-independent hash is enough to detect "no change")
+            const unsigned sig = __reduce_xor_sync(kFull, code * 2654435761u + (unsigned)(threadIdx.x & 31) * 40503u * code);
+            const double sum_mid = warp_sum(s_mid), sum_up = warp_sum(s_up);
+            const double phi = sum_mid - n_mid * nu + sum_up;
+            if (sig == sig_prev && n_mid > 0) break;          // same linear piece twice: nu is its exact root
+            sig_prev = sig;
+            if (phi > R) lo = nu; else hi = nu;
+            double nu_new = n_mid > 0 ? (sum_mid + sum_up - R) / n_mid : 0.5 * (lo + hi);
+            if (!(nu_new > lo && nu_new < hi)) { nu_new = 0.5 * (lo + hi); sig_prev = 0xffffffffu; }
+            if (nu_new == nu) break;
+            nu = nu_new;
+        }
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+            if (in[p]) x[p] = fmin(fmax(a[p] - nu, 0.0), u[p]);
+        class_sums<kMC>(x, cls, C, S);
+        any_fixed = true;
+    }
+    return any_fixed;
+}
+
 // Exact test: is the (box-clipped) action inside every network constraint?  x normalised.
 __device__ __forceinline__ bool network_feasible(const EvShared& sh, int C, int J, const double (&x)[2],
                                                  const int (&cls)[2]) {
@@ -436,6 +498,23 @@ __device__ __forceinline__ bool network_feasible(const EvShared& sh, int C, int 
         for (int c = 0; c < kMC; ++c) { wr = fma(sh.con_re[j * kMC + c], S[c], wr); wi = fma(sh.con_im[j * kMC + c], S[c], wi); }
         const double r = sh.lim[j] * (1.0 / kActionScale);
         ok = ok && !(sqrt(wr * wr + wi * wi) > r);
+    }
+    return ok;
+}
+
+// Same with a relative slack of 1e-12 (a point placed exactly on a constraint boundary by the
+// simple projection may exceed it by a few ulps).
+__device__ __forceinline__ bool network_feasible_tol(const EvShared& sh, int C, int J, const double (&x)[2],
+                                                     const int (&cls)[2]) {
+    double S[kMC];
+    class_sums<kMC>(x, cls, C, S);
+    bool ok = true;
+    for (int j = 0; j < J; ++j) {
+        double wr = 0, wi = 0;
+#pragma unroll
+        for (int c = 0; c < kMC; ++c) { wr = fma(sh.con_re[j * kMC + c], S[c], wr); wi = fma(sh.con_im[j * kMC + c], S[c], wi); }
+        const double r = sh.lim[j] * (1.0 / kActionScale);
+        ok = ok && !(sqrt(wr * wr + wi * wi) > r * (1.0 + 1e-12));
     }
     return ok;
 }
@@ -554,7 +633,11 @@ __device__ __forceinline__ void ev_env_step(const sg_ev_model& m, const sg_ev_st
         } else {
             if (!network_feasible(sh, C, J, x, cls)) {
                 bool cap = false;
-                ipm_dispatch(sh, C, J, a, u, cls, valid, x, &cap);
+                if (!(simple_project(sh, C, J, a, u, cls, valid, x) && network_feasible_tol(sh, C, J, x, cls))) {
+#pragma unroll
+                    for (int p = 0; p < 2; ++p) x[p] = valid[p] ? fmin(fmax(a[p], 0.0), u[p]) : 0.0;
+                    ipm_dispatch(sh, C, J, a, u, cls, valid, x, &cap);
+                }
                 st = SG_EV_STATUS_PROJECTED | (cap ? SG_EV_STATUS_MAXITER : 0);
             }
         }
@@ -696,6 +779,8 @@ __device__ __forceinline__ void ev_env_step(const sg_ev_model& m, const sg_ev_st
     }
 }
 
+// Persistent CTAs: every warp strides over the batch, so the table staging and the statistics
+// flush are paid once per warp instead of once per env.
 template <int MODE>
 __global__ void __launch_bounds__(kThreads, 3)
 ev_step_kernel(const sg_ev_model m, const sg_ev_state s, const long long B, const void* __restrict__ action,
@@ -705,9 +790,10 @@ ev_step_kernel(const sg_ev_model m, const sg_ev_state s, const long long B, cons
     __shared__ EvShared sh;
     load_shared(m, sh);
     const int lane = threadIdx.x & 31;
-    const long long b = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    const long long stride = (long long)gridDim.x * kWarpsPerBlock;
     StatsAcc acc;
-    if (b < B) ev_env_step<MODE>(m, s, sh, b, lane, action, flags, bins, obs, reward, done, pilots, final_obs, status, todo, acc);
+    for (long long b = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); b < B; b += stride)
+        ev_env_step<MODE>(m, s, sh, b, lane, action, flags, bins, obs, reward, done, pilots, final_obs, status, todo, acc);
     if (stats != nullptr) {
         __syncthreads();
         stats_flush_block(acc, stats, sh.stat);
@@ -790,7 +876,12 @@ ev_project_kernel(const sg_ev_model m, const long long B, const float* __restric
     int st = 0, it = 0;
     if (!network_feasible(sh, m.n_classes, m.n_constraints, x, cls)) {
         bool cap = false;
-        it = ipm_dispatch(sh, m.n_classes, m.n_constraints, a, u, cls, valid, x, &cap);
+        if (!(simple_project(sh, m.n_classes, m.n_constraints, a, u, cls, valid, x) &&
+              network_feasible_tol(sh, m.n_classes, m.n_constraints, x, cls))) {
+#pragma unroll
+            for (int p = 0; p < 2; ++p) x[p] = valid[p] ? fmin(fmax(a[p], 0.0), u[p]) : 0.0;
+            it = ipm_dispatch(sh, m.n_classes, m.n_constraints, a, u, cls, valid, x, &cap);
+        }
         st = SG_EV_STATUS_PROJECTED | (cap ? SG_EV_STATUS_MAXITER : 0);
     }
 #pragma unroll
@@ -836,7 +927,11 @@ int sg_ev_step(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, con
     SG_CHECK_ARG(!m->project || todo != nullptr, "ev_step: projection needs the todo scratch buffer");
     if (num_envs <= 0) return 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const unsigned grid = (unsigned)((num_envs + sg::kWarpsPerBlock - 1) / sg::kWarpsPerBlock);
+    int sms = sg_device_sm_count();
+    if (sms <= 0) sms = 148;
+    // persistent grid: 3 resident CTAs per SM (multiple of the SM count), fewer for tiny batches
+    const unsigned grid = (unsigned)std::min<long long>((num_envs + sg::kWarpsPerBlock - 1) / sg::kWarpsPerBlock,
+                                                        (long long)sms * 3);
     if (!m->project) {
         sg::ev_step_kernel<0><<<grid, sg::kThreads, 0, st>>>(*m, *s, num_envs, action, flags, discrete_bins, obs,
                                                            reward, done, pilots, final_obs, status, stats, todo);

@@ -95,12 +95,16 @@ class BatchedEVChargingEnv:
         rec = np.zeros(t.arrival.shape, dtype=np.dtype([("arr", "<i2"), ("dep", "<i2"), ("est", "<i2"),
                                                          ("res", "<i2"), ("energy", "<f8")]))
         rec["arr"], rec["dep"], rec["est"], rec["energy"] = t.arrival, t.departure, t.est_departure, t.energy
+        J, Cn = coef.shape
+        re = np.zeros((_lib.SG_EV_MAX_CONSTRAINTS, _lib.SG_EV_MAX_CLASSES)); re[:J, :Cn] = coef.real
+        im = np.zeros((_lib.SG_EV_MAX_CONSTRAINTS, _lib.SG_EV_MAX_CLASSES)); im[:J, :Cn] = coef.imag
+        mag = np.zeros(_lib.SG_EV_MAX_CONSTRAINTS); mag[:J] = self.cn.magnitudes
         self._c = {
             "cls": torch.from_numpy(cls.astype(np.uint8)).to(dev),
             "type": torch.from_numpy(self.cn.evse_type.astype(np.uint8)).to(dev),
-            "re": torch.from_numpy(np.ascontiguousarray(coef.real)).to(dev),
-            "im": torch.from_numpy(np.ascontiguousarray(coef.imag)).to(dev),
-            "mag": torch.from_numpy(self.cn.magnitudes.astype(np.float64)).to(dev),
+            "re": torch.from_numpy(re).to(dev),
+            "im": torch.from_numpy(im).to(dev),
+            "mag": torch.from_numpy(mag).to(dev),
             "sessions": torch.from_numpy(rec.view(np.uint8).reshape(-1)).to(dev),
             "moer": torch.from_numpy(data_generator.moer).to(dev),
         }
