@@ -219,7 +219,7 @@ __device__ __noinline__ int ipm_project(const EvShared& sh, const int C, const i
     double zl[2], zu[2];
 #pragma unroll
     for (int p = 0; p < 2; ++p) { zl[p] = fr[p] ? mu / x[p] : 0.0; zu[p] = fr[p] ? mu / (uf[p] - x[p]) : 0.0; }
-    double lam[MAXJ], wre[MAXJ], wim[MAXJ], q[MAXJ], iq[MAXJ];
+    double lam[MAXJ], wre[MAXJ], wim[MAXJ], q[MAXJ];
     class_sums<MAXC>(x, cls, C, S);
 #pragma unroll
     for (int j = 0; j < MAXJ; ++j) {
@@ -267,32 +267,34 @@ __device__ __noinline__ int ipm_project(const EvShared& sh, const int C, const i
         const double resid = warp_max(rmax);
         if (gap < tol && resid < 100.0 * tol) { *hit_cap = false; break; }
         mu = 0.1 * gap;
-        // ---- reduced Newton system ---------------------------------------------------------
-        double kap[MAXC], Kmat[MAXC][MAXC];
+        // ---- reduced Newton system -----------------------------------------------------------
+        // Unknowns: class-sum step ds = H v (H = E^(1/2), E_c = sum over free stations of 1/D_i) and
+        // the constraint multipliers' step dlam.  With K0 = 2 sum_j lam_j Q_j, B_j = 2 H G_j,
+        // T_j = q_j / lam_j, t_j = mu / lam_j - q_j:
+        //      (I + H K0 H) v + B^T dlam = H^-1 g          (stationarity, box multipliers eliminated)
+        //              -B v + T dlam   = t                 (linearised complementarity)
+        // dlam is NOT eliminated through 1/q_j (that puts 4 lam/q G G^T ~ 1e16 into the matrix and
+        // the Cholesky pivots cancel catastrophically near convergence); instead v is eliminated:
+        //      (T + B A0^-1 B^T) dlam = t + B A0^-1 ghat,   A0 = I + H K0 H   (both SPD, well scaled)
+        double G[MAXJ][MAXC], K0[MAXC][MAXC];
 #pragma unroll
-        for (int c = 0; c < MAXC; ++c) {
-            kap[c] = 0.0;
+        for (int c = 0; c < MAXC; ++c)
 #pragma unroll
-            for (int d = 0; d < MAXC; ++d) Kmat[c][d] = 0.0;
-        }
+            for (int d = 0; d < MAXC; ++d) K0[c][d] = 0.0;
 #pragma unroll
         for (int j = 0; j < MAXJ; ++j) {
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c) G[j][c] = (j < J) ? wre[j] * sh.con_re[j * kMC + c] + wim[j] * sh.con_im[j * kMC + c] : 0.0;
             if (j < J) {
-                iq[j] = fast_rcp(q[j]);
-                double G[MAXC];
+                const double l2 = 2.0 * lam[j];
 #pragma unroll
-                for (int c = 0; c < MAXC; ++c) G[c] = wre[j] * sh.con_re[j * kMC + c] + wim[j] * sh.con_im[j * kMC + c];
-                const double mq = 2.0 * mu * iq[j], l2 = 2.0 * lam[j], l4 = 4.0 * lam[j] * iq[j];
-#pragma unroll
-                for (int c = 0; c < MAXC; ++c) {
-                    kap[c] = fma(mq, G[c], kap[c]);
+                for (int c = 0; c < MAXC; ++c)
 #pragma unroll
                     for (int d = 0; d <= c; ++d) {
                         const double Q = sh.con_re[j * kMC + c] * sh.con_re[j * kMC + d] + sh.con_im[j * kMC + c] * sh.con_im[j * kMC + d];
-                        Kmat[c][d] = fma(l2, Q, fma(l4 * G[c], G[d], Kmat[c][d]));
+                        K0[c][d] = fma(l2, Q, K0[c][d]);
                     }
-                }
-            } else iq[j] = 1.0;
+            }
         }
         double ixs[2], ius[2], rho[2], inv[2], rhoD[2];
 #pragma unroll
@@ -300,30 +302,29 @@ __device__ __noinline__ int ipm_project(const EvShared& sh, const int C, const i
             ixs[p] = fast_rcp(xs[p]);
             ius[p] = fast_rcp(us[p]);
             const double Dd = fr[p] ? 1.0 + zl[p] * ixs[p] + zu[p] * ius[p] : 1.0;
-            double kc = 0.0;
+            double nuc = 0.0;
 #pragma unroll
-            for (int c = 0; c < MAXC; ++c) kc = (cls[p] == c) ? kap[c] : kc;
-            rho[p] = fr[p] ? -(x[p] - a[p]) + mu * ixs[p] - mu * ius[p] - kc : 0.0;
+            for (int c = 0; c < MAXC; ++c) nuc = (cls[p] == c) ? nu[c] : nuc;
+            rho[p] = fr[p] ? -(x[p] - a[p]) - nuc + mu * ixs[p] - mu * ius[p] : 0.0;
             inv[p] = fr[p] ? fast_rcp(Dd) : 0.0;
             rhoD[p] = rho[p] * inv[p];
         }
         double E[MAXC], g[MAXC];
         class_sums<MAXC>(inv, cls, C, E);
         class_sums<MAXC>(rhoD, cls, C, g);
-        // (I + H K H) v = g / h,  ds = H v   (SPD; classes without free stations drop out)
-        double h[MAXC], L[MAXC][MAXC], v[MAXC];
+        double h[MAXC], L[MAXC][MAXC], what[MAXC];
 #pragma unroll
         for (int c = 0; c < MAXC; ++c) {
             const bool on = (c < C) && E[c] > 0.0;
             const double ih = on ? fast_rsqrt(E[c]) : 0.0;
             h[c] = on ? E[c] * ih : 0.0;
-            v[c] = g[c] * ih;
+            what[c] = g[c] * ih;
         }
 #pragma unroll
         for (int c = 0; c < MAXC; ++c)
 #pragma unroll
-            for (int d = 0; d <= c; ++d) L[c][d] = h[c] * Kmat[c][d] * h[d] + (c == d ? 1.0 : 0.0);
-        // Cholesky in place; the diagonal stores 1/L[d][d]
+            for (int d = 0; d <= c; ++d) L[c][d] = h[c] * K0[c][d] * h[d] + (c == d ? 1.0 : 0.0);
+        // Cholesky of A0 in place; the diagonal stores 1/L[d][d]
 #pragma unroll
         for (int d = 0; d < MAXC; ++d) {
             double sum = L[d][d];
@@ -339,12 +340,76 @@ __device__ __noinline__ int ipm_project(const EvShared& sh, const int C, const i
                 L[c][d] = s2 * il;
             }
         }
+        // what = L^-1 ghat ;  W_j = L^-1 B_j
 #pragma unroll
         for (int c = 0; c < MAXC; ++c) {
-            double sum = v[c];
+            double sum = what[c];
 #pragma unroll
-            for (int e = 0; e < c; ++e) sum = fma(-L[c][e], v[e], sum);
-            v[c] = sum * L[c][c];
+            for (int e = 0; e < c; ++e) sum = fma(-L[c][e], what[e], sum);
+            what[c] = sum * L[c][c];
+        }
+        double W[MAXJ][MAXC], Sm[MAXJ][MAXJ], rhs[MAXJ];
+#pragma unroll
+        for (int j = 0; j < MAXJ; ++j) {
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c) {
+                double sum = 2.0 * G[j][c] * h[c];
+#pragma unroll
+                for (int e = 0; e < c; ++e) sum = fma(-L[c][e], W[j][e], sum);
+                W[j][c] = sum * L[c][c];
+            }
+            const double il = (j < J) ? fast_rcp(lam[j]) : 1.0;
+            double r = (j < J) ? mu * il - q[j] : 0.0;
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c) r = fma(W[j][c], what[c], r);
+            rhs[j] = r;
+#pragma unroll
+            for (int k2 = 0; k2 <= j; ++k2) {
+                double sum = (k2 == j) ? ((j < J) ? q[j] * il : 1.0) : 0.0;
+#pragma unroll
+                for (int c = 0; c < MAXC; ++c) sum = fma(W[j][c], W[k2][c], sum);
+                Sm[j][k2] = sum;
+            }
+        }
+        // Cholesky of S (J x J) and solve for dlam
+#pragma unroll
+        for (int d = 0; d < MAXJ; ++d) {
+            double sum = Sm[d][d];
+#pragma unroll
+            for (int e = 0; e < d; ++e) sum = fma(-Sm[d][e], Sm[d][e], sum);
+            const double il = fast_rsqrt(sum);
+            Sm[d][d] = il;
+#pragma unroll
+            for (int c = d + 1; c < MAXJ; ++c) {
+                double s2 = Sm[c][d];
+#pragma unroll
+                for (int e = 0; e < d; ++e) s2 = fma(-Sm[c][e], Sm[d][e], s2);
+                Sm[c][d] = s2 * il;
+            }
+        }
+        double dlam[MAXJ];
+#pragma unroll
+        for (int j = 0; j < MAXJ; ++j) {
+            double sum = rhs[j];
+#pragma unroll
+            for (int e = 0; e < j; ++e) sum = fma(-Sm[j][e], dlam[e], sum);
+            dlam[j] = sum * Sm[j][j];
+        }
+#pragma unroll
+        for (int j = MAXJ - 1; j >= 0; --j) {
+            double sum = dlam[j];
+#pragma unroll
+            for (int e = j + 1; e < MAXJ; ++e) sum = fma(-Sm[e][j], dlam[e], sum);
+            dlam[j] = sum * Sm[j][j];
+        }
+        // v = L^-T (what - W^T dlam) ; ds = H v ; y = K0 ds + 2 sum_j dlam_j G_j
+        double v[MAXC], ds[MAXC], y[MAXC];
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+            double sum = what[c];
+#pragma unroll
+            for (int j = 0; j < MAXJ; ++j) sum = fma(-W[j][c], dlam[j], sum);
+            v[c] = sum;
         }
 #pragma unroll
         for (int c = MAXC - 1; c >= 0; --c) {
@@ -353,14 +418,15 @@ __device__ __noinline__ int ipm_project(const EvShared& sh, const int C, const i
             for (int e = c + 1; e < MAXC; ++e) sum = fma(-L[e][c], v[e], sum);
             v[c] = sum * L[c][c];
         }
-        double ds[MAXC], y[MAXC];
 #pragma unroll
         for (int c = 0; c < MAXC; ++c) ds[c] = h[c] * v[c];
 #pragma unroll
         for (int c = 0; c < MAXC; ++c) {
             double sum = 0.0;
 #pragma unroll
-            for (int d = 0; d < MAXC; ++d) sum = fma(d <= c ? Kmat[c][d] : Kmat[d][c], ds[d], sum);
+            for (int d = 0; d < MAXC; ++d) sum = fma(d <= c ? K0[c][d] : K0[d][c], ds[d], sum);
+#pragma unroll
+            for (int j = 0; j < MAXJ; ++j) sum = fma(2.0 * dlam[j], G[j][c], sum);
             y[c] = sum;
         }
         // ---- directions; fraction-to-boundary step as alpha = tau / max(tau, worst ratio) ----------
@@ -380,27 +446,25 @@ __device__ __noinline__ int ipm_project(const EvShared& sh, const int C, const i
                 worst = fmax(worst, -dzu[p] * fast_rcp(zu[p]));
             }
         }
-        double dlam[MAXJ];
 #pragma unroll
         for (int j = 0; j < MAXJ; ++j) {
             if (j < J) {
-                double dwr = 0, dwi = 0, Gds = 0;
+                double dwr = 0, dwi = 0;
 #pragma unroll
                 for (int c = 0; c < MAXC; ++c) {
                     dwr = fma(sh.con_re[j * kMC + c], ds[c], dwr);
                     dwi = fma(sh.con_im[j * kMC + c], ds[c], dwi);
-                    Gds = fma(wre[j] * sh.con_re[j * kMC + c] + wim[j] * sh.con_im[j * kMC + c], ds[c], Gds);
                 }
-                dlam[j] = mu * iq[j] - lam[j] + 2.0 * lam[j] * iq[j] * Gds;
                 const double bq = wre[j] * dwr + wim[j] * dwi;
                 const double c2 = dwr * dwr + dwi * dwi;
                 const double den = bq + sqrt(fma(bq, bq, c2 * tau * q[j]));
-                worst = fmax(worst, den * iq[j]);                          // tau*q/den >= alpha
+                worst = fmax(worst, den * fast_rcp(q[j]));                 // tau*q/den >= alpha
                 worst = fmax(worst, -dlam[j] * fast_rcp(lam[j]));
-            } else dlam[j] = 0.0;
+            }
         }
         worst = warp_max(worst);
         const double alpha = worst > tau ? tau * fast_rcp(worst) : 1.0;
+        if (!(alpha > 0.0)) break;                       // NaN / breakdown guard: report as cap hit
 #pragma unroll
         for (int p = 0; p < 2; ++p) {
             x[p] = fma(alpha, dx[p], x[p]);
