@@ -154,6 +154,7 @@ typedef struct sg_ev_state {
 #define SG_EV_ACTION_F32      0
 #define SG_EV_ACTION_I64      1   /* DiscreteActionWrapper input (wrappers.py:43-45)          */
 #define SG_EV_FLAG_AUTORESET  16  /* on done: advance day (mod D), reset state, obs = reset obs */
+#define SG_EV_FLAG_GENERIC_KERNEL 256 /* use the generic kernel even when the specialised one applies */
 
 /* reset(): env.py:293-338 for envs whose `reset_mask` byte is non-zero (NULL = all).
  * `day_in`/`moer_day_in` pick the trace/MOER table (the seed->day map is host logic,

@@ -15,14 +15,14 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 BUILD_DIR = os.path.join(CSRC, "build")
-LIB_PATH = os.path.join(PKG_DIR, "libsustaingym_b200.so")
+LIB_PATH = os.environ.get("SG_LIB_PATH", os.path.join(PKG_DIR, "libsustaingym_b200.so"))
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "-I", INCLUDE,
-]
+] + os.environ.get("SG_NVCC_EXTRA", "").split()
 
 
 def _sources() -> list[str]:

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libsustaingym_b200.so")
+LIB_PATH = os.environ.get("SG_LIB_PATH", os.path.join(_PKG_DIR, "libsustaingym_b200.so"))
 
 SG_STATS_LEN = 16
 SG_EV_MOER_COLS = 37
@@ -23,6 +23,7 @@ SG_EV_STATUS_MAXITER = 2
 SG_EV_ACTION_F32 = 0
 SG_EV_ACTION_I64 = 1
 SG_EV_FLAG_AUTORESET = 16
+SG_EV_FLAG_GENERIC_KERNEL = 256
 SG_BUILDING_FLAG_AUTORESET = 16
 
 _vp = C.c_void_p

@@ -843,6 +843,290 @@ __device__ __forceinline__ void ev_env_step(const sg_ev_model& m, const sg_ev_st
     }
 }
 
+// =================================================================================================
+// Specialised main kernel (the BASELINE configuration and anything shaped like it): n even,
+// <= NC classes of <= 63 stations, <= 8... J <= 32 constraints handled one per lane, f32 or i64
+// actions, MODE 0 / 1.  Same arithmetic as ev_env_step, restructured for instruction count:
+//   * per-lane constants (class, EVSE type, packing shifts, this lane's constraint row) live in
+//     registers across the persistent env loop;
+//   * both class-sum reductions (2^-10 fixed-point actions, integer pilots) use 16-bit fields,
+//     two classes per REDUX;
+//   * charging uses per-pilot lookup tables (built with the same div_c sequence, so bit-equal)
+//     whenever neither battery limit can bind (more than 2 kWh of head-room);
+//   * the next env's clock/action/state rows are prefetched while the current one is computed.
+// =================================================================================================
+struct EvFastShared {
+    double rate[40];       // A delivered for an integer pilot when the battery does not limit it
+    double energy[40];     // kWh per period for that pilot
+    double margin[32];     // quantisation margin of the fixed-point feasibility test, per constraint
+    double stat[11 * kWarpsPerBlock];
+    EvShared base;
+};
+
+constexpr double kFix10 = 1024.0, kFix10Inv = 1.0 / 1024.0;
+
+template <int NC>
+__device__ __forceinline__ void class_sums16(unsigned v0, unsigned v1, int cls0, int cls1, double (&S)[NC]) {
+#pragma unroll
+    for (int w = 0; w < (NC + 1) / 2; ++w) {
+        const unsigned part = ((cls0 >> 1) == w ? v0 << ((cls0 & 1) * 16) : 0u) +
+                              ((cls1 >> 1) == w ? v1 << ((cls1 & 1) * 16) : 0u);
+        const unsigned tot = __reduce_add_sync(kFull, part);
+        S[2 * w] = (double)(tot & 0xffffu);
+        if (2 * w + 1 < NC) S[2 * w + 1] = (double)(tot >> 16);
+    }
+}
+
+#ifndef SG_EV_FAST_MINBLOCKS
+#define SG_EV_FAST_MINBLOCKS 2
+#endif
+template <int MODE, int NC>
+__global__ void __launch_bounds__(kThreads, SG_EV_FAST_MINBLOCKS)
+ev_step_fast_kernel(const sg_ev_model m, const sg_ev_state s, const long long B, const void* __restrict__ action,
+                    const int flags, const int bins, float* __restrict__ obs, double* __restrict__ reward,
+                    uint8_t* __restrict__ done, uint8_t* __restrict__ pilots, float* __restrict__ final_obs,
+                    uint8_t* __restrict__ status, double* __restrict__ stats, int32_t* __restrict__ todo) {
+    __shared__ EvFastShared fs;
+    load_shared(m, fs.base);
+    const int n = m.n_stations, kf = m.moer_steps, OBS = 2 * n + kf + 2, J = m.n_constraints, K = m.max_sessions;
+    if (threadIdx.x <= 32) {
+        const double pp = div_c((double)threadIdx.x * kVoltage, 1000.0, kInv1000);
+        const double rate = div_c(pp * 1000.0, kVoltage, kInv208);
+        fs.rate[threadIdx.x] = rate;
+        fs.energy[threadIdx.x] = div_c(rate * kVoltage, 1000.0, kInv1000) * kPeriodH;
+    }
+    if (threadIdx.x < 32) {
+        double mg = 1e-9;
+        if ((int)threadIdx.x < J) {
+            for (int c = 0; c < NC; ++c) {
+                int cnt = 0;
+                for (int i = 0; i < n; ++i) cnt += (fs.base.cls[i] == c);
+                const double re = fs.base.con_re[threadIdx.x * kMC + c], im = fs.base.con_im[threadIdx.x * kMC + c];
+                mg += sqrt(re * re + im * im) * cnt * (0.5 * kFix10Inv);
+            }
+        }
+        fs.margin[threadIdx.x] = mg;
+    }
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31;
+    const int i0 = 2 * lane;
+    const bool valid = i0 < n;                               // n is even: both stations or none
+    const int cls0 = valid ? fs.base.cls[i0] : 254, cls1 = valid ? fs.base.cls[i0 + 1] : 254;
+    const int type0 = valid ? fs.base.type[i0] : 0, type1 = valid ? fs.base.type[i0 + 1] : 0;
+    // this lane's constraint (lane < J), normalised limit and squared thresholds
+    double cre[NC], cim[NC];
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+        cre[c] = lane < J ? fs.base.con_re[lane * kMC + c] : 0.0;
+        cim[c] = lane < J ? fs.base.con_im[lane * kMC + c] : 0.0;
+    }
+    const double lim = lane < J ? fs.base.lim[lane] : 1e300;
+    const double lim2 = lim * lim;
+    const double rfe = lane < J ? lim * (1.0 / kActionScale) - fs.margin[lane] : 1e300;
+    const double rfe2 = rfe > 0.0 ? rfe * rfe : -1.0;
+    const bool i64 = (flags & 1) == SG_EV_ACTION_I64;
+    const float inv_bins = 0.f;
+    (void)inv_bins;
+
+    const long long stride = (long long)gridDim.x * kWarpsPerBlock;
+    long long b = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    StatsAcc acc;
+
+    // ---- software pipeline: rows of env b are loaded one iteration ahead --------------------------
+    int4 clk_n = make_int4(0, 0, 0, 0);
+    float2 act_n = make_float2(0.f, 0.f);
+    double2 del_n = make_double2(0.0, 0.0);
+    uchar2 k_n = make_uchar2(0, 0);
+    auto prefetch = [&](long long bb) {
+        if (bb < B) {
+            clk_n = *reinterpret_cast<const int4*>(s.clock + bb * 4);
+            if (valid) {
+                if (i64) {
+                    const long long* ap = reinterpret_cast<const long long*>(action) + bb * n + i0;
+                    act_n.x = __fdiv_rn((float)ap[0], (float)(bins - 1));     // wrappers.py:45
+                    act_n.y = __fdiv_rn((float)ap[1], (float)(bins - 1));
+                } else {
+                    act_n = ldg_stream_f2(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(action) + bb * n + i0));
+                }
+                del_n = *reinterpret_cast<const double2*>(s.delivered + bb * n + i0);
+                k_n = *reinterpret_cast<const uchar2*>(s.sess_idx + bb * n + i0);
+            }
+        }
+    };
+    prefetch(b);
+    const uint4* recs = reinterpret_cast<const uint4*>(m.sessions);
+    auto load_rec = [&](int base, int k, int i, int& arr, int& dep, int& est, double& energy) {
+        if (k >= K) { arr = dep = est = kEmpty; energy = 0.0; return; }
+        const uint4 r = __ldg(recs + (base + k * n + i));
+        arr = (int)(short)(r.x & 0xffffu);
+        dep = (int)(short)(r.x >> 16);
+        est = (int)(short)(r.y & 0xffffu);
+        energy = __hiloint2double((int)r.w, (int)r.z);
+    };
+
+    for (; b < B; b += stride) {
+        const int4 clk = clk_n;
+        const float2 act = act_n;
+        double del0 = del_n.x, del1 = del_n.y;
+        int k0 = k_n.x, k1 = k_n.y;
+        const int t = clk.x;
+        int day = clk.y, md = clk.z;
+        // session records of the two stations (needs day and k: issue before the prefetch so the
+        // dependent loads are in flight together with the next env's rows)
+        int arr0 = kEmpty, dep0 = kEmpty, est0 = kEmpty, arr1 = kEmpty, dep1 = kEmpty, est1 = kEmpty;
+        double en0 = 0.0, en1 = 0.0;
+        const int sbase = day * K * n;
+        if (valid) {
+            load_rec(sbase, k0, i0, arr0, dep0, est0, en0);
+            load_rec(sbase, k1, i0 + 1, arr1, dep1, est1, en1);
+        }
+        prefetch(b + stride);
+        if (t >= kEpisode) {            // finished episode that was not reset: no-op, stays terminal
+            if (lane == 0) { reward[b] = 0.0; done[b] = 1; if (status) status[b] = 0; }
+            continue;
+        }
+        const bool pl0 = valid && t >= 1 && arr0 <= t && t < dep0;
+        const bool pl1 = valid && t >= 1 && arr1 <= t && t < dep1;
+
+        // ---- action -> normalised pilot x (env.py:363-366) ---------------------------------------
+        double x0 = (double)act.x, x1 = (double)act.y;
+        if constexpr (MODE == 1) {
+            const double rem0 = en0 - del0, rem1 = en1 - del1;
+            const float dem0 = (pl0 && rem0 > kFullEps) ? (float)rem0 : 0.f;
+            const float dem1 = (pl1 && rem1 > kFullEps) ? (float)rem1 : 0.f;
+            x0 = valid ? fmin(fmax(x0, 0.0), upper_bound(dem0)) : 0.0;
+            x1 = valid ? fmin(fmax(x1, 0.0), upper_bound(dem1)) : 0.0;
+            // conservative feasibility test on 2^-10 fixed-point class sums
+            double S[NC];
+            class_sums16<NC>(__double2uint_rn(x0 * kFix10), __double2uint_rn(x1 * kFix10), cls0, cls1, S);
+            double wr = 0.0, wi = 0.0;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) { wr = fma(cre[c], S[c], wr); wi = fma(cim[c], S[c], wi); }
+            const bool bad = lane < J && !(fma(wr, wr, wi * wi) * (kFix10Inv * kFix10Inv) <= rfe2);
+            if (__any_sync(kFull, bad)) {
+                if (lane == 0) todo[2 + atomicAdd(todo, 1)] = (int)b;
+                continue;                                   // the work-list kernel redoes this env
+            }
+        }
+
+        // ---- schedule (env.py:368-378) ---------------------------------------------------------------
+        const double am0 = x0 * kActionScale, am1 = x1 * kActionScale;
+        const double pil0 = !valid ? 0.0 : (type0 == 0 ? (am0 >= 6.0 ? rint(am0) : 0.0) : rint(am0 * 0.125) * 8.0);
+        const double pil1 = !valid ? 0.0 : (type1 == 0 ? (am1 >= 6.0 ? rint(am1) : 0.0) : rint(am1 * 0.125) * 8.0);
+        const unsigned pi0 = (unsigned)__double2int_rn(pil0), pi1 = (unsigned)__double2int_rn(pil1);
+
+        // ---- charging (acnsim update_pilots -> Linear2StageBattery._charge_stepwise) ------------------
+        double rate_sum = 0.0;
+        auto charge_one = [&](const bool pl, const double energy, double& del, const double pilot, const unsigned pi) {
+            if (!pl) return;
+            const double charge = fmax(0.0, kCapacity - energy) + del;
+            if (kCapacity - charge > 2.0) {                  // neither battery limit can bind: table path
+                del += fs.energy[pi];
+                rate_sum += fs.rate[pi];
+            } else {
+                const double rate_to_full = div_c(kCapacity - charge, kPeriodH, kInvPeriodH);
+                const double soc = div_c(charge, kCapacity, kInv100);
+                const double p_pilot = div_c(pilot * kVoltage, 1000.0, kInv1000);
+                const double cap2 = soc < kTransitionSoc ? kMaxPower
+                                                         : div_c(1.0 - soc, kOneMinusTrans, kInvOMT) * kMaxPower;
+                const double power = fmin(fmin(p_pilot, cap2), rate_to_full);
+                const double rate = div_c(power * 1000.0, kVoltage, kInv208);
+                del += div_c(rate * kVoltage, 1000.0, kInv1000) * kPeriodH;
+                rate_sum += rate;
+            }
+        };
+        charge_one(pl0, en0, del0, pil0, pi0);
+        charge_one(pl1, en1, del1, pil1, pi1);
+        const double total_rate = warp_sum(rate_sum);
+
+        // ---- excess current from the rounded schedule (env.py:449-452) --------------------------------
+        double excess = 0.0;
+        {
+            double S[NC];
+            class_sums16<NC>(pi0, pi1, cls0, cls1, S);
+            double wr = 0.0, wi = 0.0;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) { wr = fma(cre[c], S[c], wr); wi = fma(cim[c], S[c], wi); }
+            const double sq = fma(wr, wr, wi * wi);
+            const bool over = sq > lim2;                     // lanes >= J have lim2 = inf
+            if (__any_sync(kFull, over)) excess = warp_sum(over ? fmax(0.0, sqrt(sq) - lim) : 0.0);
+        }
+
+        // ---- advance time, drain events with timestamp <= t+1: Unplug (0) before Plugin (10) -----------
+        const int tn = t + 1;
+        while (valid && dep0 <= tn && arr0 != kEmpty) { k0 += 1; del0 = 0.0; load_rec(sbase, k0, i0, arr0, dep0, est0, en0); }
+        while (valid && dep1 <= tn && arr1 != kEmpty) { k1 += 1; del1 = 0.0; load_rec(sbase, k1, i0 + 1, arr1, dep1, est1, en1); }
+        const double r0 = en0 - del0, r1 = en1 - del1;
+        const bool ac0 = valid && arr0 <= tn && tn < dep0 && r0 > kFullEps;     // Interface.active_sessions()
+        const bool ac1 = valid && arr1 <= tn && tn < dep1 && r1 > kFullEps;
+        float2 dem_o = make_float2(ac0 ? (float)r0 : 0.f, ac1 ? (float)r1 : 0.f);
+        float2 est_o = make_float2(ac0 ? (float)(est0 - tn) : 0.f, ac1 ? (float)(est1 - tn) : 0.f);
+        const bool dn = tn >= kEpisode;
+
+        // ---- reward (env.py:444-462) -------------------------------------------------------------------
+        const float* mrow = m.moer + ((long long)md * SG_EV_MOER_ROWS + tn) * SG_EV_MOER_COLS;
+        const float moer0f = __ldg(mrow);
+        const double profit = kProfitFactor * total_rate;
+        const double excess_charge = excess * kViolationFactor;
+        const double carbon = kCarbonFactor * total_rate * (double)moer0f;
+        const double rew = profit - carbon - excess_charge;
+        const bool autoreset = dn && (flags & SG_EV_FLAG_AUTORESET);
+
+        // ---- observation row: demands | est_departures | forecasted_moer | prev_moer | timestep --------
+        auto write_obs = [&](float* orow, const float* row, const int tstep) {
+            if (valid) {
+                stg_stream_f2(reinterpret_cast<float2*>(orow + i0), dem_o);
+                stg_stream_f2(reinterpret_cast<float2*>(orow + n + i0), est_o);
+            }
+            float* tail = orow + 2 * n;
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                const int e = lane + 32 * pass;
+                if (e < kf + 2) {
+                    float v;
+                    if (e < kf) v = __ldg(row + 1 + e);
+                    else if (e == kf) v = __ldg(row);
+                    else v = (float)((double)tstep / (double)kEpisode);     // env.py:392
+                    tail[e] = v;
+                }
+            }
+        };
+        if (!autoreset) {
+            write_obs(obs + b * OBS, mrow, tn);
+        } else {
+            if (final_obs != nullptr) write_obs(final_obs + b * OBS, mrow, tn);   // terminal observation
+            day = (day + 1) % m.n_days;                      // sequential days, event_generation.py:284-291
+            md = (md + 1) % m.n_moer_days;
+            dem_o = make_float2(0.f, 0.f); est_o = make_float2(0.f, 0.f);
+            k0 = k1 = 0; del0 = del1 = 0.0;
+            write_obs(obs + b * OBS, m.moer + ((long long)md * SG_EV_MOER_ROWS) * SG_EV_MOER_COLS, 0);
+        }
+
+        // ---- state write-back -----------------------------------------------------------------------------
+        if (valid) {
+            *reinterpret_cast<double2*>(s.delivered + b * n + i0) = make_double2(del0, del1);
+            *reinterpret_cast<uchar2*>(s.sess_idx + b * n + i0) = make_uchar2((unsigned char)k0, (unsigned char)k1);
+            if (pilots != nullptr)
+                *reinterpret_cast<uchar2*>(pilots + b * n + i0) = make_uchar2((unsigned char)pi0, (unsigned char)pi1);
+        }
+        if (lane == 0) {
+            double* bd = s.breakdown + b * 3;
+            if (t == 0) { bd[0] = profit; bd[1] = carbon; bd[2] = excess_charge; }
+            else { bd[0] += profit; bd[1] += carbon; bd[2] += excess_charge; }
+            *reinterpret_cast<int4*>(s.clock + b * 4) = make_int4(autoreset ? 0 : tn, day, md, clk.w);
+            reward[b] = rew;
+            done[b] = dn ? 1 : 0;
+            if (status != nullptr) status[b] = 0;
+            if (stats != nullptr) acc.add(rew, dn, profit, carbon, excess_charge);
+        }
+    }
+    if (stats != nullptr) {
+        __syncthreads();
+        stats_flush_block(acc, stats, fs.stat);
+    }
+}
+
 // Persistent CTAs: every warp strides over the batch, so the table staging and the statistics
 // flush are paid once per warp instead of once per env.
 template <int MODE>
@@ -995,14 +1279,23 @@ int sg_ev_step(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, con
     if (sms <= 0) sms = 148;
     // persistent grid: 3 resident CTAs per SM (multiple of the SM count), fewer for tiny batches
     const unsigned grid = (unsigned)std::min<long long>((num_envs + sg::kWarpsPerBlock - 1) / sg::kWarpsPerBlock,
-                                                        (long long)sms * 3);
+                                                        (long long)sms * SG_EV_FAST_MINBLOCKS);
+    // specialised kernel: even n, <= 5 classes, <= 32 constraints, 32-bit record index; the model
+    // flag bit 8 (SG_EV_FLAG_GENERIC_KERNEL) forces the generic one (used by the tests)
+    const bool fast = (m->n_stations % 2 == 0) && m->n_classes <= 5 && m->n_constraints <= 32 &&
+                      (long long)m->n_days * m->max_sessions * m->n_stations < (1ll << 31) &&
+                      !(flags & SG_EV_FLAG_GENERIC_KERNEL);
     if (!m->project) {
-        sg::ev_step_kernel<0><<<grid, sg::kThreads, 0, st>>>(*m, *s, num_envs, action, flags, discrete_bins, obs,
-                                                           reward, done, pilots, final_obs, status, stats, todo);
+        if (fast) sg::ev_step_fast_kernel<0, 5><<<grid, sg::kThreads, 0, st>>>(*m, *s, num_envs, action, flags, discrete_bins,
+                                                                             obs, reward, done, pilots, final_obs, status, stats, todo);
+        else sg::ev_step_kernel<0><<<grid, sg::kThreads, 0, st>>>(*m, *s, num_envs, action, flags, discrete_bins, obs,
+                                                                reward, done, pilots, final_obs, status, stats, todo);
         return sg::launch_status("ev_step_kernel<0>");
     }
-    sg::ev_step_kernel<1><<<grid, sg::kThreads, 0, st>>>(*m, *s, num_envs, action, flags, discrete_bins, obs, reward,
-                                                       done, pilots, final_obs, status, stats, todo);
+    if (fast) sg::ev_step_fast_kernel<1, 5><<<grid, sg::kThreads, 0, st>>>(*m, *s, num_envs, action, flags, discrete_bins,
+                                                                         obs, reward, done, pilots, final_obs, status, stats, todo);
+    else sg::ev_step_kernel<1><<<grid, sg::kThreads, 0, st>>>(*m, *s, num_envs, action, flags, discrete_bins, obs, reward,
+                                                            done, pilots, final_obs, status, stats, todo);
     return sg::launch_status("ev_step_kernel<1>");
 }
 

@@ -58,18 +58,18 @@ def run_parity(env, orc, net, gen, B, steps, seed, action_fn, project):
     return clean, n_obs_exact, n_slow
 
 
-@pytest.mark.parametrize("B,mean", [(64, 25.0), (257, 70.0)])
-def test_step_no_projection(native_lib, B, mean):
-    gen, env, net, orc = make(7, mean, 11, B, False)
+@pytest.mark.parametrize("B,mean,generic", [(64, 25.0, False), (257, 70.0, False), (100, 60.0, True)])
+def test_step_no_projection(native_lib, B, mean, generic):
+    gen, env, net, orc = make(7, mean, 11, B, False, force_generic_kernel=generic)
     clean, n_exact, _ = run_parity(env, orc, net, gen, B, 288, 3,
                                    lambda rng, t: rng.uniform(0, 1, (B, 54)).astype(np.float32), False)
     assert clean.all() and n_exact >= 250
     assert bool(env.done.all()) and int(env.t[0]) == 288
 
 
-@pytest.mark.parametrize("B,mean", [(64, 25.0), (200, 80.0)])
-def test_step_with_projection(native_lib, B, mean):
-    gen, env, net, orc = make(5, mean, 5, B, True)
+@pytest.mark.parametrize("B,mean,generic", [(64, 25.0, False), (200, 80.0, False), (100, 80.0, True)])
+def test_step_with_projection(native_lib, B, mean, generic):
+    gen, env, net, orc = make(5, mean, 5, B, True, force_generic_kernel=generic)
     clean, n_exact, n_slow = run_parity(env, orc, net, gen, B, 288, 9,
                                         lambda rng, t: rng.uniform(0, 1, (B, 54)).astype(np.float32), True)
     assert clean.mean() > 0.97
