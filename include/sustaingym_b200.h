@@ -201,6 +201,56 @@ int sg_ev_project(const sg_ev_model* m, int64_t num_envs, const float* action,
                   void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * CogenEnv  —  replaces sustaingym/envs/cogen/env.py:276-353 (_compute_reward, incl. the ONNX
+ *   Runtime session.run at :305), :232-274 (_dyn_constraint_volation), :145-184 (_get_obs /
+ *   _forecast_from_time), :355-387 (step), :186-230 (reset) and
+ *   sustaingym/envs/cogen/multiagent_env.py:97-101 (per-agent reward split).
+ * The plant model is the reference's model.onnx repacked by tests/golden/gen_cogen_pack.py:
+ * 23 sub-models  (x-mu)*sinv -> Dense(d,H1) -> act -> Dense(H1,H2) -> act -> Dense(H2,1).
+ * ---------------------------------------------------------------------------------------- */
+#define SG_COGEN_ACTION_DIM 15   /* model inputs 3..17 (model.json order): GTi_{PAC,EVC}_FFU, GTi_PWR,
+                                    HR1..3_HPIP_M_PROC, ST_PWR, IPPROC_M, CT_NrBays                */
+#define SG_COGEN_N_SUB      23
+#define SG_COGEN_STEPS      96
+
+typedef struct sg_cogen_model {
+    int32_t n_sub;                       /* 23                                                        */
+    int32_t forecast_horizon;            /* k (cogen/env.py:80)                                       */
+    int32_t n_days;                      /* days in the ambient table                                 */
+    int32_t reserved;
+    double  ramp_penalty;                /* cogen/env.py:77-79                                        */
+    double  supply_imbalance_penalty;
+    double  constraint_violation_penalty;
+    const float*   blob;     /* [device] packed f32 weights (W1,b1,W2,b2,W3 per sub-model, 16 B aligned) */
+    const int64_t* offsets;  /* [device] [23, 5] element offsets of W1,b1,W2,b2,W3 in blob              */
+    const int32_t* meta;     /* [device] [23, 6] d, H1, H2, act (0 sigmoid / 1 relu), y index, gate     */
+    const int32_t* feats;    /* [device] [23, 16] indices into the extended feature vector, -1 padded   */
+    const float*   mu;       /* [device] [23, 16]                                                       */
+    const float*   sinv;     /* [device] [23, 16]                                                       */
+    const float*   b3;       /* [device] [23]                                                           */
+    const double*  ambient;  /* [device] [n_days, 96, 7]: TAMB, PAMB, RHAMB, Target_Power, Target_Steam,
+                                Energy_Price, Gas_Price (load_ambients.construct_df columns)            */
+} sg_cogen_model;
+
+/* The plant model alone: X [B,18] f32 -> Y [B,29] f32 (model.json order). scratch: [B,23] f32. */
+int sg_cogen_plant(const sg_cogen_model* m, int64_t num_envs, const float* X, float* Y, float* scratch,
+                   void* stream);
+
+/* reset(): day_in [B] picks the day (seed -> day map is host logic, cogen/env.py:213-216);
+ * init_action [B,15] is the randomly drawn initial Prev_Action (cogen/env.py:222-223, host RNG). */
+int sg_cogen_reset(const sg_cogen_model* m, int64_t num_envs, const int32_t* day_in, const float* init_action,
+                   float* prev_action /* [B,15] out */, int32_t* day_t /* [B,2] out */,
+                   float* obs /* [B, 7(k+1)+33] out */, void* stream);
+
+/* One step() of B envs. action/prev_action: [B,15] f32; day_t: [B,2] {day, t}; noise: [B,k,7] f64
+ * forecast noise already scaled by forecast_noise_std, or NULL; obs: flattened Dict (sorted keys);
+ * reward [B] f64; agent_reward [B,4] f64 (GT1, GT2, GT3, ST); done [B]; Y_out [B,29] or NULL. */
+int sg_cogen_step(const sg_cogen_model* m, int64_t num_envs, const float* action, float* prev_action,
+                  int32_t* day_t, const double* noise, float* obs, double* reward, double* agent_reward,
+                  uint8_t* done, float* Y_out, float* scratch /* [B,23] */, int32_t flags, double* stats,
+                  void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Aggregate reward statistics (the one collective of the multi-GPU path):
  * kernels accumulate into a 16-double vector; the host all-reduces it (NCCL SUM / MIN / MAX).
  *   [0] count  [1] sum r  [2] sum r^2  [3] min r  [4] max r  [5] n_done  [6] n_projected

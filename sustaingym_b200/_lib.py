@@ -55,6 +55,15 @@ class EVState(C.Structure):
     ]
 
 
+class CogenModel(C.Structure):
+    _fields_ = [
+        ("n_sub", _i32), ("forecast_horizon", _i32), ("n_days", _i32), ("reserved", _i32),
+        ("ramp_penalty", _f64), ("supply_imbalance_penalty", _f64), ("constraint_violation_penalty", _f64),
+        ("blob", _vp), ("offsets", _vp), ("meta", _vp), ("feats", _vp), ("mu", _vp), ("sinv", _vp), ("b3", _vp),
+        ("ambient", _vp),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/sustaingym_b200.h declares
 SIGNATURES = {
     "sg_abi_version": (C.c_int, []),
@@ -74,6 +83,10 @@ SIGNATURES = {
                                     _vp, _vp, _vp, _vp, _vp, _vp]),
     "sg_ev_step_host": (C.c_int, [C.POINTER(EVModel), C.POINTER(EVState), _i64, _vp, _i32, _i32, _vp, _vp, _vp,
                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sg_cogen_plant": (C.c_int, [C.POINTER(CogenModel), _i64, _vp, _vp, _vp, _vp]),
+    "sg_cogen_reset": (C.c_int, [C.POINTER(CogenModel), _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sg_cogen_step": (C.c_int, [C.POINTER(CogenModel), _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                _i32, _vp, _vp]),
     "sg_ev_project": (C.c_int, [C.POINTER(EVModel), _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 

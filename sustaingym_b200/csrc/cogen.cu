@@ -1,0 +1,386 @@
+// CogenEnv batched step()/reset() for sm_100a.
+//
+// Replaces sustaingym/envs/cogen/env.py:276-353 (_compute_reward incl. the ONNX Runtime call at
+// :305), :232-274 (_dyn_constraint_volation), :145-184 (_forecast_from_time/_get_obs), :355-387
+// (step) and sustaingym/envs/cogen/multiagent_env.py:97-101 (per-agent reward split).
+//
+// The plant model is 23 independent 3-layer MLPs (1.84 M MAC per env-step)
+// — a dense contraction, the one compute-bound piece of the whole engine.  Round-1 kernel:
+// fp32 FFMA (3xTF32 tensor-core variant is the follow-up; a single TF32/BF16 pass cannot meet the
+// 1e-5 tolerance).  One CTA = 64 envs x one sub-model:
+//   layer 1 (K = d <= 14) is recomputed per 32-wide chunk of hidden-1 units straight into shared
+//   memory (transposed, so the layer-2 A operand is one float4 broadcast per thread);
+//   layer 2 (256x128 or 512x256, >95% of the FLOPs) streams its weight rows global->shared with
+//   16-byte cp.async, double buffered, and accumulates a 4 env x (H2/16) col register tile/thread;
+//   layer 3 (H2 -> 1) is fused into the epilogue with a 16-lane shuffle reduction.
+// Weights (7.4 MB) are shared by every env and stay L2-resident.  A second, memory-bound kernel
+// (one thread per env) applies the gates, derived outputs, constraint hinges, rewards and writes
+// the flattened observation.
+#include "common.cuh"
+
+namespace sg {
+namespace {
+
+constexpr int kTM = 64;        // envs per CTA
+constexpr int kKC = 32;        // hidden-1 units per chunk
+constexpr int kThreadsC = 256;
+constexpr int kNSub = 23;
+constexpr int kDPad = 16;
+constexpr int kSteps = 96;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ float act_fn(float v, int act) {
+    // act 0: sigmoid evaluated as the reference graph does, 1/(1+exp(-v)); act 1: relu
+    return act == 0 ? __fdividef(1.f, 1.f + expf(-v)) : fmaxf(v, 0.f);
+}
+__device__ __forceinline__ float gate_fn(float v) { return v != 0.f ? 1.f : 0.f; }     // |sign(v)|
+
+// extended feature vector E[25] from the 18 model inputs (gen_cogen_pack.py docstring)
+__device__ __forceinline__ float ext_feature(const float* x, int f) {
+    if (f < 18) return x[f];
+    if (f < 21) return x[3 + 3 * (f - 18)] * gate_fn(x[5 + 3 * (f - 18)]);
+    if (f < 24) return x[4 + 3 * (f - 21)] * gate_fn(x[5 + 3 * (f - 21)]);
+    return x[16] * gate_fn(x[15]);
+}
+
+// X row of env b: [TAMB, PAMB, RHAMB](f32 of the ambient row at (day,t)) ++ action[15]
+__device__ __forceinline__ void build_x(const sg_cogen_model& m, const float* X_in, const float* action,
+                                        const int32_t* day_t, long long b, float* x) {
+    if (X_in != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 18; ++i) x[i] = X_in[b * 18 + i];
+        return;
+    }
+    const int day = day_t[b * 2], t = day_t[b * 2 + 1];
+    const double* row = m.ambient + ((long long)day * kSteps + min(t, kSteps - 1)) * 7;
+    x[0] = (float)row[0]; x[1] = (float)row[1]; x[2] = (float)row[2];
+#pragma unroll
+    for (int i = 0; i < 15; ++i) x[3 + i] = action[b * 15 + i];
+}
+
+template <int H2>
+__device__ __forceinline__ void mlp_tile(const sg_cogen_model& m, const int j, const long long b0, const int nvalid,
+                                         const float* X_in, const float* action, const int32_t* day_t,
+                                         float* __restrict__ raw, unsigned char* smem) {
+    constexpr int NJ = H2 / 64;                 // float4 column groups per thread
+    float* xsT = reinterpret_cast<float*>(smem);                // [kDPad][kTM]  normalised inputs, transposed
+    float* h1T = xsT + kTM * kDPad;                             // [kKC][kTM]    hidden-1 chunk, transposed
+    float* w1s = h1T + kKC * kTM;                               // [kDPad][kKC]  layer-1 weights of the chunk
+    float* w2s = w1s + kDPad * kKC;                             // [2][kKC][H2]  layer-2 weight rows (2 stages)
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int d = m.meta[j * 6 + 0], H1 = m.meta[j * 6 + 1], act = m.meta[j * 6 + 3];
+    const float* W1 = m.blob + m.offsets[j * 5 + 0];
+    const float* b1 = m.blob + m.offsets[j * 5 + 1];
+    const float* W2 = m.blob + m.offsets[j * 5 + 2];
+    const float* b2 = m.blob + m.offsets[j * 5 + 3];
+    const float* W3 = m.blob + m.offsets[j * 5 + 4];
+
+    // normalised inputs of this sub-model for the 64 envs of the tile
+    for (int idx = tid; idx < kTM * kDPad; idx += kThreadsC) {
+        const int dd = idx / kTM, mm = idx % kTM;
+        float v = 0.f;
+        if (mm < nvalid && dd < d) {
+            float x[18];
+            build_x(m, X_in, action, day_t, b0 + mm, x);
+            v = (ext_feature(x, m.feats[j * kDPad + dd]) - m.mu[j * kDPad + dd]) * m.sinv[j * kDPad + dd];
+        }
+        xsT[idx] = v;
+    }
+    auto issue_w2 = [&](int chunk, int stage) {
+        const float* src = W2 + (long long)chunk * kKC * H2;
+        float* dst = w2s + stage * kKC * H2;
+        for (int i = tid * 4; i < kKC * H2; i += kThreadsC * 4) cp_async16(dst + i, src + i);
+        cp_async_commit();
+    };
+    const int nchunks = H1 / kKC;
+    issue_w2(0, 0);
+    float acc[4][NJ * 4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int c = 0; c < NJ * 4; ++c) acc[i][c] = 0.f;
+    __syncthreads();
+
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int stage = ch & 1;
+        if (ch + 1 < nchunks) issue_w2(ch + 1, stage ^ 1);
+        // layer 1 for hidden units [ch*32, ch*32+32): 64 envs x 32 units, 8 units per thread
+        for (int idx = tid; idx < kDPad * kKC; idx += kThreadsC) {
+            const int dd = idx / kKC, kk = idx % kKC;
+            w1s[idx] = dd < d ? __ldg(W1 + dd * H1 + ch * kKC + kk) : 0.f;
+        }
+        __syncthreads();
+        {
+            const int mm = tid & (kTM - 1), kg = (tid >> 6) * 8;
+            float xr[kDPad];
+#pragma unroll
+            for (int dd = 0; dd < kDPad; ++dd) xr[dd] = xsT[dd * kTM + mm];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int kk = kg + i;
+                float v = __ldg(b1 + ch * kKC + kk);
+#pragma unroll
+                for (int dd = 0; dd < kDPad; ++dd) v = fmaf(xr[dd], w1s[dd * kKC + kk], v);
+                h1T[kk * kTM + mm] = act_fn(v, act);
+            }
+        }
+        if (ch + 1 < nchunks) cp_async_wait<1>(); else cp_async_wait<0>();
+        __syncthreads();
+        const float* wb = w2s + stage * kKC * H2;
+#pragma unroll 4
+        for (int k = 0; k < kKC; ++k) {
+            const float4 a = *reinterpret_cast<const float4*>(h1T + k * kTM + ty * 4);
+            const float av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int jj = 0; jj < NJ; ++jj) {
+                const float4 bv = *reinterpret_cast<const float4*>(wb + k * H2 + jj * 64 + tx * 4);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    acc[i][jj * 4 + 0] = fmaf(av[i], bv.x, acc[i][jj * 4 + 0]);
+                    acc[i][jj * 4 + 1] = fmaf(av[i], bv.y, acc[i][jj * 4 + 1]);
+                    acc[i][jj * 4 + 2] = fmaf(av[i], bv.z, acc[i][jj * 4 + 2]);
+                    acc[i][jj * 4 + 3] = fmaf(av[i], bv.w, acc[i][jj * 4 + 3]);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // epilogue: h2 = act(acc + b2); y = h2 . W3 + b3, reduced over the 16 column-threads of a row
+    float part[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) {
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(b2 + jj * 64 + tx * 4));
+        const float4 ww = __ldg(reinterpret_cast<const float4*>(W3 + jj * 64 + tx * 4));
+        const float bbv[4] = {bb.x, bb.y, bb.z, bb.w}, wwv[4] = {ww.x, ww.y, ww.z, ww.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) part[i] = fmaf(act_fn(acc[i][jj * 4 + c] + bbv[c], act), wwv[c], part[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) part[i] += __shfl_xor_sync(kFull, part[i], o);
+        const int mm = ty * 4 + i;
+        if (tx == 0 && mm < nvalid) raw[(b0 + mm) * kNSub + j] = part[i] + m.b3[j];
+    }
+}
+
+__global__ void __launch_bounds__(kThreadsC, 2)
+cogen_mlp_kernel(const sg_cogen_model m, const long long B, const float* __restrict__ X_in,
+                 const float* __restrict__ action, const int32_t* __restrict__ day_t, float* __restrict__ raw) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int j = kNSub - 1 - blockIdx.y;        // big sub-models (packed last) are scheduled first
+    const long long b0 = (long long)blockIdx.x * kTM;
+    const int nvalid = (int)min((long long)kTM, B - b0);
+    if (m.meta[j * 6 + 2] == 256) mlp_tile<256>(m, j, b0, nvalid, X_in, action, day_t, raw, smem);
+    else mlp_tile<128>(m, j, b0, nvalid, X_in, action, day_t, raw, smem);
+}
+
+// Y[29] from the 23 raw sub-model outputs (gates + derived sums; Appendix B)
+__device__ __forceinline__ void assemble_y(const sg_cogen_model& m, const float* x, const float* raw, float* Y) {
+    const float gGT[3] = {gate_fn(x[5]), gate_fn(x[8]), gate_fn(x[11])};
+    const float gHR[3] = {gate_fn(x[12]), gate_fn(x[13]), gate_fn(x[13])};   // sic: HR3's gate reads HR2
+    float gates[6];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { gates[i] = gGT[i]; gates[3 + i] = gate_fn(gGT[i] + gHR[i]); }
+#pragma unroll
+    for (int i = 0; i < 29; ++i) Y[i] = 0.f;
+    for (int j = 0; j < kNSub; ++j) {
+        const int yi = m.meta[j * 6 + 4], g = m.meta[j * 6 + 5];
+        Y[yi] = g >= 0 ? raw[j] * gates[g] : raw[j];
+    }
+    Y[6] = Y[0] + Y[3]; Y[7] = Y[1] + Y[4]; Y[8] = Y[2] + Y[5];
+    Y[21] = (Y[6] + Y[7]) + Y[8];
+    Y[27] = (((x[5] + x[8]) + x[11]) + x[15]) - Y[26];
+    Y[28] = ((x[12] + x[13]) + x[14]) + x[16];
+}
+
+__global__ void cogen_plant_finish_kernel(const sg_cogen_model m, const long long B, const float* __restrict__ X,
+                                          const float* __restrict__ raw, float* __restrict__ Y) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    float x[18], r[kNSub], y[29];
+    for (int i = 0; i < 18; ++i) x[i] = X[b * 18 + i];
+    for (int i = 0; i < kNSub; ++i) r[i] = raw[b * kNSub + i];
+    assemble_y(m, x, r, y);
+    for (int i = 0; i < 29; ++i) Y[b * 29 + i] = y[i];
+}
+
+// flat observation (gymnasium flatten of the Dict, sorted keys; cogen/env.py:164-184):
+// Energy_Price[k+1] | Gas_Price[k+1] | PAMB[k+1] | Prev_Action[32] | RHAMB[k+1] | TAMB[k+1] |
+// Target_Power[k+1] | Target_Steam[k+1] | Time[1]; Prev_Action (sorted keys): CT_NrBays one-hot 12,
+// then per GT i: EVC one-hot 2, PAC one-hot 2, PWR; HR1..3; IPPROC_M; ST_PWR.
+__device__ void write_obs(const sg_cogen_model& m, const int day, const int t, const float* a /*15*/,
+                          const double* noise /* [k,7] or NULL */, float* o) {
+    const int k = m.forecast_horizon, k1 = k + 1;
+    const int col_of_group[7] = {5, 6, 1, 2, 0, 3, 4};       // ambient column of each forecast group, in obs order
+    int pos = 0;
+    for (int g = 0; g < 7; ++g) {
+        if (g == 3) {                                        // Prev_Action sits after PAMB
+            const int bays = (int)a[14];
+            for (int i = 0; i < 12; ++i) o[pos++] = (i == bays - 1) ? 1.f : 0.f;
+            for (int u = 0; u < 3; ++u) {
+                const int evc = (int)a[3 * u + 1], pac = (int)a[3 * u + 0];
+                o[pos++] = evc == 0 ? 1.f : 0.f; o[pos++] = evc == 1 ? 1.f : 0.f;
+                o[pos++] = pac == 0 ? 1.f : 0.f; o[pos++] = pac == 1 ? 1.f : 0.f;
+                o[pos++] = a[3 * u + 2];
+            }
+            o[pos++] = a[9]; o[pos++] = a[10]; o[pos++] = a[11]; o[pos++] = a[13]; o[pos++] = a[12];
+        }
+        const int c = col_of_group[g];
+        for (int r = 0; r < k1; ++r) {
+            int tt = t + r, dd = day;
+            if (tt >= kSteps) { tt -= kSteps; dd += 1; }     // spill into the next day (env.py:152-155)
+            dd = min(dd, m.n_days - 1);                      // the reference raises IndexError here; clamp
+            double v = m.ambient[((long long)dd * kSteps + tt) * 7 + c];
+            if (noise != nullptr && r >= 1) v += noise[(r - 1) * 7 + c];
+            o[pos++] = (float)v;
+        }
+    }
+    o[pos++] = (float)((double)t / (double)kSteps);
+}
+
+__global__ void cogen_step_finish_kernel(const sg_cogen_model m, const long long B, const float* __restrict__ action,
+                                         float* __restrict__ prev_action, int32_t* __restrict__ day_t,
+                                         const double* __restrict__ noise, const float* __restrict__ raw,
+                                         float* __restrict__ obs, double* __restrict__ reward,
+                                         double* __restrict__ agent_reward, uint8_t* __restrict__ done,
+                                         float* __restrict__ Y_out, const int flags, double* __restrict__ stats) {
+    __shared__ double sstat[11 * 4];
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    StatsAcc acc;
+    if (b < B) {
+        const int day = day_t[b * 2], t = day_t[b * 2 + 1];
+        float x[18], r[kNSub], Y[29], a[15], pa[15];
+        build_x(m, nullptr, action, day_t, b, x);
+        for (int i = 0; i < 15; ++i) { a[i] = x[3 + i]; pa[i] = prev_action[b * 15 + i]; }
+        for (int i = 0; i < kNSub; ++i) r[i] = raw[b * kNSub + i];
+        assemble_y(m, x, r, Y);
+        // targets of the current row (obs[...][0], env.py:341-342)
+        const double* row = m.ambient + ((long long)day * kSteps + min(t, kSteps - 1)) * 7;
+        const float target_power = (float)row[3], target_steam = (float)row[4];
+        // ---- reward: env.py:309-346 (dtypes as NumPy >= 2 produces them) ---------------------------
+        const float rp = (float)m.ramp_penalty;
+        const int pw[4] = {2, 5, 8, 12};
+        float ramp[4];
+        for (int i = 0; i < 4; ++i) ramp[i] = __fmul_rn(rp, fabsf(__fsub_rn(a[pw[i]], pa[pw[i]])));
+        const float total_ramp = __fadd_rn(__fadd_rn(__fadd_rn(ramp[0], ramp[1]), ramp[2]), ramp[3]);
+        const int lo[7] = {9, 15, 11, 17, 13, 19, 24}, xi[7] = {5, 12, 8, 13, 11, 14, 15}, hi[7] = {10, 16, 12, 18, 14, 20, 25};
+        double cv[16];
+        for (int i = 0; i < 7; ++i) {
+            cv[2 * i] = (double)fmaxf(0.f, __fsub_rn(Y[lo[i]], x[xi[i]]));
+            cv[2 * i + 1] = (double)fmaxf(0.f, __fsub_rn(x[xi[i]], Y[hi[i]]));
+        }
+        cv[14] = (double)fmaxf(0.f, __fsub_rn(x[16], Y[22]));
+        cv[15] = (double)fmaxf(0.f, __fsub_rn(x[16], Y[23]));
+        double dyn[4];
+        for (int u = 0; u < 4; ++u) dyn[u] = m.constraint_violation_penalty * (((cv[4 * u] + cv[4 * u + 1]) + cv[4 * u + 2]) + cv[4 * u + 3]);
+        const double total_dyn = ((dyn[0] + dyn[1]) + dyn[2]) + dyn[3];
+        const float steam_pen = fmaxf(0.f, __fsub_rn(target_steam, Y[28]));
+        const float energy_pen = fmaxf(0.f, __fsub_rn(target_power, Y[27]));
+        const float non_delivery = __fmul_rn((float)m.supply_imbalance_penalty, __fadd_rn(steam_pen, energy_pen));
+        const double rew = -((double)__fadd_rn(__fadd_rn(Y[21], total_ramp), non_delivery) + total_dyn);
+        const float fuel[4] = {Y[6], Y[7], Y[8], 0.f};
+        const double nd4 = (double)__fdiv_rn(non_delivery, 4.f);
+        for (int u = 0; u < 4; ++u)
+            agent_reward[b * 4 + u] = -((((double)fuel[u] + (double)ramp[u]) + dyn[u]) + nd4);   // multiagent_env.py:97-101
+        reward[b] = rew;
+        if (Y_out != nullptr) for (int i = 0; i < 29; ++i) Y_out[b * 29 + i] = Y[i];
+        // ---- advance: env.py:373-382 ------------------------------------------------------------
+        const int tn = t + 1;
+        const bool term = tn >= kSteps;
+        for (int i = 0; i < 15; ++i) prev_action[b * 15 + i] = a[i];
+        const int obs_dim = 7 * (m.forecast_horizon + 1) + 33;
+        write_obs(m, day, tn, a, noise ? noise + b * m.forecast_horizon * 7 : nullptr, obs + b * obs_dim);
+        day_t[b * 2 + 1] = tn;
+        done[b] = term ? 1 : 0;
+        acc.add(rew, term, -(double)Y[21], -(double)total_ramp, -((double)non_delivery + total_dyn));
+    }
+    if (stats != nullptr) {
+        __syncthreads();
+        stats_flush_block(acc, stats, sstat);
+    }
+}
+
+__global__ void cogen_reset_kernel(const sg_cogen_model m, const long long B, const int32_t* __restrict__ day_in,
+                                   const float* __restrict__ init_action, float* __restrict__ prev_action,
+                                   int32_t* __restrict__ day_t, float* __restrict__ obs) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int day = min(max(day_in[b], 0), m.n_days - 1);
+    float a[15];
+    for (int i = 0; i < 15; ++i) { a[i] = init_action[b * 15 + i]; prev_action[b * 15 + i] = a[i]; }
+    day_t[b * 2] = day; day_t[b * 2 + 1] = 0;
+    const int obs_dim = 7 * (m.forecast_horizon + 1) + 33;
+    write_obs(m, day, 0, a, nullptr, obs + b * obs_dim);
+}
+
+int check_cogen(const sg_cogen_model* m) {
+    SG_CHECK_ARG(m != nullptr, "cogen: model is NULL");
+    SG_CHECK_ARG(m->n_sub == kNSub, "cogen: expected 23 sub-models, got %d", m->n_sub);
+    SG_CHECK_ARG(m->forecast_horizon >= 0 && m->forecast_horizon < kSteps - 1, "cogen: forecast_horizon out of range");
+    SG_CHECK_ARG(m->blob && m->offsets && m->meta && m->feats && m->mu && m->sinv && m->b3, "cogen: NULL weight table");
+    return 0;
+}
+
+int launch_mlp(const sg_cogen_model* m, long long B, const float* X, const float* action, const int32_t* day_t,
+               float* raw, cudaStream_t st) {
+    const size_t smem = sizeof(float) * (kTM * kDPad + kKC * kTM + kDPad * kKC + 2 * kKC * 256);
+    static bool configured = false;   // attribute is per-function and idempotent; races are benign
+    if (!configured) {
+        SG_CUDA(cudaFuncSetAttribute(cogen_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    dim3 grid((unsigned)((B + kTM - 1) / kTM), kNSub);
+    cogen_mlp_kernel<<<grid, kThreadsC, smem, st>>>(*m, B, X, action, day_t, raw);
+    return launch_status("cogen_mlp_kernel");
+}
+
+}  // namespace
+}  // namespace sg
+
+extern "C" {
+
+int sg_cogen_plant(const sg_cogen_model* m, int64_t num_envs, const float* X, float* Y, float* scratch, void* stream) {
+    if (int rc = sg::check_cogen(m)) return rc;
+    SG_CHECK_ARG(X && Y && scratch, "cogen_plant: NULL argument");
+    if (num_envs <= 0) return 0;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (int rc = sg::launch_mlp(m, num_envs, X, nullptr, nullptr, scratch, st)) return rc;
+    sg::cogen_plant_finish_kernel<<<(unsigned)((num_envs + 127) / 128), 128, 0, st>>>(*m, num_envs, X, scratch, Y);
+    return sg::launch_status("cogen_plant_finish_kernel");
+}
+
+int sg_cogen_reset(const sg_cogen_model* m, int64_t num_envs, const int32_t* day_in, const float* init_action,
+                   float* prev_action, int32_t* day_t, float* obs, void* stream) {
+    if (int rc = sg::check_cogen(m)) return rc;
+    SG_CHECK_ARG(day_in && init_action && prev_action && day_t && obs && m->ambient, "cogen_reset: NULL argument");
+    if (num_envs <= 0) return 0;
+    sg::cogen_reset_kernel<<<(unsigned)((num_envs + 127) / 128), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+        *m, num_envs, day_in, init_action, prev_action, day_t, obs);
+    return sg::launch_status("cogen_reset_kernel");
+}
+
+int sg_cogen_step(const sg_cogen_model* m, int64_t num_envs, const float* action, float* prev_action,
+                  int32_t* day_t, const double* noise, float* obs, double* reward, double* agent_reward,
+                  uint8_t* done, float* Y_out, float* scratch, int32_t flags, double* stats, void* stream) {
+    if (int rc = sg::check_cogen(m)) return rc;
+    SG_CHECK_ARG(action && prev_action && day_t && obs && reward && agent_reward && done && scratch && m->ambient,
+                 "cogen_step: NULL argument");
+    if (num_envs <= 0) return 0;
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (int rc = sg::launch_mlp(m, num_envs, nullptr, action, day_t, scratch, st)) return rc;
+    sg::cogen_step_finish_kernel<<<(unsigned)((num_envs + 127) / 128), 128, 0, st>>>(
+        *m, num_envs, action, prev_action, day_t, noise, scratch, obs, reward, agent_reward, done, Y_out, flags, stats);
+    return sg::launch_status("cogen_step_finish_kernel");
+}
+
+}  // extern "C"
