@@ -56,8 +56,10 @@ def test_step_matches_oracle(native_lib, B, k):
         o_ob, o_r, o_term, _, o_info = orc.step(a, noise)
         Y = env.Y.cpu().numpy()
         assert (np.abs(Y - o_info["Y"]) / np.maximum(np.abs(o_info["Y"]), scale)).max() < 1e-5
-        np.testing.assert_allclose(r.cpu().numpy(), o_r, rtol=1e-5, atol=1e-3)
-        np.testing.assert_allclose(info["agent_rewards"].cpu().numpy(), o_info["agent_rewards"], rtol=1e-5, atol=1e-3)
+        # the reward multiplies hinges max(0, Y_j - x) by 1000: a plant output that is right to
+        # 1e-5*range_j (~3e-3) moves the reward by up to ~3 units, whatever the reward's own size
+        np.testing.assert_allclose(r.cpu().numpy(), o_r, rtol=1e-5, atol=1.0)
+        np.testing.assert_allclose(info["agent_rewards"].cpu().numpy(), o_info["agent_rewards"], rtol=1e-5, atol=1.0)
         np.testing.assert_array_equal(ob.cpu().numpy(), flatten_obs(o_ob))          # obs: table look-ups, exact
         np.testing.assert_array_equal(term.cpu().numpy(), o_term)
     assert bool(term.all())
