@@ -1237,6 +1237,24 @@ ev_project_kernel(const sg_ev_model m, const long long B, const float* __restric
     if (lane == 0) { if (status) status[b] = (uint8_t)st; if (iters) iters[b] = it; }
 }
 
+
+// Per-agent observations of MultiAgentEVChargingEnv (multiagent_env.py:102-148): agent i sees the
+// aggregate observation of `periods_delay` steps ago, except its own station's est_departure and
+// demand entries, which are current.  out[b, i, :] for all 54 agents.
+__global__ void ev_agent_obs_kernel(const float* __restrict__ cur, const float* __restrict__ past, const long long B,
+                                    const int n, const int obs_dim, float* __restrict__ out) {
+    const long long total = B * n * obs_dim;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int e = (int)(idx % obs_dim);
+        const long long bi = idx / obs_dim;
+        const int i = (int)(bi % n);
+        const long long b = bi / n;
+        const bool own = (e == i) || (e == n + i);
+        out[idx] = own ? cur[b * obs_dim + e] : past[b * obs_dim + e];
+    }
+}
+
 int check_model(const sg_ev_model* m) {
     SG_CHECK_ARG(m != nullptr, "ev: model is NULL");
     SG_CHECK_ARG(m->n_stations >= 1 && m->n_stations <= SG_EV_MAX_STATIONS, "ev: n_stations=%d outside [1,64]", m->n_stations);
@@ -1334,6 +1352,18 @@ int sg_ev_step_host(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs
     SG_CUDA(cudaMemcpyAsync(h_done, d_done, B, cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaStreamSynchronize(st));
     return 0;
+}
+
+int sg_ev_agent_obs(const float* cur_obs, const float* past_obs, int64_t num_envs, int32_t n_stations,
+                    int32_t obs_dim, float* out, void* stream) {
+    SG_CHECK_ARG(cur_obs && past_obs && out, "ev_agent_obs: NULL argument");
+    SG_CHECK_ARG(n_stations >= 1 && obs_dim >= 2 * n_stations, "ev_agent_obs: bad dimensions");
+    if (num_envs <= 0) return 0;
+    const long long total = (long long)num_envs * n_stations * obs_dim;
+    const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148ll * 16);
+    sg::ev_agent_obs_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(cur_obs, past_obs, num_envs,
+                                                                                   n_stations, obs_dim, out);
+    return sg::launch_status("ev_agent_obs_kernel");
 }
 
 int sg_ev_project(const sg_ev_model* m, int64_t num_envs, const float* action, const float* demands,

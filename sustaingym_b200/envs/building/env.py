@@ -112,7 +112,8 @@ class BatchedBuildingEnv:
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def reset(self, *, seed=None, options: dict | None = None, epochs: np.ndarray | None = None):
+    def reset(self, *, seed=None, options: dict | None = None, epochs: np.ndarray | None = None,
+              mask: np.ndarray | torch.Tensor | None = None):
         """env.py:314-386.  ``seed``: int (env i gets ``seed + i``), array of per-env seeds, or None
         (random cursors, env.py:340).  ``epochs`` overrides the cursors directly (H6: the RNG-driven
         choice is an input of the engine)."""
@@ -129,10 +130,19 @@ class BatchedBuildingEnv:
         if options is not None and "T_initial" in options:
             T0 = torch.from_numpy(np.ascontiguousarray(
                 np.broadcast_to(np.asarray(options["T_initial"], np.float64), (B, n)))).to(self.device)
+        keep = None
+        if mask is not None:        # partial reset: envs outside the mask keep their state
+            m = torch.as_tensor(mask, device=self.device).bool()
+            keep = (m, self.state.clone(), self.epoch.clone(), self.runs.clone())
         with torch.cuda.device(self.device):
             _lib.check(self.lib.sg_building_reset(C.byref(self._model), B, d_ep.data_ptr(), _lib.ptr(T0),
                                                   self.state.data_ptr(), self.epoch.data_ptr(),
                                                   self.runs.data_ptr(), self._stream()), "sg_building_reset")
+        if keep is not None:
+            m, st, ep, ru = keep
+            self.state.copy_(torch.where(m[:, None], self.state, st))
+            self.epoch.copy_(torch.where(m, self.epoch, ep))
+            self.runs.copy_(torch.where(m, self.runs, ru))
         self.kernel_launches += 1
         return self.state, {}
 

@@ -162,7 +162,8 @@ class BatchedCogenEnv:
         self.kernel_launches += 2
         return Y
 
-    def reset(self, *, seed=None, options=None, days: np.ndarray | None = None, init_actions: np.ndarray | None = None):
+    def reset(self, *, seed=None, options=None, days: np.ndarray | None = None, init_actions: np.ndarray | None = None,
+              mask: np.ndarray | torch.Tensor | None = None):
         """cogen/env.py:186-230. ``seed``: int (env i gets seed+i) or per-env array -> day = seed % n_days
         and the initial Prev_Action is drawn from a generator seeded with it; or pass ``days`` /
         ``init_actions`` explicitly (H6: RNG-driven choices are inputs of the engine)."""
@@ -179,10 +180,19 @@ class BatchedCogenEnv:
             init_actions = self.sample_actions(np.random.default_rng(int(seeds[0])))
         d_days = torch.from_numpy(np.asarray(days, np.int32)).to(self.device)
         d_act = torch.from_numpy(np.ascontiguousarray(init_actions, np.float32)).to(self.device)
+        keep = None
+        if mask is not None:        # partial reset: envs outside the mask keep their state
+            m = torch.as_tensor(mask, device=self.device).bool()
+            keep = (m, self.prev_action.clone(), self.day_t.clone(), self.obs.clone())
         with torch.cuda.device(self.device):
             _lib.check(self.lib.sg_cogen_reset(C.byref(self._model), B, d_days.data_ptr(), d_act.data_ptr(),
                                                self.prev_action.data_ptr(), self.day_t.data_ptr(), self.obs.data_ptr(),
                                                self._stream()), "sg_cogen_reset")
+        if keep is not None:
+            m, pa, dt, ob = keep
+            self.prev_action.copy_(torch.where(m[:, None], self.prev_action, pa))
+            self.day_t.copy_(torch.where(m[:, None], self.day_t, dt))
+            self.obs.copy_(torch.where(m[:, None], self.obs, ob))
         self.kernel_launches += 1
         return self.obs, {}
 
