@@ -257,6 +257,29 @@ int sg_cogen_step(const sg_cogen_model* m, int64_t num_envs, const float* action
                   void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * ElectricityMarketEnv  —  SPEC-DEFINED: the reference snapshot has no source for it (only
+ *   docs/electricitymarketenv.md:9-27).  Spec: sustaingym_b200/envs/electricitymarket/SPEC.md.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct sg_market_model {
+    int32_t n_gen;                 /* generators (<= 64), costs ascending                            */
+    int32_t k;                     /* bid / forecast horizon (1..4)                                   */
+    int32_t n_days;                /* rows of the load / MOER day tables                              */
+    int32_t use_intermediate_rewards;
+    double  e_max, e_init, p_max, eta_c, eta_d, price_cap, p_co2, terminal_price;
+    const double* gen_cost;        /* [device] [n_gen] $/MWh                                          */
+    const double* gen_cap;         /* [device] [n_gen] MW                                             */
+    const double* load;            /* [device] [n_days, 288 + k] MW                                   */
+    const double* moer;            /* [device] [n_days, 288 + k] kg CO2 / MWh                         */
+} sg_market_model;
+
+int sg_market_reset(const sg_market_model* m, int64_t num_envs, const int32_t* day_in,
+                    double* state /* [B,4]: e, x_prev, p_prev, deferred reward */, int32_t* day_t /* [B,2] */,
+                    float* prev_action /* [B,2k] */, float* obs /* [B, 6+4k] */, void* stream);
+int sg_market_step(const sg_market_model* m, int64_t num_envs, const float* action /* [B,2k] */, double* state,
+                   int32_t* day_t, float* prev_action, float* obs, double* reward, uint8_t* done,
+                   double* info /* [B,3] price, dispatch, energy or NULL */, double* stats, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Aggregate reward statistics (the one collective of the multi-GPU path):
  * kernels accumulate into a 16-double vector; the host all-reduces it (NCCL SUM / MIN / MAX).
  *   [0] count  [1] sum r  [2] sum r^2  [3] min r  [4] max r  [5] n_done  [6] n_projected

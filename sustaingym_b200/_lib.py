@@ -64,6 +64,15 @@ class CogenModel(C.Structure):
     ]
 
 
+class MarketModel(C.Structure):
+    _fields_ = [
+        ("n_gen", _i32), ("k", _i32), ("n_days", _i32), ("use_intermediate_rewards", _i32),
+        ("e_max", _f64), ("e_init", _f64), ("p_max", _f64), ("eta_c", _f64), ("eta_d", _f64),
+        ("price_cap", _f64), ("p_co2", _f64), ("terminal_price", _f64),
+        ("gen_cost", _vp), ("gen_cap", _vp), ("load", _vp), ("moer", _vp),
+    ]
+
+
 # name -> (restype, argtypes); every symbol include/sustaingym_b200.h declares
 SIGNATURES = {
     "sg_abi_version": (C.c_int, []),
@@ -88,6 +97,8 @@ SIGNATURES = {
     "sg_cogen_reset": (C.c_int, [C.POINTER(CogenModel), _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sg_cogen_step": (C.c_int, [C.POINTER(CogenModel), _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                 _i32, _vp, _vp]),
+    "sg_market_reset": (C.c_int, [C.POINTER(MarketModel), _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sg_market_step": (C.c_int, [C.POINTER(MarketModel), _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sg_ev_project": (C.c_int, [C.POINTER(EVModel), _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
