@@ -140,7 +140,8 @@ typedef struct sg_ev_model {
 
 typedef struct sg_ev_state {
     double*  delivered;   /* [device] [B, n] kWh delivered to the session now at the station  */
-    uint8_t* sess_idx;    /* [device] [B, n] slot of the station's current-or-next session    */
+    uint8_t* sess_idx;    /* [device] [B, n] slot of the station's current-or-next session;   */
+                          /*   255 = hint: no session left at this station today              */
     int32_t* clock;       /* [device] [B, 4] {t (0..288, env.py:168), day (trace index in     */
                           /*   [0,D)), moer_day (MOER table index in [0,Dm)), reserved}        */
     double*  breakdown;   /* [device] [B, 3] cumulative profit, carbon_cost, excess_charge    */
@@ -154,7 +155,8 @@ typedef struct sg_ev_state {
 #define SG_EV_ACTION_F32      0
 #define SG_EV_ACTION_I64      1   /* DiscreteActionWrapper input (wrappers.py:43-45)          */
 #define SG_EV_FLAG_AUTORESET  16  /* on done: advance day (mod D), reset state, obs = reset obs */
-#define SG_EV_FLAG_GENERIC_KERNEL 256 /* use the generic kernel even when the specialised one applies */
+#define SG_EV_FLAG_GENERIC_KERNEL 256 /* use the generic warp-per-env kernel                        */
+#define SG_EV_FLAG_WARP_KERNEL    512 /* use the specialised warp-per-env kernel instead of the tile kernel */
 
 /* reset(): env.py:293-338 for envs whose `reset_mask` byte is non-zero (NULL = all).
  * `day_in`/`moer_day_in` pick the trace/MOER table (the seed->day map is host logic,

@@ -24,6 +24,7 @@ SG_EV_ACTION_F32 = 0
 SG_EV_ACTION_I64 = 1
 SG_EV_FLAG_AUTORESET = 16
 SG_EV_FLAG_GENERIC_KERNEL = 256
+SG_EV_FLAG_WARP_KERNEL = 512
 SG_BUILDING_FLAG_AUTORESET = 16
 
 _vp = C.c_void_p

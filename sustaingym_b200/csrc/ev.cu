@@ -1127,6 +1127,355 @@ ev_step_fast_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
     }
 }
 
+// =================================================================================================
+// Tile kernel (default main kernel).  The warp-per-env kernels above spend ~800 warp instructions
+// per env because every per-env scalar operation is replicated over 32 lanes and both stations of
+// a lane run the f64 battery path although ~85 % of the stations are empty.  Here one warp owns a
+// TILE of 32 consecutive envs and one THREAD advances one env:
+//   phase 0  the tile's action rows and sess_idx bytes are copied global->shared with coalesced
+//            8/16-byte accesses (the only place the env-major layout is touched), clock rows are
+//            one coalesced 16-byte load per lane;
+//   phase 1  each thread scans its env's stations (cheap: one byte per station; stations known to
+//            have no current-or-next session carry the hint sess_idx = 255) and appends the
+//            stations whose session has started or starts now to a compact list in shared memory;
+//            the f64 battery arithmetic then runs over the LISTS (trip count ~ the largest list,
+//            mostly-active lanes); class sums are per-thread accumulators — no shuffles at all;
+//            `delivered` is read/written only for listed stations (sparse 8-byte accesses);
+//   phase 2  observation rows are assembled from the shared tiles and stored row by row with
+//            8-byte vectors; sess_idx / pilots tiles go back with coalesced copies.
+// Envs whose clipped action is not inside the network constraints are queued for the solver
+// kernel exactly as before and leave no trace in global memory.
+// =================================================================================================
+constexpr int kTileE = 32;
+
+struct TileLayout {
+    int RS, off_est, off_k, off_pil, off_lst, off_S, off_P, off_rate, off_energy, bytes;
+    __host__ __device__ explicit TileLayout(int n) {
+        RS = n | 1;                                        // odd row stride: conflict-free column walks
+        int o = kTileE * RS * 4;                           // act/dem tile  f32 [32][RS]
+        off_est = o; o += kTileE * RS * 2;                 // est tile      i16 [32][RS]
+        o = (o + 15) & ~15;
+        off_k = o; o += kTileE * n;                        // sess_idx tile u8  [32*n] (global layout)
+        o = (o + 15) & ~15;
+        off_pil = o; o += kTileE * n;                      // pilots tile   u8  [32*n]
+        o = (o + 15) & ~15;
+        off_lst = o; o += kTileE * n;                      // station lists u8  [32][n]
+        o = (o + 15) & ~15;
+        off_S = o; o += kMC * kTileE * 8;                  // class sums of x        f64 [8][32]
+        off_P = o; o += kMC * kTileE * 4;                  // class sums of pilots   i32 [8][32]
+        o = (o + 15) & ~15;
+        off_rate = o; o += 40 * 8;
+        off_energy = o; o += 40 * 8;
+        bytes = o;
+    }
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kTileE)
+ev_step_tile_kernel(const sg_ev_model m, const sg_ev_state s, const long long B, const void* __restrict__ action,
+                    const int flags, const int bins, float* __restrict__ obs, double* __restrict__ reward,
+                    uint8_t* __restrict__ done, uint8_t* __restrict__ pilots, float* __restrict__ final_obs,
+                    uint8_t* __restrict__ status, double* __restrict__ stats, int32_t* __restrict__ todo) {
+    extern __shared__ __align__(16) unsigned char tsm[];
+    const int n = m.n_stations, kf = m.moer_steps, OBS = 2 * n + kf + 2, C = m.n_classes, J = m.n_constraints;
+    const int K = m.max_sessions;
+    const TileLayout L(n);
+    const int RS = L.RS;
+    float* tact = reinterpret_cast<float*>(tsm);
+    short* test = reinterpret_cast<short*>(tsm + L.off_est);
+    uint8_t* tk = tsm + L.off_k;
+    uint8_t* tpil = tsm + L.off_pil;
+    uint8_t* tlst = tsm + L.off_lst;
+    double* sS = reinterpret_cast<double*>(tsm + L.off_S);
+    int* sP = reinterpret_cast<int*>(tsm + L.off_P);
+    double* srate = reinterpret_cast<double*>(tsm + L.off_rate);
+    double* senergy = reinterpret_cast<double*>(tsm + L.off_energy);
+    const int lane = threadIdx.x;
+    for (int pI = lane; pI <= 32; pI += 32) {
+        const double pp = div_c((double)pI * kVoltage, 1000.0, kInv1000);
+        const double rate = div_c(pp * 1000.0, kVoltage, kInv208);
+        srate[pI] = rate;
+        senergy[pI] = div_c(rate * kVoltage, 1000.0, kInv1000) * kPeriodH;
+    }
+    __syncwarp();
+    const bool i64 = (flags & 1) == SG_EV_ACTION_I64;
+    const uint4* recs = reinterpret_cast<const uint4*>(m.sessions);
+    const uint8_t* __restrict__ gcls = m.station_class;
+    const uint8_t* __restrict__ gtype = m.station_type;
+    const long long ntiles = (B + kTileE - 1) / kTileE;
+    StatsAcc acc;
+
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long b0 = tile * kTileE;
+        const int nv = (int)min((long long)kTileE, B - b0);
+        const long long b = b0 + lane;
+        const bool env = lane < nv;
+
+        // ---------------- phase 0: coalesced tile loads ------------------------------------------
+        int4 clk = make_int4(kEpisode, 0, 0, 0);
+        if (env) clk = *reinterpret_cast<const int4*>(s.clock + b * 4);
+        for (int r = 0; r < nv; ++r) {
+            if (2 * lane < n) {
+                float2 v;
+                if (i64) {
+                    const long long* ap = reinterpret_cast<const long long*>(action) + (b0 + r) * n + 2 * lane;
+                    v.x = __fdiv_rn((float)ap[0], (float)(bins - 1));            // wrappers.py:45
+                    v.y = __fdiv_rn((float)ap[1], (float)(bins - 1));
+                } else {
+                    v = ldg_stream_f2(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(action) + (b0 + r) * n) + lane);
+                }
+                tact[r * RS + 2 * lane] = v.x;
+                tact[r * RS + 2 * lane + 1] = v.y;
+            }
+        }
+        {
+            const uint8_t* gk = s.sess_idx + b0 * n;
+            const int nbytes = nv * n, nvec = nbytes >> 4;
+            for (int c = lane; c < nvec; c += 32) reinterpret_cast<uint4*>(tk)[c] = reinterpret_cast<const uint4*>(gk)[c];
+            for (int c = (nvec << 4) + lane; c < nbytes; c += 32) tk[c] = gk[c];
+        }
+        __syncwarp();
+
+        // ---------------- phase 1: one thread = one env ------------------------------------------
+        const int t = clk.x, tn = t + 1;
+        int day = clk.y, md = clk.z;
+        const bool live = env && t < kEpisode;
+        bool commit = live;
+        const int sbase = day * K * n;
+        for (int c = 0; c < C; ++c) { sS[c * kTileE + lane] = 0.0; sP[c * kTileE + lane] = 0; }
+        int nl = 0;
+        float* myact = tact + lane * RS;
+        short* myest = test + lane * RS;
+        uint8_t* myk = tk + lane * n;
+        uint8_t* mypil = tpil + lane * n;
+        uint8_t* mylst = tlst + lane * n;
+        if (live) {
+            for (int i = 0; i < n; ++i) {
+                const int k = myk[i];
+                bool listed = false;
+                if (k != 255) {
+                    int arr = kEmpty;
+                    if (k < K) arr = (int)(short)(__ldg(reinterpret_cast<const unsigned*>(recs + (sbase + k * n + i))) & 0xffffu);
+                    if (arr == kEmpty) myk[i] = 255;                 // nothing (more) at this station today
+                    else if (arr <= tn) { mylst[nl++] = (uint8_t)i; listed = true; }
+                }
+                myest[i] = 0;
+                if constexpr (MODE == 0) {
+                    // every EVSE receives a pilot, occupied or not (it counts in the constraint currents)
+                    const float amps = myact[i] * 32.f;
+                    const float pf = gtype[i] == 0 ? (amps >= 6.f ? rintf(amps) : 0.f) : rintf(amps * 0.125f) * 8.f;
+                    const int pi = (int)pf;
+                    mypil[i] = (uint8_t)pi;
+                    sP[gcls[i] * kTileE + lane] += pi;
+                } else {
+                    mypil[i] = 0;
+                }
+                if (!listed) myact[i] = 0.f;                          // 'demands' of an empty station
+            }
+        }
+        auto load_rec = [&](int k, int i, int& arr, int& dep, int& est, double& energy) {
+            if (k >= K) { arr = dep = est = kEmpty; energy = 0.0; return; }
+            const uint4 r = __ldg(recs + (sbase + k * n + i));
+            arr = (int)(short)(r.x & 0xffffu);
+            dep = (int)(short)(r.x >> 16);
+            est = (int)(short)(r.y & 0xffffu);
+            energy = __hiloint2double((int)r.w, (int)r.z);
+        };
+        // pass A (projection only): clipped action and its class sums -> feasibility
+        if constexpr (MODE == 1) {
+            const int nmax = __reduce_max_sync(kFull, live ? nl : 0);
+            for (int e = 0; e < nmax; ++e) {
+                if (e < nl) {
+                    const int i = mylst[e];
+                    int arr, dep, est; double energy;
+                    load_rec(myk[i], i, arr, dep, est, energy);
+                    const bool plugged = t >= 1 && arr <= t && t < dep;
+                    if (plugged) {
+                        const double rem = energy - s.delivered[b * n + i];
+                        const float dem = rem > kFullEps ? (float)rem : 0.f;
+                        const double x = fmin(fmax((double)myact[i], 0.0), upper_bound(dem));
+                        sS[gcls[i] * kTileE + lane] += x;
+                    }
+                }
+            }
+            if (live) {
+                bool ok = true;
+                for (int j = 0; j < J; ++j) {
+                    double wr = 0, wi = 0;
+                    for (int c = 0; c < C; ++c) {
+                        const double S = sS[c * kTileE + lane];
+                        wr = fma(__ldg(m.con_re + j * kMC + c), S, wr);
+                        wi = fma(__ldg(m.con_im + j * kMC + c), S, wi);
+                    }
+                    const double r = __ldg(m.magnitudes + j) * (1.0 / kActionScale);
+                    ok = ok && (fma(wr, wr, wi * wi) <= r * r);
+                }
+                if (!ok) {
+                    commit = false;
+                    todo[2 + atomicAdd(todo, 1)] = (int)b;        // the work-list kernel redoes this env
+                }
+            }
+        }
+        // pass B: pilots, charging, events, new demands / departures for the listed stations
+        double rate_sum = 0.0;
+        {
+            const int nmax = __reduce_max_sync(kFull, commit ? nl : 0);
+            for (int e = 0; e < nmax; ++e) {
+                if (commit && e < nl) {
+                    const int i = mylst[e];
+                    int k = myk[i];
+                    int arr, dep, est; double energy;
+                    load_rec(k, i, arr, dep, est, energy);
+                    const bool plugged = t >= 1 && arr <= t && t < dep;
+                    double del = 0.0;
+                    if (plugged) {
+                        del = s.delivered[b * n + i];
+                        int pi;
+                        double pilot;
+                        if constexpr (MODE == 1) {
+                            const double rem = energy - del;
+                            const float dem = rem > kFullEps ? (float)rem : 0.f;
+                            const double x = fmin(fmax((double)myact[i], 0.0), upper_bound(dem));
+                            pilot = to_pilot(x, gtype[i]);
+                            pi = __double2int_rn(pilot);
+                            mypil[i] = (uint8_t)pi;
+                            sP[gcls[i] * kTileE + lane] += pi;
+                        } else {
+                            pi = mypil[i];
+                            pilot = (double)pi;
+                        }
+                        const double charge = fmax(0.0, kCapacity - energy) + del;
+                        if (kCapacity - charge > 2.0) {              // neither battery limit can bind
+                            del += senergy[pi];
+                            rate_sum += srate[pi];
+                        } else {
+                            const double rate_to_full = div_c(kCapacity - charge, kPeriodH, kInvPeriodH);
+                            const double soc = div_c(charge, kCapacity, kInv100);
+                            const double p_pilot = div_c(pilot * kVoltage, 1000.0, kInv1000);
+                            const double cap2 = soc < kTransitionSoc ? kMaxPower
+                                                                     : div_c(1.0 - soc, kOneMinusTrans, kInvOMT) * kMaxPower;
+                            const double power = fmin(fmin(p_pilot, cap2), rate_to_full);
+                            const double rate = div_c(power * 1000.0, kVoltage, kInv208);
+                            del += div_c(rate * kVoltage, 1000.0, kInv1000) * kPeriodH;
+                            rate_sum += rate;
+                        }
+                    }
+                    bool moved = false;
+                    while (dep <= tn && arr != kEmpty) {              // session over (or zero-length): next slot
+                        k += 1; del = 0.0; moved = true;
+                        load_rec(k, i, arr, dep, est, energy);
+                    }
+                    if (moved) myk[i] = (arr == kEmpty) ? 255 : (uint8_t)k;
+                    if (plugged || moved) s.delivered[b * n + i] = del;
+                    const double rem = energy - del;
+                    const bool active = arr <= tn && tn < dep && rem > kFullEps;    // Interface.active_sessions()
+                    myact[i] = active ? (float)rem : 0.f;
+                    myest[i] = active ? (short)(est - tn) : (short)0;
+                }
+            }
+        }
+        // ---------------- per-env epilogue: reward, clock, statistics -----------------------------
+        const bool dn = tn >= kEpisode;
+        const bool autoreset = commit && dn && (flags & SG_EV_FLAG_AUTORESET);
+        int md_out = md, t_out = tn;
+        if (commit) {
+            double excess = 0.0;
+            for (int j = 0; j < J; ++j) {
+                double wr = 0, wi = 0;
+                for (int c = 0; c < C; ++c) {
+                    const double S = (double)sP[c * kTileE + lane];
+                    wr = fma(__ldg(m.con_re + j * kMC + c), S, wr);
+                    wi = fma(__ldg(m.con_im + j * kMC + c), S, wi);
+                }
+                const double lim = __ldg(m.magnitudes + j), sq = fma(wr, wr, wi * wi);
+                if (sq > lim * lim) excess += fmax(0.0, sqrt(sq) - lim);
+            }
+            const double moer0 = (double)__ldg(m.moer + ((long long)md * SG_EV_MOER_ROWS + tn) * SG_EV_MOER_COLS);
+            const double profit = kProfitFactor * rate_sum;
+            const double excess_charge = excess * kViolationFactor;
+            const double carbon = kCarbonFactor * rate_sum * moer0;
+            const double rew = profit - carbon - excess_charge;
+            double* bd = s.breakdown + b * 3;
+            if (t == 0) { bd[0] = profit; bd[1] = carbon; bd[2] = excess_charge; }
+            else { bd[0] += profit; bd[1] += carbon; bd[2] += excess_charge; }
+            if (autoreset) {
+                day = (day + 1) % m.n_days;                           // sequential days, event_generation.py:284-291
+                md_out = (md + 1) % m.n_moer_days;
+                t_out = 0;
+                for (int i = 0; i < n; ++i) myk[i] = 0;               // delivered is already 0: every session ended
+            }
+            *reinterpret_cast<int4*>(s.clock + b * 4) = make_int4(t_out, day, md_out, clk.w);
+            reward[b] = rew;
+            done[b] = dn ? 1 : 0;
+            if (status != nullptr) status[b] = 0;
+            if (stats != nullptr) acc.add(rew, dn, profit, carbon, excess_charge);
+        } else if (env && t >= kEpisode) {                            // finished episode, not reset: stays terminal
+            reward[b] = 0.0; done[b] = 1;
+            if (status != nullptr) status[b] = 0;
+        }
+        __syncwarp();
+
+        // ---------------- phase 2: coalesced write-back ------------------------------------------
+        const unsigned commit_mask = __ballot_sync(kFull, commit);
+        for (int r = 0; r < nv; ++r) {
+            if (!((commit_mask >> r) & 1u)) continue;
+            const int md_r = __shfl_sync(kFull, md, r), mdo_r = __shfl_sync(kFull, md_out, r);
+            const int tn_r = __shfl_sync(kFull, tn, r), ar_r = __shfl_sync(kFull, (int)autoreset, r);
+            const float* mrow = m.moer + ((long long)md_r * SG_EV_MOER_ROWS + tn_r) * SG_EV_MOER_COLS;
+            auto put_row = [&](float* orow, const bool from_tiles, const float* row, const int tstep) {
+                if (2 * lane < n) {
+                    float2 d = make_float2(0.f, 0.f), q = make_float2(0.f, 0.f);
+                    if (from_tiles) {
+                        d = make_float2(tact[r * RS + 2 * lane], tact[r * RS + 2 * lane + 1]);
+                        q = make_float2((float)test[r * RS + 2 * lane], (float)test[r * RS + 2 * lane + 1]);
+                    }
+                    stg_stream_f2(reinterpret_cast<float2*>(orow) + lane, d);
+                    stg_stream_f2(reinterpret_cast<float2*>(orow + n) + lane, q);
+                }
+#pragma unroll
+                for (int pass = 0; pass < 2; ++pass) {
+                    const int e = lane + 32 * pass;
+                    if (e < kf + 2) {
+                        float v;
+                        if (e < kf) v = __ldg(row + 1 + e);
+                        else if (e == kf) v = __ldg(row);
+                        else v = (float)((double)tstep / (double)kEpisode);     // env.py:392
+                        orow[2 * n + e] = v;
+                    }
+                }
+            };
+            if (!ar_r) {
+                put_row(obs + (b0 + r) * OBS, true, mrow, tn_r);
+            } else {
+                if (final_obs != nullptr) put_row(final_obs + (b0 + r) * OBS, true, mrow, tn_r);
+                put_row(obs + (b0 + r) * OBS, false, m.moer + ((long long)mdo_r * SG_EV_MOER_ROWS) * SG_EV_MOER_COLS, 0);
+            }
+            if (pilots != nullptr && 2 * lane < n)
+                reinterpret_cast<uchar2*>(pilots + (b0 + r) * n)[lane] = make_uchar2(tpil[r * n + 2 * lane], tpil[r * n + 2 * lane + 1]);
+        }
+        {
+            uint8_t* gk = s.sess_idx + b0 * n;
+            const int nbytes = nv * n, nvec = nbytes >> 4;
+            for (int c = lane; c < nvec; c += 32) reinterpret_cast<uint4*>(gk)[c] = reinterpret_cast<const uint4*>(tk)[c];
+            for (int c = (nvec << 4) + lane; c < nbytes; c += 32) gk[c] = tk[c];
+        }
+        __syncwarp();
+    }
+    if (stats != nullptr) {
+        // one warp per CTA: plain warp reduction + one set of atomics
+        double v[11] = {acc.count, acc.sum, acc.sumsq, acc.mn, acc.mx, acc.n_done, acc.n_proj, acc.n_maxiter, acc.c0, acc.c1, acc.c2};
+#pragma unroll
+        for (int i = 0; i < 11; ++i) {
+            const double r = (i == 3) ? warp_min(v[i]) : (i == 4) ? warp_max(v[i]) : warp_sum(v[i]);
+            if (lane == 0) {
+                if (i == 3) atomic_min_double(stats + 3, r);
+                else if (i == 4) atomic_max_double(stats + 4, r);
+                else if (r != 0.0) atomicAdd(stats + i, r);
+            }
+        }
+    }
+}
+
 // Persistent CTAs: every warp strides over the batch, so the table staging and the statistics
 // flush are paid once per warp instead of once per env.
 template <int MODE>
@@ -1300,9 +1649,29 @@ int sg_ev_step(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, con
                                                         (long long)sms * SG_EV_FAST_MINBLOCKS);
     // specialised kernel: even n, <= 5 classes, <= 32 constraints, 32-bit record index; the model
     // flag bit 8 (SG_EV_FLAG_GENERIC_KERNEL) forces the generic one (used by the tests)
-    const bool fast = (m->n_stations % 2 == 0) && m->n_classes <= 5 && m->n_constraints <= 32 &&
-                      (long long)m->n_days * m->max_sessions * m->n_stations < (1ll << 31) &&
+    const bool small_index = (long long)m->n_days * m->max_sessions * m->n_stations < (1ll << 31);
+    const bool fast = (m->n_stations % 2 == 0) && m->n_classes <= 5 && m->n_constraints <= 32 && small_index &&
                       !(flags & SG_EV_FLAG_GENERIC_KERNEL);
+    // default: the tile kernel (one thread per env on 32-env tiles staged through shared memory)
+    if ((m->n_stations % 2 == 0) && small_index && m->max_sessions < 255 &&
+        !(flags & (SG_EV_FLAG_GENERIC_KERNEL | SG_EV_FLAG_WARP_KERNEL))) {
+        const sg::TileLayout L(m->n_stations);
+        const int per_sm = std::max(1, std::min(16, (220 * 1024) / (L.bytes + 1024)));
+        const long long ntiles = (num_envs + sg::kTileE - 1) / sg::kTileE;
+        const unsigned tgrid = (unsigned)std::min<long long>(ntiles, (long long)sms * per_sm);
+        if (!m->project) {
+            auto kern = sg::ev_step_tile_kernel<0>;
+            if (L.bytes > 48 * 1024) SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.bytes));
+            kern<<<tgrid, sg::kTileE, L.bytes, st>>>(*m, *s, num_envs, action, flags, discrete_bins, obs, reward, done,
+                                                     pilots, final_obs, status, stats, todo);
+        } else {
+            auto kern = sg::ev_step_tile_kernel<1>;
+            if (L.bytes > 48 * 1024) SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.bytes));
+            kern<<<tgrid, sg::kTileE, L.bytes, st>>>(*m, *s, num_envs, action, flags, discrete_bins, obs, reward, done,
+                                                     pilots, final_obs, status, stats, todo);
+        }
+        return sg::launch_status("ev_step_tile_kernel");
+    }
     if (!m->project) {
         if (fast) sg::ev_step_fast_kernel<0, 5><<<grid, sg::kThreads, 0, st>>>(*m, *s, num_envs, action, flags, discrete_bins,
                                                                              obs, reward, done, pilots, final_obs, status, stats, todo);

@@ -80,8 +80,8 @@ def pack_sessions(days: list, num_stations: int, max_sessions: int | None = None
         if K > max_sessions:
             raise ValueError(f"a station has {K} sessions in one day but max_sessions={max_sessions}")
         K = max_sessions
-    if K > 255:
-        raise ValueError("more than 255 sessions per station per day")
+    if K > 254:
+        raise ValueError("more than 254 sessions per station per day (255 is the kernels' empty hint)")
     D = len(days)
     arrival = np.full((D, K, num_stations), EMPTY, np.int16)
     departure = np.full((D, K, num_stations), EMPTY, np.int16)

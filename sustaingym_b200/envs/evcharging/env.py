@@ -50,7 +50,8 @@ class BatchedEVChargingEnv:
     def __init__(self, data_generator: AbstractTraceGenerator, num_envs: int = 1,
                  moer_forecast_steps: int = 36, project_action_in_env: bool = True, verbose: int = 0,
                  device: str | torch.device | None = None, auto_reset: bool = False,
-                 discrete_bins: int = -1, collect_stats: bool = False, force_generic_kernel: bool = False):
+                 discrete_bins: int = -1, collect_stats: bool = False, force_generic_kernel: bool = False,
+                 force_warp_kernel: bool = False):
         assert 1 <= moer_forecast_steps <= 36                                   # env.py:120
         self.lib = _lib.load()                                                  # fails loudly if not built
         if not torch.cuda.is_available():
@@ -144,7 +145,8 @@ class BatchedEVChargingEnv:
         self._h_done = torch.zeros(B, dtype=torch.uint8).pin_memory()
         self._flags = (_lib.SG_EV_ACTION_I64 if discrete_bins > 0 else _lib.SG_EV_ACTION_F32) | \
             (_lib.SG_EV_FLAG_AUTORESET if auto_reset else 0) | \
-            (_lib.SG_EV_FLAG_GENERIC_KERNEL if force_generic_kernel else 0)
+            (_lib.SG_EV_FLAG_GENERIC_KERNEL if force_generic_kernel else 0) | \
+            (_lib.SG_EV_FLAG_WARP_KERNEL if force_warp_kernel else 0)
         self.kernel_launches = 0
         self._needs_reset = True
 

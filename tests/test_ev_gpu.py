@@ -58,18 +58,23 @@ def run_parity(env, orc, net, gen, B, steps, seed, action_fn, project):
     return clean, n_obs_exact, n_slow
 
 
-@pytest.mark.parametrize("B,mean,generic", [(64, 25.0, False), (257, 70.0, False), (100, 60.0, True)])
-def test_step_no_projection(native_lib, B, mean, generic):
-    gen, env, net, orc = make(7, mean, 11, B, False, force_generic_kernel=generic)
+KERNELS = {"tile": {}, "warp": {"force_warp_kernel": True}, "generic": {"force_generic_kernel": True}}
+
+
+@pytest.mark.parametrize("B,mean,kernel", [(64, 25.0, "tile"), (257, 70.0, "tile"), (33, 120.0, "tile"),
+                                           (100, 60.0, "warp"), (100, 60.0, "generic")])
+def test_step_no_projection(native_lib, B, mean, kernel):
+    gen, env, net, orc = make(7, mean, 11, B, False, **KERNELS[kernel])
     clean, n_exact, _ = run_parity(env, orc, net, gen, B, 288, 3,
                                    lambda rng, t: rng.uniform(0, 1, (B, 54)).astype(np.float32), False)
     assert clean.all() and n_exact >= 250
     assert bool(env.done.all()) and int(env.t[0]) == 288
 
 
-@pytest.mark.parametrize("B,mean,generic", [(64, 25.0, False), (200, 80.0, False), (100, 80.0, True)])
-def test_step_with_projection(native_lib, B, mean, generic):
-    gen, env, net, orc = make(5, mean, 5, B, True, force_generic_kernel=generic)
+@pytest.mark.parametrize("B,mean,kernel", [(64, 25.0, "tile"), (200, 80.0, "tile"), (100, 80.0, "warp"),
+                                           (100, 80.0, "generic")])
+def test_step_with_projection(native_lib, B, mean, kernel):
+    gen, env, net, orc = make(5, mean, 5, B, True, **KERNELS[kernel])
     clean, n_exact, n_slow = run_parity(env, orc, net, gen, B, 288, 9,
                                         lambda rng, t: rng.uniform(0, 1, (B, 54)).astype(np.float32), True)
     assert clean.mean() > 0.97
