@@ -1149,7 +1149,7 @@ ev_step_fast_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
 constexpr int kTileE = 32;
 
 struct TileLayout {
-    int RS, off_est, off_k, off_pil, off_lst, off_S, off_P, off_rate, off_energy, bytes;
+    int RS, off_est, off_k, off_pil, off_lst, off_S, off_P, off_rate, off_energy, off_con, bytes;
     __host__ __device__ explicit TileLayout(int n) {
         RS = n | 1;                                        // odd row stride: conflict-free column walks
         int o = kTileE * RS * 4;                           // act/dem tile  f32 [32][RS]
@@ -1166,6 +1166,8 @@ struct TileLayout {
         o = (o + 15) & ~15;
         off_rate = o; o += 40 * 8;
         off_energy = o; o += 40 * 8;
+        off_con = o; o += (2 * SG_EV_MAX_CONSTRAINTS * kMC + SG_EV_MAX_CONSTRAINTS) * 8 + 2 * SG_EV_MAX_STATIONS;
+        o = (o + 15) & ~15;
         bytes = o;
     }
 };
@@ -1190,6 +1192,11 @@ ev_step_tile_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
     int* sP = reinterpret_cast<int*>(tsm + L.off_P);
     double* srate = reinterpret_cast<double*>(tsm + L.off_rate);
     double* senergy = reinterpret_cast<double*>(tsm + L.off_energy);
+    double* scre = reinterpret_cast<double*>(tsm + L.off_con);          // [16][8]
+    double* scim = scre + SG_EV_MAX_CONSTRAINTS * kMC;                  // [16][8]
+    double* slim = scim + SG_EV_MAX_CONSTRAINTS * kMC;                  // [16]
+    uint8_t* scls = reinterpret_cast<uint8_t*>(slim + SG_EV_MAX_CONSTRAINTS);   // [64]
+    uint8_t* stype = scls + SG_EV_MAX_STATIONS;                          // [64]
     const int lane = threadIdx.x;
     for (int pI = lane; pI <= 32; pI += 32) {
         const double pp = div_c((double)pI * kVoltage, 1000.0, kInv1000);
@@ -1197,11 +1204,15 @@ ev_step_tile_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
         srate[pI] = rate;
         senergy[pI] = div_c(rate * kVoltage, 1000.0, kInv1000) * kPeriodH;
     }
+    for (int i = lane; i < SG_EV_MAX_CONSTRAINTS * kMC; i += 32) { scre[i] = m.con_re[i]; scim[i] = m.con_im[i]; }
+    if (lane < SG_EV_MAX_CONSTRAINTS) slim[lane] = m.magnitudes[lane];
+    for (int i = lane; i < SG_EV_MAX_STATIONS; i += 32) {
+        scls[i] = i < n ? m.station_class[i] : 0;
+        stype[i] = i < n ? m.station_type[i] : 0;
+    }
     __syncwarp();
     const bool i64 = (flags & 1) == SG_EV_ACTION_I64;
     const uint4* recs = reinterpret_cast<const uint4*>(m.sessions);
-    const uint8_t* __restrict__ gcls = m.station_class;
-    const uint8_t* __restrict__ gtype = m.station_type;
     const long long ntiles = (B + kTileE - 1) / kTileE;
     StatsAcc acc;
 
@@ -1211,28 +1222,34 @@ ev_step_tile_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
         const long long b = b0 + lane;
         const bool env = lane < nv;
 
-        // ---------------- phase 0: coalesced tile loads ------------------------------------------
+        // ---------------- phase 0: coalesced tile loads (8 rows of loads in flight) -----------------
         int4 clk = make_int4(kEpisode, 0, 0, 0);
         if (env) clk = *reinterpret_cast<const int4*>(s.clock + b * 4);
-        for (int r = 0; r < nv; ++r) {
-            if (2 * lane < n) {
-                float2 v;
-                if (i64) {
-                    const long long* ap = reinterpret_cast<const long long*>(action) + (b0 + r) * n + 2 * lane;
-                    v.x = __fdiv_rn((float)ap[0], (float)(bins - 1));            // wrappers.py:45
-                    v.y = __fdiv_rn((float)ap[1], (float)(bins - 1));
-                } else {
-                    v = ldg_stream_f2(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(action) + (b0 + r) * n) + lane);
-                }
-                tact[r * RS + 2 * lane] = v.x;
-                tact[r * RS + 2 * lane + 1] = v.y;
-            }
-        }
         {
             const uint8_t* gk = s.sess_idx + b0 * n;
             const int nbytes = nv * n, nvec = nbytes >> 4;
             for (int c = lane; c < nvec; c += 32) reinterpret_cast<uint4*>(tk)[c] = reinterpret_cast<const uint4*>(gk)[c];
             for (int c = (nvec << 4) + lane; c < nbytes; c += 32) tk[c] = gk[c];
+        }
+        const bool col = 2 * lane < n;
+        for (int r0 = 0; r0 < nv; r0 += 8) {
+            float2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                v[u] = make_float2(0.f, 0.f);
+                if (col && r0 + u < nv) {
+                    if (i64) {
+                        const long long* ap = reinterpret_cast<const long long*>(action) + (b0 + r0 + u) * n + 2 * lane;
+                        v[u].x = __fdiv_rn((float)ap[0], (float)(bins - 1));            // wrappers.py:45
+                        v[u].y = __fdiv_rn((float)ap[1], (float)(bins - 1));
+                    } else {
+                        v[u] = ldg_stream_f2(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(action) + (b0 + r0 + u) * n) + lane);
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                if (col && r0 + u < nv) { tact[(r0 + u) * RS + 2 * lane] = v[u].x; tact[(r0 + u) * RS + 2 * lane + 1] = v[u].y; }
         }
         __syncwarp();
 
@@ -1249,52 +1266,84 @@ ev_step_tile_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
         uint8_t* myk = tk + lane * n;
         uint8_t* mypil = tpil + lane * n;
         uint8_t* mylst = tlst + lane * n;
+        // moer0 of the row the reward needs: issue early
+        float moer0f = 0.f;
+        if (live) moer0f = __ldg(m.moer + ((long long)md * SG_EV_MOER_ROWS + tn) * SG_EV_MOER_COLS);
         if (live) {
-            for (int i = 0; i < n; ++i) {
-                const int k = myk[i];
-                bool listed = false;
-                if (k != 255) {
-                    int arr = kEmpty;
-                    if (k < K) arr = (int)(short)(__ldg(reinterpret_cast<const unsigned*>(recs + (sbase + k * n + i))) & 0xffffu);
-                    if (arr == kEmpty) myk[i] = 255;                 // nothing (more) at this station today
-                    else if (arr <= tn) { mylst[nl++] = (uint8_t)i; listed = true; }
+            constexpr int U = 9;
+            for (int i0 = 0; i0 < n; i0 += U) {
+                int kk[U], arrv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) kk[u] = (i0 + u < n) ? myk[i0 + u] : 255;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {                         // U independent L2 look-ups in flight
+                    arrv[u] = kEmpty;
+                    if (kk[u] < K) arrv[u] = (int)(short)(__ldg(reinterpret_cast<const unsigned*>(recs + (sbase + kk[u] * n + i0 + u))) & 0xffffu);
                 }
-                myest[i] = 0;
-                if constexpr (MODE == 0) {
-                    // every EVSE receives a pilot, occupied or not (it counts in the constraint currents)
-                    const float amps = myact[i] * 32.f;
-                    const float pf = gtype[i] == 0 ? (amps >= 6.f ? rintf(amps) : 0.f) : rintf(amps * 0.125f) * 8.f;
-                    const int pi = (int)pf;
-                    mypil[i] = (uint8_t)pi;
-                    sP[gcls[i] * kTileE + lane] += pi;
-                } else {
-                    mypil[i] = 0;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int i = i0 + u;
+                    if (i < n) {
+                        bool listed = false;
+                        if (kk[u] != 255) {
+                            if (arrv[u] == kEmpty) myk[i] = 255;     // nothing (more) at this station today
+                            else if (arrv[u] <= tn) { mylst[nl++] = (uint8_t)i; listed = true; }
+                        }
+                        myest[i] = 0;
+                        if constexpr (MODE == 0) {
+                            // every EVSE receives a pilot, occupied or not (it counts in the constraint currents)
+                            const float amps = myact[i] * 32.f;
+                            const float pf = stype[i] == 0 ? (amps >= 6.f ? rintf(amps) : 0.f) : rintf(amps * 0.125f) * 8.f;
+                            const int pi = (int)pf;
+                            mypil[i] = (uint8_t)pi;
+                            sP[scls[i] * kTileE + lane] += pi;
+                        } else {
+                            mypil[i] = 0;
+                        }
+                        if (!listed) myact[i] = 0.f;                  // 'demands' of an empty station
+                    }
                 }
-                if (!listed) myact[i] = 0.f;                          // 'demands' of an empty station
             }
         }
-        auto load_rec = [&](int k, int i, int& arr, int& dep, int& est, double& energy) {
-            if (k >= K) { arr = dep = est = kEmpty; energy = 0.0; return; }
-            const uint4 r = __ldg(recs + (sbase + k * n + i));
-            arr = (int)(short)(r.x & 0xffffu);
-            dep = (int)(short)(r.x >> 16);
-            est = (int)(short)(r.y & 0xffffu);
-            energy = __hiloint2double((int)r.w, (int)r.z);
+        constexpr int V = 4;                                          // listed stations processed per batch
+        struct Rec { int i, k, arr, dep, est; double energy, del; bool on, plugged; };
+        auto load_batch = [&](int e0, bool enable, Rec (&q)[V]) {
+#pragma unroll
+            for (int u = 0; u < V; ++u) {
+                q[u].on = enable && e0 + u < nl;
+                q[u].i = q[u].on ? mylst[e0 + u] : 0;
+                q[u].k = q[u].on ? myk[q[u].i] : 255;
+            }
+            uint4 raw[V];
+#pragma unroll
+            for (int u = 0; u < V; ++u) {
+                raw[u] = make_uint4(0x7fff7fffu, 0x7fffu, 0u, 0u);
+                if (q[u].on && q[u].k < K) raw[u] = __ldg(recs + (sbase + q[u].k * n + q[u].i));
+            }
+#pragma unroll
+            for (int u = 0; u < V; ++u) {
+                q[u].arr = (int)(short)(raw[u].x & 0xffffu);
+                q[u].dep = (int)(short)(raw[u].x >> 16);
+                q[u].est = (int)(short)(raw[u].y & 0xffffu);
+                q[u].energy = __hiloint2double((int)raw[u].w, (int)raw[u].z);
+                q[u].plugged = q[u].on && t >= 1 && q[u].arr <= t && t < q[u].dep;
+            }
+#pragma unroll
+            for (int u = 0; u < V; ++u) q[u].del = q[u].plugged ? s.delivered[b * n + q[u].i] : 0.0;
         };
         // pass A (projection only): clipped action and its class sums -> feasibility
         if constexpr (MODE == 1) {
             const int nmax = __reduce_max_sync(kFull, live ? nl : 0);
-            for (int e = 0; e < nmax; ++e) {
-                if (e < nl) {
-                    const int i = mylst[e];
-                    int arr, dep, est; double energy;
-                    load_rec(myk[i], i, arr, dep, est, energy);
-                    const bool plugged = t >= 1 && arr <= t && t < dep;
-                    if (plugged) {
-                        const double rem = energy - s.delivered[b * n + i];
+            for (int e0 = 0; e0 < nmax; e0 += V) {
+                Rec q[V];
+                load_batch(e0, live, q);
+#pragma unroll
+                for (int u = 0; u < V; ++u) {
+                    if (q[u].plugged) {
+                        const double rem = q[u].energy - q[u].del;
                         const float dem = rem > kFullEps ? (float)rem : 0.f;
-                        const double x = fmin(fmax((double)myact[i], 0.0), upper_bound(dem));
-                        sS[gcls[i] * kTileE + lane] += x;
+                        const double x = fmin(fmax((double)myact[q[u].i], 0.0), upper_bound(dem));
+                        sS[scls[q[u].i] * kTileE + lane] += x;
                     }
                 }
             }
@@ -1304,10 +1353,10 @@ ev_step_tile_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
                     double wr = 0, wi = 0;
                     for (int c = 0; c < C; ++c) {
                         const double S = sS[c * kTileE + lane];
-                        wr = fma(__ldg(m.con_re + j * kMC + c), S, wr);
-                        wi = fma(__ldg(m.con_im + j * kMC + c), S, wi);
+                        wr = fma(scre[j * kMC + c], S, wr);
+                        wi = fma(scim[j * kMC + c], S, wi);
                     }
-                    const double r = __ldg(m.magnitudes + j) * (1.0 / kActionScale);
+                    const double r = slim[j] * (1.0 / kActionScale);
                     ok = ok && (fma(wr, wr, wi * wi) <= r * r);
                 }
                 if (!ok) {
@@ -1320,26 +1369,27 @@ ev_step_tile_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
         double rate_sum = 0.0;
         {
             const int nmax = __reduce_max_sync(kFull, commit ? nl : 0);
-            for (int e = 0; e < nmax; ++e) {
-                if (commit && e < nl) {
-                    const int i = mylst[e];
-                    int k = myk[i];
-                    int arr, dep, est; double energy;
-                    load_rec(k, i, arr, dep, est, energy);
-                    const bool plugged = t >= 1 && arr <= t && t < dep;
-                    double del = 0.0;
+            for (int e0 = 0; e0 < nmax; e0 += V) {
+                Rec q[V];
+                load_batch(e0, commit, q);
+#pragma unroll
+                for (int u = 0; u < V; ++u) {
+                    if (!q[u].on) continue;
+                    const int i = q[u].i;
+                    int k = q[u].k, arr = q[u].arr, dep = q[u].dep, est = q[u].est;
+                    double energy = q[u].energy, del = q[u].del;
+                    const bool plugged = q[u].plugged;
                     if (plugged) {
-                        del = s.delivered[b * n + i];
                         int pi;
                         double pilot;
                         if constexpr (MODE == 1) {
                             const double rem = energy - del;
                             const float dem = rem > kFullEps ? (float)rem : 0.f;
                             const double x = fmin(fmax((double)myact[i], 0.0), upper_bound(dem));
-                            pilot = to_pilot(x, gtype[i]);
+                            pilot = to_pilot(x, stype[i]);
                             pi = __double2int_rn(pilot);
                             mypil[i] = (uint8_t)pi;
-                            sP[gcls[i] * kTileE + lane] += pi;
+                            sP[scls[i] * kTileE + lane] += pi;
                         } else {
                             pi = mypil[i];
                             pilot = (double)pi;
@@ -1363,7 +1413,12 @@ ev_step_tile_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
                     bool moved = false;
                     while (dep <= tn && arr != kEmpty) {              // session over (or zero-length): next slot
                         k += 1; del = 0.0; moved = true;
-                        load_rec(k, i, arr, dep, est, energy);
+                        arr = dep = est = kEmpty; energy = 0.0;
+                        if (k < K) {
+                            const uint4 r = __ldg(recs + (sbase + k * n + i));
+                            arr = (int)(short)(r.x & 0xffffu); dep = (int)(short)(r.x >> 16);
+                            est = (int)(short)(r.y & 0xffffu); energy = __hiloint2double((int)r.w, (int)r.z);
+                        }
                     }
                     if (moved) myk[i] = (arr == kEmpty) ? 255 : (uint8_t)k;
                     if (plugged || moved) s.delivered[b * n + i] = del;
@@ -1384,13 +1439,13 @@ ev_step_tile_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
                 double wr = 0, wi = 0;
                 for (int c = 0; c < C; ++c) {
                     const double S = (double)sP[c * kTileE + lane];
-                    wr = fma(__ldg(m.con_re + j * kMC + c), S, wr);
-                    wi = fma(__ldg(m.con_im + j * kMC + c), S, wi);
+                    wr = fma(scre[j * kMC + c], S, wr);
+                    wi = fma(scim[j * kMC + c], S, wi);
                 }
-                const double lim = __ldg(m.magnitudes + j), sq = fma(wr, wr, wi * wi);
+                const double lim = slim[j], sq = fma(wr, wr, wi * wi);
                 if (sq > lim * lim) excess += fmax(0.0, sqrt(sq) - lim);
             }
-            const double moer0 = (double)__ldg(m.moer + ((long long)md * SG_EV_MOER_ROWS + tn) * SG_EV_MOER_COLS);
+            const double moer0 = (double)moer0f;
             const double profit = kProfitFactor * rate_sum;
             const double excess_charge = excess * kViolationFactor;
             const double carbon = kCarbonFactor * rate_sum * moer0;
@@ -1415,49 +1470,65 @@ ev_step_tile_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
         }
         __syncwarp();
 
-        // ---------------- phase 2: coalesced write-back ------------------------------------------
+        // ---------------- phase 2: coalesced write-back (tails of 8 rows in flight) ----------------
         const unsigned commit_mask = __ballot_sync(kFull, commit);
-        for (int r = 0; r < nv; ++r) {
-            if (!((commit_mask >> r) & 1u)) continue;
-            const int md_r = __shfl_sync(kFull, md, r), mdo_r = __shfl_sync(kFull, md_out, r);
-            const int tn_r = __shfl_sync(kFull, tn, r), ar_r = __shfl_sync(kFull, (int)autoreset, r);
-            const float* mrow = m.moer + ((long long)md_r * SG_EV_MOER_ROWS + tn_r) * SG_EV_MOER_COLS;
-            auto put_row = [&](float* orow, const bool from_tiles, const float* row, const int tstep) {
-                if (2 * lane < n) {
-                    float2 d = make_float2(0.f, 0.f), q = make_float2(0.f, 0.f);
-                    if (from_tiles) {
-                        d = make_float2(tact[r * RS + 2 * lane], tact[r * RS + 2 * lane + 1]);
-                        q = make_float2((float)test[r * RS + 2 * lane], (float)test[r * RS + 2 * lane + 1]);
-                    }
-                    stg_stream_f2(reinterpret_cast<float2*>(orow) + lane, d);
-                    stg_stream_f2(reinterpret_cast<float2*>(orow + n) + lane, q);
-                }
-#pragma unroll
-                for (int pass = 0; pass < 2; ++pass) {
-                    const int e = lane + 32 * pass;
-                    if (e < kf + 2) {
-                        float v;
-                        if (e < kf) v = __ldg(row + 1 + e);
-                        else if (e == kf) v = __ldg(row);
-                        else v = (float)((double)tstep / (double)kEpisode);     // env.py:392
-                        orow[2 * n + e] = v;
-                    }
-                }
-            };
-            if (!ar_r) {
-                put_row(obs + (b0 + r) * OBS, true, mrow, tn_r);
-            } else {
-                if (final_obs != nullptr) put_row(final_obs + (b0 + r) * OBS, true, mrow, tn_r);
-                put_row(obs + (b0 + r) * OBS, false, m.moer + ((long long)mdo_r * SG_EV_MOER_ROWS) * SG_EV_MOER_COLS, 0);
-            }
-            if (pilots != nullptr && 2 * lane < n)
-                reinterpret_cast<uchar2*>(pilots + (b0 + r) * n)[lane] = make_uchar2(tpil[r * n + 2 * lane], tpil[r * n + 2 * lane + 1]);
-        }
         {
             uint8_t* gk = s.sess_idx + b0 * n;
             const int nbytes = nv * n, nvec = nbytes >> 4;
             for (int c = lane; c < nvec; c += 32) reinterpret_cast<uint4*>(gk)[c] = reinterpret_cast<const uint4*>(tk)[c];
             for (int c = (nvec << 4) + lane; c < nbytes; c += 32) gk[c] = tk[c];
+        }
+        const float ts_new = (float)((double)tn / (double)kEpisode);            // env.py:392 (same t for a lock-step tile row)
+        for (int r0 = 0; r0 < nv; r0 += 8) {
+            float tail0[8], tail1[8];
+            int arr8 = 0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int r = min(r0 + u, kTileE - 1);
+                const int md_r = __shfl_sync(kFull, md, r), tn_r = __shfl_sync(kFull, tn, r);
+                arr8 |= __shfl_sync(kFull, (int)autoreset, r) << u;
+                tail0[u] = tail1[u] = 0.f;
+                if (r0 + u < nv && ((commit_mask >> r) & 1u)) {
+                    const float* row = m.moer + ((long long)md_r * SG_EV_MOER_ROWS + tn_r) * SG_EV_MOER_COLS;
+                    if (lane < kf) tail0[u] = __ldg(row + 1 + lane); else if (lane == kf) tail0[u] = __ldg(row);
+                    const int e = lane + 32;
+                    if (e < kf) tail1[u] = __ldg(row + 1 + e); else if (e == kf) tail1[u] = __ldg(row);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int r = r0 + u;
+                if (r >= nv || !((commit_mask >> r) & 1u)) continue;
+                const bool ar = (arr8 >> u) & 1;
+                const float ts_r = __shfl_sync(kFull, ts_new, r);
+                float* orow = (ar && final_obs != nullptr) ? final_obs + (b0 + r) * OBS : obs + (b0 + r) * OBS;
+                if (!(ar && final_obs == nullptr)) {                  // the step's own observation (terminal one if auto-reset)
+                    if (col) {
+                        stg_stream_f2(reinterpret_cast<float2*>(orow) + lane,
+                                      make_float2(tact[r * RS + 2 * lane], tact[r * RS + 2 * lane + 1]));
+                        stg_stream_f2(reinterpret_cast<float2*>(orow + n) + lane,
+                                      make_float2((float)test[r * RS + 2 * lane], (float)test[r * RS + 2 * lane + 1]));
+                    }
+                    if (lane <= kf) orow[2 * n + lane] = tail0[u]; else if (lane == kf + 1) orow[2 * n + lane] = ts_r;
+                    if (lane + 32 <= kf) orow[2 * n + lane + 32] = tail1[u]; else if (lane + 32 == kf + 1) orow[2 * n + lane + 32] = ts_r;
+                }
+                if (ar) {                                             // reset observation of the next episode
+                    const int mdo_r = __shfl_sync(kFull, md_out, r);
+                    const float* row = m.moer + ((long long)mdo_r * SG_EV_MOER_ROWS) * SG_EV_MOER_COLS;
+                    float* o2 = obs + (b0 + r) * OBS;
+                    if (col) {
+                        stg_stream_f2(reinterpret_cast<float2*>(o2) + lane, make_float2(0.f, 0.f));
+                        stg_stream_f2(reinterpret_cast<float2*>(o2 + n) + lane, make_float2(0.f, 0.f));
+                    }
+#pragma unroll
+                    for (int pass = 0; pass < 2; ++pass) {
+                        const int e = lane + 32 * pass;
+                        if (e < kf + 2) o2[2 * n + e] = e < kf ? __ldg(row + 1 + e) : (e == kf ? __ldg(row) : 0.f);
+                    }
+                }
+                if (pilots != nullptr && col)
+                    reinterpret_cast<uchar2*>(pilots + (b0 + r) * n)[lane] = make_uchar2(tpil[r * n + 2 * lane], tpil[r * n + 2 * lane + 1]);
+            }
         }
         __syncwarp();
     }
