@@ -136,6 +136,11 @@ typedef struct sg_ev_model {
     const double*  magnitudes;    /* [device] [16] limits in A, zero-padded                    */
     const void*    sessions;      /* [device] [D, K, n] 16-byte records (sg_ev_session)        */
     const float*   moer;          /* [device] [Dm, 289, 37]                                   */
+    const uint32_t* arrivals;     /* [device] [D, max_day_sessions + 1] the day's sessions sorted by
+                                     arrival: arrival | station << 16 | slot << 24, terminated by
+                                     0x7fff entries; NULL disables the event-driven kernel          */
+    int32_t max_day_sessions;     /* row length of `arrivals` minus the terminator                  */
+    int32_t reserved;
 } sg_ev_model;
 
 typedef struct sg_ev_state {
@@ -143,8 +148,10 @@ typedef struct sg_ev_state {
     uint8_t* sess_idx;    /* [device] [B, n] slot of the station's current-or-next session;   */
                           /*   255 = hint: no session left at this station today              */
     int32_t* clock;       /* [device] [B, 4] {t (0..288, env.py:168), day (trace index in     */
-                          /*   [0,D)), moer_day (MOER table index in [0,Dm)), reserved}        */
+                          /*   [0,D)), moer_day (MOER table index in [0,Dm)), arrival cursor  */
+                          /*   (sessions of the day with arrival <= t)}                        */
     double*  breakdown;   /* [device] [B, 3] cumulative profit, carbon_cost, excess_charge    */
+    uint64_t* occ;        /* [device] [B] bit i set: station i has a plugged-in session now    */
 } sg_ev_state;
 
 /* status bits written per env by sg_ev_step */
@@ -156,7 +163,7 @@ typedef struct sg_ev_state {
 #define SG_EV_ACTION_I64      1   /* DiscreteActionWrapper input (wrappers.py:43-45)          */
 #define SG_EV_FLAG_AUTORESET  16  /* on done: advance day (mod D), reset state, obs = reset obs */
 #define SG_EV_FLAG_GENERIC_KERNEL 256 /* use the generic warp-per-env kernel                        */
-#define SG_EV_FLAG_WARP_KERNEL    512 /* use the specialised warp-per-env kernel instead of the tile kernel */
+#define SG_EV_FLAG_TILE_KERNEL    512 /* use the dense tile kernel instead of the event-driven one       */
 
 /* reset(): env.py:293-338 for envs whose `reset_mask` byte is non-zero (NULL = all).
  * `day_in`/`moer_day_in` pick the trace/MOER table (the seed->day map is host logic,

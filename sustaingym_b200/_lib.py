@@ -24,7 +24,7 @@ SG_EV_ACTION_F32 = 0
 SG_EV_ACTION_I64 = 1
 SG_EV_FLAG_AUTORESET = 16
 SG_EV_FLAG_GENERIC_KERNEL = 256
-SG_EV_FLAG_WARP_KERNEL = 512
+SG_EV_FLAG_TILE_KERNEL = 512
 SG_BUILDING_FLAG_AUTORESET = 16
 
 _vp = C.c_void_p
@@ -46,13 +46,14 @@ class EVModel(C.Structure):
         ("n_stations", _i32), ("n_classes", _i32), ("n_constraints", _i32), ("moer_steps", _i32),
         ("max_sessions", _i32), ("n_days", _i32), ("n_moer_days", _i32), ("project", _i32),
         ("station_class", _vp), ("station_type", _vp), ("con_re", _vp), ("con_im", _vp),
-        ("magnitudes", _vp), ("sessions", _vp), ("moer", _vp),
+        ("magnitudes", _vp), ("sessions", _vp), ("moer", _vp), ("arrivals", _vp),
+        ("max_day_sessions", _i32), ("reserved", _i32),
     ]
 
 
 class EVState(C.Structure):
     _fields_ = [
-        ("delivered", _vp), ("sess_idx", _vp), ("clock", _vp), ("breakdown", _vp),
+        ("delivered", _vp), ("sess_idx", _vp), ("clock", _vp), ("breakdown", _vp), ("occ", _vp),
     ]
 
 

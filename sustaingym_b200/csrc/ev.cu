@@ -827,13 +827,30 @@ __device__ __forceinline__ void ev_env_step(const sg_ev_model& m, const sg_ev_st
             }
         }
     }
+    // occupancy mask (bit i: station i has a plugged-in session at the new time) and arrival cursor
+    // of the event-driven kernel — derived state every kernel keeps consistent
+    unsigned occ_lo, occ_hi;
+    {
+        bool pln[2];
+#pragma unroll
+        for (int p = 0; p < 2; ++p) pln[p] = !autoreset && valid[p] && ses[p].arr <= tn && tn < ses[p].dep;
+        const unsigned long long mine = ((unsigned long long)pln[0] << (i0 & 63)) | ((unsigned long long)pln[1] << ((i0 + 1) & 63));
+        occ_lo = __reduce_or_sync(kFull, (unsigned)(mine & 0xffffffffull));
+        occ_hi = __reduce_or_sync(kFull, (unsigned)(mine >> 32));
+    }
     if (lane == 0) {
         // cumulative reward breakdown (env.py:460-462); cleared on the first step of an episode so
         // that after an auto-reset the finished episode's totals stay readable until the next step
         double* bd = s.breakdown + b * 3;
         if (t == 0) { bd[0] = profit; bd[1] = carbon; bd[2] = excess_charge; }
         else { bd[0] += profit; bd[1] += carbon; bd[2] += excess_charge; }
-        *reinterpret_cast<int4*>(s.clock + b * 4) = make_int4(autoreset ? 0 : tn, day, md, clk.w);
+        int nidx = autoreset ? 0 : clk.w;
+        if (!autoreset && m.arrivals != nullptr) {
+            const unsigned* arow = m.arrivals + (long long)clk.y * (m.max_day_sessions + 1);
+            while ((int)(__ldg(arow + nidx) & 0x7fffu) <= tn) ++nidx;
+        }
+        if (s.occ != nullptr) s.occ[b] = ((unsigned long long)occ_hi << 32) | occ_lo;
+        *reinterpret_cast<int4*>(s.clock + b * 4) = make_int4(autoreset ? 0 : tn, day, md, nidx);
         reward[b] = rew;
         done[b] = dn ? 1 : 0;
         if (status != nullptr) status[b] = (uint8_t)st;
@@ -844,291 +861,7 @@ __device__ __forceinline__ void ev_env_step(const sg_ev_model& m, const sg_ev_st
 }
 
 // =================================================================================================
-// Specialised main kernel (the BASELINE configuration and anything shaped like it): n even,
-// <= NC classes of <= 63 stations, <= 8... J <= 32 constraints handled one per lane, f32 or i64
-// actions, MODE 0 / 1.  Same arithmetic as ev_env_step, restructured for instruction count:
-//   * per-lane constants (class, EVSE type, packing shifts, this lane's constraint row) live in
-//     registers across the persistent env loop;
-//   * both class-sum reductions (2^-10 fixed-point actions, integer pilots) use 16-bit fields,
-//     two classes per REDUX;
-//   * charging uses per-pilot lookup tables (built with the same div_c sequence, so bit-equal)
-//     whenever neither battery limit can bind (more than 2 kWh of head-room);
-//   * the next env's clock/action/state rows are prefetched while the current one is computed.
-// =================================================================================================
-struct EvFastShared {
-    double rate[40];       // A delivered for an integer pilot when the battery does not limit it
-    double energy[40];     // kWh per period for that pilot
-    double margin[32];     // quantisation margin of the fixed-point feasibility test, per constraint
-    double stat[11 * kWarpsPerBlock];
-    EvShared base;
-};
-
-constexpr double kFix10 = 1024.0, kFix10Inv = 1.0 / 1024.0;
-
-template <int NC>
-__device__ __forceinline__ void class_sums16(unsigned v0, unsigned v1, int cls0, int cls1, double (&S)[NC]) {
-#pragma unroll
-    for (int w = 0; w < (NC + 1) / 2; ++w) {
-        const unsigned part = ((cls0 >> 1) == w ? v0 << ((cls0 & 1) * 16) : 0u) +
-                              ((cls1 >> 1) == w ? v1 << ((cls1 & 1) * 16) : 0u);
-        const unsigned tot = __reduce_add_sync(kFull, part);
-        S[2 * w] = (double)(tot & 0xffffu);
-        if (2 * w + 1 < NC) S[2 * w + 1] = (double)(tot >> 16);
-    }
-}
-
-#ifndef SG_EV_FAST_MINBLOCKS
-#define SG_EV_FAST_MINBLOCKS 2
-#endif
-template <int MODE, int NC>
-__global__ void __launch_bounds__(kThreads, SG_EV_FAST_MINBLOCKS)
-ev_step_fast_kernel(const sg_ev_model m, const sg_ev_state s, const long long B, const void* __restrict__ action,
-                    const int flags, const int bins, float* __restrict__ obs, double* __restrict__ reward,
-                    uint8_t* __restrict__ done, uint8_t* __restrict__ pilots, float* __restrict__ final_obs,
-                    uint8_t* __restrict__ status, double* __restrict__ stats, int32_t* __restrict__ todo) {
-    __shared__ EvFastShared fs;
-    load_shared(m, fs.base);
-    const int n = m.n_stations, kf = m.moer_steps, OBS = 2 * n + kf + 2, J = m.n_constraints, K = m.max_sessions;
-    if (threadIdx.x <= 32) {
-        const double pp = div_c((double)threadIdx.x * kVoltage, 1000.0, kInv1000);
-        const double rate = div_c(pp * 1000.0, kVoltage, kInv208);
-        fs.rate[threadIdx.x] = rate;
-        fs.energy[threadIdx.x] = div_c(rate * kVoltage, 1000.0, kInv1000) * kPeriodH;
-    }
-    if (threadIdx.x < 32) {
-        double mg = 1e-9;
-        if ((int)threadIdx.x < J) {
-            for (int c = 0; c < NC; ++c) {
-                int cnt = 0;
-                for (int i = 0; i < n; ++i) cnt += (fs.base.cls[i] == c);
-                const double re = fs.base.con_re[threadIdx.x * kMC + c], im = fs.base.con_im[threadIdx.x * kMC + c];
-                mg += sqrt(re * re + im * im) * cnt * (0.5 * kFix10Inv);
-            }
-        }
-        fs.margin[threadIdx.x] = mg;
-    }
-    __syncthreads();
-
-    const int lane = threadIdx.x & 31;
-    const int i0 = 2 * lane;
-    const bool valid = i0 < n;                               // n is even: both stations or none
-    const int cls0 = valid ? fs.base.cls[i0] : 254, cls1 = valid ? fs.base.cls[i0 + 1] : 254;
-    const int type0 = valid ? fs.base.type[i0] : 0, type1 = valid ? fs.base.type[i0 + 1] : 0;
-    // this lane's constraint (lane < J), normalised limit and squared thresholds
-    double cre[NC], cim[NC];
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-        cre[c] = lane < J ? fs.base.con_re[lane * kMC + c] : 0.0;
-        cim[c] = lane < J ? fs.base.con_im[lane * kMC + c] : 0.0;
-    }
-    const double lim = lane < J ? fs.base.lim[lane] : 1e300;
-    const double lim2 = lim * lim;
-    const double rfe = lane < J ? lim * (1.0 / kActionScale) - fs.margin[lane] : 1e300;
-    const double rfe2 = rfe > 0.0 ? rfe * rfe : -1.0;
-    const bool i64 = (flags & 1) == SG_EV_ACTION_I64;
-    const float inv_bins = 0.f;
-    (void)inv_bins;
-
-    const long long stride = (long long)gridDim.x * kWarpsPerBlock;
-    long long b = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
-    StatsAcc acc;
-
-    // ---- software pipeline: rows of env b are loaded one iteration ahead --------------------------
-    int4 clk_n = make_int4(0, 0, 0, 0);
-    float2 act_n = make_float2(0.f, 0.f);
-    double2 del_n = make_double2(0.0, 0.0);
-    uchar2 k_n = make_uchar2(0, 0);
-    auto prefetch = [&](long long bb) {
-        if (bb < B) {
-            clk_n = *reinterpret_cast<const int4*>(s.clock + bb * 4);
-            if (valid) {
-                if (i64) {
-                    const long long* ap = reinterpret_cast<const long long*>(action) + bb * n + i0;
-                    act_n.x = __fdiv_rn((float)ap[0], (float)(bins - 1));     // wrappers.py:45
-                    act_n.y = __fdiv_rn((float)ap[1], (float)(bins - 1));
-                } else {
-                    act_n = ldg_stream_f2(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(action) + bb * n + i0));
-                }
-                del_n = *reinterpret_cast<const double2*>(s.delivered + bb * n + i0);
-                k_n = *reinterpret_cast<const uchar2*>(s.sess_idx + bb * n + i0);
-            }
-        }
-    };
-    prefetch(b);
-    const uint4* recs = reinterpret_cast<const uint4*>(m.sessions);
-    auto load_rec = [&](int base, int k, int i, int& arr, int& dep, int& est, double& energy) {
-        if (k >= K) { arr = dep = est = kEmpty; energy = 0.0; return; }
-        const uint4 r = __ldg(recs + (base + k * n + i));
-        arr = (int)(short)(r.x & 0xffffu);
-        dep = (int)(short)(r.x >> 16);
-        est = (int)(short)(r.y & 0xffffu);
-        energy = __hiloint2double((int)r.w, (int)r.z);
-    };
-
-    for (; b < B; b += stride) {
-        const int4 clk = clk_n;
-        const float2 act = act_n;
-        double del0 = del_n.x, del1 = del_n.y;
-        int k0 = k_n.x, k1 = k_n.y;
-        const int t = clk.x;
-        int day = clk.y, md = clk.z;
-        // session records of the two stations (needs day and k: issue before the prefetch so the
-        // dependent loads are in flight together with the next env's rows)
-        int arr0 = kEmpty, dep0 = kEmpty, est0 = kEmpty, arr1 = kEmpty, dep1 = kEmpty, est1 = kEmpty;
-        double en0 = 0.0, en1 = 0.0;
-        const int sbase = day * K * n;
-        if (valid) {
-            load_rec(sbase, k0, i0, arr0, dep0, est0, en0);
-            load_rec(sbase, k1, i0 + 1, arr1, dep1, est1, en1);
-        }
-        prefetch(b + stride);
-        if (t >= kEpisode) {            // finished episode that was not reset: no-op, stays terminal
-            if (lane == 0) { reward[b] = 0.0; done[b] = 1; if (status) status[b] = 0; }
-            continue;
-        }
-        const bool pl0 = valid && t >= 1 && arr0 <= t && t < dep0;
-        const bool pl1 = valid && t >= 1 && arr1 <= t && t < dep1;
-
-        // ---- action -> normalised pilot x (env.py:363-366) ---------------------------------------
-        double x0 = (double)act.x, x1 = (double)act.y;
-        if constexpr (MODE == 1) {
-            const double rem0 = en0 - del0, rem1 = en1 - del1;
-            const float dem0 = (pl0 && rem0 > kFullEps) ? (float)rem0 : 0.f;
-            const float dem1 = (pl1 && rem1 > kFullEps) ? (float)rem1 : 0.f;
-            x0 = valid ? fmin(fmax(x0, 0.0), upper_bound(dem0)) : 0.0;
-            x1 = valid ? fmin(fmax(x1, 0.0), upper_bound(dem1)) : 0.0;
-            // conservative feasibility test on 2^-10 fixed-point class sums
-            double S[NC];
-            class_sums16<NC>(__double2uint_rn(x0 * kFix10), __double2uint_rn(x1 * kFix10), cls0, cls1, S);
-            double wr = 0.0, wi = 0.0;
-#pragma unroll
-            for (int c = 0; c < NC; ++c) { wr = fma(cre[c], S[c], wr); wi = fma(cim[c], S[c], wi); }
-            const bool bad = lane < J && !(fma(wr, wr, wi * wi) * (kFix10Inv * kFix10Inv) <= rfe2);
-            if (__any_sync(kFull, bad)) {
-                if (lane == 0) todo[2 + atomicAdd(todo, 1)] = (int)b;
-                continue;                                   // the work-list kernel redoes this env
-            }
-        }
-
-        // ---- schedule (env.py:368-378) ---------------------------------------------------------------
-        const double am0 = x0 * kActionScale, am1 = x1 * kActionScale;
-        const double pil0 = !valid ? 0.0 : (type0 == 0 ? (am0 >= 6.0 ? rint(am0) : 0.0) : rint(am0 * 0.125) * 8.0);
-        const double pil1 = !valid ? 0.0 : (type1 == 0 ? (am1 >= 6.0 ? rint(am1) : 0.0) : rint(am1 * 0.125) * 8.0);
-        const unsigned pi0 = (unsigned)__double2int_rn(pil0), pi1 = (unsigned)__double2int_rn(pil1);
-
-        // ---- charging (acnsim update_pilots -> Linear2StageBattery._charge_stepwise) ------------------
-        double rate_sum = 0.0;
-        auto charge_one = [&](const bool pl, const double energy, double& del, const double pilot, const unsigned pi) {
-            if (!pl) return;
-            const double charge = fmax(0.0, kCapacity - energy) + del;
-            if (kCapacity - charge > 2.0) {                  // neither battery limit can bind: table path
-                del += fs.energy[pi];
-                rate_sum += fs.rate[pi];
-            } else {
-                const double rate_to_full = div_c(kCapacity - charge, kPeriodH, kInvPeriodH);
-                const double soc = div_c(charge, kCapacity, kInv100);
-                const double p_pilot = div_c(pilot * kVoltage, 1000.0, kInv1000);
-                const double cap2 = soc < kTransitionSoc ? kMaxPower
-                                                         : div_c(1.0 - soc, kOneMinusTrans, kInvOMT) * kMaxPower;
-                const double power = fmin(fmin(p_pilot, cap2), rate_to_full);
-                const double rate = div_c(power * 1000.0, kVoltage, kInv208);
-                del += div_c(rate * kVoltage, 1000.0, kInv1000) * kPeriodH;
-                rate_sum += rate;
-            }
-        };
-        charge_one(pl0, en0, del0, pil0, pi0);
-        charge_one(pl1, en1, del1, pil1, pi1);
-        const double total_rate = warp_sum(rate_sum);
-
-        // ---- excess current from the rounded schedule (env.py:449-452) --------------------------------
-        double excess = 0.0;
-        {
-            double S[NC];
-            class_sums16<NC>(pi0, pi1, cls0, cls1, S);
-            double wr = 0.0, wi = 0.0;
-#pragma unroll
-            for (int c = 0; c < NC; ++c) { wr = fma(cre[c], S[c], wr); wi = fma(cim[c], S[c], wi); }
-            const double sq = fma(wr, wr, wi * wi);
-            const bool over = sq > lim2;                     // lanes >= J have lim2 = inf
-            if (__any_sync(kFull, over)) excess = warp_sum(over ? fmax(0.0, sqrt(sq) - lim) : 0.0);
-        }
-
-        // ---- advance time, drain events with timestamp <= t+1: Unplug (0) before Plugin (10) -----------
-        const int tn = t + 1;
-        while (valid && dep0 <= tn && arr0 != kEmpty) { k0 += 1; del0 = 0.0; load_rec(sbase, k0, i0, arr0, dep0, est0, en0); }
-        while (valid && dep1 <= tn && arr1 != kEmpty) { k1 += 1; del1 = 0.0; load_rec(sbase, k1, i0 + 1, arr1, dep1, est1, en1); }
-        const double r0 = en0 - del0, r1 = en1 - del1;
-        const bool ac0 = valid && arr0 <= tn && tn < dep0 && r0 > kFullEps;     // Interface.active_sessions()
-        const bool ac1 = valid && arr1 <= tn && tn < dep1 && r1 > kFullEps;
-        float2 dem_o = make_float2(ac0 ? (float)r0 : 0.f, ac1 ? (float)r1 : 0.f);
-        float2 est_o = make_float2(ac0 ? (float)(est0 - tn) : 0.f, ac1 ? (float)(est1 - tn) : 0.f);
-        const bool dn = tn >= kEpisode;
-
-        // ---- reward (env.py:444-462) -------------------------------------------------------------------
-        const float* mrow = m.moer + ((long long)md * SG_EV_MOER_ROWS + tn) * SG_EV_MOER_COLS;
-        const float moer0f = __ldg(mrow);
-        const double profit = kProfitFactor * total_rate;
-        const double excess_charge = excess * kViolationFactor;
-        const double carbon = kCarbonFactor * total_rate * (double)moer0f;
-        const double rew = profit - carbon - excess_charge;
-        const bool autoreset = dn && (flags & SG_EV_FLAG_AUTORESET);
-
-        // ---- observation row: demands | est_departures | forecasted_moer | prev_moer | timestep --------
-        auto write_obs = [&](float* orow, const float* row, const int tstep) {
-            if (valid) {
-                stg_stream_f2(reinterpret_cast<float2*>(orow + i0), dem_o);
-                stg_stream_f2(reinterpret_cast<float2*>(orow + n + i0), est_o);
-            }
-            float* tail = orow + 2 * n;
-#pragma unroll
-            for (int pass = 0; pass < 2; ++pass) {
-                const int e = lane + 32 * pass;
-                if (e < kf + 2) {
-                    float v;
-                    if (e < kf) v = __ldg(row + 1 + e);
-                    else if (e == kf) v = __ldg(row);
-                    else v = (float)((double)tstep / (double)kEpisode);     // env.py:392
-                    tail[e] = v;
-                }
-            }
-        };
-        if (!autoreset) {
-            write_obs(obs + b * OBS, mrow, tn);
-        } else {
-            if (final_obs != nullptr) write_obs(final_obs + b * OBS, mrow, tn);   // terminal observation
-            day = (day + 1) % m.n_days;                      // sequential days, event_generation.py:284-291
-            md = (md + 1) % m.n_moer_days;
-            dem_o = make_float2(0.f, 0.f); est_o = make_float2(0.f, 0.f);
-            k0 = k1 = 0; del0 = del1 = 0.0;
-            write_obs(obs + b * OBS, m.moer + ((long long)md * SG_EV_MOER_ROWS) * SG_EV_MOER_COLS, 0);
-        }
-
-        // ---- state write-back -----------------------------------------------------------------------------
-        if (valid) {
-            *reinterpret_cast<double2*>(s.delivered + b * n + i0) = make_double2(del0, del1);
-            *reinterpret_cast<uchar2*>(s.sess_idx + b * n + i0) = make_uchar2((unsigned char)k0, (unsigned char)k1);
-            if (pilots != nullptr)
-                *reinterpret_cast<uchar2*>(pilots + b * n + i0) = make_uchar2((unsigned char)pi0, (unsigned char)pi1);
-        }
-        if (lane == 0) {
-            double* bd = s.breakdown + b * 3;
-            if (t == 0) { bd[0] = profit; bd[1] = carbon; bd[2] = excess_charge; }
-            else { bd[0] += profit; bd[1] += carbon; bd[2] += excess_charge; }
-            *reinterpret_cast<int4*>(s.clock + b * 4) = make_int4(autoreset ? 0 : tn, day, md, clk.w);
-            reward[b] = rew;
-            done[b] = dn ? 1 : 0;
-            if (status != nullptr) status[b] = 0;
-            if (stats != nullptr) acc.add(rew, dn, profit, carbon, excess_charge);
-        }
-    }
-    if (stats != nullptr) {
-        __syncthreads();
-        stats_flush_block(acc, stats, fs.stat);
-    }
-}
-
-// =================================================================================================
-// Tile kernel (default main kernel).  The warp-per-env kernels above spend ~800 warp instructions
+// Tile kernel (dense main kernel: default without projection, optional with it).  The warp-per-env kernels above spend ~800 warp instructions
 // per env because every per-env scalar operation is replicated over 32 lanes and both stations of
 // a lane run the f64 battery path although ~85 % of the stations are empty.  Here one warp owns a
 // TILE of 32 consecutive envs and one THREAD advances one env:
@@ -1367,6 +1100,7 @@ ev_step_tile_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
         }
         // pass B: pilots, charging, events, new demands / departures for the listed stations
         double rate_sum = 0.0;
+        unsigned long long occ_new = 0ull;
         {
             const int nmax = __reduce_max_sync(kFull, commit ? nl : 0);
             for (int e0 = 0; e0 < nmax; e0 += V) {
@@ -1423,7 +1157,9 @@ ev_step_tile_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
                     if (moved) myk[i] = (arr == kEmpty) ? 255 : (uint8_t)k;
                     if (plugged || moved) s.delivered[b * n + i] = del;
                     const double rem = energy - del;
-                    const bool active = arr <= tn && tn < dep && rem > kFullEps;    // Interface.active_sessions()
+                    const bool pln = arr <= tn && tn < dep;
+                    const bool active = pln && rem > kFullEps;                     // Interface.active_sessions()
+                    if (pln) occ_new |= 1ull << i;
                     myact[i] = active ? (float)rem : 0.f;
                     myest[i] = active ? (short)(est - tn) : (short)0;
                 }
@@ -1453,13 +1189,19 @@ ev_step_tile_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
             double* bd = s.breakdown + b * 3;
             if (t == 0) { bd[0] = profit; bd[1] = carbon; bd[2] = excess_charge; }
             else { bd[0] += profit; bd[1] += carbon; bd[2] += excess_charge; }
+            int nidx = clk.w;
+            if (m.arrivals != nullptr) {
+                const unsigned* arow = m.arrivals + (long long)day * (m.max_day_sessions + 1);
+                while ((int)(__ldg(arow + nidx) & 0x7fffu) <= tn) ++nidx;
+            }
             if (autoreset) {
                 day = (day + 1) % m.n_days;                           // sequential days, event_generation.py:284-291
                 md_out = (md + 1) % m.n_moer_days;
-                t_out = 0;
+                t_out = 0; nidx = 0; occ_new = 0ull;
                 for (int i = 0; i < n; ++i) myk[i] = 0;               // delivered is already 0: every session ended
             }
-            *reinterpret_cast<int4*>(s.clock + b * 4) = make_int4(t_out, day, md_out, clk.w);
+            if (s.occ != nullptr) s.occ[b] = occ_new;
+            *reinterpret_cast<int4*>(s.clock + b * 4) = make_int4(t_out, day, md_out, nidx);
             reward[b] = rew;
             done[b] = dn ? 1 : 0;
             if (status != nullptr) status[b] = 0;
@@ -1547,6 +1289,323 @@ ev_step_tile_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
     }
 }
 
+// =================================================================================================
+// Event-driven kernel (default main kernel when the action projection is on).
+//
+// With the projection on, a station without a plugged-in EV has upper bound 0 (env.py:188-189): its
+// pilot is 0, it delivers nothing and its observation entries are 0.  So one step only has to
+// touch the OCCUPIED stations (~15 % of the 54).  Per env the engine keeps a 64-bit occupancy mask
+// and a cursor into the day's arrival-sorted session list; one thread advances one env:
+//   * walk the set bits of the mask: sparse loads of sess_idx / action / delivered and the session
+//     record, battery arithmetic, sparse stores; no shared-memory tiles -> high occupancy;
+//   * departures clear bits, arrivals (cursor) set them;
+//   * the observation rows are zero-filled with coalesced vector stores by the whole warp and the
+//     few non-zero entries are patched by the owning thread; the MOER tails are copied row by row.
+// Envs whose clipped action violates the network are queued for the solver kernel untouched.
+// =================================================================================================
+struct SparseShared {
+    double con_re[SG_EV_MAX_CONSTRAINTS * kMC], con_im[SG_EV_MAX_CONSTRAINTS * kMC], lim[SG_EV_MAX_CONSTRAINTS];
+    double rate[40], energy[40];
+    uint8_t cls[SG_EV_MAX_STATIONS], type[SG_EV_MAX_STATIONS];
+};
+constexpr int kSparseWarps = 4;
+
+__global__ void __launch_bounds__(kSparseWarps * 32, 4)
+ev_step_sparse_kernel(const sg_ev_model m, const sg_ev_state s, const long long B, const void* __restrict__ action,
+                      const int flags, const int bins, float* __restrict__ obs, double* __restrict__ reward,
+                      uint8_t* __restrict__ done, uint8_t* __restrict__ pilots, float* __restrict__ final_obs,
+                      uint8_t* __restrict__ status, double* __restrict__ stats, int32_t* __restrict__ todo) {
+    __shared__ SparseShared sh;
+    __shared__ double sstat[11 * kSparseWarps];
+    const int n = m.n_stations, kf = m.moer_steps, OBS = 2 * n + kf + 2, C = m.n_classes, J = m.n_constraints;
+    const int K = m.max_sessions;
+    for (int i = threadIdx.x; i < SG_EV_MAX_CONSTRAINTS * kMC; i += blockDim.x) { sh.con_re[i] = m.con_re[i]; sh.con_im[i] = m.con_im[i]; }
+    if (threadIdx.x < SG_EV_MAX_CONSTRAINTS) sh.lim[threadIdx.x] = m.magnitudes[threadIdx.x];
+    if (threadIdx.x < SG_EV_MAX_STATIONS) {
+        sh.cls[threadIdx.x] = (int)threadIdx.x < n ? m.station_class[threadIdx.x] : 0;
+        sh.type[threadIdx.x] = (int)threadIdx.x < n ? m.station_type[threadIdx.x] : 0;
+    }
+    if (threadIdx.x <= 32) {
+        const double pp = div_c((double)threadIdx.x * kVoltage, 1000.0, kInv1000);
+        const double rate = div_c(pp * 1000.0, kVoltage, kInv208);
+        sh.rate[threadIdx.x] = rate;
+        sh.energy[threadIdx.x] = div_c(rate * kVoltage, 1000.0, kInv1000) * kPeriodH;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const bool i64 = (flags & 1) == SG_EV_ACTION_I64;
+    const uint4* recs = reinterpret_cast<const uint4*>(m.sessions);
+    const long long ntiles = (B + 31) / 32;
+    const long long wstride = (long long)gridDim.x * kSparseWarps;
+    const bool col = 2 * lane < n;
+    StatsAcc acc;
+
+    struct Stn { int i, k, arr, dep, est; double energy, del; float a; bool plugged; };
+    constexpr int V = 4;
+
+    for (long long tile = (long long)blockIdx.x * kSparseWarps + (threadIdx.x >> 5); tile < ntiles; tile += wstride) {
+        const long long b0 = tile * 32;
+        const int nv = (int)min(32ll, B - b0);
+        const long long b = b0 + lane;
+        const bool env = lane < nv;
+        int4 clk = make_int4(kEpisode, 0, 0, 0);
+        unsigned long long occ = 0ull;
+        if (env) { clk = *reinterpret_cast<const int4*>(s.clock + b * 4); occ = s.occ[b]; }
+        const int t = clk.x, tn = t + 1;
+        int day = clk.y, md = clk.z, nidx = clk.w;
+        const bool live = env && t < kEpisode;
+        bool commit = live;
+        if (!live) occ = 0ull;
+        const int sbase = day * K * n;
+        float moer0f = 0.f;
+        if (live) moer0f = __ldg(m.moer + ((long long)md * SG_EV_MOER_ROWS + tn) * SG_EV_MOER_COLS);
+
+        // batch loader over the set bits of `mask` (V stations, all loads of a level in flight together)
+        auto load_batch = [&](unsigned long long& mask, Stn (&q)[V]) {
+#pragma unroll
+            for (int u = 0; u < V; ++u) {
+                q[u].i = -1;
+                if (mask) { q[u].i = __ffsll((long long)mask) - 1; mask &= mask - 1; }
+            }
+#pragma unroll
+            for (int u = 0; u < V; ++u) {
+                q[u].k = 255; q[u].a = 0.f; q[u].del = 0.0;
+                if (q[u].i >= 0) {
+                    const long long o = b * n + q[u].i;
+                    q[u].k = s.sess_idx[o];
+                    q[u].del = s.delivered[o];
+                    q[u].a = i64 ? __fdiv_rn((float)reinterpret_cast<const long long*>(action)[o], (float)(bins - 1))
+                                 : __ldg(reinterpret_cast<const float*>(action) + o);
+                }
+            }
+            uint4 raw[V];
+#pragma unroll
+            for (int u = 0; u < V; ++u) {
+                raw[u] = make_uint4(0x7fff7fffu, 0x7fffu, 0u, 0u);
+                if (q[u].i >= 0 && q[u].k < K) raw[u] = __ldg(recs + (sbase + q[u].k * n + q[u].i));
+            }
+#pragma unroll
+            for (int u = 0; u < V; ++u) {
+                q[u].arr = (int)(short)(raw[u].x & 0xffffu);
+                q[u].dep = (int)(short)(raw[u].x >> 16);
+                q[u].est = (int)(short)(raw[u].y & 0xffffu);
+                q[u].energy = __hiloint2double((int)raw[u].w, (int)raw[u].z);
+                q[u].plugged = q[u].i >= 0 && t >= 1 && q[u].arr <= t && t < q[u].dep;
+            }
+        };
+        auto clipped = [&](const Stn& q) {
+            const double rem = q.energy - q.del;
+            const float dem = rem > kFullEps ? (float)rem : 0.f;                 // obs 'demands', env.py:388
+            return fmin(fmax((double)q.a, 0.0), upper_bound(dem));
+        };
+
+        // ---- pass A: class sums of the clipped action -> is it inside the network constraints? ----
+        {
+            double S[kMC];
+#pragma unroll
+            for (int c = 0; c < kMC; ++c) S[c] = 0.0;
+            unsigned long long mask = occ;
+            while (__any_sync(kFull, mask != 0ull)) {
+                Stn q[V];
+                load_batch(mask, q);
+#pragma unroll
+                for (int u = 0; u < V; ++u) {
+                    if (q[u].plugged) {
+                        const double x = clipped(q[u]);
+                        const int c = sh.cls[q[u].i];
+#pragma unroll
+                        for (int cc = 0; cc < kMC; ++cc) S[cc] += (cc == c) ? x : 0.0;
+                    }
+                }
+            }
+            if (live) {
+                bool ok = true;
+                for (int j = 0; j < J; ++j) {
+                    double wr = 0, wi = 0;
+#pragma unroll
+                    for (int c = 0; c < kMC; ++c) { wr = fma(sh.con_re[j * kMC + c], S[c], wr); wi = fma(sh.con_im[j * kMC + c], S[c], wi); }
+                    const double r = sh.lim[j] * (1.0 / kActionScale);
+                    ok = ok && (fma(wr, wr, wi * wi) <= r * r);
+                }
+                if (!ok) { commit = false; todo[2 + atomicAdd(todo, 1)] = (int)b; }
+            }
+        }
+        const unsigned commit_mask = __ballot_sync(kFull, commit);
+        const bool dn = tn >= kEpisode;
+        const bool autoreset = commit && dn && (flags & SG_EV_FLAG_AUTORESET);
+        const unsigned ar_mask = __ballot_sync(kFull, autoreset);
+
+        // ---- zero-fill the committed rows (coalesced); the owners patch the few non-zero entries ----
+        for (int r = 0; r < nv; ++r) {
+            if (!((commit_mask >> r) & 1u)) continue;
+            float* orow = (((ar_mask >> r) & 1u) && final_obs != nullptr) ? final_obs + (b0 + r) * OBS : obs + (b0 + r) * OBS;
+            if (col) {
+                stg_stream_f2(reinterpret_cast<float2*>(orow) + lane, make_float2(0.f, 0.f));
+                stg_stream_f2(reinterpret_cast<float2*>(orow + n) + lane, make_float2(0.f, 0.f));
+                if (pilots != nullptr) reinterpret_cast<uchar2*>(pilots + (b0 + r) * n)[lane] = make_uchar2(0, 0);
+            }
+        }
+        __syncwarp();
+        float* myrow = (autoreset && final_obs != nullptr) ? final_obs + b * OBS : obs + b * OBS;
+        const bool patch = commit && !(autoreset && final_obs == nullptr);      // terminal obs kept only if asked for
+
+        // ---- pass B: pilots, charging, departures for the occupied stations -------------------------
+        double rate_sum = 0.0;
+        int P[kMC];
+#pragma unroll
+        for (int c = 0; c < kMC; ++c) P[c] = 0;
+        unsigned long long occ_new = commit ? occ : 0ull;
+        {
+            unsigned long long mask = commit ? occ : 0ull;
+            while (__any_sync(kFull, mask != 0ull)) {
+                Stn q[V];
+                load_batch(mask, q);
+#pragma unroll
+                for (int u = 0; u < V; ++u) {
+                    if (q[u].i < 0) continue;
+                    const int i = q[u].i;
+                    double del = q[u].del;
+                    if (q[u].plugged) {
+                        const double pilot = to_pilot(clipped(q[u]), sh.type[i]);
+                        const int pi = __double2int_rn(pilot);
+                        const int c = sh.cls[i];
+#pragma unroll
+                        for (int cc = 0; cc < kMC; ++cc) P[cc] += (cc == c) ? pi : 0;
+                        if (pilots != nullptr && pi != 0) pilots[b * n + i] = (uint8_t)pi;
+                        const double charge = fmax(0.0, kCapacity - q[u].energy) + del;
+                        if (kCapacity - charge > 2.0) {              // neither battery limit can bind
+                            del += sh.energy[pi];
+                            rate_sum += sh.rate[pi];
+                        } else {
+                            const double rate_to_full = div_c(kCapacity - charge, kPeriodH, kInvPeriodH);
+                            const double soc = div_c(charge, kCapacity, kInv100);
+                            const double p_pilot = div_c(pilot * kVoltage, 1000.0, kInv1000);
+                            const double cap2 = soc < kTransitionSoc ? kMaxPower
+                                                                     : div_c(1.0 - soc, kOneMinusTrans, kInvOMT) * kMaxPower;
+                            const double power = fmin(fmin(p_pilot, cap2), rate_to_full);
+                            const double rate = div_c(power * 1000.0, kVoltage, kInv208);
+                            del += div_c(rate * kVoltage, 1000.0, kInv1000) * kPeriodH;
+                            rate_sum += rate;
+                        }
+                    }
+                    if (q[u].dep <= tn) {                             // Unplug event (timestamp = departure)
+                        occ_new &= ~(1ull << i);
+                        s.delivered[b * n + i] = 0.0;
+                    } else {
+                        if (q[u].plugged) s.delivered[b * n + i] = del;
+                        const double rem = q[u].energy - del;
+                        if (patch && rem > kFullEps) {                // Interface.active_sessions()
+                            myrow[i] = (float)rem;
+                            myrow[n + i] = (float)(q[u].est - tn);
+                        }
+                    }
+                }
+            }
+        }
+        // ---- arrivals: Plugin events with timestamp <= t+1 (after the Unplug events) ------------------
+        if (commit && !autoreset) {
+            const unsigned* arow = m.arrivals + (long long)day * (m.max_day_sessions + 1);
+            unsigned ent = __ldg(arow + nidx);
+            while ((int)(ent & 0x7fffu) <= tn) {
+                const int i = (ent >> 16) & 0xff, k = ent >> 24;
+                const uint4 r = __ldg(recs + (sbase + k * n + i));
+                const int dep = (int)(short)(r.x >> 16), est = (int)(short)(r.y & 0xffffu);
+                s.sess_idx[b * n + i] = (uint8_t)k;
+                if (dep > tn) {                                       // (zero-length sessions never charge)
+                    occ_new |= 1ull << i;
+                    const double energy = __hiloint2double((int)r.w, (int)r.z);
+                    if (patch && energy > kFullEps) { myrow[i] = (float)energy; myrow[n + i] = (float)(est - tn); }
+                }
+                ++nidx;
+                ent = __ldg(arow + nidx);
+            }
+        }
+        // ---- per-env epilogue ---------------------------------------------------------------------------
+        int md_out = md;
+        if (commit) {
+            double excess = 0.0;
+            for (int j = 0; j < J; ++j) {
+                double wr = 0, wi = 0;
+#pragma unroll
+                for (int c = 0; c < kMC; ++c) { wr = fma(sh.con_re[j * kMC + c], (double)P[c], wr); wi = fma(sh.con_im[j * kMC + c], (double)P[c], wi); }
+                const double lim = sh.lim[j], sq = fma(wr, wr, wi * wi);
+                if (sq > lim * lim) excess += fmax(0.0, sqrt(sq) - lim);
+            }
+            const double profit = kProfitFactor * rate_sum;
+            const double excess_charge = excess * kViolationFactor;
+            const double carbon = kCarbonFactor * rate_sum * (double)moer0f;
+            const double rew = profit - carbon - excess_charge;
+            double* bd = s.breakdown + b * 3;
+            if (t == 0) { bd[0] = profit; bd[1] = carbon; bd[2] = excess_charge; }
+            else { bd[0] += profit; bd[1] += carbon; bd[2] += excess_charge; }
+            int t_out = tn;
+            if (autoreset) {
+                day = (day + 1) % m.n_days;                           // sequential days, event_generation.py:284-291
+                md_out = (md + 1) % m.n_moer_days;
+                t_out = 0; nidx = 0; occ_new = 0ull;
+            }
+            s.occ[b] = occ_new;
+            *reinterpret_cast<int4*>(s.clock + b * 4) = make_int4(t_out, day, md_out, nidx);
+            reward[b] = rew;
+            done[b] = dn ? 1 : 0;
+            if (status != nullptr) status[b] = 0;
+            if (stats != nullptr) acc.add(rew, dn, profit, carbon, excess_charge);
+        } else if (env && t >= kEpisode) {                            // finished episode, not reset: stays terminal
+            reward[b] = 0.0; done[b] = 1;
+            if (status != nullptr) status[b] = 0;
+        }
+        // ---- MOER tails (and the reset rows of auto-reset envs), 8 rows of loads in flight -------------
+        const float ts_new = (float)((double)tn / (double)kEpisode);            // env.py:392
+        for (int r0 = 0; r0 < nv; r0 += 8) {
+            float tail0[8], tail1[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int r = min(r0 + u, 31);
+                const int md_r = __shfl_sync(kFull, md, r), tn_r = __shfl_sync(kFull, tn, r);
+                tail0[u] = tail1[u] = 0.f;
+                if (r0 + u < nv && ((commit_mask >> r) & 1u)) {
+                    const float* row = m.moer + ((long long)md_r * SG_EV_MOER_ROWS + tn_r) * SG_EV_MOER_COLS;
+                    if (lane < kf) tail0[u] = __ldg(row + 1 + lane); else if (lane == kf) tail0[u] = __ldg(row);
+                    const int e = lane + 32;
+                    if (e < kf) tail1[u] = __ldg(row + 1 + e); else if (e == kf) tail1[u] = __ldg(row);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int r = r0 + u;
+                if (r >= nv || !((commit_mask >> r) & 1u)) continue;
+                const bool ar = (ar_mask >> r) & 1u;
+                const float ts_r = __shfl_sync(kFull, ts_new, r);
+                if (!(ar && final_obs == nullptr)) {
+                    float* orow = (ar ? final_obs : obs) + (b0 + r) * OBS;
+                    if (lane <= kf) orow[2 * n + lane] = tail0[u]; else if (lane == kf + 1) orow[2 * n + lane] = ts_r;
+                    if (lane + 32 <= kf) orow[2 * n + lane + 32] = tail1[u]; else if (lane + 32 == kf + 1) orow[2 * n + lane + 32] = ts_r;
+                }
+                if (ar) {                                             // reset observation of the next episode
+                    const int mdo_r = __shfl_sync(kFull, md_out, r);
+                    const float* row = m.moer + ((long long)mdo_r * SG_EV_MOER_ROWS) * SG_EV_MOER_COLS;
+                    float* o2 = obs + (b0 + r) * OBS;
+                    if (col && final_obs != nullptr) {                // (already zero when the terminal obs is not kept)
+                        stg_stream_f2(reinterpret_cast<float2*>(o2) + lane, make_float2(0.f, 0.f));
+                        stg_stream_f2(reinterpret_cast<float2*>(o2 + n) + lane, make_float2(0.f, 0.f));
+                    }
+#pragma unroll
+                    for (int pass = 0; pass < 2; ++pass) {
+                        const int e = lane + 32 * pass;
+                        if (e < kf + 2) o2[2 * n + e] = e < kf ? __ldg(row + 1 + e) : (e == kf ? __ldg(row) : 0.f);
+                    }
+                    for (int i = lane; i < n; i += 32) s.sess_idx[(b0 + r) * n + i] = 0;    // new day: slot 0 everywhere
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (stats != nullptr) {
+        __syncthreads();
+        stats_flush_block(acc, stats, sstat);
+    }
+}
+
 // Persistent CTAs: every warp strides over the batch, so the table staging and the statistics
 // flush are paid once per warp instead of once per env.
 template <int MODE>
@@ -1615,7 +1674,8 @@ __global__ void ev_reset_kernel(const sg_ev_model m, const sg_ev_state s, const 
     const float* mrow = m.moer + ((long long)md * SG_EV_MOER_ROWS) * SG_EV_MOER_COLS;
     for (int e = lane; e < kf + 2; e += 32) orow[2 * n + e] = e < kf ? mrow[1 + e] : (e == kf ? mrow[0] : 0.f);
     if (lane == 0) {
-        s.clock[b * 4 + 0] = 0; s.clock[b * 4 + 1] = day; s.clock[b * 4 + 2] = md;
+        s.clock[b * 4 + 0] = 0; s.clock[b * 4 + 1] = day; s.clock[b * 4 + 2] = md; s.clock[b * 4 + 3] = 0;
+        if (s.occ != nullptr) s.occ[b] = 0ull;
         s.breakdown[b * 3] = s.breakdown[b * 3 + 1] = s.breakdown[b * 3 + 2] = 0.0;
     }
 }
@@ -1717,15 +1777,22 @@ int sg_ev_step(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, con
     if (sms <= 0) sms = 148;
     // persistent grid: 3 resident CTAs per SM (multiple of the SM count), fewer for tiny batches
     const unsigned grid = (unsigned)std::min<long long>((num_envs + sg::kWarpsPerBlock - 1) / sg::kWarpsPerBlock,
-                                                        (long long)sms * SG_EV_FAST_MINBLOCKS);
+                                                        (long long)sms * 3);
     // specialised kernel: even n, <= 5 classes, <= 32 constraints, 32-bit record index; the model
     // flag bit 8 (SG_EV_FLAG_GENERIC_KERNEL) forces the generic one (used by the tests)
     const bool small_index = (long long)m->n_days * m->max_sessions * m->n_stations < (1ll << 31);
-    const bool fast = (m->n_stations % 2 == 0) && m->n_classes <= 5 && m->n_constraints <= 32 && small_index &&
-                      !(flags & SG_EV_FLAG_GENERIC_KERNEL);
-    // default: the tile kernel (one thread per env on 32-env tiles staged through shared memory)
-    if ((m->n_stations % 2 == 0) && small_index && m->max_sessions < 255 &&
-        !(flags & (SG_EV_FLAG_GENERIC_KERNEL | SG_EV_FLAG_WARP_KERNEL))) {
+    const bool dense_ok = (m->n_stations % 2 == 0) && small_index && m->max_sessions < 255 &&
+                          !(flags & SG_EV_FLAG_GENERIC_KERNEL);
+    // projection on: event-driven kernel (work proportional to the occupied stations)
+    if (m->project && dense_ok && m->arrivals != nullptr && s->occ != nullptr && !(flags & SG_EV_FLAG_TILE_KERNEL)) {
+        const long long ntiles = (num_envs + 31) / 32;
+        const unsigned sgrid = (unsigned)std::min<long long>((ntiles + sg::kSparseWarps - 1) / sg::kSparseWarps, (long long)sms * 4);
+        sg::ev_step_sparse_kernel<<<sgrid, sg::kSparseWarps * 32, 0, st>>>(*m, *s, num_envs, action, flags, discrete_bins, obs,
+                                                                        reward, done, pilots, final_obs, status, stats, todo);
+        return sg::launch_status("ev_step_sparse_kernel");
+    }
+    // dense tile kernel: one thread per env on 32-env tiles staged through shared memory
+    if (dense_ok) {
         const sg::TileLayout L(m->n_stations);
         const int per_sm = std::max(1, std::min(16, (220 * 1024) / (L.bytes + 1024)));
         const long long ntiles = (num_envs + sg::kTileE - 1) / sg::kTileE;
@@ -1743,17 +1810,14 @@ int sg_ev_step(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, con
         }
         return sg::launch_status("ev_step_tile_kernel");
     }
+    // generic warp-per-env kernel (any network / odd station counts)
     if (!m->project) {
-        if (fast) sg::ev_step_fast_kernel<0, 5><<<grid, sg::kThreads, 0, st>>>(*m, *s, num_envs, action, flags, discrete_bins,
-                                                                             obs, reward, done, pilots, final_obs, status, stats, todo);
-        else sg::ev_step_kernel<0><<<grid, sg::kThreads, 0, st>>>(*m, *s, num_envs, action, flags, discrete_bins, obs,
-                                                                reward, done, pilots, final_obs, status, stats, todo);
+        sg::ev_step_kernel<0><<<grid, sg::kThreads, 0, st>>>(*m, *s, num_envs, action, flags, discrete_bins, obs,
+                                                           reward, done, pilots, final_obs, status, stats, todo);
         return sg::launch_status("ev_step_kernel<0>");
     }
-    if (fast) sg::ev_step_fast_kernel<1, 5><<<grid, sg::kThreads, 0, st>>>(*m, *s, num_envs, action, flags, discrete_bins,
-                                                                         obs, reward, done, pilots, final_obs, status, stats, todo);
-    else sg::ev_step_kernel<1><<<grid, sg::kThreads, 0, st>>>(*m, *s, num_envs, action, flags, discrete_bins, obs, reward,
-                                                            done, pilots, final_obs, status, stats, todo);
+    sg::ev_step_kernel<1><<<grid, sg::kThreads, 0, st>>>(*m, *s, num_envs, action, flags, discrete_bins, obs, reward,
+                                                       done, pilots, final_obs, status, stats, todo);
     return sg::launch_status("ev_step_kernel<1>");
 }
 

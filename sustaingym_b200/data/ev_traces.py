@@ -54,6 +54,24 @@ class TraceTables:
         out.sort(key=lambda s: (s[0], s[4]))
         return out
 
+    def arrival_table(self) -> np.ndarray:
+        """[D, Smax + 1] uint32: the day's sessions sorted by (arrival, station), packed as
+        ``arrival | station << 16 | slot << 24`` and terminated by 0x7fff entries — the event list the
+        event-driven kernel walks instead of scanning all stations (the reference's EventQueue of
+        PluginEvents, event_generation.py:188-196)."""
+        D, K, n = self.arrival.shape
+        rows = []
+        for d in range(D):
+            k, i = np.nonzero(self.arrival[d] != EMPTY)
+            arr = self.arrival[d, k, i].astype(np.int64)
+            order = np.lexsort((i, arr))
+            rows.append((arr[order] | (i[order].astype(np.int64) << 16) | (k[order].astype(np.int64) << 24)).astype(np.uint32))
+        smax = max(1, max(len(r) for r in rows))
+        tab = np.full((D, smax + 1), 0x7FFF, np.uint32)
+        for d, r in enumerate(rows):
+            tab[d, :len(r)] = r
+        return tab
+
     def max_profit(self, marginal_profit_per_kwh: float = 0.03, a_pers_to_kwh: float = 5 / 60 * 0.208,
                    scale: float = 32.0) -> np.ndarray:
         """``EVChargingEnv._calculate_max_profit`` (env.py:422-429) for every day: [D]."""

@@ -51,7 +51,7 @@ class BatchedEVChargingEnv:
                  moer_forecast_steps: int = 36, project_action_in_env: bool = True, verbose: int = 0,
                  device: str | torch.device | None = None, auto_reset: bool = False,
                  discrete_bins: int = -1, collect_stats: bool = False, force_generic_kernel: bool = False,
-                 force_warp_kernel: bool = False):
+                 force_tile_kernel: bool = False):
         assert 1 <= moer_forecast_steps <= 36                                   # env.py:120
         self.lib = _lib.load()                                                  # fails loudly if not built
         if not torch.cuda.is_available():
@@ -108,24 +108,27 @@ class BatchedEVChargingEnv:
             "mag": torch.from_numpy(mag).to(dev),
             "sessions": torch.from_numpy(rec.view(np.uint8).reshape(-1)).to(dev),
             "moer": torch.from_numpy(data_generator.moer).to(dev),
+            "arrivals": torch.from_numpy(t.arrival_table().view(np.int32)).to(dev),
         }
         self._max_profit_per_day = t.max_profit(self.MARGINAL_PROFIT_PER_KWH, self.A_PERS_TO_KWH, self.ACTION_SCALE_FACTOR)
         self._model = _lib.EVModel(
             n, coef.shape[1], coef.shape[0], k, t.max_sessions, t.num_days, data_generator.moer.shape[0],
             int(project_action_in_env), self._c["cls"].data_ptr(), self._c["type"].data_ptr(),
             self._c["re"].data_ptr(), self._c["im"].data_ptr(), self._c["mag"].data_ptr(),
-            self._c["sessions"].data_ptr(), self._c["moer"].data_ptr())
+            self._c["sessions"].data_ptr(), self._c["moer"].data_ptr(), self._c["arrivals"].data_ptr(),
+            self._c["arrivals"].shape[1] - 1, 0)
 
         # ---- per-env state and outputs ---------------------------------------------------------------
         B = self.num_envs
         z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)  # noqa: E731
         self.delivered = z(B, n, dtype=torch.float64)
         self.sess_idx = z(B, n, dtype=torch.uint8)
-        self.clock = z(B, 4, dtype=torch.int32)          # columns: t, day, moer_day, reserved
+        self.clock = z(B, 4, dtype=torch.int32)          # columns: t, day, moer_day, arrival cursor
         self.t, self.day, self.moer_day = self.clock[:, 0], self.clock[:, 1], self.clock[:, 2]
         self.breakdown = z(B, 3, dtype=torch.float64)
+        self.occ = z(B, dtype=torch.int64)                # occupancy bit mask of the event-driven kernel
         self._state = _lib.EVState(self.delivered.data_ptr(), self.sess_idx.data_ptr(), self.clock.data_ptr(),
-                                   self.breakdown.data_ptr())
+                                   self.breakdown.data_ptr(), self.occ.data_ptr())
         self.obs = z(B, self.obs_dim, dtype=torch.float32)
         self.final_obs = z(B, self.obs_dim, dtype=torch.float32) if auto_reset else None
         self.reward = z(B, dtype=torch.float64)
@@ -146,7 +149,7 @@ class BatchedEVChargingEnv:
         self._flags = (_lib.SG_EV_ACTION_I64 if discrete_bins > 0 else _lib.SG_EV_ACTION_F32) | \
             (_lib.SG_EV_FLAG_AUTORESET if auto_reset else 0) | \
             (_lib.SG_EV_FLAG_GENERIC_KERNEL if force_generic_kernel else 0) | \
-            (_lib.SG_EV_FLAG_WARP_KERNEL if force_warp_kernel else 0)
+            (_lib.SG_EV_FLAG_TILE_KERNEL if force_tile_kernel else 0)
         self.kernel_launches = 0
         self._needs_reset = True
 

@@ -58,11 +58,11 @@ def run_parity(env, orc, net, gen, B, steps, seed, action_fn, project):
     return clean, n_obs_exact, n_slow
 
 
-KERNELS = {"tile": {}, "warp": {"force_warp_kernel": True}, "generic": {"force_generic_kernel": True}}
+KERNELS = {"default": {}, "tile": {"force_tile_kernel": True}, "generic": {"force_generic_kernel": True}}
 
 
-@pytest.mark.parametrize("B,mean,kernel", [(64, 25.0, "tile"), (257, 70.0, "tile"), (33, 120.0, "tile"),
-                                           (100, 60.0, "warp"), (100, 60.0, "generic")])
+@pytest.mark.parametrize("B,mean,kernel", [(64, 25.0, "default"), (257, 70.0, "default"), (33, 120.0, "default"),
+                                           (100, 60.0, "generic")])
 def test_step_no_projection(native_lib, B, mean, kernel):
     gen, env, net, orc = make(7, mean, 11, B, False, **KERNELS[kernel])
     clean, n_exact, _ = run_parity(env, orc, net, gen, B, 288, 3,
@@ -71,8 +71,8 @@ def test_step_no_projection(native_lib, B, mean, kernel):
     assert bool(env.done.all()) and int(env.t[0]) == 288
 
 
-@pytest.mark.parametrize("B,mean,kernel", [(64, 25.0, "tile"), (200, 80.0, "tile"), (100, 80.0, "warp"),
-                                           (100, 80.0, "generic")])
+@pytest.mark.parametrize("B,mean,kernel", [(64, 25.0, "default"), (200, 80.0, "default"), (33, 120.0, "default"),
+                                           (100, 80.0, "tile"), (100, 80.0, "generic")])
 def test_step_with_projection(native_lib, B, mean, kernel):
     gen, env, net, orc = make(5, mean, 5, B, True, **KERNELS[kernel])
     clean, n_exact, n_slow = run_parity(env, orc, net, gen, B, 288, 9,
