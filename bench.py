@@ -10,7 +10,7 @@ pilot rounding -> acnsim period -> observation -> reward).  Reported on ONE JSON
   value      env-steps/s, whole job, actions already resident in HBM, CUDA-event timed, max over ranks
   e2e        the same through the public host API ``env.step(pinned host actions)`` with the H2D copy
              of the actions and the D2H copy of obs/reward/done inside the timed region
-  roofline   main kernel (ev_step_kernel<1>): algorithmic bytes per launch (1709 B/env-step,
+  roofline   the step kernel (ev_step_main_kernel<1>): algorithmic bytes per launch (1709 B/env-step,
              SURVEY.md 8d) / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the NumPy oracle port timed on this box's host cores on a bounded sample
 
@@ -256,9 +256,9 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     value = world * B * args.steps / (ms_total * 1e-3)
-    launches = 2 * args.steps
+    launches = args.steps
 
-    # ---- roofline: duration of the dominant kernel alone (ev_step_kernel<1>) ------------------------
+    # ---- roofline: duration of the step kernel alone (ev_step_main_kernel<1>) ---------------------------
     L = 120
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(L)]
     filler = torch.empty(1 << 28, dtype=torch.float32, device=dev)
@@ -268,16 +268,15 @@ def main():
     for i in range(L):
         env, a = envs[i % N_SETS], acts[i % N_SETS]
         evs[i][0].record()
-        env.launch_step(a, phase=1)
+        env.launch_step(a)
         evs[i][1].record()
-        env.launch_step(a, phase=2)
     torch.cuda.synchronize()
     del filler
     durs = sorted(a_.elapsed_time(b_) for a_, b_ in evs)
     kern_ms = float(np.mean(durs[L // 10: L - L // 10]))     # trimmed mean
     peak, peak_src = peaks()
     achieved = ALGO_BYTES_PER_ENV_STEP * B / (kern_ms * 1e-3) / 1e9
-    launches += 2 * L
+    launches += L
 
     # ---- e2e: public host API, pinned host actions in, obs/reward/done out, every step ---------------
     E = 30
@@ -294,7 +293,7 @@ def main():
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_value = world * B * E / float(dt.item())
-    launches += 2 * (E + 3)
+    launches += E + 3
     h2d = B * N_STATIONS * 4
     d2h = B * OBS_DIM * 4 + B * 8 + B
 
@@ -317,9 +316,9 @@ def main():
                        "parallelism": f"env-sharded x{world}", "trace_pool_days": POOL_DAYS,
                        "mean_sessions_per_day": MEAN_SESSIONS,
                        "l2_policy": f"{N_SETS} env sets stepped round-robin: ~{N_SETS * 85} MB touched between reuses (> 126 MB L2)",
-                       "launch": "one CUDA graph (2 kernels) per step"},
+                       "launch": "one CUDA graph (1 kernel) per step"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "kernel": "ev_step_kernel<1>",
+                         "frac": achieved / peak, "traffic": None, "kernel": "ev_step_main_kernel<1>",
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * B,
                          "peak_source": peak_src},
             "cpu_baseline": cpu_base,

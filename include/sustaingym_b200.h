@@ -136,22 +136,24 @@ typedef struct sg_ev_model {
     const double*  magnitudes;    /* [device] [16] limits in A, zero-padded                    */
     const void*    sessions;      /* [device] [D, K, n] 16-byte records (sg_ev_session)        */
     const float*   moer;          /* [device] [Dm, 289, 37]                                   */
-    const uint32_t* arrivals;     /* [device] [D, max_day_sessions + 1] the day's sessions sorted by
-                                     arrival: arrival | station << 16 | slot << 24, terminated by
-                                     0x7fff entries; NULL disables the event-driven kernel          */
+    const uint32_t* arrivals;     /* [device] [D, max_day_sessions + 1] the day's PluginEvents (event_generation.py:188-196)
+                                     sorted by (arrival, station): arrival | station << 16 | slot << 24,
+                                     terminated by 0x7fff entries                                       */
     int32_t max_day_sessions;     /* row length of `arrivals` minus the terminator                  */
     int32_t reserved;
 } sg_ev_model;
 
+/* Per-env state.  A plugged-in session is one 32-byte record
+ *     { f64 requested kWh, f64 delivered kWh, i32 departure, i32 est_departure, i32 arrival, i32 trace slot }
+ * stored per (copy, env, station); the step at clock t reads copy (t & 1) and writes the other one, and
+ * only the stations whose bit is set in `occ` hold a live record (sg_ev_export_state gives dense views). */
 typedef struct sg_ev_state {
-    double*  delivered;   /* [device] [B, n] kWh delivered to the session now at the station  */
-    uint8_t* sess_idx;    /* [device] [B, n] slot of the station's current-or-next session;   */
-                          /*   255 = hint: no session left at this station today              */
-    int32_t* clock;       /* [device] [B, 4] {t (0..288, env.py:168), day (trace index in     */
-                          /*   [0,D)), moer_day (MOER table index in [0,Dm)), arrival cursor  */
-                          /*   (sessions of the day with arrival <= t)}                        */
-    double*  breakdown;   /* [device] [B, 3] cumulative profit, carbon_cost, excess_charge    */
-    uint64_t* occ;        /* [device] [B] bit i set: station i has a plugged-in session now    */
+    void*    slots;       /* [device] [2, B, n] 32-byte session records, 32-byte aligned             */
+    int32_t* clock;       /* [device] [B, 4] {t (0..288, env.py:168), day (trace index in [0,D)),    */
+                          /*   moer_day (MOER table index in [0,Dm)), arrival cursor (sessions of    */
+                          /*   the day with arrival <= t)}                                            */
+    double*  breakdown;   /* [device] [B, 3] cumulative profit, carbon_cost, excess_charge           */
+    uint64_t* occ;        /* [device] [B] bit i set: station i has a plugged-in session now           */
 } sg_ev_state;
 
 /* status bits written per env by sg_ev_step */
@@ -162,8 +164,6 @@ typedef struct sg_ev_state {
 #define SG_EV_ACTION_F32      0
 #define SG_EV_ACTION_I64      1   /* DiscreteActionWrapper input (wrappers.py:43-45)          */
 #define SG_EV_FLAG_AUTORESET  16  /* on done: advance day (mod D), reset state, obs = reset obs */
-#define SG_EV_FLAG_GENERIC_KERNEL 256 /* use the generic warp-per-env kernel                        */
-#define SG_EV_FLAG_TILE_KERNEL    512 /* use the dense tile kernel instead of the event-driven one       */
 
 /* reset(): env.py:293-338 for envs whose `reset_mask` byte is non-zero (NULL = all).
  * `day_in`/`moer_day_in` pick the trace/MOER table (the seed->day map is host logic,
@@ -180,28 +180,26 @@ int sg_ev_reset(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs,
  *   pilots : [B, n] u8 amps actually sent (schedule of env.py:368-378) or NULL
  *   final_obs: with AUTORESET, receives the terminal observation of envs that finished, or NULL
  *   status : [B] u8 or NULL;  stats: [16] f64 accumulators or NULL (see sg_stats_*)
- *   todo   : [B+2] i32 zero-initialised device scratch (work list of envs whose clipped action
- *            violates the network); required when m->project != 0
- * With m->project != 0 a step is two launches: sg_ev_step advances every env whose box-clipped
- * action is already feasible (then it is the exact projection) and queues the others;
- * sg_ev_step_finish (same arguments) runs the interior-point projection for the queued envs and
- * advances them, then re-arms the work list.  Call both, in order, on the same stream.
+ * One launch per step.  With m->project != 0 the box-clipped action is tested against the network
+ * constraints per env; envs that violate them run the exact projection (single-class solve or
+ * interior point) inside the same kernel and report SG_EV_STATUS_PROJECTED.
  */
 int sg_ev_step(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs,
                const void* action, int32_t flags, int32_t discrete_bins,
                float* obs, double* reward, uint8_t* done, uint8_t* pilots, float* final_obs,
-               uint8_t* status, double* stats, int32_t* todo, void* stream);
-int sg_ev_step_finish(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs,
-                      const void* action, int32_t flags, int32_t discrete_bins,
-                      float* obs, double* reward, uint8_t* done, uint8_t* pilots, float* final_obs,
-                      uint8_t* status, double* stats, int32_t* todo, void* stream);
+               uint8_t* status, double* stats, void* stream);
 
 /* Host-buffer variant: H2D(action) -> step -> D2H(obs, reward, done) -> sync. */
 int sg_ev_step_host(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs,
                     const void* h_action, int32_t flags, int32_t discrete_bins,
                     float* h_obs, double* h_reward, uint8_t* h_done,
                     void* d_action, float* d_obs, double* d_reward, uint8_t* d_done,
-                    uint8_t* d_status, double* d_stats, int32_t* d_todo, void* stream);
+                    uint8_t* d_status, double* d_stats, void* stream);
+
+/* Dense views of the sparse state: delivered [B,n] f64 (kWh delivered to the session plugged in at
+ * each station, 0 where empty) and sess_idx [B,n] u8 (its trace slot, 255 where empty); either may be NULL. */
+int sg_ev_export_state(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs,
+                       double* delivered, uint8_t* sess_idx, void* stream);
 
 /* The projection alone (env.py:200-221): x = argmin ||x-a||_2 s.t. 0<=x<=min(1,d/(c*32)),
  * 32*|A~ x| <= magnitudes.  a: [B,n] f32, demands: [B,n] f32, x out: [B,n] f64. */

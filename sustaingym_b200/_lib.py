@@ -23,8 +23,6 @@ SG_EV_STATUS_MAXITER = 2
 SG_EV_ACTION_F32 = 0
 SG_EV_ACTION_I64 = 1
 SG_EV_FLAG_AUTORESET = 16
-SG_EV_FLAG_GENERIC_KERNEL = 256
-SG_EV_FLAG_TILE_KERNEL = 512
 SG_BUILDING_FLAG_AUTORESET = 16
 
 _vp = C.c_void_p
@@ -53,7 +51,7 @@ class EVModel(C.Structure):
 
 class EVState(C.Structure):
     _fields_ = [
-        ("delivered", _vp), ("sess_idx", _vp), ("clock", _vp), ("breakdown", _vp), ("occ", _vp),
+        ("slots", _vp), ("clock", _vp), ("breakdown", _vp), ("occ", _vp),
     ]
 
 
@@ -89,11 +87,10 @@ SIGNATURES = {
                                         _vp, _vp, _vp]),
     "sg_ev_reset": (C.c_int, [C.POINTER(EVModel), C.POINTER(EVState), _i64, _vp, _vp, _vp, _vp, _vp]),
     "sg_ev_step": (C.c_int, [C.POINTER(EVModel), C.POINTER(EVState), _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp,
-                             _vp, _vp, _vp, _vp, _vp]),
-    "sg_ev_step_finish": (C.c_int, [C.POINTER(EVModel), C.POINTER(EVState), _i64, _vp, _i32, _i32, _vp, _vp, _vp,
-                                    _vp, _vp, _vp, _vp, _vp, _vp]),
+                             _vp, _vp, _vp, _vp]),
     "sg_ev_step_host": (C.c_int, [C.POINTER(EVModel), C.POINTER(EVState), _i64, _vp, _i32, _i32, _vp, _vp, _vp,
-                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sg_ev_export_state": (C.c_int, [C.POINTER(EVModel), C.POINTER(EVState), _i64, _vp, _vp, _vp]),
     "sg_ev_agent_obs": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "sg_cogen_plant": (C.c_int, [C.POINTER(CogenModel), _i64, _vp, _vp, _vp, _vp]),
     "sg_cogen_reset": (C.c_int, [C.POINTER(CogenModel), _i64, _vp, _vp, _vp, _vp, _vp, _vp]),

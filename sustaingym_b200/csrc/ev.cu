@@ -10,25 +10,21 @@
 //   _get_reward                   env.py:431-464
 //   DiscreteActionWrapper.action  sustaingym/envs/wrappers.py:43-45
 //
-// Mapping: one warp advances one env; lane l owns stations 2l and 2l+1 (54 stations -> 27
-// lanes), so the env-major rows action[B,n] (f32), delivered[B,n] (f64), sess_idx[B,n] (u8) and
-// obs[B,2n+k+2] (f32) are read/written as 8/16/2-byte vectors that are contiguous across the
-// warp and across consecutive warps (fully coalesced, each byte touched once).  The network
-// constraints depend on the schedule only through <= 8 per-class sums:
-//   * the integer pilots are summed with packed 16-bit fields through REDUX (2 classes / word);
-//   * the fast-path feasibility test of the projection sums 2^-20 fixed-point actions the same
-//     way, with a safety margin; anything not certainly feasible is queued for the solver kernel.
-// The small constraint tables are staged in shared memory once per CTA.  Trace (16-byte session
-// records) and MOER tables are shared by all envs of a day and stay L2-resident.
+// One kernel launch per step (ev_step_main_kernel, documented at its definition): a warp owns a tile
+// of 32 consecutive envs, the observation/pilot rows of the tile are written with coalesced vector
+// stores by the whole warp, and one thread advances one env by walking only its OCCUPIED stations
+// (64-bit occupancy mask + 32-byte session records, double-buffered).  The network constraints
+// depend on the schedule only through <= 8 per-class sums, kept per thread.
+//
+// The projection has a fast path (box-clipped action already satisfies the network: it IS the
+// projection), decided per thread with an f32 margin test, and a slow path run warp-cooperatively
+// inside the same kernel for the rare envs that need it: exact test, exact single-class (pod)
+// solve, else a primal-dual interior point on the QCQP whose Newton systems are reduced to
+// n_classes x n_classes + n_constraints x n_constraints Cholesky factorisations.
 //
 // All divisions by constants use the FMA-corrected reciprocal (Markstein) which reproduces the
 // IEEE quotient the reference's Python arithmetic produces (checked on 2e7 samples per constant,
 // tests/test_div_const.py), so results stay bit-comparable with the oracle.
-//
-// The projection has a fast path (box-clipped action already satisfies the network: it IS the
-// projection) executed inline, and a slow path (primal-dual interior point on the QCQP, Newton
-// systems reduced to n_classes x n_classes by Woodbury) executed by a second, register-heavy
-// kernel over a device-side work list — so the common path keeps a small register footprint.
 //
 // Bound: HBM.  Algorithmic bytes per env-step: SURVEY.md 8d (1709 B at n=54, k=36).
 #include <algorithm>
@@ -103,27 +99,13 @@ __device__ __forceinline__ void load_shared(const sg_ev_model& m, EvShared& sh) 
         sh.con_re[i] = m.con_re[i];
         sh.con_im[i] = m.con_im[i];
     }
-    if (threadIdx.x < SG_EV_MAX_CONSTRAINTS) sh.lim[threadIdx.x] = m.magnitudes[threadIdx.x];
-    if (threadIdx.x < SG_EV_MAX_STATIONS) {
-        const bool in = (int)threadIdx.x < m.n_stations;
-        sh.cls[threadIdx.x] = in ? m.station_class[threadIdx.x] : 255;
-        sh.type[threadIdx.x] = in ? m.station_type[threadIdx.x] : 0;
+    for (int i = threadIdx.x; i < SG_EV_MAX_CONSTRAINTS; i += blockDim.x) sh.lim[i] = m.magnitudes[i];
+    for (int i = threadIdx.x; i < SG_EV_MAX_STATIONS; i += blockDim.x) {
+        const bool in = i < m.n_stations;
+        sh.cls[i] = in ? m.station_class[i] : 255;
+        sh.type[i] = in ? m.station_type[i] : 0;
     }
     __syncthreads();
-}
-
-struct Session { int arr, dep, est; double energy; };
-
-__device__ __forceinline__ Session load_session(const sg_ev_model& m, int day, int k, int i) {
-    Session s;
-    if (k >= m.max_sessions) { s.arr = s.dep = s.est = kEmpty; s.energy = 0.0; return s; }
-    const uint4* recs = reinterpret_cast<const uint4*>(m.sessions);
-    const uint4 r = __ldg(recs + ((long long)day * m.max_sessions + k) * m.n_stations + i);
-    s.arr = (int)(short)(r.x & 0xffffu);
-    s.dep = (int)(short)(r.x >> 16);
-    s.est = (int)(short)(r.y & 0xffffu);
-    s.energy = __longlong_as_double((long long)(((unsigned long long)r.w << 32) | r.z));
-    return s;
 }
 
 // class sums of a per-station f64 value (two stations per lane) -> every lane gets all sums
@@ -132,16 +114,6 @@ __device__ __forceinline__ void class_sums(const double (&v)[2], const int (&cls
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) {
         if (c < C) S[c] = warp_sum((cls[0] == c ? v[0] : 0.0) + (cls[1] == c ? v[1] : 0.0));
-        else S[c] = 0.0;
-    }
-}
-
-// class sums of small non-negative integers (< 2^26 / n per station): one REDUX per class
-__device__ __forceinline__ void class_sums_u32(const unsigned (&v)[2], const int (&cls)[2], int C, double (&S)[kMC],
-                                               double scale) {
-#pragma unroll
-    for (int c = 0; c < kMC; ++c) {
-        if (c < C) S[c] = (double)__reduce_add_sync(kFull, (cls[0] == c ? v[0] : 0u) + (cls[1] == c ? v[1] : 0u)) * scale;
         else S[c] = 0.0;
     }
 }
@@ -583,1078 +555,592 @@ __device__ __forceinline__ bool network_feasible_tol(const EvShared& sh, int C, 
     return ok;
 }
 
-// Conservative test (fast path): fixed-point class sums through REDUX; true only when every
-// constraint holds with a margin that covers the quantisation error.
-__device__ __forceinline__ bool network_certainly_feasible(const EvShared& sh, int C, int J, int lane,
-                                                           const double (&x)[2], const int (&cls)[2]) {
-    const unsigned xi[2] = {__double2uint_rn(x[0] * kFixScale), __double2uint_rn(x[1] * kFixScale)};
-    double S[kMC];
-    class_sums_u32(xi, cls, C, S, kFixInv);
-    bool bad = false;
-    if (lane < J) {
-        double wr = 0, wi = 0;
-#pragma unroll
-        for (int c = 0; c < kMC; ++c) { wr = fma(sh.con_re[lane * kMC + c], S[c], wr); wi = fma(sh.con_im[lane * kMC + c], S[c], wi); }
-        const double r = sh.lim[lane] * (1.0 / kActionScale) - kFeasMargin;
-        bad = !(r > 0.0 && fma(wr, wr, wi * wi) <= r * r);
-    }
-    return !__any_sync(kFull, bad);
-}
 
 // =================================================================================================
-// One env, one step.  MODE 0: no projection.  MODE 1: projection, fast path inline, otherwise
-// defer to the work list.  MODE 2: projection with the solver inline (work-list kernel).
+// Per-env state (include/sustaingym_b200.h, sg_ev_state).  A plugged-in session is one 32-byte
+// record = one DRAM/L2 sector, read and written with single 256-bit accesses:
+//     { f64 requested kWh, f64 delivered kWh, i32 departure, i32 est_departure, i32 arrival, i32 slot }
+// kept per (env, station) in two copies: step t reads copy (t & 1) and writes copy (1 - t & 1).
+// Only the occupied stations (bit set in the env's 64-bit occupancy mask) hold live records, so one
+// step touches ~occupancy x 64 B of state instead of a dense [n] row, and because a step never
+// overwrites its own inputs it can be re-executed for an env (the projection fallback below does
+// that) without an undo log.
 // =================================================================================================
-template <int MODE>
-__device__ __forceinline__ void ev_env_step(const sg_ev_model& m, const sg_ev_state& s, const EvShared& sh,
-                                            const long long b, const int lane, const void* __restrict__ action,
-                                            const int flags, const int bins, float* __restrict__ obs,
-                                            double* __restrict__ reward, uint8_t* __restrict__ done,
-                                            uint8_t* __restrict__ pilots, float* __restrict__ final_obs,
-                                            uint8_t* __restrict__ status, int32_t* __restrict__ todo,
-                                            StatsAcc& acc) {
-    const int n = m.n_stations, kf = m.moer_steps, OBS = 2 * n + kf + 2;
-    const int C = m.n_classes, J = m.n_constraints;
-    const int4 clk = *reinterpret_cast<const int4*>(s.clock + b * 4);
-    const int t = clk.x;
-    if (t >= kEpisode) {            // finished episode that was not reset: no-op, stays terminal
-        if (lane == 0) { reward[b] = 0.0; done[b] = 1; if (status) status[b] = 0; }
-        return;
-    }
-    int day = clk.y, md = clk.z;
+struct __align__(32) Slot {
+    double energy, delivered;
+    int dep, est, arr, k;
+};
+
+__device__ __forceinline__ Slot ld_slot(const Slot* p) {
+    unsigned long long a, b, c, d;
+    asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+    Slot s;
+    s.energy = __longlong_as_double((long long)a);
+    s.delivered = __longlong_as_double((long long)b);
+    s.dep = (int)(unsigned)(c & 0xffffffffull); s.est = (int)(unsigned)(c >> 32);
+    s.arr = (int)(unsigned)(d & 0xffffffffull); s.k = (int)(unsigned)(d >> 32);
+    return s;
+}
+__device__ __forceinline__ void st_slot(Slot* p, const Slot& s) {
+    const unsigned long long a = (unsigned long long)__double_as_longlong(s.energy);
+    const unsigned long long b = (unsigned long long)__double_as_longlong(s.delivered);
+    const unsigned long long c = (unsigned long long)(unsigned)s.dep | ((unsigned long long)(unsigned)s.est << 32);
+    const unsigned long long d = (unsigned long long)(unsigned)s.arr | ((unsigned long long)(unsigned)s.k << 32);
+    asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
+
+constexpr int kMainWarps = 2;                        // warps per CTA of the main kernel
+constexpr int kMainThreads = kMainWarps * 32;
+constexpr int kItemCap = 256;                        // (env, station) work items staged per warp and chunk
+constexpr float kPreMargin = 2e-3f;                  // normalised units; covers the f32 accumulation error
+
+// result of one (env, occupied station) work item, consumed by the thread that owns the env
+struct __align__(16) ItemRec {
+    double rate;                                     // charging rate in A
+    float x;                                         // normalised pilot before rounding (class sums of the projection test)
+    unsigned meta;                                   // pilot | class << 8 | departed << 16 | station << 24
+};
+
+struct WarpShared {
+    ItemRec items[kItemCap];                         // the key (env lane << 8 | station) of item j is staged in items[j].meta
+    float S[kMC][32];                                // per-env class sums of the clipped action
+    int P[kMC][32];                                  // per-env class sums of the integer pilots
+    double xs[SG_EV_MAX_STATIONS];                   // projected action of the env being re-done
+};
+
+struct MainShared {
+    float re[SG_EV_MAX_CONSTRAINTS * kMC], im[SG_EV_MAX_CONSTRAINTS * kMC];   // f32 copies for the pre-checks
+    float r_in[SG_EV_MAX_CONSTRAINTS];               // (limit/32 - margin)^2 in normalised action units
+    float lim2_lo[SG_EV_MAX_CONSTRAINTS];            // 0.999 * limit^2 (A^2): below it the rounded schedule has no excess
+    double ppilot[40];                               // pilot (A) -> kW at 208 V, the reference's IEEE operation sequence
+    WarpShared w[kMainWarps];
+    double stat[11 * kMainWarps];
+};
+
+// One period of Linear2StageBattery._charge_stepwise + EV.charge for a plugged-in EV (capacity
+// 100 kWh, max_power 100 kW, transition SoC 0.8), branch-free: returns the charging rate in A and
+// advances `delivered`.  p_pilot = pilot * 208 / 1000 kW comes from a 33-entry table.
+__device__ __forceinline__ double charge_period(const double energy, double& delivered, const double p_pilot) {
+    const double charge = fmax(0.0, kCapacity - energy) + delivered;
+    const double rate_to_full = div_c(kCapacity - charge, kPeriodH, kInvPeriodH);
+    const double soc = div_c(charge, kCapacity, kInv100);
+    const double cap2 = soc < kTransitionSoc ? kMaxPower : div_c(1.0 - soc, kOneMinusTrans, kInvOMT) * kMaxPower;
+    const double power = fmin(fmin(p_pilot, cap2), rate_to_full);
+    const double rate = div_c(power * 1000.0, kVoltage, kInv208);                     // A
+    delivered += div_c(rate * kVoltage, 1000.0, kInv1000) * kPeriodH;                 // EV.charge
+    return rate;
+}
+
+// env.py:373-378 on an f32 action: amps = a * 32 is exact in f32, so rintf == np.round.
+__device__ __forceinline__ int pilot_f32(const float a, const int type) {
+    const float amps = a * 32.f;
+    const float pf = type == 0 ? (amps >= 6.f ? rintf(amps) : 0.f) : rintf(amps * 0.125f) * 8.f;
+    return min(max(__float2int_rn(pf), 0), 32);      // table index safety for out-of-space actions
+}
+
+// env.py:188-189 + 363-378 for one occupied station, branch-free and exact: with q = dem / A_PERS_TO_KWH,
+// 32 * clip(a, 0, min(1, q / 32)) == min(32 * max(a, 0), min(32, q)) because scaling by 32 is exact.
+__device__ __forceinline__ int pilot_clipped(const float af, const float dem, const int type, float* x_out) {
+    const double q = div_c((double)dem, kAPersToKwh, kInvAPers);
+    const double amps = fmin((double)(fmaxf(af, 0.f) * 32.f), fmin(32.0, q));
+    *x_out = (float)amps * 0.03125f;
+    const double p = type == 0 ? (amps >= 6.0 ? rint(amps) : 0.0) : rint(amps * 0.125) * 8.0;
+    return __double2int_rn(p);
+}
+
+__device__ __forceinline__ float timestep_frac(const int t) {     // env.py:392, t / 288 as f32 (exhaustively checked)
+    return (float)((double)t * (1.0 / (double)kEpisode));
+}
+
+// Warp-cooperative exact projection of ONE env (lane l owns stations 2l, 2l+1): exact feasibility
+// test of the box-clipped action, then the single-class (pod) projection, then the interior-point
+// solver.  Writes the projected normalised action to xs[0..n) and returns the status bits (0: the
+// clipped action is feasible, nothing to redo).
+__device__ __noinline__ int project_env(const EvShared& sh, const int n, const int C, const int J, const long long b,
+                                         const int lane, const void* __restrict__ action, const bool i64,
+                                         const int bins, const Slot* __restrict__ cur,
+                                         const unsigned long long occ_b, double* xs) {
     const int i0 = 2 * lane;
     const bool valid[2] = {i0 < n, i0 + 1 < n};
-    const bool vec = ((n & 1) == 0);     // rows are 8/16-byte aligned when n is even
-
-    // ---- coalesced row loads -------------------------------------------------------------------
-    float af[2] = {0.f, 0.f};
-    if ((flags & 1) == SG_EV_ACTION_I64) {
-        const long long* ap = reinterpret_cast<const long long*>(action) + b * n;
-#pragma unroll
-        for (int p = 0; p < 2; ++p)
-            if (valid[p]) af[p] = __fdiv_rn((float)ap[i0 + p], (float)(bins - 1));   // wrappers.py:45
-    } else {
-        const float* ap = reinterpret_cast<const float*>(action) + b * n;
-        if (vec) {
-            if (valid[0]) { const float2 v = ldg_stream_f2(reinterpret_cast<const float2*>(ap + i0)); af[0] = v.x; af[1] = v.y; }
-        } else {
-#pragma unroll
-            for (int p = 0; p < 2; ++p) if (valid[p]) af[p] = __ldg(ap + i0 + p);
-        }
-    }
-    double del[2] = {0.0, 0.0};
-    int k[2] = {0, 0};
-    {
-        const double* dp = s.delivered + b * n;
-        const uint8_t* kp = s.sess_idx + b * n;
-        if (vec) {
-            if (valid[0]) {
-                const double2 v = *reinterpret_cast<const double2*>(dp + i0);
-                del[0] = v.x; del[1] = v.y;
-                const uchar2 kk = *reinterpret_cast<const uchar2*>(kp + i0);
-                k[0] = kk.x; k[1] = kk.y;
-            }
-        } else {
-#pragma unroll
-            for (int p = 0; p < 2; ++p) if (valid[p]) { del[p] = dp[i0 + p]; k[p] = kp[i0 + p]; }
-        }
-    }
-    int cls[2], type[2];
-    Session ses[2];
-    bool plugged[2];
+    double a[2], u[2], x[2];
+    int cls[2];
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
-        cls[p] = valid[p] ? sh.cls[i0 + p] : 255;
-        type[p] = valid[p] ? sh.type[i0 + p] : 0;
-        if (valid[p]) ses[p] = load_session(m, day, k[p], i0 + p);
-        else { ses[p].arr = ses[p].dep = ses[p].est = kEmpty; ses[p].energy = 0.0; }
-        // plugged in during period t: its Plugin event (timestamp <= t) has been processed (events
-        // are only drained after the first charge, so nothing is plugged at t = 0) and its Unplug
-        // event (timestamp = departure) has not.
-        plugged[p] = valid[p] && t >= 1 && ses[p].arr <= t && t < ses[p].dep;
+        const int i = i0 + p;
+        a[p] = 0.0; u[p] = 0.0; cls[p] = 255;
+        if (valid[p]) {
+            const float af = i64 ? __fdiv_rn((float)reinterpret_cast<const long long*>(action)[b * n + i], (float)(bins - 1))
+                                 : reinterpret_cast<const float*>(action)[b * n + i];
+            a[p] = (double)af;
+            cls[p] = sh.cls[i];
+            if ((occ_b >> i) & 1ull) {
+                const Slot s = ld_slot(cur + i);
+                const double rem = s.energy - s.delivered;
+                const float dem = rem > kFullEps ? (float)rem : 0.f;          // obs 'demands', env.py:388
+                u[p] = upper_bound(dem);
+            }
+        }
+        x[p] = valid[p] ? fmin(fmax(a[p], 0.0), u[p]) : 0.0;
     }
-
-    // ---- action -> normalised pilot x (env.py:363-366) -------------------------------------------
-    double x[2];
     int st = 0;
-    if constexpr (MODE == 0) {
-        x[0] = (double)af[0]; x[1] = (double)af[1];
-    } else {
-        double a[2], u[2];
+    if (!network_feasible(sh, C, J, x, cls)) {
+        bool cap = false;
+        if (!(simple_project(sh, C, J, a, u, cls, valid, x) && network_feasible_tol(sh, C, J, x, cls))) {
 #pragma unroll
-        for (int p = 0; p < 2; ++p) {
-            const double rem = ses[p].energy - del[p];
-            const float dem = (plugged[p] && rem > kFullEps) ? (float)rem : 0.f;     // obs 'demands', env.py:388
-            a[p] = (double)af[p];
-            u[p] = upper_bound(dem);
-            x[p] = valid[p] ? fmin(fmax(a[p], 0.0), u[p]) : 0.0;
+            for (int p = 0; p < 2; ++p) x[p] = valid[p] ? fmin(fmax(a[p], 0.0), u[p]) : 0.0;
+            ipm_dispatch(sh, C, J, a, u, cls, valid, x, &cap);
         }
-        if constexpr (MODE == 1) {
-            if (!network_certainly_feasible(sh, C, J, lane, x, cls)) {
-                if (lane == 0) todo[2 + atomicAdd(todo, 1)] = (int)b;
-                return;                                     // the work-list kernel redoes this env
-            }
+        st = SG_EV_STATUS_PROJECTED | (cap ? SG_EV_STATUS_MAXITER : 0);
+    }
+#pragma unroll
+    for (int p = 0; p < 2; ++p) if (valid[p]) xs[i0 + p] = x[p];
+    __syncwarp();
+    return st;
+}
+
+// Re-execution of one env's occupied stations with the projected action xs (one thread, rare path).
+// Inputs are read from the state copy of the current step (untouched by the first pass), outputs
+// overwrite what the first pass wrote.  P: this env's column of the pilot class sums (stride 32).
+struct RedoOut { double rate_sum; unsigned long long occ_new; };
+__device__ __noinline__ RedoOut redo_env(const uint8_t* __restrict__ s_type, const uint8_t* __restrict__ s_cls,
+                                          const double* __restrict__ ppilot, int* P, const double* xs, const int n,
+                                          const int tn, const unsigned long long occ, const Slot* __restrict__ cur,
+                                          Slot* __restrict__ nxt, float* __restrict__ row,
+                                          uint8_t* __restrict__ pilot_row) {
+    RedoOut out;
+    out.rate_sum = 0.0;
+    out.occ_new = occ;
+    for (int c = 0; c < kMC; ++c) P[c * 32] = 0;
+    for (unsigned long long mask = occ; mask; mask &= mask - 1) {
+        const int i = __ffsll((long long)mask) - 1;
+        Slot q = ld_slot(cur + i);
+        const int pi = min(max(__double2int_rn(to_pilot(xs[i], s_type[i])), 0), 32);
+        P[s_cls[i] * 32] += pi;
+        out.rate_sum += charge_period(q.energy, q.delivered, ppilot[pi]);
+        if (pilot_row != nullptr) pilot_row[i] = (uint8_t)pi;
+        bool active = false;
+        if (q.dep <= tn) {                                            // Unplug event (timestamp = departure)
+            out.occ_new &= ~(1ull << i);
         } else {
-            if (!network_feasible(sh, C, J, x, cls)) {
-                bool cap = false;
-                if (!(simple_project(sh, C, J, a, u, cls, valid, x) && network_feasible_tol(sh, C, J, x, cls))) {
-#pragma unroll
-                    for (int p = 0; p < 2; ++p) x[p] = valid[p] ? fmin(fmax(a[p], 0.0), u[p]) : 0.0;
-                    ipm_dispatch(sh, C, J, a, u, cls, valid, x, &cap);
-                }
-                st = SG_EV_STATUS_PROJECTED | (cap ? SG_EV_STATUS_MAXITER : 0);
-            }
+            st_slot(nxt + i, q);
+            active = q.energy - q.delivered > kFullEps;               // Interface.active_sessions()
+        }
+        if (row != nullptr) {
+            row[i] = active ? (float)(q.energy - q.delivered) : 0.f;
+            row[n + i] = active ? (float)(q.est - tn) : 0.f;
         }
     }
-
-    // ---- schedule (env.py:368-378), charging (acnsim update_pilots), rates ------------------------
-    double pilot[2], rate_sum = 0.0;
-#pragma unroll
-    for (int p = 0; p < 2; ++p) {
-        pilot[p] = valid[p] ? to_pilot(x[p], type[p]) : 0.0;
-        if (plugged[p]) {
-            // Linear2StageBattery._charge_stepwise (capacity 100 kWh, max_power 100 kW, transition 0.8)
-            const double charge = fmax(0.0, kCapacity - ses[p].energy) + del[p];
-            const double rate_to_full = div_c(kCapacity - charge, kPeriodH, kInvPeriodH);
-            const double soc = div_c(charge, kCapacity, kInv100);
-            const double p_pilot = div_c(pilot[p] * kVoltage, 1000.0, kInv1000);
-            const double cap2 = soc < kTransitionSoc ? kMaxPower
-                                                     : div_c(1.0 - soc, kOneMinusTrans, kInvOMT) * kMaxPower;
-            const double power = fmin(fmin(p_pilot, cap2), rate_to_full);
-            const double rate = div_c(power * 1000.0, kVoltage, kInv208);                 // A
-            del[p] += div_c(rate * kVoltage, 1000.0, kInv1000) * kPeriodH;               // EV.charge
-            rate_sum += rate;
-        }
-    }
-    const double total_rate = warp_sum(rate_sum);
-
-    // ---- excess current from the rounded schedule (env.py:449-452) ---------------------------------
-    double excess = 0.0;
-    {
-        const unsigned pi[2] = {(unsigned)pilot[0], (unsigned)pilot[1]};
-        double S[kMC];
-        class_sums_pilots(pi, cls, C, S);
-        double sq = 0.0, lim = 0.0;
-        if (lane < J) {
-            double wr = 0, wi = 0;
-#pragma unroll
-            for (int c = 0; c < kMC; ++c) { wr = fma(sh.con_re[lane * kMC + c], S[c], wr); wi = fma(sh.con_im[lane * kMC + c], S[c], wi); }
-            sq = fma(wr, wr, wi * wi);
-            lim = sh.lim[lane];
-        }
-        const bool over = lane < J && sq > lim * lim;
-        if (__any_sync(kFull, over)) excess = warp_sum(over ? fmax(0.0, sqrt(sq) - lim) : 0.0);
-    }
-
-    // ---- advance time, drain events with timestamp <= t+1: Unplug (0) before Plugin (10) ------------
-    const int tn = t + 1;
-    float dem_o[2], est_o[2];
-#pragma unroll
-    for (int p = 0; p < 2; ++p) {
-        while (valid[p] && ses[p].dep <= tn && ses[p].arr != kEmpty) {   // session over (or zero-length)
-            k[p] += 1; del[p] = 0.0;
-            ses[p] = load_session(m, day, k[p], i0 + p);
-        }
-        const bool pl = valid[p] && ses[p].arr <= tn && tn < ses[p].dep;
-        const double rem = ses[p].energy - del[p];
-        const bool active = pl && rem > kFullEps;                         // Interface.active_sessions()
-        dem_o[p] = active ? (float)rem : 0.f;
-        est_o[p] = active ? (float)(ses[p].est - tn) : 0.f;
-    }
-    const bool dn = tn >= kEpisode;
-
-    // ---- reward (env.py:444-462) ---------------------------------------------------------------------
-    const float* mrow = m.moer + ((long long)md * SG_EV_MOER_ROWS + tn) * SG_EV_MOER_COLS;
-    const double moer0 = (double)__ldg(mrow);
-    const double profit = kProfitFactor * total_rate;
-    const double excess_charge = excess * kViolationFactor;
-    const double carbon = kCarbonFactor * total_rate * moer0;
-    const double rew = profit - carbon - excess_charge;
-
-    const bool autoreset = dn && (flags & SG_EV_FLAG_AUTORESET);
-
-    // ---- observation row: demands | est_departures | forecasted_moer | prev_moer | timestep ----------
-    auto write_obs = [&](float* orow, const float* row, const int tstep) {
-        if (vec) {
-            if (valid[0]) {
-                stg_stream_f2(reinterpret_cast<float2*>(orow + i0), make_float2(dem_o[0], dem_o[1]));
-                stg_stream_f2(reinterpret_cast<float2*>(orow + n + i0), make_float2(est_o[0], est_o[1]));
-            }
-        } else {
-#pragma unroll
-            for (int p = 0; p < 2; ++p) if (valid[p]) { orow[i0 + p] = dem_o[p]; orow[n + i0 + p] = est_o[p]; }
-        }
-        for (int e = lane; e < kf + 2; e += 32) {
-            float v;
-            if (e < kf) v = __ldg(row + 1 + e);
-            else if (e == kf) v = __ldg(row);
-            else v = (float)((double)tstep / (double)kEpisode);     // env.py:392
-            orow[2 * n + e] = v;
-        }
-    };
-    if (!autoreset) {
-        write_obs(obs + b * OBS, mrow, tn);
-    } else {
-        if (final_obs != nullptr) write_obs(final_obs + b * OBS, mrow, tn);   // terminal observation
-        // reset observation of the next episode (env.py:293-338): next day, empty garage, t = 0
-        day = (day + 1) % m.n_days;                      // sequential days, event_generation.py:284-291
-        md = (md + 1) % m.n_moer_days;
-        dem_o[0] = dem_o[1] = est_o[0] = est_o[1] = 0.f;
-        k[0] = k[1] = 0; del[0] = del[1] = 0.0;
-        write_obs(obs + b * OBS, m.moer + ((long long)md * SG_EV_MOER_ROWS) * SG_EV_MOER_COLS, 0);
-    }
-
-    // ---- state write-back ------------------------------------------------------------------------------
-    {
-        double* dp = s.delivered + b * n;
-        uint8_t* kp = s.sess_idx + b * n;
-        if (vec) {
-            if (valid[0]) {
-                *reinterpret_cast<double2*>(dp + i0) = make_double2(del[0], del[1]);
-                *reinterpret_cast<uchar2*>(kp + i0) = make_uchar2((unsigned char)k[0], (unsigned char)k[1]);
-            }
-        } else {
-#pragma unroll
-            for (int p = 0; p < 2; ++p) if (valid[p]) { dp[i0 + p] = del[p]; kp[i0 + p] = (uint8_t)k[p]; }
-        }
-        if (pilots != nullptr) {
-            if (vec) {
-                if (valid[0]) *reinterpret_cast<uchar2*>(pilots + b * n + i0) =
-                    make_uchar2((unsigned char)pilot[0], (unsigned char)pilot[1]);
-            } else {
-#pragma unroll
-                for (int p = 0; p < 2; ++p) if (valid[p]) pilots[b * n + i0 + p] = (uint8_t)pilot[p];
-            }
-        }
-    }
-    // occupancy mask (bit i: station i has a plugged-in session at the new time) and arrival cursor
-    // of the event-driven kernel — derived state every kernel keeps consistent
-    unsigned occ_lo, occ_hi;
-    {
-        bool pln[2];
-#pragma unroll
-        for (int p = 0; p < 2; ++p) pln[p] = !autoreset && valid[p] && ses[p].arr <= tn && tn < ses[p].dep;
-        const unsigned long long mine = ((unsigned long long)pln[0] << (i0 & 63)) | ((unsigned long long)pln[1] << ((i0 + 1) & 63));
-        occ_lo = __reduce_or_sync(kFull, (unsigned)(mine & 0xffffffffull));
-        occ_hi = __reduce_or_sync(kFull, (unsigned)(mine >> 32));
-    }
-    if (lane == 0) {
-        // cumulative reward breakdown (env.py:460-462); cleared on the first step of an episode so
-        // that after an auto-reset the finished episode's totals stay readable until the next step
-        double* bd = s.breakdown + b * 3;
-        if (t == 0) { bd[0] = profit; bd[1] = carbon; bd[2] = excess_charge; }
-        else { bd[0] += profit; bd[1] += carbon; bd[2] += excess_charge; }
-        int nidx = autoreset ? 0 : clk.w;
-        if (!autoreset && m.arrivals != nullptr) {
-            const unsigned* arow = m.arrivals + (long long)clk.y * (m.max_day_sessions + 1);
-            while ((int)(__ldg(arow + nidx) & 0x7fffu) <= tn) ++nidx;
-        }
-        if (s.occ != nullptr) s.occ[b] = ((unsigned long long)occ_hi << 32) | occ_lo;
-        *reinterpret_cast<int4*>(s.clock + b * 4) = make_int4(autoreset ? 0 : tn, day, md, nidx);
-        reward[b] = rew;
-        done[b] = dn ? 1 : 0;
-        if (status != nullptr) status[b] = (uint8_t)st;
-        acc.add(rew, dn, profit, carbon, excess_charge);
-        acc.n_proj += (st & SG_EV_STATUS_PROJECTED) ? 1.0 : 0.0;
-        acc.n_maxiter += (st & SG_EV_STATUS_MAXITER) ? 1.0 : 0.0;
-    }
+    return out;
 }
 
 // =================================================================================================
-// Tile kernel (dense main kernel: default without projection, optional with it).  The warp-per-env kernels above spend ~800 warp instructions
-// per env because every per-env scalar operation is replicated over 32 lanes and both stations of
-// a lane run the f64 battery path although ~85 % of the stations are empty.  Here one warp owns a
-// TILE of 32 consecutive envs and one THREAD advances one env:
-//   phase 0  the tile's action rows and sess_idx bytes are copied global->shared with coalesced
-//            8/16-byte accesses (the only place the env-major layout is touched), clock rows are
-//            one coalesced 16-byte load per lane;
-//   phase 1  each thread scans its env's stations (cheap: one byte per station; stations known to
-//            have no current-or-next session carry the hint sess_idx = 255) and appends the
-//            stations whose session has started or starts now to a compact list in shared memory;
-//            the f64 battery arithmetic then runs over the LISTS (trip count ~ the largest list,
-//            mostly-active lanes); class sums are per-thread accumulators — no shuffles at all;
-//            `delivered` is read/written only for listed stations (sparse 8-byte accesses);
-//   phase 2  observation rows are assembled from the shared tiles and stored row by row with
-//            8-byte vectors; sess_idx / pilots tiles go back with coalesced copies.
-// Envs whose clipped action is not inside the network constraints are queued for the solver
-// kernel exactly as before and leave no trace in global memory.
+// Main kernel: one launch = one step() of all envs.  A warp owns a tile of 32 consecutive envs.
+//
+//   fill     the tile's observation rows (contiguous in memory) are written by the whole warp with
+//            coalesced 8-byte stores: zeros for demands / est_departures (an empty station reads 0)
+//            and the MOER row + timestep tail; pilot rows are zeroed (projection on: an empty station
+//            has upper bound 0) or computed densely with their class sums (projection off);
+//   items    the occupied stations of the 32 envs (bits of the per-env 64-bit masks) are enumerated
+//            into one work list and processed one (env, station) item per lane, so the lanes stay
+//            balanced whatever the per-env occupancy: one 32-byte session record (single 256-bit
+//            load) + one action value in, battery arithmetic (branch-free, exact), the record goes
+//            to the other state copy, the two observation entries and the pilot byte are patched
+//            into the pre-filled rows, the item's rate / pilot / clipped action go to a record in
+//            shared memory;
+//   owner    thread e sums the records of env e in station order (deterministic f64 sums) and tests
+//            the class sums of the clipped action against the network constraints in f32 with a
+//            margin; an env that is not certainly feasible is handed to the warp-cooperative exact
+//            projection (project_env) and its stations are re-done with the projected action (its
+//            inputs are still intact in the current state copy);
+//   arrivals Plugin events with timestamp <= t+1 from the day's arrival-sorted list;
+//   epilogue excess current of the rounded schedule, reward, cumulative breakdown, clock, mask.
 // =================================================================================================
-constexpr int kTileE = 32;
-
-struct TileLayout {
-    int RS, off_est, off_k, off_pil, off_lst, off_S, off_P, off_rate, off_energy, off_con, bytes;
-    __host__ __device__ explicit TileLayout(int n) {
-        RS = n | 1;                                        // odd row stride: conflict-free column walks
-        int o = kTileE * RS * 4;                           // act/dem tile  f32 [32][RS]
-        off_est = o; o += kTileE * RS * 2;                 // est tile      i16 [32][RS]
-        o = (o + 15) & ~15;
-        off_k = o; o += kTileE * n;                        // sess_idx tile u8  [32*n] (global layout)
-        o = (o + 15) & ~15;
-        off_pil = o; o += kTileE * n;                      // pilots tile   u8  [32*n]
-        o = (o + 15) & ~15;
-        off_lst = o; o += kTileE * n;                      // station lists u8  [32][n]
-        o = (o + 15) & ~15;
-        off_S = o; o += kMC * kTileE * 8;                  // class sums of x        f64 [8][32]
-        off_P = o; o += kMC * kTileE * 4;                  // class sums of pilots   i32 [8][32]
-        o = (o + 15) & ~15;
-        off_rate = o; o += 40 * 8;
-        off_energy = o; o += 40 * 8;
-        off_con = o; o += (2 * SG_EV_MAX_CONSTRAINTS * kMC + SG_EV_MAX_CONSTRAINTS) * 8 + 2 * SG_EV_MAX_STATIONS;
-        o = (o + 15) & ~15;
-        bytes = o;
-    }
-};
-
 template <int MODE>
-__global__ void __launch_bounds__(kTileE)
-ev_step_tile_kernel(const sg_ev_model m, const sg_ev_state s, const long long B, const void* __restrict__ action,
+__global__ void __launch_bounds__(kMainThreads, 8)
+ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B, const void* __restrict__ action,
                     const int flags, const int bins, float* __restrict__ obs, double* __restrict__ reward,
                     uint8_t* __restrict__ done, uint8_t* __restrict__ pilots, float* __restrict__ final_obs,
-                    uint8_t* __restrict__ status, double* __restrict__ stats, int32_t* __restrict__ todo) {
-    extern __shared__ __align__(16) unsigned char tsm[];
-    const int n = m.n_stations, kf = m.moer_steps, OBS = 2 * n + kf + 2, C = m.n_classes, J = m.n_constraints;
-    const int K = m.max_sessions;
-    const TileLayout L(n);
-    const int RS = L.RS;
-    float* tact = reinterpret_cast<float*>(tsm);
-    short* test = reinterpret_cast<short*>(tsm + L.off_est);
-    uint8_t* tk = tsm + L.off_k;
-    uint8_t* tpil = tsm + L.off_pil;
-    uint8_t* tlst = tsm + L.off_lst;
-    double* sS = reinterpret_cast<double*>(tsm + L.off_S);
-    int* sP = reinterpret_cast<int*>(tsm + L.off_P);
-    double* srate = reinterpret_cast<double*>(tsm + L.off_rate);
-    double* senergy = reinterpret_cast<double*>(tsm + L.off_energy);
-    double* scre = reinterpret_cast<double*>(tsm + L.off_con);          // [16][8]
-    double* scim = scre + SG_EV_MAX_CONSTRAINTS * kMC;                  // [16][8]
-    double* slim = scim + SG_EV_MAX_CONSTRAINTS * kMC;                  // [16]
-    uint8_t* scls = reinterpret_cast<uint8_t*>(slim + SG_EV_MAX_CONSTRAINTS);   // [64]
-    uint8_t* stype = scls + SG_EV_MAX_STATIONS;                          // [64]
-    const int lane = threadIdx.x;
-    for (int pI = lane; pI <= 32; pI += 32) {
-        const double pp = div_c((double)pI * kVoltage, 1000.0, kInv1000);
-        const double rate = div_c(pp * 1000.0, kVoltage, kInv208);
-        srate[pI] = rate;
-        senergy[pI] = div_c(rate * kVoltage, 1000.0, kInv1000) * kPeriodH;
+                    uint8_t* __restrict__ status, double* __restrict__ stats) {
+    __shared__ EvShared sh;
+    __shared__ MainShared ms;
+    const int n = m.n_stations, kf = m.moer_steps, OBS = 2 * n + kf + 2, J = m.n_constraints, C = m.n_classes;
+    load_shared(m, sh);
+    for (int i = threadIdx.x; i < SG_EV_MAX_CONSTRAINTS * kMC; i += blockDim.x) {
+        ms.re[i] = (float)sh.con_re[i];
+        ms.im[i] = (float)sh.con_im[i];
     }
-    for (int i = lane; i < SG_EV_MAX_CONSTRAINTS * kMC; i += 32) { scre[i] = m.con_re[i]; scim[i] = m.con_im[i]; }
-    if (lane < SG_EV_MAX_CONSTRAINTS) slim[lane] = m.magnitudes[lane];
-    for (int i = lane; i < SG_EV_MAX_STATIONS; i += 32) {
-        scls[i] = i < n ? m.station_class[i] : 0;
-        stype[i] = i < n ? m.station_type[i] : 0;
+    for (int i = threadIdx.x; i < SG_EV_MAX_CONSTRAINTS; i += blockDim.x) {
+        const double lim = sh.lim[i];
+        const double r = lim * (1.0 / kActionScale) - (double)kPreMargin;
+        ms.r_in[i] = r > 0.0 ? (float)(r * r * 0.99999) : -1.f;
+        ms.lim2_lo[i] = (float)(lim * lim * 0.999);
     }
-    __syncwarp();
-    const bool i64 = (flags & 1) == SG_EV_ACTION_I64;
-    const uint4* recs = reinterpret_cast<const uint4*>(m.sessions);
-    const long long ntiles = (B + kTileE - 1) / kTileE;
-    StatsAcc acc;
-
-    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const long long b0 = tile * kTileE;
-        const int nv = (int)min((long long)kTileE, B - b0);
-        const long long b = b0 + lane;
-        const bool env = lane < nv;
-
-        // ---------------- phase 0: coalesced tile loads (8 rows of loads in flight) -----------------
-        int4 clk = make_int4(kEpisode, 0, 0, 0);
-        if (env) clk = *reinterpret_cast<const int4*>(s.clock + b * 4);
-        {
-            const uint8_t* gk = s.sess_idx + b0 * n;
-            const int nbytes = nv * n, nvec = nbytes >> 4;
-            for (int c = lane; c < nvec; c += 32) reinterpret_cast<uint4*>(tk)[c] = reinterpret_cast<const uint4*>(gk)[c];
-            for (int c = (nvec << 4) + lane; c < nbytes; c += 32) tk[c] = gk[c];
-        }
-        const bool col = 2 * lane < n;
-        for (int r0 = 0; r0 < nv; r0 += 8) {
-            float2 v[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                v[u] = make_float2(0.f, 0.f);
-                if (col && r0 + u < nv) {
-                    if (i64) {
-                        const long long* ap = reinterpret_cast<const long long*>(action) + (b0 + r0 + u) * n + 2 * lane;
-                        v[u].x = __fdiv_rn((float)ap[0], (float)(bins - 1));            // wrappers.py:45
-                        v[u].y = __fdiv_rn((float)ap[1], (float)(bins - 1));
-                    } else {
-                        v[u] = ldg_stream_f2(reinterpret_cast<const float2*>(reinterpret_cast<const float*>(action) + (b0 + r0 + u) * n) + lane);
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u)
-                if (col && r0 + u < nv) { tact[(r0 + u) * RS + 2 * lane] = v[u].x; tact[(r0 + u) * RS + 2 * lane + 1] = v[u].y; }
-        }
-        __syncwarp();
-
-        // ---------------- phase 1: one thread = one env ------------------------------------------
-        const int t = clk.x, tn = t + 1;
-        int day = clk.y, md = clk.z;
-        const bool live = env && t < kEpisode;
-        bool commit = live;
-        const int sbase = day * K * n;
-        for (int c = 0; c < C; ++c) { sS[c * kTileE + lane] = 0.0; sP[c * kTileE + lane] = 0; }
-        int nl = 0;
-        float* myact = tact + lane * RS;
-        short* myest = test + lane * RS;
-        uint8_t* myk = tk + lane * n;
-        uint8_t* mypil = tpil + lane * n;
-        uint8_t* mylst = tlst + lane * n;
-        // moer0 of the row the reward needs: issue early
-        float moer0f = 0.f;
-        if (live) moer0f = __ldg(m.moer + ((long long)md * SG_EV_MOER_ROWS + tn) * SG_EV_MOER_COLS);
-        if (live) {
-            constexpr int U = 9;
-            for (int i0 = 0; i0 < n; i0 += U) {
-                int kk[U], arrv[U];
-#pragma unroll
-                for (int u = 0; u < U; ++u) kk[u] = (i0 + u < n) ? myk[i0 + u] : 255;
-#pragma unroll
-                for (int u = 0; u < U; ++u) {                         // U independent L2 look-ups in flight
-                    arrv[u] = kEmpty;
-                    if (kk[u] < K) arrv[u] = (int)(short)(__ldg(reinterpret_cast<const unsigned*>(recs + (sbase + kk[u] * n + i0 + u))) & 0xffffu);
-                }
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const int i = i0 + u;
-                    if (i < n) {
-                        bool listed = false;
-                        if (kk[u] != 255) {
-                            if (arrv[u] == kEmpty) myk[i] = 255;     // nothing (more) at this station today
-                            else if (arrv[u] <= tn) { mylst[nl++] = (uint8_t)i; listed = true; }
-                        }
-                        myest[i] = 0;
-                        if constexpr (MODE == 0) {
-                            // every EVSE receives a pilot, occupied or not (it counts in the constraint currents)
-                            const float amps = myact[i] * 32.f;
-                            const float pf = stype[i] == 0 ? (amps >= 6.f ? rintf(amps) : 0.f) : rintf(amps * 0.125f) * 8.f;
-                            const int pi = (int)pf;
-                            mypil[i] = (uint8_t)pi;
-                            sP[scls[i] * kTileE + lane] += pi;
-                        } else {
-                            mypil[i] = 0;
-                        }
-                        if (!listed) myact[i] = 0.f;                  // 'demands' of an empty station
-                    }
-                }
-            }
-        }
-        constexpr int V = 4;                                          // listed stations processed per batch
-        struct Rec { int i, k, arr, dep, est; double energy, del; bool on, plugged; };
-        auto load_batch = [&](int e0, bool enable, Rec (&q)[V]) {
-#pragma unroll
-            for (int u = 0; u < V; ++u) {
-                q[u].on = enable && e0 + u < nl;
-                q[u].i = q[u].on ? mylst[e0 + u] : 0;
-                q[u].k = q[u].on ? myk[q[u].i] : 255;
-            }
-            uint4 raw[V];
-#pragma unroll
-            for (int u = 0; u < V; ++u) {
-                raw[u] = make_uint4(0x7fff7fffu, 0x7fffu, 0u, 0u);
-                if (q[u].on && q[u].k < K) raw[u] = __ldg(recs + (sbase + q[u].k * n + q[u].i));
-            }
-#pragma unroll
-            for (int u = 0; u < V; ++u) {
-                q[u].arr = (int)(short)(raw[u].x & 0xffffu);
-                q[u].dep = (int)(short)(raw[u].x >> 16);
-                q[u].est = (int)(short)(raw[u].y & 0xffffu);
-                q[u].energy = __hiloint2double((int)raw[u].w, (int)raw[u].z);
-                q[u].plugged = q[u].on && t >= 1 && q[u].arr <= t && t < q[u].dep;
-            }
-#pragma unroll
-            for (int u = 0; u < V; ++u) q[u].del = q[u].plugged ? s.delivered[b * n + q[u].i] : 0.0;
-        };
-        // pass A (projection only): clipped action and its class sums -> feasibility
-        if constexpr (MODE == 1) {
-            const int nmax = __reduce_max_sync(kFull, live ? nl : 0);
-            for (int e0 = 0; e0 < nmax; e0 += V) {
-                Rec q[V];
-                load_batch(e0, live, q);
-#pragma unroll
-                for (int u = 0; u < V; ++u) {
-                    if (q[u].plugged) {
-                        const double rem = q[u].energy - q[u].del;
-                        const float dem = rem > kFullEps ? (float)rem : 0.f;
-                        const double x = fmin(fmax((double)myact[q[u].i], 0.0), upper_bound(dem));
-                        sS[scls[q[u].i] * kTileE + lane] += x;
-                    }
-                }
-            }
-            if (live) {
-                bool ok = true;
-                for (int j = 0; j < J; ++j) {
-                    double wr = 0, wi = 0;
-                    for (int c = 0; c < C; ++c) {
-                        const double S = sS[c * kTileE + lane];
-                        wr = fma(scre[j * kMC + c], S, wr);
-                        wi = fma(scim[j * kMC + c], S, wi);
-                    }
-                    const double r = slim[j] * (1.0 / kActionScale);
-                    ok = ok && (fma(wr, wr, wi * wi) <= r * r);
-                }
-                if (!ok) {
-                    commit = false;
-                    todo[2 + atomicAdd(todo, 1)] = (int)b;        // the work-list kernel redoes this env
-                }
-            }
-        }
-        // pass B: pilots, charging, events, new demands / departures for the listed stations
-        double rate_sum = 0.0;
-        unsigned long long occ_new = 0ull;
-        {
-            const int nmax = __reduce_max_sync(kFull, commit ? nl : 0);
-            for (int e0 = 0; e0 < nmax; e0 += V) {
-                Rec q[V];
-                load_batch(e0, commit, q);
-#pragma unroll
-                for (int u = 0; u < V; ++u) {
-                    if (!q[u].on) continue;
-                    const int i = q[u].i;
-                    int k = q[u].k, arr = q[u].arr, dep = q[u].dep, est = q[u].est;
-                    double energy = q[u].energy, del = q[u].del;
-                    const bool plugged = q[u].plugged;
-                    if (plugged) {
-                        int pi;
-                        double pilot;
-                        if constexpr (MODE == 1) {
-                            const double rem = energy - del;
-                            const float dem = rem > kFullEps ? (float)rem : 0.f;
-                            const double x = fmin(fmax((double)myact[i], 0.0), upper_bound(dem));
-                            pilot = to_pilot(x, stype[i]);
-                            pi = __double2int_rn(pilot);
-                            mypil[i] = (uint8_t)pi;
-                            sP[scls[i] * kTileE + lane] += pi;
-                        } else {
-                            pi = mypil[i];
-                            pilot = (double)pi;
-                        }
-                        const double charge = fmax(0.0, kCapacity - energy) + del;
-                        if (kCapacity - charge > 2.0) {              // neither battery limit can bind
-                            del += senergy[pi];
-                            rate_sum += srate[pi];
-                        } else {
-                            const double rate_to_full = div_c(kCapacity - charge, kPeriodH, kInvPeriodH);
-                            const double soc = div_c(charge, kCapacity, kInv100);
-                            const double p_pilot = div_c(pilot * kVoltage, 1000.0, kInv1000);
-                            const double cap2 = soc < kTransitionSoc ? kMaxPower
-                                                                     : div_c(1.0 - soc, kOneMinusTrans, kInvOMT) * kMaxPower;
-                            const double power = fmin(fmin(p_pilot, cap2), rate_to_full);
-                            const double rate = div_c(power * 1000.0, kVoltage, kInv208);
-                            del += div_c(rate * kVoltage, 1000.0, kInv1000) * kPeriodH;
-                            rate_sum += rate;
-                        }
-                    }
-                    bool moved = false;
-                    while (dep <= tn && arr != kEmpty) {              // session over (or zero-length): next slot
-                        k += 1; del = 0.0; moved = true;
-                        arr = dep = est = kEmpty; energy = 0.0;
-                        if (k < K) {
-                            const uint4 r = __ldg(recs + (sbase + k * n + i));
-                            arr = (int)(short)(r.x & 0xffffu); dep = (int)(short)(r.x >> 16);
-                            est = (int)(short)(r.y & 0xffffu); energy = __hiloint2double((int)r.w, (int)r.z);
-                        }
-                    }
-                    if (moved) myk[i] = (arr == kEmpty) ? 255 : (uint8_t)k;
-                    if (plugged || moved) s.delivered[b * n + i] = del;
-                    const double rem = energy - del;
-                    const bool pln = arr <= tn && tn < dep;
-                    const bool active = pln && rem > kFullEps;                     // Interface.active_sessions()
-                    if (pln) occ_new |= 1ull << i;
-                    myact[i] = active ? (float)rem : 0.f;
-                    myest[i] = active ? (short)(est - tn) : (short)0;
-                }
-            }
-        }
-        // ---------------- per-env epilogue: reward, clock, statistics -----------------------------
-        const bool dn = tn >= kEpisode;
-        const bool autoreset = commit && dn && (flags & SG_EV_FLAG_AUTORESET);
-        int md_out = md, t_out = tn;
-        if (commit) {
-            double excess = 0.0;
-            for (int j = 0; j < J; ++j) {
-                double wr = 0, wi = 0;
-                for (int c = 0; c < C; ++c) {
-                    const double S = (double)sP[c * kTileE + lane];
-                    wr = fma(scre[j * kMC + c], S, wr);
-                    wi = fma(scim[j * kMC + c], S, wi);
-                }
-                const double lim = slim[j], sq = fma(wr, wr, wi * wi);
-                if (sq > lim * lim) excess += fmax(0.0, sqrt(sq) - lim);
-            }
-            const double moer0 = (double)moer0f;
-            const double profit = kProfitFactor * rate_sum;
-            const double excess_charge = excess * kViolationFactor;
-            const double carbon = kCarbonFactor * rate_sum * moer0;
-            const double rew = profit - carbon - excess_charge;
-            double* bd = s.breakdown + b * 3;
-            if (t == 0) { bd[0] = profit; bd[1] = carbon; bd[2] = excess_charge; }
-            else { bd[0] += profit; bd[1] += carbon; bd[2] += excess_charge; }
-            int nidx = clk.w;
-            if (m.arrivals != nullptr) {
-                const unsigned* arow = m.arrivals + (long long)day * (m.max_day_sessions + 1);
-                while ((int)(__ldg(arow + nidx) & 0x7fffu) <= tn) ++nidx;
-            }
-            if (autoreset) {
-                day = (day + 1) % m.n_days;                           // sequential days, event_generation.py:284-291
-                md_out = (md + 1) % m.n_moer_days;
-                t_out = 0; nidx = 0; occ_new = 0ull;
-                for (int i = 0; i < n; ++i) myk[i] = 0;               // delivered is already 0: every session ended
-            }
-            if (s.occ != nullptr) s.occ[b] = occ_new;
-            *reinterpret_cast<int4*>(s.clock + b * 4) = make_int4(t_out, day, md_out, nidx);
-            reward[b] = rew;
-            done[b] = dn ? 1 : 0;
-            if (status != nullptr) status[b] = 0;
-            if (stats != nullptr) acc.add(rew, dn, profit, carbon, excess_charge);
-        } else if (env && t >= kEpisode) {                            // finished episode, not reset: stays terminal
-            reward[b] = 0.0; done[b] = 1;
-            if (status != nullptr) status[b] = 0;
-        }
-        __syncwarp();
-
-        // ---------------- phase 2: coalesced write-back (tails of 8 rows in flight) ----------------
-        const unsigned commit_mask = __ballot_sync(kFull, commit);
-        {
-            uint8_t* gk = s.sess_idx + b0 * n;
-            const int nbytes = nv * n, nvec = nbytes >> 4;
-            for (int c = lane; c < nvec; c += 32) reinterpret_cast<uint4*>(gk)[c] = reinterpret_cast<const uint4*>(tk)[c];
-            for (int c = (nvec << 4) + lane; c < nbytes; c += 32) gk[c] = tk[c];
-        }
-        const float ts_new = (float)((double)tn / (double)kEpisode);            // env.py:392 (same t for a lock-step tile row)
-        for (int r0 = 0; r0 < nv; r0 += 8) {
-            float tail0[8], tail1[8];
-            int arr8 = 0;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int r = min(r0 + u, kTileE - 1);
-                const int md_r = __shfl_sync(kFull, md, r), tn_r = __shfl_sync(kFull, tn, r);
-                arr8 |= __shfl_sync(kFull, (int)autoreset, r) << u;
-                tail0[u] = tail1[u] = 0.f;
-                if (r0 + u < nv && ((commit_mask >> r) & 1u)) {
-                    const float* row = m.moer + ((long long)md_r * SG_EV_MOER_ROWS + tn_r) * SG_EV_MOER_COLS;
-                    if (lane < kf) tail0[u] = __ldg(row + 1 + lane); else if (lane == kf) tail0[u] = __ldg(row);
-                    const int e = lane + 32;
-                    if (e < kf) tail1[u] = __ldg(row + 1 + e); else if (e == kf) tail1[u] = __ldg(row);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int r = r0 + u;
-                if (r >= nv || !((commit_mask >> r) & 1u)) continue;
-                const bool ar = (arr8 >> u) & 1;
-                const float ts_r = __shfl_sync(kFull, ts_new, r);
-                float* orow = (ar && final_obs != nullptr) ? final_obs + (b0 + r) * OBS : obs + (b0 + r) * OBS;
-                if (!(ar && final_obs == nullptr)) {                  // the step's own observation (terminal one if auto-reset)
-                    if (col) {
-                        stg_stream_f2(reinterpret_cast<float2*>(orow) + lane,
-                                      make_float2(tact[r * RS + 2 * lane], tact[r * RS + 2 * lane + 1]));
-                        stg_stream_f2(reinterpret_cast<float2*>(orow + n) + lane,
-                                      make_float2((float)test[r * RS + 2 * lane], (float)test[r * RS + 2 * lane + 1]));
-                    }
-                    if (lane <= kf) orow[2 * n + lane] = tail0[u]; else if (lane == kf + 1) orow[2 * n + lane] = ts_r;
-                    if (lane + 32 <= kf) orow[2 * n + lane + 32] = tail1[u]; else if (lane + 32 == kf + 1) orow[2 * n + lane + 32] = ts_r;
-                }
-                if (ar) {                                             // reset observation of the next episode
-                    const int mdo_r = __shfl_sync(kFull, md_out, r);
-                    const float* row = m.moer + ((long long)mdo_r * SG_EV_MOER_ROWS) * SG_EV_MOER_COLS;
-                    float* o2 = obs + (b0 + r) * OBS;
-                    if (col) {
-                        stg_stream_f2(reinterpret_cast<float2*>(o2) + lane, make_float2(0.f, 0.f));
-                        stg_stream_f2(reinterpret_cast<float2*>(o2 + n) + lane, make_float2(0.f, 0.f));
-                    }
-#pragma unroll
-                    for (int pass = 0; pass < 2; ++pass) {
-                        const int e = lane + 32 * pass;
-                        if (e < kf + 2) o2[2 * n + e] = e < kf ? __ldg(row + 1 + e) : (e == kf ? __ldg(row) : 0.f);
-                    }
-                }
-                if (pilots != nullptr && col)
-                    reinterpret_cast<uchar2*>(pilots + (b0 + r) * n)[lane] = make_uchar2(tpil[r * n + 2 * lane], tpil[r * n + 2 * lane + 1]);
-            }
-        }
-        __syncwarp();
-    }
-    if (stats != nullptr) {
-        // one warp per CTA: plain warp reduction + one set of atomics
-        double v[11] = {acc.count, acc.sum, acc.sumsq, acc.mn, acc.mx, acc.n_done, acc.n_proj, acc.n_maxiter, acc.c0, acc.c1, acc.c2};
-#pragma unroll
-        for (int i = 0; i < 11; ++i) {
-            const double r = (i == 3) ? warp_min(v[i]) : (i == 4) ? warp_max(v[i]) : warp_sum(v[i]);
-            if (lane == 0) {
-                if (i == 3) atomic_min_double(stats + 3, r);
-                else if (i == 4) atomic_max_double(stats + 4, r);
-                else if (r != 0.0) atomicAdd(stats + i, r);
-            }
-        }
-    }
-}
-
-// =================================================================================================
-// Event-driven kernel (default main kernel when the action projection is on).
-//
-// With the projection on, a station without a plugged-in EV has upper bound 0 (env.py:188-189): its
-// pilot is 0, it delivers nothing and its observation entries are 0.  So one step only has to
-// touch the OCCUPIED stations (~15 % of the 54).  Per env the engine keeps a 64-bit occupancy mask
-// and a cursor into the day's arrival-sorted session list; one thread advances one env:
-//   * walk the set bits of the mask: sparse loads of sess_idx / action / delivered and the session
-//     record, battery arithmetic, sparse stores; no shared-memory tiles -> high occupancy;
-//   * departures clear bits, arrivals (cursor) set them;
-//   * the observation rows are zero-filled with coalesced vector stores by the whole warp and the
-//     few non-zero entries are patched by the owning thread; the MOER tails are copied row by row.
-// Envs whose clipped action violates the network are queued for the solver kernel untouched.
-// =================================================================================================
-struct SparseShared {
-    double con_re[SG_EV_MAX_CONSTRAINTS * kMC], con_im[SG_EV_MAX_CONSTRAINTS * kMC], lim[SG_EV_MAX_CONSTRAINTS];
-    double rate[40], energy[40];
-    uint8_t cls[SG_EV_MAX_STATIONS], type[SG_EV_MAX_STATIONS];
-};
-constexpr int kSparseWarps = 4;
-
-__global__ void __launch_bounds__(kSparseWarps * 32, 4)
-ev_step_sparse_kernel(const sg_ev_model m, const sg_ev_state s, const long long B, const void* __restrict__ action,
-                      const int flags, const int bins, float* __restrict__ obs, double* __restrict__ reward,
-                      uint8_t* __restrict__ done, uint8_t* __restrict__ pilots, float* __restrict__ final_obs,
-                      uint8_t* __restrict__ status, double* __restrict__ stats, int32_t* __restrict__ todo) {
-    __shared__ SparseShared sh;
-    __shared__ double sstat[11 * kSparseWarps];
-    const int n = m.n_stations, kf = m.moer_steps, OBS = 2 * n + kf + 2, C = m.n_classes, J = m.n_constraints;
-    const int K = m.max_sessions;
-    for (int i = threadIdx.x; i < SG_EV_MAX_CONSTRAINTS * kMC; i += blockDim.x) { sh.con_re[i] = m.con_re[i]; sh.con_im[i] = m.con_im[i]; }
-    if (threadIdx.x < SG_EV_MAX_CONSTRAINTS) sh.lim[threadIdx.x] = m.magnitudes[threadIdx.x];
-    if (threadIdx.x < SG_EV_MAX_STATIONS) {
-        sh.cls[threadIdx.x] = (int)threadIdx.x < n ? m.station_class[threadIdx.x] : 0;
-        sh.type[threadIdx.x] = (int)threadIdx.x < n ? m.station_type[threadIdx.x] : 0;
-    }
-    if (threadIdx.x <= 32) {
-        const double pp = div_c((double)threadIdx.x * kVoltage, 1000.0, kInv1000);
-        const double rate = div_c(pp * 1000.0, kVoltage, kInv208);
-        sh.rate[threadIdx.x] = rate;
-        sh.energy[threadIdx.x] = div_c(rate * kVoltage, 1000.0, kInv1000) * kPeriodH;
-    }
+    for (int i = threadIdx.x; i <= 32; i += blockDim.x) ms.ppilot[i] = div_c((double)i * kVoltage, 1000.0, kInv1000);
     __syncthreads();
-    const int lane = threadIdx.x & 31;
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpShared& ws = ms.w[warp];
     const bool i64 = (flags & 1) == SG_EV_ACTION_I64;
-    const uint4* recs = reinterpret_cast<const uint4*>(m.sessions);
+    const float* __restrict__ moer = m.moer;
+    const uint4* __restrict__ recs = reinterpret_cast<const uint4*>(m.sessions);
+    Slot* slots = reinterpret_cast<Slot*>(s.slots);
     const long long ntiles = (B + 31) / 32;
-    const long long wstride = (long long)gridDim.x * kSparseWarps;
-    const bool col = 2 * lane < n;
+    const long long wstride = (long long)gridDim.x * kMainWarps;
+    const bool pair_rows = ((kf & 1) == 0);            // OBS even: rows are 8-byte aligned, tail pairs never straddle
+    const int tp = (kf + 2) >> 1;                      // float2 pairs in a row's MOER + timestep tail
     StatsAcc acc;
 
-    struct Stn { int i, k, arr, dep, est; double energy, del; float a; bool plugged; };
-    constexpr int V = 4;
+    auto act_at = [&](const long long o) -> float {
+        return i64 ? __fdiv_rn((float)reinterpret_cast<const long long*>(action)[o], (float)(bins - 1))   // wrappers.py:45
+                   : __ldg(reinterpret_cast<const float*>(action) + o);
+    };
 
-    for (long long tile = (long long)blockIdx.x * kSparseWarps + (threadIdx.x >> 5); tile < ntiles; tile += wstride) {
+    for (long long tile = (long long)blockIdx.x * kMainWarps + warp; tile < ntiles; tile += wstride) {
         const long long b0 = tile * 32;
         const int nv = (int)min(32ll, B - b0);
         const long long b = b0 + lane;
         const bool env = lane < nv;
         int4 clk = make_int4(kEpisode, 0, 0, 0);
-        unsigned long long occ = 0ull;
-        if (env) { clk = *reinterpret_cast<const int4*>(s.clock + b * 4); occ = s.occ[b]; }
+        if (env) clk = *reinterpret_cast<const int4*>(s.clock + b * 4);
         const int t = clk.x, tn = t + 1;
-        int day = clk.y, md = clk.z, nidx = clk.w;
+        int day = clk.y, nidx = clk.w;
+        const int md = clk.z;
         const bool live = env && t < kEpisode;
-        bool commit = live;
-        if (!live) occ = 0ull;
-        const int sbase = day * K * n;
+        unsigned long long occ = 0ull;
+        double bd0 = 0.0, bd1 = 0.0, bd2 = 0.0;
+        if (live) {
+            occ = s.occ[b];
+            if (t != 0) { const double* bd = s.breakdown + b * 3; bd0 = bd[0]; bd1 = bd[1]; bd2 = bd[2]; }
+        }
+        const bool dn = tn >= kEpisode;
+        const bool autoreset = live && dn && (flags & SG_EV_FLAG_AUTORESET);
+        const int md_out = autoreset ? (md + 1) % m.n_moer_days : md;
+        const unsigned live_mask = __ballot_sync(kFull, live);
+        const unsigned ar_mask = __ballot_sync(kFull, autoreset);
+        const int moff = (md * SG_EV_MOER_ROWS + min(tn, SG_EV_MOER_ROWS - 1)) * SG_EV_MOER_COLS;
+        const float tsf = timestep_frac(tn);
         float moer0f = 0.f;
-        if (live) moer0f = __ldg(m.moer + ((long long)md * SG_EV_MOER_ROWS + tn) * SG_EV_MOER_COLS);
+        if (live) moer0f = __ldg(moer + moff);
+        // the day's next two pending arrivals (prefetched: the arrivals phase comes last)
+        const unsigned* arow = m.arrivals + (long long)day * (m.max_day_sessions + 1);
+        unsigned ent = 0x7fffu, ent2 = 0x7fffu;
+        if (live && !autoreset) {
+            ent = __ldg(arow + nidx);
+            if (nidx < m.max_day_sessions) ent2 = __ldg(arow + nidx + 1);
+        }
+        const int par = t & 1;
+        const int info = tn | (par << 16) | ((int)autoreset << 17);
+#pragma unroll
+        for (int c = 0; c < kMC; ++c) { ws.S[c][lane] = 0.f; ws.P[c][lane] = 0; }
 
-        // batch loader over the set bits of `mask` (V stations, all loads of a level in flight together)
-        auto load_batch = [&](unsigned long long& mask, Stn (&q)[V]) {
-#pragma unroll
-            for (int u = 0; u < V; ++u) {
-                q[u].i = -1;
-                if (mask) { q[u].i = __ffsll((long long)mask) - 1; mask &= mask - 1; }
+        // ---------------- fill: coalesced observation (and pilot) rows ------------------------------
+        if (nv == 32 && live_mask == kFull && ar_mask == 0u && pair_rows) {
+            float2* o2 = reinterpret_cast<float2*>(obs + b0 * OBS);
+            const int rp = OBS >> 1;                                   // float2 pairs per row
+            const float2 z2 = make_float2(0.f, 0.f);
+#pragma unroll 4
+            for (int r = 0; r < 32; ++r) {
+                if (lane < n) stg_stream_f2(o2 + r * rp + lane, z2);
+                if (lane + 32 < n) stg_stream_f2(o2 + r * rp + lane + 32, z2);
             }
-#pragma unroll
-            for (int u = 0; u < V; ++u) {
-                q[u].k = 255; q[u].a = 0.f; q[u].del = 0.0;
-                if (q[u].i >= 0) {
-                    const long long o = b * n + q[u].i;
-                    q[u].k = s.sess_idx[o];
-                    q[u].del = s.delivered[o];
-                    q[u].a = i64 ? __fdiv_rn((float)reinterpret_cast<const long long*>(action)[o], (float)(bins - 1))
-                                 : __ldg(reinterpret_cast<const float*>(action) + o);
-                }
+            // tails: 32 rows x tp pairs, one pair per lane and iteration
+            int row = lane / tp, col = lane - row * tp;
+            const int drow = 32 / tp, dcol = 32 - drow * tp;
+            for (int it = 0; it < tp; ++it) {
+                const int moff_r = __shfl_sync(kFull, moff, row);
+                const float ts_r = __shfl_sync(kFull, tsf, row);
+                const int e = 2 * col;
+                const float* p = moer + moff_r;
+                float2 v;
+                v.x = e < kf ? __ldg(p + 1 + e) : __ldg(p);
+                v.y = e + 1 < kf ? __ldg(p + 2 + e) : (e + 1 == kf ? __ldg(p) : ts_r);
+                stg_stream_f2(o2 + row * rp + n + col, v);
+                row += drow; col += dcol;
+                if (col >= tp) { col -= tp; row += 1; }
             }
-            uint4 raw[V];
-#pragma unroll
-            for (int u = 0; u < V; ++u) {
-                raw[u] = make_uint4(0x7fff7fffu, 0x7fffu, 0u, 0u);
-                if (q[u].i >= 0 && q[u].k < K) raw[u] = __ldg(recs + (sbase + q[u].k * n + q[u].i));
+            if (MODE != 0 && pilots != nullptr) {
+                uint4* p4 = reinterpret_cast<uint4*>(pilots + b0 * n);  // 32 n bytes, 16-byte aligned
+                for (int c = lane; c < 2 * n; c += 32) p4[c] = make_uint4(0u, 0u, 0u, 0u);
             }
-#pragma unroll
-            for (int u = 0; u < V; ++u) {
-                q[u].arr = (int)(short)(raw[u].x & 0xffffu);
-                q[u].dep = (int)(short)(raw[u].x >> 16);
-                q[u].est = (int)(short)(raw[u].y & 0xffffu);
-                q[u].energy = __hiloint2double((int)raw[u].w, (int)raw[u].z);
-                q[u].plugged = q[u].i >= 0 && t >= 1 && q[u].arr <= t && t < q[u].dep;
-            }
-        };
-        auto clipped = [&](const Stn& q) {
-            const double rem = q.energy - q.del;
-            const float dem = rem > kFullEps ? (float)rem : 0.f;                 // obs 'demands', env.py:388
-            return fmin(fmax((double)q.a, 0.0), upper_bound(dem));
-        };
-
-        // ---- pass A: class sums of the clipped action -> is it inside the network constraints? ----
-        {
-            double S[kMC];
-#pragma unroll
-            for (int c = 0; c < kMC; ++c) S[c] = 0.0;
-            unsigned long long mask = occ;
-            while (__any_sync(kFull, mask != 0ull)) {
-                Stn q[V];
-                load_batch(mask, q);
-#pragma unroll
-                for (int u = 0; u < V; ++u) {
-                    if (q[u].plugged) {
-                        const double x = clipped(q[u]);
-                        const int c = sh.cls[q[u].i];
-#pragma unroll
-                        for (int cc = 0; cc < kMC; ++cc) S[cc] += (cc == c) ? x : 0.0;
+        } else {
+            for (int r = 0; r < nv; ++r) {
+                if (!((live_mask >> r) & 1u)) continue;
+                const bool ar = (ar_mask >> r) & 1u;
+                const int moff_r = __shfl_sync(kFull, moff, r);
+                const float ts_r = __shfl_sync(kFull, tsf, r);
+                float* orow = ar ? (final_obs != nullptr ? final_obs + (b0 + r) * OBS : nullptr) : obs + (b0 + r) * OBS;
+                auto fill_row = [&](float* dst, const float* row, const float tsv) {
+                    for (int e = lane; e < OBS; e += 32) {
+                        const int q = e - 2 * n;
+                        dst[e] = q < 0 ? 0.f : (q < kf ? __ldg(row + 1 + q) : (q == kf ? __ldg(row) : tsv));
                     }
+                };
+                if (orow != nullptr) fill_row(orow, moer + moff_r, ts_r);
+                if (ar) {                                  // reset observation of the next episode (env.py:293-338)
+                    const int mdo_r = __shfl_sync(kFull, md_out, r);
+                    fill_row(obs + (b0 + r) * OBS, moer + (long long)mdo_r * SG_EV_MOER_ROWS * SG_EV_MOER_COLS, 0.f);
                 }
-            }
-            if (live) {
-                bool ok = true;
-                for (int j = 0; j < J; ++j) {
-                    double wr = 0, wi = 0;
-#pragma unroll
-                    for (int c = 0; c < kMC; ++c) { wr = fma(sh.con_re[j * kMC + c], S[c], wr); wi = fma(sh.con_im[j * kMC + c], S[c], wi); }
-                    const double r = sh.lim[j] * (1.0 / kActionScale);
-                    ok = ok && (fma(wr, wr, wi * wi) <= r * r);
-                }
-                if (!ok) { commit = false; todo[2 + atomicAdd(todo, 1)] = (int)b; }
+                if (MODE != 0 && pilots != nullptr)
+                    for (int i = lane; i < n; i += 32) pilots[(b0 + r) * n + i] = 0;
             }
         }
-        const unsigned commit_mask = __ballot_sync(kFull, commit);
-        const bool dn = tn >= kEpisode;
-        const bool autoreset = commit && dn && (flags & SG_EV_FLAG_AUTORESET);
-        const unsigned ar_mask = __ballot_sync(kFull, autoreset);
-
-        // ---- zero-fill the committed rows (coalesced); the owners patch the few non-zero entries ----
-        for (int r = 0; r < nv; ++r) {
-            if (!((commit_mask >> r) & 1u)) continue;
-            float* orow = (((ar_mask >> r) & 1u) && final_obs != nullptr) ? final_obs + (b0 + r) * OBS : obs + (b0 + r) * OBS;
-            if (col) {
-                stg_stream_f2(reinterpret_cast<float2*>(orow) + lane, make_float2(0.f, 0.f));
-                stg_stream_f2(reinterpret_cast<float2*>(orow + n) + lane, make_float2(0.f, 0.f));
-                if (pilots != nullptr) reinterpret_cast<uchar2*>(pilots + (b0 + r) * n)[lane] = make_uchar2(0, 0);
+        if constexpr (MODE == 0) {
+            // every EVSE receives a pilot, occupied or not (env.py:368-378); class sums for the excess current
+            for (int r = 0; r < nv; ++r) {
+                if (!((live_mask >> r) & 1u)) continue;
+                const int i0 = 2 * lane;
+                unsigned pv[2] = {0u, 0u};
+                int cl[2] = {255, 255};
+#pragma unroll
+                for (int p = 0; p < 2; ++p)
+                    if (i0 + p < n) {
+                        cl[p] = sh.cls[i0 + p];
+                        pv[p] = (unsigned)pilot_f32(act_at((b0 + r) * n + i0 + p), sh.type[i0 + p]);
+                    }
+                if (pilots != nullptr) {
+#pragma unroll
+                    for (int p = 0; p < 2; ++p) if (i0 + p < n) pilots[(b0 + r) * n + i0 + p] = (uint8_t)pv[p];
+                }
+#pragma unroll
+                for (int w = 0; w < kMC / 2; ++w) {
+                    unsigned part = 0;
+#pragma unroll
+                    for (int p = 0; p < 2; ++p)
+                        if ((cl[p] >> 1) == w) part += pv[p] << ((cl[p] & 1) * 16);
+                    const unsigned tot = __reduce_add_sync(kFull, part);
+                    if (lane == r) { ws.P[2 * w][lane] = (int)(tot & 0xffffu); ws.P[2 * w + 1][lane] = (int)(tot >> 16); }
+                }
             }
         }
         __syncwarp();
-        float* myrow = (autoreset && final_obs != nullptr) ? final_obs + b * OBS : obs + b * OBS;
-        const bool patch = commit && !(autoreset && final_obs == nullptr);      // terminal obs kept only if asked for
 
-        // ---- pass B: pilots, charging, departures for the occupied stations -------------------------
-        double rate_sum = 0.0;
-        int P[kMC];
+        // ---------------- items: one (env, occupied station) per lane ------------------------------------
+        const int cnt = __popcll(occ);
+        int off = cnt;                                                 // inclusive scan over the lanes
 #pragma unroll
-        for (int c = 0; c < kMC; ++c) P[c] = 0;
-        unsigned long long occ_new = commit ? occ : 0ull;
-        {
-            unsigned long long mask = commit ? occ : 0ull;
-            while (__any_sync(kFull, mask != 0ull)) {
-                Stn q[V];
-                load_batch(mask, q);
+        for (int d = 1; d < 32; d <<= 1) {
+            const int v = __shfl_up_sync(kFull, off, d);
+            if (lane >= d) off += v;
+        }
+        const int total = __shfl_sync(kFull, off, 31);
+        off -= cnt;
+        double rate_sum = 0.0;
+        unsigned long long occ_new = occ;
+        for (int c0 = 0; c0 < total; c0 += kItemCap) {
+            const int nitems = min(kItemCap, total - c0);
+            {   // keys of this chunk
+                int j = off - c0;
+                for (unsigned long long mask = occ; mask; mask &= mask - 1, ++j)
+                    if (j >= 0 && j < kItemCap) ws.items[j].meta = ((unsigned)lane << 8) | (unsigned)(__ffsll((long long)mask) - 1);
+            }
+            __syncwarp();
+            constexpr int V = 2;
+            for (int base = 0; base < nitems; base += 32 * V) {
+                int e[V], si[V], inf[V];
+                Slot q[V];
+                float af[V];
+                bool on[V];
 #pragma unroll
                 for (int u = 0; u < V; ++u) {
-                    if (q[u].i < 0) continue;
-                    const int i = q[u].i;
-                    double del = q[u].del;
-                    if (q[u].plugged) {
-                        const double pilot = to_pilot(clipped(q[u]), sh.type[i]);
-                        const int pi = __double2int_rn(pilot);
-                        const int c = sh.cls[i];
+                    const int j = base + u * 32 + lane;
+                    on[u] = j < nitems;
+                    const unsigned key = on[u] ? ws.items[j].meta : 0u;
+                    e[u] = (int)(key >> 8); si[u] = (int)(key & 0xffu);
+                    inf[u] = __shfl_sync(kFull, info, e[u]);
+                }
 #pragma unroll
-                        for (int cc = 0; cc < kMC; ++cc) P[cc] += (cc == c) ? pi : 0;
-                        if (pilots != nullptr && pi != 0) pilots[b * n + i] = (uint8_t)pi;
-                        const double charge = fmax(0.0, kCapacity - q[u].energy) + del;
-                        if (kCapacity - charge > 2.0) {              // neither battery limit can bind
-                            del += sh.energy[pi];
-                            rate_sum += sh.rate[pi];
-                        } else {
-                            const double rate_to_full = div_c(kCapacity - charge, kPeriodH, kInvPeriodH);
-                            const double soc = div_c(charge, kCapacity, kInv100);
-                            const double p_pilot = div_c(pilot * kVoltage, 1000.0, kInv1000);
-                            const double cap2 = soc < kTransitionSoc ? kMaxPower
-                                                                     : div_c(1.0 - soc, kOneMinusTrans, kInvOMT) * kMaxPower;
-                            const double power = fmin(fmin(p_pilot, cap2), rate_to_full);
-                            const double rate = div_c(power * 1000.0, kVoltage, kInv208);
-                            del += div_c(rate * kVoltage, 1000.0, kInv1000) * kPeriodH;
-                            rate_sum += rate;
-                        }
+                for (int u = 0; u < V; ++u) {
+                    af[u] = 0.f;
+                    q[u].energy = 0.0; q[u].delivered = 0.0; q[u].dep = q[u].est = q[u].arr = q[u].k = 0;
+                    if (on[u]) {
+                        const long long be = b0 + e[u];
+                        q[u] = ld_slot(slots + ((long long)((inf[u] >> 16) & 1) * B + be) * n + si[u]);
+                        af[u] = act_at(be * n + si[u]);
                     }
-                    if (q[u].dep <= tn) {                             // Unplug event (timestamp = departure)
-                        occ_new &= ~(1ull << i);
-                        s.delivered[b * n + i] = 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < V; ++u) {
+                    if (!on[u]) continue;
+                    const int i = si[u], tn_e = inf[u] & 0xffff, par_e = (inf[u] >> 16) & 1;
+                    const bool ar_e = (inf[u] >> 17) & 1;
+                    const long long be = b0 + e[u];
+                    const int type = sh.type[i], cls = sh.cls[i];
+                    int pi;
+                    float xf = 0.f;
+                    if (MODE == 0) {
+                        pi = pilot_f32(af[u], type);
                     } else {
-                        if (q[u].plugged) s.delivered[b * n + i] = del;
-                        const double rem = q[u].energy - del;
-                        if (patch && rem > kFullEps) {                // Interface.active_sessions()
-                            myrow[i] = (float)rem;
-                            myrow[n + i] = (float)(q[u].est - tn);
+                        const double rem = q[u].energy - q[u].delivered;
+                        const float dem = rem > kFullEps ? (float)rem : 0.f;              // obs 'demands', env.py:388
+                        pi = pilot_clipped(af[u], dem, type, &xf);
+                        if (pilots != nullptr && pi != 0) pilots[be * n + i] = (uint8_t)pi;
+                    }
+                    ItemRec rec;
+                    rec.rate = charge_period(q[u].energy, q[u].delivered, ms.ppilot[pi]);
+                    rec.x = xf;
+                    const bool departed = q[u].dep <= tn_e;                               // Unplug event (timestamp = departure)
+                    rec.meta = (unsigned)pi | ((unsigned)cls << 8) | ((unsigned)departed << 16) | ((unsigned)i << 24);
+                    ws.items[base + u * 32 + lane] = rec;
+                    if (!departed) {
+                        st_slot(slots + ((long long)(par_e ^ 1) * B + be) * n + i, q[u]);
+                        const double rem = q[u].energy - q[u].delivered;
+                        float* row = ar_e ? final_obs : obs;                              // terminal observation only if asked for
+                        if (rem > kFullEps && row != nullptr) {                           // Interface.active_sessions()
+                            row[be * OBS + i] = (float)rem;
+                            row[be * OBS + n + i] = (float)(q[u].est - tn_e);
                         }
                     }
                 }
             }
+            __syncwarp();
+            // owner: thread e sums the records of env e in station order
+            {
+                const int lo = max(off - c0, 0), hi = min(off + cnt - c0, nitems);
+                for (int j = lo; __any_sync(kFull, j < hi); ++j) {
+                    if (j < hi) {
+                        const ItemRec rec = ws.items[j];
+                        const int cls = (rec.meta >> 8) & 0xff;
+                        rate_sum += rec.rate;
+                        if (MODE != 0) {
+                            ws.S[cls][lane] += rec.x;
+                            ws.P[cls][lane] += (int)(rec.meta & 0xffu);
+                        }
+                        if ((rec.meta >> 16) & 1u) occ_new &= ~(1ull << (rec.meta >> 24));
+                    }
+                }
+            }
+            __syncwarp();
         }
-        // ---- arrivals: Plugin events with timestamp <= t+1 (after the Unplug events) ------------------
-        if (commit && !autoreset) {
-            const unsigned* arow = m.arrivals + (long long)day * (m.max_day_sessions + 1);
-            unsigned ent = __ldg(arow + nidx);
-            while ((int)(ent & 0x7fffu) <= tn) {
+
+        // ---------------- network constraints on the clipped action (projection only) -------------------
+        int st = 0;
+        if constexpr (MODE != 0) {
+            bool ok = true;
+            if (live && cnt > 0) {
+                float Sf[kMC];
+#pragma unroll
+                for (int c = 0; c < kMC; ++c) Sf[c] = ws.S[c][lane];
+                for (int j = 0; j < J; ++j) {
+                    float wr = 0.f, wi = 0.f;
+#pragma unroll
+                    for (int c = 0; c < kMC; ++c) { wr = fmaf(ms.re[j * kMC + c], Sf[c], wr); wi = fmaf(ms.im[j * kMC + c], Sf[c], wi); }
+                    ok = ok && (fmaf(wr, wr, wi * wi) <= ms.r_in[j]);
+                }
+            }
+            unsigned bad = __ballot_sync(kFull, !ok);
+            while (bad) {
+                const int r = __ffs((int)bad) - 1;
+                bad &= bad - 1;
+                const unsigned long long occ_r = __shfl_sync(kFull, occ, r);
+                const int par_r = (__shfl_sync(kFull, info, r) >> 16) & 1;
+                const Slot* cur_r = slots + ((long long)par_r * B + (b0 + r)) * n;
+                const int st_r = project_env(sh, n, C, J, b0 + r, lane, action, i64, bins, cur_r, occ_r, ws.xs);
+                if (lane == r) {
+                    st = st_r;
+                    if (st_r != 0) {
+                        float* row = autoreset ? final_obs : obs;
+                        const RedoOut ro = redo_env(sh.type, sh.cls, ms.ppilot, &ws.P[0][lane], ws.xs, n, tn, occ, cur_r,
+                                                    slots + ((long long)(par_r ^ 1) * B + b) * n,
+                                                    row != nullptr ? row + b * OBS : nullptr,
+                                                    pilots != nullptr ? pilots + b * n : nullptr);
+                        rate_sum = ro.rate_sum;
+                        occ_new = ro.occ_new;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+
+        // ---------------- arrivals: Plugin events with timestamp <= t+1 (after the Unplug events) -------
+        if ((int)(ent & 0x7fffu) <= tn) {
+            float* row = autoreset ? final_obs : obs;
+            Slot* nxt = slots + ((long long)(par ^ 1) * B + b) * n;
+            do {
                 const int i = (ent >> 16) & 0xff, k = ent >> 24;
-                const uint4 r = __ldg(recs + (sbase + k * n + i));
-                const int dep = (int)(short)(r.x >> 16), est = (int)(short)(r.y & 0xffffu);
-                s.sess_idx[b * n + i] = (uint8_t)k;
-                if (dep > tn) {                                       // (zero-length sessions never charge)
+                const uint4 rr = __ldg(recs + ((long long)day * m.max_sessions + k) * n + i);
+                Slot ns;
+                ns.arr = (int)(short)(rr.x & 0xffffu);
+                ns.dep = (int)(short)(rr.x >> 16);
+                ns.est = (int)(short)(rr.y & 0xffffu);
+                ns.k = k;
+                ns.energy = __hiloint2double((int)rr.w, (int)rr.z);
+                ns.delivered = 0.0;
+                if (ns.dep > tn) {                                        // (zero-length sessions never charge)
                     occ_new |= 1ull << i;
-                    const double energy = __hiloint2double((int)r.w, (int)r.z);
-                    if (patch && energy > kFullEps) { myrow[i] = (float)energy; myrow[n + i] = (float)(est - tn); }
+                    st_slot(nxt + i, ns);
+                    if (row != nullptr && ns.energy > kFullEps) {
+                        row[b * OBS + i] = (float)ns.energy;
+                        row[b * OBS + n + i] = (float)(ns.est - tn);
+                    }
                 }
                 ++nidx;
-                ent = __ldg(arow + nidx);
-            }
+                ent = ent2;
+                ent2 = (int)(ent & 0x7fffu) <= tn ? __ldg(arow + nidx + 1) : 0x7fffu;
+            } while ((int)(ent & 0x7fffu) <= tn);
         }
-        // ---- per-env epilogue ---------------------------------------------------------------------------
-        int md_out = md;
-        if (commit) {
+
+        // ---------------- per-env epilogue: excess current, reward, clock ---------------------------------
+        if (live) {
             double excess = 0.0;
-            for (int j = 0; j < J; ++j) {
-                double wr = 0, wi = 0;
+            {
+                float Pf[kMC];
 #pragma unroll
-                for (int c = 0; c < kMC; ++c) { wr = fma(sh.con_re[j * kMC + c], (double)P[c], wr); wi = fma(sh.con_im[j * kMC + c], (double)P[c], wi); }
-                const double lim = sh.lim[j], sq = fma(wr, wr, wi * wi);
-                if (sq > lim * lim) excess += fmax(0.0, sqrt(sq) - lim);
+                for (int c = 0; c < kMC; ++c) Pf[c] = (float)ws.P[c][lane];
+                bool near = false;
+                for (int j = 0; j < J; ++j) {
+                    float wr = 0.f, wi = 0.f;
+#pragma unroll
+                    for (int c = 0; c < kMC; ++c) { wr = fmaf(ms.re[j * kMC + c], Pf[c], wr); wi = fmaf(ms.im[j * kMC + c], Pf[c], wi); }
+                    near = near || (fmaf(wr, wr, wi * wi) > ms.lim2_lo[j]);
+                }
+                if (near) {                                               // exact (env.py:449-452)
+                    for (int j = 0; j < J; ++j) {
+                        double wr = 0, wi = 0;
+#pragma unroll
+                        for (int c = 0; c < kMC; ++c) {
+                            wr = fma(sh.con_re[j * kMC + c], (double)ws.P[c][lane], wr);
+                            wi = fma(sh.con_im[j * kMC + c], (double)ws.P[c][lane], wi);
+                        }
+                        const double lim = sh.lim[j], sq = fma(wr, wr, wi * wi);
+                        if (sq > lim * lim) excess += fmax(0.0, sqrt(sq) - lim);
+                    }
+                }
             }
             const double profit = kProfitFactor * rate_sum;
             const double excess_charge = excess * kViolationFactor;
             const double carbon = kCarbonFactor * rate_sum * (double)moer0f;
             const double rew = profit - carbon - excess_charge;
+            // cumulative reward breakdown (env.py:460-462); restarted on the first step of an episode so that
+            // after an auto-reset the finished episode's totals stay readable until the next step
             double* bd = s.breakdown + b * 3;
-            if (t == 0) { bd[0] = profit; bd[1] = carbon; bd[2] = excess_charge; }
-            else { bd[0] += profit; bd[1] += carbon; bd[2] += excess_charge; }
+            bd[0] = bd0 + profit; bd[1] = bd1 + carbon; bd[2] = bd2 + excess_charge;
             int t_out = tn;
             if (autoreset) {
-                day = (day + 1) % m.n_days;                           // sequential days, event_generation.py:284-291
-                md_out = (md + 1) % m.n_moer_days;
+                day = (day + 1) % m.n_days;                               // sequential days, event_generation.py:284-291
                 t_out = 0; nidx = 0; occ_new = 0ull;
             }
             s.occ[b] = occ_new;
             *reinterpret_cast<int4*>(s.clock + b * 4) = make_int4(t_out, day, md_out, nidx);
             reward[b] = rew;
             done[b] = dn ? 1 : 0;
-            if (status != nullptr) status[b] = 0;
-            if (stats != nullptr) acc.add(rew, dn, profit, carbon, excess_charge);
-        } else if (env && t >= kEpisode) {                            // finished episode, not reset: stays terminal
+            if (status != nullptr) status[b] = (uint8_t)st;
+            if (stats != nullptr) {
+                acc.add(rew, dn, profit, carbon, excess_charge);
+                acc.n_proj += (st & SG_EV_STATUS_PROJECTED) ? 1.0 : 0.0;
+                acc.n_maxiter += (st & SG_EV_STATUS_MAXITER) ? 1.0 : 0.0;
+            }
+        } else if (env) {                                                 // finished episode, not reset: stays terminal
             reward[b] = 0.0; done[b] = 1;
             if (status != nullptr) status[b] = 0;
-        }
-        // ---- MOER tails (and the reset rows of auto-reset envs), 8 rows of loads in flight -------------
-        const float ts_new = (float)((double)tn / (double)kEpisode);            // env.py:392
-        for (int r0 = 0; r0 < nv; r0 += 8) {
-            float tail0[8], tail1[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int r = min(r0 + u, 31);
-                const int md_r = __shfl_sync(kFull, md, r), tn_r = __shfl_sync(kFull, tn, r);
-                tail0[u] = tail1[u] = 0.f;
-                if (r0 + u < nv && ((commit_mask >> r) & 1u)) {
-                    const float* row = m.moer + ((long long)md_r * SG_EV_MOER_ROWS + tn_r) * SG_EV_MOER_COLS;
-                    if (lane < kf) tail0[u] = __ldg(row + 1 + lane); else if (lane == kf) tail0[u] = __ldg(row);
-                    const int e = lane + 32;
-                    if (e < kf) tail1[u] = __ldg(row + 1 + e); else if (e == kf) tail1[u] = __ldg(row);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const int r = r0 + u;
-                if (r >= nv || !((commit_mask >> r) & 1u)) continue;
-                const bool ar = (ar_mask >> r) & 1u;
-                const float ts_r = __shfl_sync(kFull, ts_new, r);
-                if (!(ar && final_obs == nullptr)) {
-                    float* orow = (ar ? final_obs : obs) + (b0 + r) * OBS;
-                    if (lane <= kf) orow[2 * n + lane] = tail0[u]; else if (lane == kf + 1) orow[2 * n + lane] = ts_r;
-                    if (lane + 32 <= kf) orow[2 * n + lane + 32] = tail1[u]; else if (lane + 32 == kf + 1) orow[2 * n + lane + 32] = ts_r;
-                }
-                if (ar) {                                             // reset observation of the next episode
-                    const int mdo_r = __shfl_sync(kFull, md_out, r);
-                    const float* row = m.moer + ((long long)mdo_r * SG_EV_MOER_ROWS) * SG_EV_MOER_COLS;
-                    float* o2 = obs + (b0 + r) * OBS;
-                    if (col && final_obs != nullptr) {                // (already zero when the terminal obs is not kept)
-                        stg_stream_f2(reinterpret_cast<float2*>(o2) + lane, make_float2(0.f, 0.f));
-                        stg_stream_f2(reinterpret_cast<float2*>(o2 + n) + lane, make_float2(0.f, 0.f));
-                    }
-#pragma unroll
-                    for (int pass = 0; pass < 2; ++pass) {
-                        const int e = lane + 32 * pass;
-                        if (e < kf + 2) o2[2 * n + e] = e < kf ? __ldg(row + 1 + e) : (e == kf ? __ldg(row) : 0.f);
-                    }
-                    for (int i = lane; i < n; i += 32) s.sess_idx[(b0 + r) * n + i] = 0;    // new day: slot 0 everywhere
-                }
-            }
         }
         __syncwarp();
     }
     if (stats != nullptr) {
         __syncthreads();
-        stats_flush_block(acc, stats, sstat);
+        stats_flush_block(acc, stats, ms.stat);
     }
 }
 
-// Persistent CTAs: every warp strides over the batch, so the table staging and the statistics
-// flush are paid once per warp instead of once per env.
-template <int MODE>
-__global__ void __launch_bounds__(kThreads, 3)
-ev_step_kernel(const sg_ev_model m, const sg_ev_state s, const long long B, const void* __restrict__ action,
-               const int flags, const int bins, float* __restrict__ obs, double* __restrict__ reward,
-               uint8_t* __restrict__ done, uint8_t* __restrict__ pilots, float* __restrict__ final_obs,
-               uint8_t* __restrict__ status, double* __restrict__ stats, int32_t* __restrict__ todo) {
-    __shared__ EvShared sh;
-    load_shared(m, sh);
-    const int lane = threadIdx.x & 31;
-    const long long stride = (long long)gridDim.x * kWarpsPerBlock;
-    StatsAcc acc;
-    for (long long b = (long long)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5); b < B; b += stride)
-        ev_env_step<MODE>(m, s, sh, b, lane, action, flags, bins, obs, reward, done, pilots, final_obs, status, todo, acc);
-    if (stats != nullptr) {
-        __syncthreads();
-        stats_flush_block(acc, stats, sh.stat);
-    }
-}
-
-// Work-list kernel: envs whose clipped action was not certainly feasible (MODE 1 deferred them).
-__global__ void __launch_bounds__(128)
-ev_step_solve_kernel(const sg_ev_model m, const sg_ev_state s, const void* __restrict__ action, const int flags,
-                     const int bins, float* __restrict__ obs, double* __restrict__ reward,
-                     uint8_t* __restrict__ done, uint8_t* __restrict__ pilots, float* __restrict__ final_obs,
-                     uint8_t* __restrict__ status, double* __restrict__ stats, int32_t* __restrict__ todo) {
-    __shared__ EvShared sh;
-    load_shared(m, sh);
-    const int lane = threadIdx.x & 31;
-    const int count = todo[0];
-    const int nwarps = gridDim.x * (blockDim.x >> 5);
-    StatsAcc acc;
-    // warp w of CTA c takes item c + w*gridDim.x: the first items spread over different SMs
-    for (int w = blockIdx.x + (threadIdx.x >> 5) * gridDim.x; w < count; w += nwarps) {
-        const long long b = todo[2 + w];
-        ev_env_step<2>(m, s, sh, b, lane, action, flags, bins, obs, reward, done, pilots, final_obs, status, nullptr, acc);
-    }
-    if (stats != nullptr) {
-        __syncthreads();
-        stats_flush_block(acc, stats, sh.stat);
-    }
-    // last CTA to finish re-arms the work list for the next step (no memset node needed)
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(todo + 1, 1) == (int)gridDim.x - 1) { todo[0] = 0; todo[1] = 0; __threadfence(); }
-    }
-}
 
 __global__ void ev_reset_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
                                 const uint8_t* __restrict__ mask, const int32_t* __restrict__ day_in,
@@ -1668,15 +1154,36 @@ __global__ void ev_reset_kernel(const sg_ev_model m, const sg_ev_state s, const 
     int md = moer_day_in ? moer_day_in[b] : s.clock[b * 4 + 2];
     day = ((day % m.n_days) + m.n_days) % m.n_days;
     md = ((md % m.n_moer_days) + m.n_moer_days) % m.n_moer_days;
-    for (int i = lane; i < n; i += 32) { s.delivered[b * n + i] = 0.0; s.sess_idx[b * n + i] = 0; }
     float* orow = obs + b * OBS;
     for (int i = lane; i < 2 * n; i += 32) orow[i] = 0.f;
     const float* mrow = m.moer + ((long long)md * SG_EV_MOER_ROWS) * SG_EV_MOER_COLS;
     for (int e = lane; e < kf + 2; e += 32) orow[2 * n + e] = e < kf ? mrow[1 + e] : (e == kf ? mrow[0] : 0.f);
     if (lane == 0) {
+        // empty garage: no occupied station, so no session record is live (the records need no clearing)
         s.clock[b * 4 + 0] = 0; s.clock[b * 4 + 1] = day; s.clock[b * 4 + 2] = md; s.clock[b * 4 + 3] = 0;
-        if (s.occ != nullptr) s.occ[b] = 0ull;
+        s.occ[b] = 0ull;
         s.breakdown[b * 3] = s.breakdown[b * 3 + 1] = s.breakdown[b * 3 + 2] = 0.0;
+    }
+}
+
+// Dense per-station views of the sparse state (debugging, checkpoint inspection, multi-agent info):
+// delivered kWh and trace slot of the session plugged in at each station, 0 / 255 where empty.
+__global__ void ev_export_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
+                                 double* __restrict__ delivered, uint8_t* __restrict__ sess_idx) {
+    const int n = m.n_stations;
+    const long long total = B * n;
+    const Slot* slots = reinterpret_cast<const Slot*>(s.slots);
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long b = idx / n;
+        const int i = (int)(idx % n);
+        const int t = s.clock[b * 4];
+        const bool on = (s.occ[b] >> i) & 1ull;
+        double d = 0.0;
+        int k = 255;
+        if (on) { const Slot q = ld_slot(slots + ((long long)(t & 1) * B + b) * n + i); d = q.delivered; k = q.k; }
+        if (delivered != nullptr) delivered[idx] = d;
+        if (sess_idx != nullptr) sess_idx[idx] = (uint8_t)k;
     }
 }
 
@@ -1745,6 +1252,12 @@ int check_model(const sg_ev_model* m) {
     return 0;
 }
 
+int check_state(const sg_ev_state* s) {
+    SG_CHECK_ARG(s != nullptr && s->slots && s->clock && s->breakdown && s->occ, "ev: NULL state array");
+    SG_CHECK_ARG((reinterpret_cast<uintptr_t>(s->slots) & 31u) == 0, "ev: state.slots must be 32-byte aligned");
+    return 0;
+}
+
 }  // namespace
 }  // namespace sg
 
@@ -1753,7 +1266,8 @@ extern "C" {
 int sg_ev_reset(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, const uint8_t* reset_mask,
                 const int32_t* day_in, const int32_t* moer_day_in, float* obs, void* stream) {
     if (int rc = sg::check_model(m)) return rc;
-    SG_CHECK_ARG(s && obs && m->moer, "ev_reset: NULL argument");
+    if (int rc = sg::check_state(s)) return rc;
+    SG_CHECK_ARG(obs && m->moer, "ev_reset: NULL argument");
     SG_CHECK_ARG(m->n_days >= 1 && m->n_moer_days >= 1, "ev_reset: empty trace/MOER pool");
     if (num_envs <= 0) return 0;
     const unsigned grid = (unsigned)((num_envs + 3) / 4);
@@ -1764,83 +1278,34 @@ int sg_ev_reset(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, co
 
 int sg_ev_step(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, const void* action, int32_t flags,
                int32_t discrete_bins, float* obs, double* reward, uint8_t* done, uint8_t* pilots,
-               float* final_obs, uint8_t* status, double* stats, int32_t* todo, void* stream) {
+               float* final_obs, uint8_t* status, double* stats, void* stream) {
     if (int rc = sg::check_model(m)) return rc;
-    SG_CHECK_ARG(s && action && obs && reward && done, "ev_step: NULL argument");
-    SG_CHECK_ARG(m->sessions && m->moer && m->n_days >= 1 && m->n_moer_days >= 1 && m->max_sessions >= 1,
+    if (int rc = sg::check_state(s)) return rc;
+    SG_CHECK_ARG(action && obs && reward && done, "ev_step: NULL argument");
+    SG_CHECK_ARG(m->sessions && m->moer && m->arrivals && m->n_days >= 1 && m->n_moer_days >= 1 && m->max_sessions >= 1,
                  "ev_step: empty trace/MOER pool");
+    SG_CHECK_ARG(m->max_sessions <= 256, "ev_step: more than 256 session slots per station per day");
     SG_CHECK_ARG(!((flags & 1) == SG_EV_ACTION_I64) || discrete_bins >= 2, "ev_step: discrete_bins must be >= 2");
-    SG_CHECK_ARG(!m->project || todo != nullptr, "ev_step: projection needs the todo scratch buffer");
     if (num_envs <= 0) return 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     int sms = sg_device_sm_count();
     if (sms <= 0) sms = 148;
-    // persistent grid: 3 resident CTAs per SM (multiple of the SM count), fewer for tiny batches
-    const unsigned grid = (unsigned)std::min<long long>((num_envs + sg::kWarpsPerBlock - 1) / sg::kWarpsPerBlock,
-                                                        (long long)sms * 3);
-    // specialised kernel: even n, <= 5 classes, <= 32 constraints, 32-bit record index; the model
-    // flag bit 8 (SG_EV_FLAG_GENERIC_KERNEL) forces the generic one (used by the tests)
-    const bool small_index = (long long)m->n_days * m->max_sessions * m->n_stations < (1ll << 31);
-    const bool dense_ok = (m->n_stations % 2 == 0) && small_index && m->max_sessions < 255 &&
-                          !(flags & SG_EV_FLAG_GENERIC_KERNEL);
-    // projection on: event-driven kernel (work proportional to the occupied stations)
-    if (m->project && dense_ok && m->arrivals != nullptr && s->occ != nullptr && !(flags & SG_EV_FLAG_TILE_KERNEL)) {
-        const long long ntiles = (num_envs + 31) / 32;
-        const unsigned sgrid = (unsigned)std::min<long long>((ntiles + sg::kSparseWarps - 1) / sg::kSparseWarps, (long long)sms * 4);
-        sg::ev_step_sparse_kernel<<<sgrid, sg::kSparseWarps * 32, 0, st>>>(*m, *s, num_envs, action, flags, discrete_bins, obs,
-                                                                        reward, done, pilots, final_obs, status, stats, todo);
-        return sg::launch_status("ev_step_sparse_kernel");
-    }
-    // dense tile kernel: one thread per env on 32-env tiles staged through shared memory
-    if (dense_ok) {
-        const sg::TileLayout L(m->n_stations);
-        const int per_sm = std::max(1, std::min(16, (220 * 1024) / (L.bytes + 1024)));
-        const long long ntiles = (num_envs + sg::kTileE - 1) / sg::kTileE;
-        const unsigned tgrid = (unsigned)std::min<long long>(ntiles, (long long)sms * per_sm);
-        if (!m->project) {
-            auto kern = sg::ev_step_tile_kernel<0>;
-            if (L.bytes > 48 * 1024) SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.bytes));
-            kern<<<tgrid, sg::kTileE, L.bytes, st>>>(*m, *s, num_envs, action, flags, discrete_bins, obs, reward, done,
-                                                     pilots, final_obs, status, stats, todo);
-        } else {
-            auto kern = sg::ev_step_tile_kernel<1>;
-            if (L.bytes > 48 * 1024) SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.bytes));
-            kern<<<tgrid, sg::kTileE, L.bytes, st>>>(*m, *s, num_envs, action, flags, discrete_bins, obs, reward, done,
-                                                     pilots, final_obs, status, stats, todo);
-        }
-        return sg::launch_status("ev_step_tile_kernel");
-    }
-    // generic warp-per-env kernel (any network / odd station counts)
-    if (!m->project) {
-        sg::ev_step_kernel<0><<<grid, sg::kThreads, 0, st>>>(*m, *s, num_envs, action, flags, discrete_bins, obs,
-                                                           reward, done, pilots, final_obs, status, stats, todo);
-        return sg::launch_status("ev_step_kernel<0>");
-    }
-    sg::ev_step_kernel<1><<<grid, sg::kThreads, 0, st>>>(*m, *s, num_envs, action, flags, discrete_bins, obs, reward,
-                                                       done, pilots, final_obs, status, stats, todo);
-    return sg::launch_status("ev_step_kernel<1>");
-}
-
-int sg_ev_step_finish(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, const void* action,
-                      int32_t flags, int32_t discrete_bins, float* obs, double* reward, uint8_t* done,
-                      uint8_t* pilots, float* final_obs, uint8_t* status, double* stats, int32_t* todo,
-                      void* stream) {
-    if (int rc = sg::check_model(m)) return rc;
-    if (!m->project || num_envs <= 0) return 0;          // nothing is ever deferred without projection
-    SG_CHECK_ARG(s && action && obs && reward && done && todo, "ev_step_finish: NULL argument");
-    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    int sms = sg_device_sm_count();
-    if (sms <= 0) sms = 148;
-    const unsigned sgrid = (unsigned)std::min<long long>((num_envs + 3) / 4, (long long)sms * 2);
-    sg::ev_step_solve_kernel<<<sgrid, 128, 0, st>>>(*m, *s, action, flags, discrete_bins, obs, reward, done, pilots,
-                                                  final_obs, status, stats, todo);
-    return sg::launch_status("ev_step_solve_kernel");
+    // one warp per 32-env tile; at most 8 resident CTAs per SM, larger batches loop (persistent)
+    const long long ntiles = (num_envs + 31) / 32;
+    const unsigned grid = (unsigned)std::min<long long>((ntiles + sg::kMainWarps - 1) / sg::kMainWarps, (long long)sms * 8);
+    if (m->project)
+        sg::ev_step_main_kernel<1><<<grid, sg::kMainThreads, 0, st>>>(*m, *s, num_envs, action, flags, discrete_bins, obs,
+                                                                    reward, done, pilots, final_obs, status, stats);
+    else
+        sg::ev_step_main_kernel<0><<<grid, sg::kMainThreads, 0, st>>>(*m, *s, num_envs, action, flags, discrete_bins, obs,
+                                                                    reward, done, pilots, final_obs, status, stats);
+    return sg::launch_status("ev_step_main_kernel");
 }
 
 int sg_ev_step_host(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, const void* h_action,
                     int32_t flags, int32_t discrete_bins, float* h_obs, double* h_reward, uint8_t* h_done,
                     void* d_action, float* d_obs, double* d_reward, uint8_t* d_done, uint8_t* d_status,
-                    double* d_stats, int32_t* d_todo, void* stream) {
+                    double* d_stats, void* stream) {
     SG_CHECK_ARG(m && h_action && h_obs && h_reward && h_done && d_action && d_obs && d_reward && d_done,
                  "ev_step_host: NULL argument");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -1848,14 +1313,23 @@ int sg_ev_step_host(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs
     const size_t abytes = B * n * (((flags & 1) == SG_EV_ACTION_I64) ? 8 : 4);
     SG_CUDA(cudaMemcpyAsync(d_action, h_action, abytes, cudaMemcpyHostToDevice, st));
     if (int rc = sg_ev_step(m, s, num_envs, d_action, flags, discrete_bins, d_obs, d_reward, d_done, nullptr,
-                            nullptr, d_status, d_stats, d_todo, stream)) return rc;
-    if (int rc = sg_ev_step_finish(m, s, num_envs, d_action, flags, discrete_bins, d_obs, d_reward, d_done, nullptr,
-                                   nullptr, d_status, d_stats, d_todo, stream)) return rc;
+                            nullptr, d_status, d_stats, stream)) return rc;
     SG_CUDA(cudaMemcpyAsync(h_obs, d_obs, B * OBS * 4, cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaMemcpyAsync(h_reward, d_reward, B * 8, cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaMemcpyAsync(h_done, d_done, B, cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaStreamSynchronize(st));
     return 0;
+}
+
+int sg_ev_export_state(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, double* delivered,
+                       uint8_t* sess_idx, void* stream) {
+    if (int rc = sg::check_model(m)) return rc;
+    if (int rc = sg::check_state(s)) return rc;
+    if (num_envs <= 0) return 0;
+    const long long total = (long long)num_envs * m->n_stations;
+    const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148ll * 16);
+    sg::ev_export_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*m, *s, num_envs, delivered, sess_idx);
+    return sg::launch_status("ev_export_kernel");
 }
 
 int sg_ev_agent_obs(const float* cur_obs, const float* past_obs, int64_t num_envs, int32_t n_stations,

@@ -50,8 +50,7 @@ class BatchedEVChargingEnv:
     def __init__(self, data_generator: AbstractTraceGenerator, num_envs: int = 1,
                  moer_forecast_steps: int = 36, project_action_in_env: bool = True, verbose: int = 0,
                  device: str | torch.device | None = None, auto_reset: bool = False,
-                 discrete_bins: int = -1, collect_stats: bool = False, force_generic_kernel: bool = False,
-                 force_tile_kernel: bool = False):
+                 discrete_bins: int = -1, collect_stats: bool = False):
         assert 1 <= moer_forecast_steps <= 36                                   # env.py:120
         self.lib = _lib.load()                                                  # fails loudly if not built
         if not torch.cuda.is_available():
@@ -121,21 +120,21 @@ class BatchedEVChargingEnv:
         # ---- per-env state and outputs ---------------------------------------------------------------
         B = self.num_envs
         z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)  # noqa: E731
-        self.delivered = z(B, n, dtype=torch.float64)
-        self.sess_idx = z(B, n, dtype=torch.uint8)
+        # session records of the plugged-in EVs: [2 copies, B, n] x 32 bytes (see sg_ev_state); torch
+        # allocations are 512-byte aligned, which the 256-bit record accesses need
+        self.slots = z(2, B, n, 4, dtype=torch.float64)
         self.clock = z(B, 4, dtype=torch.int32)          # columns: t, day, moer_day, arrival cursor
         self.t, self.day, self.moer_day = self.clock[:, 0], self.clock[:, 1], self.clock[:, 2]
         self.breakdown = z(B, 3, dtype=torch.float64)
-        self.occ = z(B, dtype=torch.int64)                # occupancy bit mask of the event-driven kernel
-        self._state = _lib.EVState(self.delivered.data_ptr(), self.sess_idx.data_ptr(), self.clock.data_ptr(),
-                                   self.breakdown.data_ptr(), self.occ.data_ptr())
+        self.occ = z(B, dtype=torch.int64)                # bit i: station i has a plugged-in session
+        self._state = _lib.EVState(self.slots.data_ptr(), self.clock.data_ptr(), self.breakdown.data_ptr(),
+                                   self.occ.data_ptr())
         self.obs = z(B, self.obs_dim, dtype=torch.float32)
         self.final_obs = z(B, self.obs_dim, dtype=torch.float32) if auto_reset else None
         self.reward = z(B, dtype=torch.float64)
         self.done = z(B, dtype=torch.uint8)
         self.status = z(B, dtype=torch.uint8)
         self.pilots = z(B, n, dtype=torch.uint8)
-        self.todo = z(B + 2, dtype=torch.int32)
         self.stats = z(_lib.SG_STATS_LEN, dtype=torch.float64) if collect_stats else None
         if self.stats is not None:
             self.reset_stats()
@@ -147,9 +146,7 @@ class BatchedEVChargingEnv:
         self._h_reward = torch.zeros(B, dtype=torch.float64).pin_memory()
         self._h_done = torch.zeros(B, dtype=torch.uint8).pin_memory()
         self._flags = (_lib.SG_EV_ACTION_I64 if discrete_bins > 0 else _lib.SG_EV_ACTION_F32) | \
-            (_lib.SG_EV_FLAG_AUTORESET if auto_reset else 0) | \
-            (_lib.SG_EV_FLAG_GENERIC_KERNEL if force_generic_kernel else 0) | \
-            (_lib.SG_EV_FLAG_TILE_KERNEL if force_tile_kernel else 0)
+            (_lib.SG_EV_FLAG_AUTORESET if auto_reset else 0)
         self.kernel_launches = 0
         self._needs_reset = True
 
@@ -224,8 +221,8 @@ class BatchedEVChargingEnv:
                     max(self.discrete_bins, 0), self._h_obs.data_ptr(), self._h_reward.data_ptr(),
                     self._h_done.data_ptr(), self._d_action.data_ptr(), self.obs.data_ptr(),
                     self.reward.data_ptr(), self.done.data_ptr(), self.status.data_ptr(),
-                    _lib.ptr(self.stats), self.todo.data_ptr(), self._stream()), "sg_ev_step_host")
-            self.kernel_launches += 2 if self.project_action_in_env else 1
+                    _lib.ptr(self.stats), self._stream()), "sg_ev_step_host")
+            self.kernel_launches += 1
             if host_np:
                 done = self._h_done.numpy().astype(bool)
                 return (self._h_obs.numpy().copy(), self._h_reward.numpy().copy(), done,
@@ -238,21 +235,28 @@ class BatchedEVChargingEnv:
         self.launch_step(actions)
         return self.obs, self.reward, self.done.bool(), torch.zeros_like(self.done, dtype=torch.bool), self._infos()
 
-    def launch_step(self, actions: torch.Tensor, phase: int = 0) -> None:
-        """Enqueues the step kernels on the current stream without building return values (used by
-        ``step``, CUDA-graph capture and the benchmark).  ``phase``: 0 both, 1 only the main kernel,
-        2 only the work-list (projection solver) kernel."""
-        args = (C.byref(self._model), C.byref(self._state), self.num_envs, actions.data_ptr(), self._flags,
+    def launch_step(self, actions: torch.Tensor) -> None:
+        """Enqueues the step kernel on the current stream without building return values (used by
+        ``step``, CUDA-graph capture and the benchmark)."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sg_ev_step(
+                C.byref(self._model), C.byref(self._state), self.num_envs, actions.data_ptr(), self._flags,
                 max(self.discrete_bins, 0), self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
                 self.pilots.data_ptr(), _lib.ptr(self.final_obs), self.status.data_ptr(), _lib.ptr(self.stats),
-                self.todo.data_ptr(), self._stream())
+                self._stream()), "sg_ev_step")
+        self.kernel_launches += 1
+
+    def export_state(self):
+        """Dense views of the sparse per-station state: (delivered kWh f64 [B,n], trace slot u8 [B,n],
+        255 where the station is empty)."""
+        B, n = self.num_envs, self.num_stations
+        delivered = torch.empty(B, n, dtype=torch.float64, device=self.device)
+        sess_idx = torch.empty(B, n, dtype=torch.uint8, device=self.device)
         with torch.cuda.device(self.device):
-            if phase in (0, 1):
-                _lib.check(self.lib.sg_ev_step(*args), "sg_ev_step")
-                self.kernel_launches += 1
-            if phase in (0, 2) and self.project_action_in_env:
-                _lib.check(self.lib.sg_ev_step_finish(*args), "sg_ev_step_finish")
-                self.kernel_launches += 1
+            _lib.check(self.lib.sg_ev_export_state(C.byref(self._model), C.byref(self._state), B,
+                                                   delivered.data_ptr(), sess_idx.data_ptr(), self._stream()),
+                       "sg_ev_export_state")
+        return delivered, sess_idx
 
     def capture_graph(self, actions: torch.Tensor) -> "torch.cuda.CUDAGraph":
         """Captures one step (reading ``actions`` in place) into a CUDA graph; ``graph.replay()``

@@ -58,23 +58,18 @@ def run_parity(env, orc, net, gen, B, steps, seed, action_fn, project):
     return clean, n_obs_exact, n_slow
 
 
-KERNELS = {"default": {}, "tile": {"force_tile_kernel": True}, "generic": {"force_generic_kernel": True}}
-
-
-@pytest.mark.parametrize("B,mean,kernel", [(64, 25.0, "default"), (257, 70.0, "default"), (33, 120.0, "default"),
-                                           (100, 60.0, "generic")])
-def test_step_no_projection(native_lib, B, mean, kernel):
-    gen, env, net, orc = make(7, mean, 11, B, False, **KERNELS[kernel])
+@pytest.mark.parametrize("B,mean", [(64, 25.0), (257, 70.0), (33, 120.0), (100, 60.0)])
+def test_step_no_projection(native_lib, B, mean):
+    gen, env, net, orc = make(7, mean, 11, B, False)
     clean, n_exact, _ = run_parity(env, orc, net, gen, B, 288, 3,
                                    lambda rng, t: rng.uniform(0, 1, (B, 54)).astype(np.float32), False)
     assert clean.all() and n_exact >= 250
     assert bool(env.done.all()) and int(env.t[0]) == 288
 
 
-@pytest.mark.parametrize("B,mean,kernel", [(64, 25.0, "default"), (200, 80.0, "default"), (33, 120.0, "default"),
-                                           (100, 80.0, "tile"), (100, 80.0, "generic")])
-def test_step_with_projection(native_lib, B, mean, kernel):
-    gen, env, net, orc = make(5, mean, 5, B, True, **KERNELS[kernel])
+@pytest.mark.parametrize("B,mean", [(64, 25.0), (200, 80.0), (33, 120.0), (100, 100.0)])
+def test_step_with_projection(native_lib, B, mean):
+    gen, env, net, orc = make(5, mean, 5, B, True)
     clean, n_exact, n_slow = run_parity(env, orc, net, gen, B, 288, 9,
                                         lambda rng, t: rng.uniform(0, 1, (B, 54)).astype(np.float32), True)
     assert clean.mean() > 0.97
