@@ -106,6 +106,7 @@ int sg_building_step_host(const sg_building_model* m, int64_t num_envs,
 #define SG_EV_MOER_COLS       37   /* load_moer.py:364-377: col 0 historical + 36 forecasts  */
 #define SG_EV_MOER_ROWS       289
 #define SG_EV_EPISODE_STEPS   288
+#define SG_EV_TABLE_BYTES     4096
 
 /* One charging session = one row of the events DataFrame (event_generation.py:125-147) after
  * the requested-energy cap (:169-170).  Slot k of station i on day d lives at
@@ -141,6 +142,8 @@ typedef struct sg_ev_model {
                                      terminated by 0x7fff entries                                       */
     int32_t max_day_sessions;     /* row length of `arrivals` minus the terminator                  */
     int32_t reserved;
+    const void* tables;           /* [device] SG_EV_TABLE_BYTES, 16-byte aligned: derived constant tables filled
+                                     once per model by sg_ev_prepare_tables (the kernels stage them in shared memory) */
 } sg_ev_model;
 
 /* Per-env state.  A plugged-in session is one 32-byte record
@@ -164,6 +167,12 @@ typedef struct sg_ev_state {
 #define SG_EV_ACTION_F32      0
 #define SG_EV_ACTION_I64      1   /* DiscreteActionWrapper input (wrappers.py:43-45)          */
 #define SG_EV_FLAG_AUTORESET  16  /* on done: advance day (mod D), reset state, obs = reset obs */
+
+/* Fills the derived constant tables of a model (f32 copies of the constraint coefficients, squared
+ * limits, the pilot -> kW table, padded class / EVSE-type maps) into `tables`; call once per model,
+ * then store the pointer in m->tables.  Replaces EVChargingEnv.__init__ / _init_action_projection
+ * bookkeeping (env.py:131-134, 178-198). */
+int sg_ev_prepare_tables(const sg_ev_model* m, void* tables /* [device] [SG_EV_TABLE_BYTES] */, void* stream);
 
 /* reset(): env.py:293-338 for envs whose `reset_mask` byte is non-zero (NULL = all).
  * `day_in`/`moer_day_in` pick the trace/MOER table (the seed->day map is host logic,

@@ -15,6 +15,7 @@ SG_STATS_LEN = 16
 SG_EV_MOER_COLS = 37
 SG_EV_MOER_ROWS = 289
 SG_EV_EPISODE_STEPS = 288
+SG_EV_TABLE_BYTES = 4096
 SG_EV_MAX_STATIONS = 64
 SG_EV_MAX_CLASSES = 8
 SG_EV_MAX_CONSTRAINTS = 16
@@ -45,7 +46,7 @@ class EVModel(C.Structure):
         ("max_sessions", _i32), ("n_days", _i32), ("n_moer_days", _i32), ("project", _i32),
         ("station_class", _vp), ("station_type", _vp), ("con_re", _vp), ("con_im", _vp),
         ("magnitudes", _vp), ("sessions", _vp), ("moer", _vp), ("arrivals", _vp),
-        ("max_day_sessions", _i32), ("reserved", _i32),
+        ("max_day_sessions", _i32), ("reserved", _i32), ("tables", _vp),
     ]
 
 
@@ -85,6 +86,7 @@ SIGNATURES = {
                                       _i32, _vp, _vp]),
     "sg_building_step_host": (C.c_int, [C.POINTER(BuildingModel), _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                         _vp, _vp, _vp]),
+    "sg_ev_prepare_tables": (C.c_int, [C.POINTER(EVModel), _vp, _vp]),
     "sg_ev_reset": (C.c_int, [C.POINTER(EVModel), C.POINTER(EVState), _i64, _vp, _vp, _vp, _vp, _vp]),
     "sg_ev_step": (C.c_int, [C.POINTER(EVModel), C.POINTER(EVState), _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp,
                              _vp, _vp, _vp, _vp]),

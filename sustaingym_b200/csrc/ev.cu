@@ -83,29 +83,49 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
     return y * fma(-0.5 * x * y, y, 1.5);
 }
 
-struct EvShared {
+// Per-model constant tables, built once by sg_ev_prepare_tables (ev_prepare_kernel) and copied to
+// shared memory by every CTA with 16-byte vector loads.  con_re / con_im are zero-padded to
+// [SG_EV_MAX_CONSTRAINTS][SG_EV_MAX_CLASSES] and lim to [SG_EV_MAX_CONSTRAINTS].
+constexpr float kPreMargin = 2e-3f;                  // normalised units; covers the f32 accumulation error
+struct __align__(16) EvTables {
     double con_re[SG_EV_MAX_CONSTRAINTS * kMC];
     double con_im[SG_EV_MAX_CONSTRAINTS * kMC];
-    double lim[SG_EV_MAX_CONSTRAINTS];     // magnitudes in A
-    uint8_t cls[SG_EV_MAX_STATIONS];
+    double lim[SG_EV_MAX_CONSTRAINTS];               // magnitudes in A
+    double ppilot[40];                               // pilot (A) -> kW at 208 V, the reference's IEEE operation sequence
+    float re[SG_EV_MAX_CONSTRAINTS * kMC], im[SG_EV_MAX_CONSTRAINTS * kMC];   // f32 copies for the pre-checks
+    float r_in[SG_EV_MAX_CONSTRAINTS];               // (limit/32 - margin)^2 in normalised action units
+    float lim2_lo[SG_EV_MAX_CONSTRAINTS];            // 0.999 * limit^2 (A^2): below it the rounded schedule has no excess
+    uint8_t cls[SG_EV_MAX_STATIONS];                 // class of each station, 255 = padding
     uint8_t type[SG_EV_MAX_STATIONS];
-    double stat[11 * kWarpsPerBlock];
 };
+static_assert(sizeof(EvTables) % 16 == 0 && sizeof(EvTables) <= SG_EV_TABLE_BYTES, "table block size");
+using EvShared = EvTables;
 
-// The host pads con_re / con_im to [SG_EV_MAX_CONSTRAINTS][SG_EV_MAX_CLASSES] and magnitudes to
-// [SG_EV_MAX_CONSTRAINTS] with zeros, so staging is a straight copy (no index arithmetic).
-__device__ __forceinline__ void load_shared(const sg_ev_model& m, EvShared& sh) {
+__global__ void ev_prepare_kernel(const sg_ev_model m, EvTables* __restrict__ tb) {
     for (int i = threadIdx.x; i < SG_EV_MAX_CONSTRAINTS * kMC; i += blockDim.x) {
-        sh.con_re[i] = m.con_re[i];
-        sh.con_im[i] = m.con_im[i];
+        tb->con_re[i] = m.con_re[i]; tb->con_im[i] = m.con_im[i];
+        tb->re[i] = (float)m.con_re[i]; tb->im[i] = (float)m.con_im[i];
     }
-    for (int i = threadIdx.x; i < SG_EV_MAX_CONSTRAINTS; i += blockDim.x) sh.lim[i] = m.magnitudes[i];
+    for (int i = threadIdx.x; i < SG_EV_MAX_CONSTRAINTS; i += blockDim.x) {
+        const double lim = m.magnitudes[i];
+        const double r = lim * (1.0 / kActionScale) - (double)kPreMargin;
+        tb->lim[i] = lim;
+        tb->r_in[i] = r > 0.0 ? (float)(r * r * 0.99999) : -1.f;
+        tb->lim2_lo[i] = (float)(lim * lim * 0.999);
+    }
+    for (int i = threadIdx.x; i < 40; i += blockDim.x) tb->ppilot[i] = div_c((double)i * kVoltage, 1000.0, kInv1000);
     for (int i = threadIdx.x; i < SG_EV_MAX_STATIONS; i += blockDim.x) {
         const bool in = i < m.n_stations;
-        sh.cls[i] = in ? m.station_class[i] : 255;
-        sh.type[i] = in ? m.station_type[i] : 0;
+        tb->cls[i] = in ? m.station_class[i] : 255;
+        tb->type[i] = in ? m.station_type[i] : 0;
     }
-    __syncthreads();
+}
+
+// CTA-wide copy of the table block into shared memory (caller synchronises)
+__device__ __forceinline__ void load_tables(const void* __restrict__ src, EvTables& sh) {
+    const uint4* g = reinterpret_cast<const uint4*>(src);
+    uint4* d = reinterpret_cast<uint4*>(&sh);
+    for (int i = threadIdx.x; i < (int)(sizeof(EvTables) / 16); i += blockDim.x) d[i] = __ldg(g + i);
 }
 
 // class sums of a per-station f64 value (two stations per lane) -> every lane gets all sums
@@ -589,32 +609,69 @@ __device__ __forceinline__ void st_slot(Slot* p, const Slot& s) {
     asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
 }
 
-constexpr int kMainWarps = 2;                        // warps per CTA of the main kernel
-constexpr int kMainThreads = kMainWarps * 32;
-constexpr int kItemCap = 256;                        // (env, station) work items staged per warp and chunk
-constexpr float kPreMargin = 2e-3f;                  // normalised units; covers the f32 accumulation error
+// Same record as two 16-byte stores.  Used on the rare path: inside the large non-inlined fallback
+// function ptxas 12.9 was observed to narrow the 256-bit asm store to its first 8 bytes (SASS
+// STG.E.64), which the parity tests caught; the split form compiles to two ST.E.128.
+__device__ __forceinline__ void st_slot_2x16(Slot* p, const Slot& s) {
+    uint4 lo, hi;
+    lo.x = (unsigned)__double2loint(s.energy); lo.y = (unsigned)__double2hiint(s.energy);
+    lo.z = (unsigned)__double2loint(s.delivered); lo.w = (unsigned)__double2hiint(s.delivered);
+    hi.x = (unsigned)s.dep; hi.y = (unsigned)s.est; hi.z = (unsigned)s.arr; hi.w = (unsigned)s.k;
+    reinterpret_cast<uint4*>(p)[0] = lo;
+    reinterpret_cast<uint4*>(p)[1] = hi;
+}
 
-// result of one (env, occupied station) work item, consumed by the thread that owns the env
-struct __align__(16) ItemRec {
-    double rate;                                     // charging rate in A
-    float x;                                         // normalised pilot before rounding (class sums of the projection test)
-    unsigned meta;                                   // pilot | class << 8 | departed << 16 | station << 24
-};
+#ifndef SG_EV_KE
+#define SG_EV_KE 16
+#endif
+#ifndef SG_EV_MINB
+#define SG_EV_MINB 4
+#endif
+#ifndef SG_EV_KV
+#define SG_EV_KV 3
+#endif
+#ifndef SG_EV_ABL
+#define SG_EV_ABL 0      // timing ablations (diagnostic builds only; results are wrong when non-zero)
+#endif
+constexpr int kE = SG_EV_KE;                         // envs per warp tile
+constexpr int kQ = 32 / kE;                          // lanes per env in the spread phases
+constexpr int kSegBits = 64 / kQ;                    // occupancy bits enumerated by one lane
+constexpr int kMainWarps = 4;                        // warps per CTA of the main kernel
+constexpr int kMainThreads = kMainWarps * 32;
+constexpr int kV = SG_EV_KV;                         // work items per lane and chunk (loads in flight)
+constexpr int kItemCap = 32 * kV;                    // (env, station) work items staged per warp and chunk
+constexpr int kTailMax = (SG_EV_MOER_COLS + 1) / 2;  // float2 pairs in the longest MOER + timestep tail
+constexpr int kTailPerLane = (kTailMax + kQ - 1) / kQ;
+static_assert(kE == 8 || kE == 16 || kE == 32, "tile size");
 
 struct WarpShared {
-    ItemRec items[kItemCap];                         // the key (env lane << 8 | station) of item j is staged in items[j].meta
-    float S[kMC][32];                                // per-env class sums of the clipped action
-    int P[kMC][32];                                  // per-env class sums of the integer pilots
-    double xs[SG_EV_MAX_STATIONS];                   // projected action of the env being re-done
+    double rate[kItemCap];                           // charging rate (A) of item j
+    unsigned short key[kItemCap];                    // env << 8 | station of item j
+    int S[kMC][kE];                                  // per-env class sums of the clipped action, 2^-20 fixed point
+    int P[kMC][kE];                                  // per-env class sums of the integer pilots
+    unsigned occ_clr[kE][2];                         // occupancy bits cleared by Unplug events
+    int todo[32];                                    // envs (index within the batch) left to the rare path
+    double stat[12];                                 // this warp's reward statistics (SG_STATS layout)
 };
 
-struct MainShared {
-    float re[SG_EV_MAX_CONSTRAINTS * kMC], im[SG_EV_MAX_CONSTRAINTS * kMC];   // f32 copies for the pre-checks
-    float r_in[SG_EV_MAX_CONSTRAINTS];               // (limit/32 - margin)^2 in normalised action units
-    float lim2_lo[SG_EV_MAX_CONSTRAINTS];            // 0.999 * limit^2 (A^2): below it the rounded schedule has no excess
-    double ppilot[40];                               // pilot (A) -> kW at 208 V, the reference's IEEE operation sequence
-    WarpShared w[kMainWarps];
-    double stat[11 * kMainWarps];
+// the fields of sg_ev_model / sg_ev_state / launch arguments the rare path needs, passed by value
+struct EvCtx {
+    int n, kf, C, J, K, n_days, n_moer_days, max_day_sessions, flags, bins;
+    long long B;
+    const float* moer;
+    const uint4* recs;
+    const unsigned* arrivals;
+    const void* action;
+    Slot* slots;
+    int32_t* clock;
+    double* breakdown;
+    unsigned long long* occ;
+    float* obs;
+    float* final_obs;
+    double* reward;
+    uint8_t* done;
+    uint8_t* pilots;
+    uint8_t* status;
 };
 
 // One period of Linear2StageBattery._charge_stepwise + EV.charge for a plugged-in EV (capacity
@@ -652,30 +709,57 @@ __device__ __forceinline__ float timestep_frac(const int t) {     // env.py:392,
     return (float)((double)t * (1.0 / (double)kEpisode));
 }
 
-// Warp-cooperative exact projection of ONE env (lane l owns stations 2l, 2l+1): exact feasibility
-// test of the box-clipped action, then the single-class (pod) projection, then the interior-point
-// solver.  Writes the projected normalised action to xs[0..n) and returns the status bits (0: the
-// clipped action is feasible, nothing to redo).
-__device__ __noinline__ int project_env(const EvShared& sh, const int n, const int C, const int J, const long long b,
-                                         const int lane, const void* __restrict__ action, const bool i64,
-                                         const int bins, const Slot* __restrict__ cur,
-                                         const unsigned long long occ_b, double* xs) {
+__device__ __forceinline__ float act_value(const void* __restrict__ action, const bool i64, const int bins, const long long o) {
+    return i64 ? __fdiv_rn((float)reinterpret_cast<const long long*>(action)[o], (float)(bins - 1))   // wrappers.py:45
+               : __ldg(reinterpret_cast<const float*>(action) + o);
+}
+
+__device__ __forceinline__ float moer_tail(const float* __restrict__ row, const int q, const int kf, const float ts) {
+    return q < kf ? __ldg(row + 1 + q) : (q == kf ? __ldg(row) : ts);    // forecasted_moer | prev_moer | timestep
+}
+
+// =================================================================================================
+// Rare path: the complete step of ONE env by a whole warp (lane l owns stations 2l and 2l+1), with
+// the exact action projection: exact feasibility test of the box-clipped action, the single-class
+// (pod) projection, else the interior-point solver.  Called for the envs the main path could not
+// certify as feasible; re-reads the env's state (the main path never overwrites the state copy of
+// the current step) and rewrites everything the main path wrote for this env.  The WITH_IPM = false
+// instance (small) returns false without side effects when the interior-point solver is needed;
+// the caller then runs the WITH_IPM = true instance.
+// =================================================================================================
+template <bool WITH_IPM>
+__device__ __noinline__ bool fallback_env(const EvTables& sh, const EvCtx cx, const long long b, const int lane,
+                                           double* wstat) {
+    const int n = cx.n, kf = cx.kf, OBS = 2 * n + kf + 2, C = cx.C, J = cx.J;
+    const bool i64 = (cx.flags & 1) == SG_EV_ACTION_I64;
+    const int4 clk = *reinterpret_cast<const int4*>(cx.clock + b * 4);
+    const unsigned long long occ = cx.occ[b];
+    const int t = clk.x, tn = t + 1, md = clk.z;
+    int day = clk.y, nidx = clk.w;
+    const int par = t & 1;
+    const bool dn = tn >= kEpisode;
+    const bool autoreset = dn && (cx.flags & SG_EV_FLAG_AUTORESET);
+    const int md_out = autoreset ? (md + 1) % cx.n_moer_days : md;
+    const Slot* cur = cx.slots + ((long long)par * cx.B + b) * n;
+    Slot* nxt = cx.slots + ((long long)(par ^ 1) * cx.B + b) * n;
     const int i0 = 2 * lane;
     const bool valid[2] = {i0 < n, i0 + 1 < n};
     double a[2], u[2], x[2];
-    int cls[2];
+    int cls[2], type[2];
+    bool occd[2];
+    Slot q[2];
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
         const int i = i0 + p;
-        a[p] = 0.0; u[p] = 0.0; cls[p] = 255;
+        a[p] = 0.0; u[p] = 0.0; cls[p] = 255; type[p] = 0;
+        occd[p] = valid[p] && ((occ >> i) & 1ull);
+        q[p].energy = 0.0; q[p].delivered = 0.0; q[p].dep = q[p].est = q[p].arr = q[p].k = 0;
         if (valid[p]) {
-            const float af = i64 ? __fdiv_rn((float)reinterpret_cast<const long long*>(action)[b * n + i], (float)(bins - 1))
-                                 : reinterpret_cast<const float*>(action)[b * n + i];
-            a[p] = (double)af;
-            cls[p] = sh.cls[i];
-            if ((occ_b >> i) & 1ull) {
-                const Slot s = ld_slot(cur + i);
-                const double rem = s.energy - s.delivered;
+            a[p] = (double)act_value(cx.action, i64, cx.bins, b * n + i);
+            cls[p] = sh.cls[i]; type[p] = sh.type[i];
+            if (occd[p]) {
+                q[p] = ld_slot(cur + i);
+                const double rem = q[p].energy - q[p].delivered;
                 const float dem = rem > kFullEps ? (float)rem : 0.f;          // obs 'demands', env.py:388
                 u[p] = upper_bound(dem);
             }
@@ -686,132 +770,230 @@ __device__ __noinline__ int project_env(const EvShared& sh, const int n, const i
     if (!network_feasible(sh, C, J, x, cls)) {
         bool cap = false;
         if (!(simple_project(sh, C, J, a, u, cls, valid, x) && network_feasible_tol(sh, C, J, x, cls))) {
+            if (!WITH_IPM) return false;                 // (warp-uniform)
 #pragma unroll
             for (int p = 0; p < 2; ++p) x[p] = valid[p] ? fmin(fmax(a[p], 0.0), u[p]) : 0.0;
-            ipm_dispatch(sh, C, J, a, u, cls, valid, x, &cap);
+            if (WITH_IPM) ipm_dispatch(sh, C, J, a, u, cls, valid, x, &cap);
         }
         st = SG_EV_STATUS_PROJECTED | (cap ? SG_EV_STATUS_MAXITER : 0);
     }
+    // schedule (env.py:368-378), charging, Unplug events
+    unsigned pil[2] = {0u, 0u};
+    float dem_o[2] = {0.f, 0.f}, est_o[2] = {0.f, 0.f};
+    double rate_part = 0.0;
+    unsigned long long mine = 0ull;
 #pragma unroll
-    for (int p = 0; p < 2; ++p) if (valid[p]) xs[i0 + p] = x[p];
-    __syncwarp();
-    return st;
-}
-
-// Re-execution of one env's occupied stations with the projected action xs (one thread, rare path).
-// Inputs are read from the state copy of the current step (untouched by the first pass), outputs
-// overwrite what the first pass wrote.  P: this env's column of the pilot class sums (stride 32).
-struct RedoOut { double rate_sum; unsigned long long occ_new; };
-__device__ __noinline__ RedoOut redo_env(const uint8_t* __restrict__ s_type, const uint8_t* __restrict__ s_cls,
-                                          const double* __restrict__ ppilot, int* P, const double* xs, const int n,
-                                          const int tn, const unsigned long long occ, const Slot* __restrict__ cur,
-                                          Slot* __restrict__ nxt, float* __restrict__ row,
-                                          uint8_t* __restrict__ pilot_row) {
-    RedoOut out;
-    out.rate_sum = 0.0;
-    out.occ_new = occ;
-    for (int c = 0; c < kMC; ++c) P[c * 32] = 0;
-    for (unsigned long long mask = occ; mask; mask &= mask - 1) {
-        const int i = __ffsll((long long)mask) - 1;
-        Slot q = ld_slot(cur + i);
-        const int pi = min(max(__double2int_rn(to_pilot(xs[i], s_type[i])), 0), 32);
-        P[s_cls[i] * 32] += pi;
-        out.rate_sum += charge_period(q.energy, q.delivered, ppilot[pi]);
-        if (pilot_row != nullptr) pilot_row[i] = (uint8_t)pi;
-        bool active = false;
-        if (q.dep <= tn) {                                            // Unplug event (timestamp = departure)
-            out.occ_new &= ~(1ull << i);
-        } else {
-            st_slot(nxt + i, q);
-            active = q.energy - q.delivered > kFullEps;               // Interface.active_sessions()
-        }
-        if (row != nullptr) {
-            row[i] = active ? (float)(q.energy - q.delivered) : 0.f;
-            row[n + i] = active ? (float)(q.est - tn) : 0.f;
+    for (int p = 0; p < 2; ++p) {
+        if (!valid[p]) continue;
+        const int i = i0 + p;
+        const int pi = min(max(__double2int_rn(to_pilot(x[p], type[p])), 0), 32);
+        pil[p] = (unsigned)pi;
+        if (occd[p]) {
+            rate_part += charge_period(q[p].energy, q[p].delivered, sh.ppilot[pi]);
+            if (q[p].dep > tn) {
+                st_slot_2x16(nxt + i, q[p]);
+                mine |= 1ull << i;
+                const double rem = q[p].energy - q[p].delivered;
+                if (rem > kFullEps) { dem_o[p] = (float)rem; est_o[p] = (float)(q[p].est - tn); }   // Interface.active_sessions()
+            }
         }
     }
-    return out;
+    const double total_rate = warp_sum(rate_part);
+    // Plugin events with timestamp <= t+1; the lane that owns the station takes the event
+    if (!autoreset) {
+        const unsigned* arow = cx.arrivals + (long long)day * (cx.max_day_sessions + 1);
+        unsigned ent = __ldg(arow + nidx);
+        while ((int)(ent & 0x7fffu) <= tn) {
+            const int i = (ent >> 16) & 0xff, k = ent >> 24;
+            if ((i >> 1) == lane) {
+                const uint4 rr = __ldg(cx.recs + ((long long)day * cx.K + k) * n + i);
+                Slot ns;
+                ns.arr = (int)(short)(rr.x & 0xffffu); ns.dep = (int)(short)(rr.x >> 16);
+                ns.est = (int)(short)(rr.y & 0xffffu); ns.k = k;
+                ns.energy = __hiloint2double((int)rr.w, (int)rr.z); ns.delivered = 0.0;
+                if (ns.dep > tn) {
+                    st_slot_2x16(nxt + i, ns);
+                    mine |= 1ull << i;
+                    const int p = i & 1;
+                    if (ns.energy > kFullEps) { dem_o[p] = (float)ns.energy; est_o[p] = (float)(ns.est - tn); }
+                }
+            }
+            ++nidx;
+            ent = __ldg(arow + nidx);
+        }
+    }
+    const unsigned occ_lo = __reduce_or_sync(kFull, (unsigned)(mine & 0xffffffffull));
+    const unsigned occ_hi = __reduce_or_sync(kFull, (unsigned)(mine >> 32));
+    // excess current from the rounded schedule (env.py:449-452)
+    double excess = 0.0;
+    {
+        double S[kMC];
+        class_sums_pilots(pil, cls, C, S);
+        double sq = 0.0, lim = 0.0;
+        if (lane < J) {
+            double wr = 0, wi = 0;
+#pragma unroll
+            for (int c = 0; c < kMC; ++c) { wr = fma(sh.con_re[lane * kMC + c], S[c], wr); wi = fma(sh.con_im[lane * kMC + c], S[c], wi); }
+            sq = fma(wr, wr, wi * wi);
+            lim = sh.lim[lane];
+        }
+        const bool over = lane < J && sq > lim * lim;
+        if (__any_sync(kFull, over)) excess = warp_sum(over ? fmax(0.0, sqrt(sq) - lim) : 0.0);
+        // (constraints beyond lane 31 cannot exist: J <= 16)
+    }
+    // observation row(s) and pilot row
+    const float* mrow = cx.moer + ((long long)md * SG_EV_MOER_ROWS + min(tn, SG_EV_MOER_ROWS - 1)) * SG_EV_MOER_COLS;
+    const float ts = timestep_frac(tn);
+    float* orow = autoreset ? (cx.final_obs != nullptr ? cx.final_obs + b * OBS : nullptr) : cx.obs + b * OBS;
+    if (orow != nullptr) {
+#pragma unroll
+        for (int p = 0; p < 2; ++p) if (valid[p]) { orow[i0 + p] = dem_o[p]; orow[n + i0 + p] = est_o[p]; }
+        for (int e = lane; e < kf + 2; e += 32) orow[2 * n + e] = moer_tail(mrow, e, kf, ts);
+    }
+    if (autoreset) {                                   // reset observation of the next episode (env.py:293-338)
+        float* o2 = cx.obs + b * OBS;
+        const float* r0 = cx.moer + (long long)md_out * SG_EV_MOER_ROWS * SG_EV_MOER_COLS;
+        for (int e = lane; e < OBS; e += 32) o2[e] = e < 2 * n ? 0.f : moer_tail(r0, e - 2 * n, kf, 0.f);
+    }
+    if (cx.pilots != nullptr) {
+#pragma unroll
+        for (int p = 0; p < 2; ++p) if (valid[p]) cx.pilots[b * n + i0 + p] = (uint8_t)pil[p];
+    }
+    if (lane == 0) {
+        const double moer0 = (double)__ldg(mrow);
+        const double profit = kProfitFactor * total_rate;
+        const double excess_charge = excess * kViolationFactor;
+        const double carbon = kCarbonFactor * total_rate * moer0;
+        const double rew = profit - carbon - excess_charge;
+        double* bd = cx.breakdown + b * 3;
+        if (t == 0) { bd[0] = profit; bd[1] = carbon; bd[2] = excess_charge; }
+        else { bd[0] += profit; bd[1] += carbon; bd[2] += excess_charge; }
+        int t_out = tn;
+        unsigned long long occ_new = ((unsigned long long)occ_hi << 32) | occ_lo;
+        if (autoreset) { day = (day + 1) % cx.n_days; t_out = 0; nidx = 0; occ_new = 0ull; }
+        cx.occ[b] = occ_new;
+        *reinterpret_cast<int4*>(cx.clock + b * 4) = make_int4(t_out, day, md_out, nidx);
+        cx.reward[b] = rew;
+        cx.done[b] = dn ? 1 : 0;
+        if (cx.status != nullptr) cx.status[b] = (uint8_t)st;
+        if (wstat != nullptr) {
+            wstat[0] += 1.0; wstat[1] += rew; wstat[2] += rew * rew;
+            wstat[3] = fmin(wstat[3], rew); wstat[4] = fmax(wstat[4], rew);
+            wstat[5] += dn ? 1.0 : 0.0;
+            wstat[6] += (st & SG_EV_STATUS_PROJECTED) ? 1.0 : 0.0;
+            wstat[7] += (st & SG_EV_STATUS_MAXITER) ? 1.0 : 0.0;
+            wstat[8] += profit; wstat[9] += carbon; wstat[10] += excess_charge;
+        }
+    }
+    __syncwarp();
+    return true;
 }
 
 // =================================================================================================
-// Main kernel: one launch = one step() of all envs.  A warp owns a tile of 32 consecutive envs.
+// Main kernel: one launch = one step() of all envs.  A warp owns a tile of kE consecutive envs; lane
+// e < kE keeps env e's scalars ("owner"), and the phases that have more parallelism than envs are
+// spread over all 32 lanes:
 //
-//   fill     the tile's observation rows (contiguous in memory) are written by the whole warp with
-//            coalesced 8-byte stores: zeros for demands / est_departures (an empty station reads 0)
-//            and the MOER row + timestep tail; pilot rows are zeroed (projection on: an empty station
-//            has upper bound 0) or computed densely with their class sums (projection off);
-//   items    the occupied stations of the 32 envs (bits of the per-env 64-bit masks) are enumerated
-//            into one work list and processed one (env, station) item per lane, so the lanes stay
-//            balanced whatever the per-env occupancy: one 32-byte session record (single 256-bit
-//            load) + one action value in, battery arithmetic (branch-free, exact), the record goes
-//            to the other state copy, the two observation entries and the pilot byte are patched
-//            into the pre-filled rows, the item's rate / pilot / clipped action go to a record in
-//            shared memory;
-//   owner    thread e sums the records of env e in station order (deterministic f64 sums) and tests
-//            the class sums of the clipped action against the network constraints in f32 with a
-//            margin; an env that is not certainly feasible is handed to the warp-cooperative exact
-//            projection (project_env) and its stations are re-done with the projected action (its
-//            inputs are still intact in the current state copy);
+//   stage    the tile's observation rows and pilot rows (both contiguous in global memory) are
+//            assembled in shared memory: zero-filled with 16-byte stores (an empty station reads 0
+//            and, with the projection on, has pilot 0), the MOER row + timestep tail copied by kQ
+//            lanes per env; with the projection off the pilot rows are computed densely with their
+//            class sums.  At the end of the tile ONE bulk asynchronous copy (cp.async.bulk, the TMA
+//            engine) per array writes the finished rows to global memory: full aligned sectors, each
+//            byte written once, no store instructions on the SM;
+//   items    the occupied stations of the tile's envs (bits of the per-env 64-bit masks) are
+//            enumerated into one work list and processed one (env, station) item per lane, so lanes
+//            stay balanced whatever the per-env occupancy: one 32-byte session record (single
+//            256-bit load) + one action value in, battery arithmetic (branch-free, exact), the record
+//            goes to the other state copy, the two observation entries and the pilot byte are
+//            patched into the staged rows, class sums of the clipped action / pilots are
+//            accumulated with shared-memory atomics, the rate goes to a list in shared memory;
+//   owner    lane e sums the rates of env e in station order (deterministic f64 sum);
+//   check    one (env, constraint) pair per lane: class sums of the clipped action against the
+//            network constraints in f32 with a margin (and the same for the excess current of the
+//            rounded schedule); an env that is not certainly feasible is left to fallback_env;
 //   arrivals Plugin events with timestamp <= t+1 from the day's arrival-sorted list;
-//   epilogue excess current of the rounded schedule, reward, cumulative breakdown, clock, mask.
+//   epilogue reward, cumulative breakdown, clock, mask, statistics.
+// The kernel contains no function call on its main path (the rare path is entered at the very end
+// of a tile, when nothing but the tile index is live).
 // =================================================================================================
+#ifdef SG_EV_TRACE
+__device__ unsigned long long* g_trace = nullptr;     // [ntiles][16] phase timestamps (diagnostic builds only)
+#define EV_TRACE(k)                                                                                      \
+    do {                                                                                                 \
+        if (g_trace != nullptr && lane == 0) {                                                           \
+            unsigned long long gt;                                                                       \
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));                                       \
+            g_trace[tile * 16 + (k)] = gt;                                                               \
+        }                                                                                                \
+    } while (0)
+#else
+#define EV_TRACE(k) do { } while (0)
+#endif
+
 template <int MODE>
-__global__ void __launch_bounds__(kMainThreads, 8)
+__global__ void __launch_bounds__(kMainThreads, SG_EV_MINB)
 ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B, const void* __restrict__ action,
                     const int flags, const int bins, float* __restrict__ obs, double* __restrict__ reward,
                     uint8_t* __restrict__ done, uint8_t* __restrict__ pilots, float* __restrict__ final_obs,
                     uint8_t* __restrict__ status, double* __restrict__ stats) {
-    __shared__ EvShared sh;
-    __shared__ MainShared ms;
-    const int n = m.n_stations, kf = m.moer_steps, OBS = 2 * n + kf + 2, J = m.n_constraints, C = m.n_classes;
-    load_shared(m, sh);
-    for (int i = threadIdx.x; i < SG_EV_MAX_CONSTRAINTS * kMC; i += blockDim.x) {
-        ms.re[i] = (float)sh.con_re[i];
-        ms.im[i] = (float)sh.con_im[i];
+    __shared__ EvTables sh;
+    __shared__ WarpShared wsm[kMainWarps];
+    extern __shared__ __align__(128) unsigned char stage_raw[];       // per warp: kE observation rows | kE pilot rows
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long ntiles = (B + kE - 1) / kE;
+    const long long wstride = (long long)gridDim.x * kMainWarps;
+    long long tile = (long long)blockIdx.x * kMainWarps + warp;
+    EV_TRACE(10);
+    // the first tile's clock / occupancy rows are requested before the table copy
+    int4 clk_next = make_int4(kEpisode, 0, 0, 0);
+    unsigned long long occ_next = 0ull;
+    if (tile < ntiles && tile * kE + lane < B && lane < kE) {
+        clk_next = *reinterpret_cast<const int4*>(s.clock + (tile * kE + lane) * 4);
+        occ_next = s.occ[tile * kE + lane];
     }
-    for (int i = threadIdx.x; i < SG_EV_MAX_CONSTRAINTS; i += blockDim.x) {
-        const double lim = sh.lim[i];
-        const double r = lim * (1.0 / kActionScale) - (double)kPreMargin;
-        ms.r_in[i] = r > 0.0 ? (float)(r * r * 0.99999) : -1.f;
-        ms.lim2_lo[i] = (float)(lim * lim * 0.999);
-    }
-    for (int i = threadIdx.x; i <= 32; i += blockDim.x) ms.ppilot[i] = div_c((double)i * kVoltage, 1000.0, kInv1000);
+    load_tables(m.tables, sh);
+    WarpShared& ws = wsm[warp];
+    if (lane < 12) ws.stat[lane] = lane == 3 ? 1e300 : (lane == 4 ? -1e300 : 0.0);
     __syncthreads();
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpShared& ws = ms.w[warp];
+    const int n = m.n_stations, kf = m.moer_steps, OBS = 2 * n + kf + 2, J = m.n_constraints;
+    const int eq = lane / kQ, sub = lane % kQ;         // spread phases: lane works for env eq
     const bool i64 = (flags & 1) == SG_EV_ACTION_I64;
     const float* __restrict__ moer = m.moer;
     const uint4* __restrict__ recs = reinterpret_cast<const uint4*>(m.sessions);
     Slot* slots = reinterpret_cast<Slot*>(s.slots);
-    const long long ntiles = (B + 31) / 32;
-    const long long wstride = (long long)gridDim.x * kMainWarps;
-    const bool pair_rows = ((kf & 1) == 0);            // OBS even: rows are 8-byte aligned, tail pairs never straddle
-    const int tp = (kf + 2) >> 1;                      // float2 pairs in a row's MOER + timestep tail
-    StatsAcc acc;
+    const int tp = (kf + 3) >> 1;                      // float2-sized pairs covering a row's MOER + timestep tail
+    constexpr unsigned kOwnerMask = kE == 32 ? 0xffffffffu : ((1u << kE) - 1u);
+    const int row_bytes = (kE * OBS * 4 + 15) & ~15, pil_bytes = (kE * n + 15) & ~15;
+    float* srows = reinterpret_cast<float*>(stage_raw + (size_t)warp * (row_bytes + pil_bytes));
+    uint8_t* spil = reinterpret_cast<uint8_t*>(srows) + row_bytes;
+    // the bulk copies need 16-byte aligned, 16-byte multiple global ranges
+    const bool bulk_rows = ((kE * OBS) & 3) == 0 && (reinterpret_cast<uintptr_t>(obs) & 15u) == 0;
+    const bool bulk_pil = pilots != nullptr && ((kE * n) & 15) == 0 && (reinterpret_cast<uintptr_t>(pilots) & 15u) == 0;
 
-    auto act_at = [&](const long long o) -> float {
-        return i64 ? __fdiv_rn((float)reinterpret_cast<const long long*>(action)[o], (float)(bins - 1))   // wrappers.py:45
-                   : __ldg(reinterpret_cast<const float*>(action) + o);
-    };
-
-    for (long long tile = (long long)blockIdx.x * kMainWarps + warp; tile < ntiles; tile += wstride) {
-        const long long b0 = tile * 32;
-        const int nv = (int)min(32ll, B - b0);
+  while (tile < ntiles) {
+    int n_todo = 0;                                   // rare-path queue of this warp (ws.todo)
+    for (; tile < ntiles && n_todo <= 32 - kE; tile += wstride) {
+        const long long b0 = tile * kE;
+        const int nv = (int)min((long long)kE, B - b0);
         const long long b = b0 + lane;
-        const bool env = lane < nv;
-        int4 clk = make_int4(kEpisode, 0, 0, 0);
-        if (env) clk = *reinterpret_cast<const int4*>(s.clock + b * 4);
+        const bool env = lane < nv;                    // owner lanes
+        const int4 clk = clk_next;
+        const unsigned long long occ_ld = occ_next;
+        {   // next tile's rows (persistent grids only)
+            const long long tb = (tile + wstride) * kE + lane;
+            clk_next = make_int4(kEpisode, 0, 0, 0); occ_next = 0ull;
+            if (tile + wstride < ntiles && tb < B && lane < kE) {
+                clk_next = *reinterpret_cast<const int4*>(s.clock + tb * 4);
+                occ_next = s.occ[tb];
+            }
+        }
         const int t = clk.x, tn = t + 1;
         int day = clk.y, nidx = clk.w;
         const int md = clk.z;
         const bool live = env && t < kEpisode;
-        unsigned long long occ = 0ull;
-        double bd0 = 0.0, bd1 = 0.0, bd2 = 0.0;
-        if (live) {
-            occ = s.occ[b];
-            if (t != 0) { const double* bd = s.breakdown + b * 3; bd0 = bd[0]; bd1 = bd[1]; bd2 = bd[2]; }
-        }
+        const unsigned long long occ = live ? occ_ld : 0ull;
         const bool dn = tn >= kEpisode;
         const bool autoreset = live && dn && (flags & SG_EV_FLAG_AUTORESET);
         const int md_out = autoreset ? (md + 1) % m.n_moer_days : md;
@@ -829,60 +1011,35 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
             if (nidx < m.max_day_sessions) ent2 = __ldg(arow + nidx + 1);
         }
         const int par = t & 1;
-        const int info = tn | (par << 16) | ((int)autoreset << 17);
-#pragma unroll
-        for (int c = 0; c < kMC; ++c) { ws.S[c][lane] = 0.f; ws.P[c][lane] = 0; }
+        const int info = tn | (par << 16);
+        EV_TRACE(0);
 
-        // ---------------- fill: coalesced observation (and pilot) rows ------------------------------
-        if (nv == 32 && live_mask == kFull && ar_mask == 0u && pair_rows) {
-            float2* o2 = reinterpret_cast<float2*>(obs + b0 * OBS);
-            const int rp = OBS >> 1;                                   // float2 pairs per row
-            const float2 z2 = make_float2(0.f, 0.f);
-#pragma unroll 4
-            for (int r = 0; r < 32; ++r) {
-                if (lane < n) stg_stream_f2(o2 + r * rp + lane, z2);
-                if (lane + 32 < n) stg_stream_f2(o2 + r * rp + lane + 32, z2);
+        // ---------------- stage: zeroed rows, MOER + timestep tails, dense pilots (projection off) -------
+        {
+            // tails first (their loads are the only dependency of this phase): kQ lanes per env
+            const float* p = moer + __shfl_sync(kFull, moff, eq);
+            const float ts_e = __shfl_sync(kFull, tsf, eq);
+            float tv[2 * kTailPerLane];
+#pragma unroll
+            for (int k = 0; k < kTailPerLane; ++k) {
+                const int q0 = 2 * (sub + k * kQ);
+                tv[2 * k] = q0 < kf + 2 ? moer_tail(p, q0, kf, ts_e) : 0.f;
+                tv[2 * k + 1] = q0 + 1 < kf + 2 ? moer_tail(p, q0 + 1, kf, ts_e) : 0.f;
             }
-            // tails: 32 rows x tp pairs, one pair per lane and iteration
-            int row = lane / tp, col = lane - row * tp;
-            const int drow = 32 / tp, dcol = 32 - drow * tp;
-            for (int it = 0; it < tp; ++it) {
-                const int moff_r = __shfl_sync(kFull, moff, row);
-                const float ts_r = __shfl_sync(kFull, tsf, row);
-                const int e = 2 * col;
-                const float* p = moer + moff_r;
-                float2 v;
-                v.x = e < kf ? __ldg(p + 1 + e) : __ldg(p);
-                v.y = e + 1 < kf ? __ldg(p + 2 + e) : (e + 1 == kf ? __ldg(p) : ts_r);
-                stg_stream_f2(o2 + row * rp + n + col, v);
-                row += drow; col += dcol;
-                if (col >= tp) { col -= tp; row += 1; }
+            for (int i = lane; i < kMC * kE; i += 32) { (&ws.S[0][0])[i] = 0; (&ws.P[0][0])[i] = 0; }
+            if (lane < kE) { ws.occ_clr[lane][0] = 0u; ws.occ_clr[lane][1] = 0u; }
+            uint4* z = reinterpret_cast<uint4*>(srows);
+            if (!(SG_EV_ABL & 8))
+            for (int i = lane; i < (row_bytes + pil_bytes) >> 4; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
+            __syncwarp();
+            float* dst = srows + eq * OBS + 2 * n;
+#pragma unroll
+            for (int k = 0; k < kTailPerLane; ++k) {
+                const int q0 = 2 * (sub + k * kQ);
+                if (q0 < kf + 2) dst[q0] = tv[2 * k];
+                if (q0 + 1 < kf + 2) dst[q0 + 1] = tv[2 * k + 1];
             }
-            if (MODE != 0 && pilots != nullptr) {
-                uint4* p4 = reinterpret_cast<uint4*>(pilots + b0 * n);  // 32 n bytes, 16-byte aligned
-                for (int c = lane; c < 2 * n; c += 32) p4[c] = make_uint4(0u, 0u, 0u, 0u);
-            }
-        } else {
-            for (int r = 0; r < nv; ++r) {
-                if (!((live_mask >> r) & 1u)) continue;
-                const bool ar = (ar_mask >> r) & 1u;
-                const int moff_r = __shfl_sync(kFull, moff, r);
-                const float ts_r = __shfl_sync(kFull, tsf, r);
-                float* orow = ar ? (final_obs != nullptr ? final_obs + (b0 + r) * OBS : nullptr) : obs + (b0 + r) * OBS;
-                auto fill_row = [&](float* dst, const float* row, const float tsv) {
-                    for (int e = lane; e < OBS; e += 32) {
-                        const int q = e - 2 * n;
-                        dst[e] = q < 0 ? 0.f : (q < kf ? __ldg(row + 1 + q) : (q == kf ? __ldg(row) : tsv));
-                    }
-                };
-                if (orow != nullptr) fill_row(orow, moer + moff_r, ts_r);
-                if (ar) {                                  // reset observation of the next episode (env.py:293-338)
-                    const int mdo_r = __shfl_sync(kFull, md_out, r);
-                    fill_row(obs + (b0 + r) * OBS, moer + (long long)mdo_r * SG_EV_MOER_ROWS * SG_EV_MOER_COLS, 0.f);
-                }
-                if (MODE != 0 && pilots != nullptr)
-                    for (int i = lane; i < n; i += 32) pilots[(b0 + r) * n + i] = 0;
-            }
+            (void)tp;
         }
         if constexpr (MODE == 0) {
             // every EVSE receives a pilot, occupied or not (env.py:368-378); class sums for the excess current
@@ -895,12 +1052,9 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
                 for (int p = 0; p < 2; ++p)
                     if (i0 + p < n) {
                         cl[p] = sh.cls[i0 + p];
-                        pv[p] = (unsigned)pilot_f32(act_at((b0 + r) * n + i0 + p), sh.type[i0 + p]);
+                        pv[p] = (unsigned)pilot_f32(act_value(action, i64, bins, (b0 + r) * n + i0 + p), sh.type[i0 + p]);
+                        spil[r * n + i0 + p] = (uint8_t)pv[p];
                     }
-                if (pilots != nullptr) {
-#pragma unroll
-                    for (int p = 0; p < 2; ++p) if (i0 + p < n) pilots[(b0 + r) * n + i0 + p] = (uint8_t)pv[p];
-                }
 #pragma unroll
                 for (int w = 0; w < kMC / 2; ++w) {
                     unsigned part = 0;
@@ -908,152 +1062,140 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
                     for (int p = 0; p < 2; ++p)
                         if ((cl[p] >> 1) == w) part += pv[p] << ((cl[p] & 1) * 16);
                     const unsigned tot = __reduce_add_sync(kFull, part);
-                    if (lane == r) { ws.P[2 * w][lane] = (int)(tot & 0xffffu); ws.P[2 * w + 1][lane] = (int)(tot >> 16); }
+                    if (lane == 0) { ws.P[2 * w][r] = (int)(tot & 0xffffu); ws.P[2 * w + 1][r] = (int)(tot >> 16); }
                 }
             }
         }
         __syncwarp();
+        EV_TRACE(2);
 
         // ---------------- items: one (env, occupied station) per lane ------------------------------------
         const int cnt = __popcll(occ);
-        int off = cnt;                                                 // inclusive scan over the lanes
+        int off = cnt;                                                 // inclusive scan over the owner lanes
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
+        for (int d = 1; d < kE; d <<= 1) {
             const int v = __shfl_up_sync(kFull, off, d);
             if (lane >= d) off += v;
         }
-        const int total = __shfl_sync(kFull, off, 31);
+        const int total = (SG_EV_ABL & 4) ? 0 : __shfl_sync(kFull, off, kE - 1);
         off -= cnt;
         double rate_sum = 0.0;
-        unsigned long long occ_new = occ;
+        // this lane's segment of env eq's occupancy bits, and the list position of its first item
+        const unsigned long long occ_e = __shfl_sync(kFull, occ, eq);
+        const unsigned long long seg = kQ == 1 ? occ_e : (occ_e >> (sub * kSegBits)) & ((1ull << (kSegBits & 63)) - 1ull);
+        const int j0 = __shfl_sync(kFull, off, eq) +
+                       (kQ == 1 ? 0 : __popcll(occ_e & ((1ull << ((sub * kSegBits) & 63)) - 1ull)));
         for (int c0 = 0; c0 < total; c0 += kItemCap) {
             const int nitems = min(kItemCap, total - c0);
             {   // keys of this chunk
-                int j = off - c0;
-                for (unsigned long long mask = occ; mask; mask &= mask - 1, ++j)
-                    if (j >= 0 && j < kItemCap) ws.items[j].meta = ((unsigned)lane << 8) | (unsigned)(__ffsll((long long)mask) - 1);
+                int j = j0 - c0;
+                if (kSegBits <= 32) {
+                    for (unsigned m2 = (unsigned)seg; m2; m2 &= m2 - 1, ++j)
+                        if (j >= 0 && j < kItemCap) ws.key[j] = (unsigned short)((eq << 8) | (sub * kSegBits + __ffs((int)m2) - 1));
+                } else {
+                    for (unsigned long long m2 = seg; m2; m2 &= m2 - 1, ++j)
+                        if (j >= 0 && j < kItemCap) ws.key[j] = (unsigned short)((eq << 8) | (__ffsll((long long)m2) - 1));
+                }
             }
             __syncwarp();
-            constexpr int V = 2;
-            for (int base = 0; base < nitems; base += 32 * V) {
-                int e[V], si[V], inf[V];
-                Slot q[V];
-                float af[V];
-                bool on[V];
+            EV_TRACE(3);
+            int e[kV], si[kV], inf[kV];
+            Slot q[kV];
+            float af[kV];
+            bool on[kV];
 #pragma unroll
-                for (int u = 0; u < V; ++u) {
-                    const int j = base + u * 32 + lane;
-                    on[u] = j < nitems;
-                    const unsigned key = on[u] ? ws.items[j].meta : 0u;
-                    e[u] = (int)(key >> 8); si[u] = (int)(key & 0xffu);
-                    inf[u] = __shfl_sync(kFull, info, e[u]);
-                }
+            for (int u = 0; u < kV; ++u) {
+                const int j = u * 32 + lane;
+                on[u] = j < nitems;
+                const unsigned key = on[u] ? ws.key[j] : 0u;
+                e[u] = (int)(key >> 8); si[u] = (int)(key & 0xffu);
+                inf[u] = __shfl_sync(kFull, info, e[u]);
+            }
 #pragma unroll
-                for (int u = 0; u < V; ++u) {
-                    af[u] = 0.f;
-                    q[u].energy = 0.0; q[u].delivered = 0.0; q[u].dep = q[u].est = q[u].arr = q[u].k = 0;
-                    if (on[u]) {
-                        const long long be = b0 + e[u];
-                        q[u] = ld_slot(slots + ((long long)((inf[u] >> 16) & 1) * B + be) * n + si[u]);
-                        af[u] = act_at(be * n + si[u]);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < V; ++u) {
-                    if (!on[u]) continue;
-                    const int i = si[u], tn_e = inf[u] & 0xffff, par_e = (inf[u] >> 16) & 1;
-                    const bool ar_e = (inf[u] >> 17) & 1;
+            for (int u = 0; u < kV; ++u) {
+                af[u] = 0.f;
+                q[u].energy = 0.0; q[u].delivered = 0.0; q[u].dep = q[u].est = q[u].arr = q[u].k = 0;
+                if (on[u]) {
                     const long long be = b0 + e[u];
-                    const int type = sh.type[i], cls = sh.cls[i];
-                    int pi;
-                    float xf = 0.f;
-                    if (MODE == 0) {
-                        pi = pilot_f32(af[u], type);
-                    } else {
-                        const double rem = q[u].energy - q[u].delivered;
-                        const float dem = rem > kFullEps ? (float)rem : 0.f;              // obs 'demands', env.py:388
-                        pi = pilot_clipped(af[u], dem, type, &xf);
-                        if (pilots != nullptr && pi != 0) pilots[be * n + i] = (uint8_t)pi;
-                    }
-                    ItemRec rec;
-                    rec.rate = charge_period(q[u].energy, q[u].delivered, ms.ppilot[pi]);
-                    rec.x = xf;
-                    const bool departed = q[u].dep <= tn_e;                               // Unplug event (timestamp = departure)
-                    rec.meta = (unsigned)pi | ((unsigned)cls << 8) | ((unsigned)departed << 16) | ((unsigned)i << 24);
-                    ws.items[base + u * 32 + lane] = rec;
-                    if (!departed) {
-                        st_slot(slots + ((long long)(par_e ^ 1) * B + be) * n + i, q[u]);
-                        const double rem = q[u].energy - q[u].delivered;
-                        float* row = ar_e ? final_obs : obs;                              // terminal observation only if asked for
-                        if (rem > kFullEps && row != nullptr) {                           // Interface.active_sessions()
-                            row[be * OBS + i] = (float)rem;
-                            row[be * OBS + n + i] = (float)(q[u].est - tn_e);
-                        }
+                    q[u] = ld_slot(slots + ((long long)((inf[u] >> 16) & 1) * B + be) * n + si[u]);
+                    af[u] = act_value(action, i64, bins, be * n + si[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kV; ++u) {
+                if (!on[u]) continue;
+                const int i = si[u], tn_e = inf[u] & 0xffff, par_e = (inf[u] >> 16) & 1;
+                const long long be = b0 + e[u];
+                const int type = sh.type[i], cls = sh.cls[i];
+                int pi;
+                if (MODE == 0) {
+                    pi = pilot_f32(af[u], type);
+                } else {
+                    const double rem = q[u].energy - q[u].delivered;
+                    const float dem = rem > kFullEps ? (float)rem : 0.f;                  // obs 'demands', env.py:388
+                    float xf;
+                    pi = pilot_clipped(af[u], dem, type, &xf);
+                    atomicAdd(&ws.S[cls][e[u]], __float2int_rn(xf * 1048576.f));
+                    atomicAdd(&ws.P[cls][e[u]], pi);
+                    spil[e[u] * n + i] = (uint8_t)pi;
+                }
+                ws.rate[u * 32 + lane] = charge_period(q[u].energy, q[u].delivered, sh.ppilot[pi]);
+                if (q[u].dep <= tn_e) {                                                   // Unplug event (timestamp = departure)
+                    atomicOr(&ws.occ_clr[e[u]][i >> 5], 1u << (i & 31));
+                } else {
+                    if (!(SG_EV_ABL & 2)) st_slot(slots + ((long long)(par_e ^ 1) * B + be) * n + i, q[u]);
+                    const double rem = q[u].energy - q[u].delivered;
+                    if (rem > kFullEps) {                                                 // Interface.active_sessions()
+                        srows[e[u] * OBS + i] = (float)rem;
+                        srows[e[u] * OBS + n + i] = (float)(q[u].est - tn_e);
                     }
                 }
             }
             __syncwarp();
-            // owner: thread e sums the records of env e in station order
+            EV_TRACE(4);
+            // owner: lane e sums the rates of env e in station order
             {
                 const int lo = max(off - c0, 0), hi = min(off + cnt - c0, nitems);
-                for (int j = lo; __any_sync(kFull, j < hi); ++j) {
-                    if (j < hi) {
-                        const ItemRec rec = ws.items[j];
-                        const int cls = (rec.meta >> 8) & 0xff;
-                        rate_sum += rec.rate;
-                        if (MODE != 0) {
-                            ws.S[cls][lane] += rec.x;
-                            ws.P[cls][lane] += (int)(rec.meta & 0xffu);
-                        }
-                        if ((rec.meta >> 16) & 1u) occ_new &= ~(1ull << (rec.meta >> 24));
-                    }
-                }
+                for (int j = lo; __any_sync(kFull, j < hi); ++j)
+                    if (j < hi) rate_sum += ws.rate[j];
             }
             __syncwarp();
         }
+        EV_TRACE(5);
 
-        // ---------------- network constraints on the clipped action (projection only) -------------------
-        int st = 0;
-        if constexpr (MODE != 0) {
-            bool ok = true;
-            if (live && cnt > 0) {
-                float Sf[kMC];
+        // ---------------- network constraints: one (env, constraint) pair per lane and iteration ---------
+        // bad: the clipped action is not certainly feasible (projection needed); near: the rounded
+        // schedule is close to or over a limit (exact excess current needed)
+        unsigned bad = 0u, near = 0u;
+        {
+            bool mybad = false, mynear = false;
+            for (int idx = lane; idx < ((SG_EV_ABL & 16) ? 0 : kE * J); idx += 32) {   // pair (env idx % kE, constraint idx / kE)
+                const int j = idx / kE, e = idx & (kE - 1);
+                float wr = 0.f, wi = 0.f, vr = 0.f, vi = 0.f;
 #pragma unroll
-                for (int c = 0; c < kMC; ++c) Sf[c] = ws.S[c][lane];
-                for (int j = 0; j < J; ++j) {
-                    float wr = 0.f, wi = 0.f;
+                for (int c = 0; c < kMC; ++c) {
+                    const float cre = sh.re[j * kMC + c], cim = sh.im[j * kMC + c];
+                    const float pv = (float)ws.P[c][e];
+                    vr = fmaf(cre, pv, vr); vi = fmaf(cim, pv, vi);
+                    if (MODE != 0) { const float sv = (float)ws.S[c][e] * (1.f / 1048576.f); wr = fmaf(cre, sv, wr); wi = fmaf(cim, sv, wi); }
+                }
+                if (MODE != 0) mybad = mybad || !(fmaf(wr, wr, wi * wi) <= sh.r_in[j]);
+                mynear = mynear || (fmaf(vr, vr, vi * vi) > sh.lim2_lo[j]);
+            }
+            bad = __ballot_sync(kFull, mybad);
+            near = __ballot_sync(kFull, mynear);
 #pragma unroll
-                    for (int c = 0; c < kMC; ++c) { wr = fmaf(ms.re[j * kMC + c], Sf[c], wr); wi = fmaf(ms.im[j * kMC + c], Sf[c], wi); }
-                    ok = ok && (fmaf(wr, wr, wi * wi) <= ms.r_in[j]);
-                }
-            }
-            unsigned bad = __ballot_sync(kFull, !ok);
-            while (bad) {
-                const int r = __ffs((int)bad) - 1;
-                bad &= bad - 1;
-                const unsigned long long occ_r = __shfl_sync(kFull, occ, r);
-                const int par_r = (__shfl_sync(kFull, info, r) >> 16) & 1;
-                const Slot* cur_r = slots + ((long long)par_r * B + (b0 + r)) * n;
-                const int st_r = project_env(sh, n, C, J, b0 + r, lane, action, i64, bins, cur_r, occ_r, ws.xs);
-                if (lane == r) {
-                    st = st_r;
-                    if (st_r != 0) {
-                        float* row = autoreset ? final_obs : obs;
-                        const RedoOut ro = redo_env(sh.type, sh.cls, ms.ppilot, &ws.P[0][lane], ws.xs, n, tn, occ, cur_r,
-                                                    slots + ((long long)(par_r ^ 1) * B + b) * n,
-                                                    row != nullptr ? row + b * OBS : nullptr,
-                                                    pilots != nullptr ? pilots + b * n : nullptr);
-                        rate_sum = ro.rate_sum;
-                        occ_new = ro.occ_new;
-                    }
-                }
-                __syncwarp();
-            }
+            for (int shf = kE; shf < 32; shf <<= 1) { bad |= bad >> shf; near |= near >> shf; }
+            bad &= live_mask & kOwnerMask;
         }
+        const bool mine_ok = live && !((bad >> lane) & 1u);              // this owner lane finishes its env here
+        EV_TRACE(6);
 
         // ---------------- arrivals: Plugin events with timestamp <= t+1 (after the Unplug events) -------
-        if ((int)(ent & 0x7fffu) <= tn) {
-            float* row = autoreset ? final_obs : obs;
+        unsigned long long occ_new = occ & ~(((unsigned long long)ws.occ_clr[lane & (kE - 1)][1] << 32) |
+                                             ws.occ_clr[lane & (kE - 1)][0]);
+        if (mine_ok && (int)(ent & 0x7fffu) <= tn) {
+            float* row = srows + lane * OBS;
             Slot* nxt = slots + ((long long)(par ^ 1) * B + b) * n;
             do {
                 const int i = (ent >> 16) & 0xff, k = ent >> 24;
@@ -1068,52 +1210,40 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
                 if (ns.dep > tn) {                                        // (zero-length sessions never charge)
                     occ_new |= 1ull << i;
                     st_slot(nxt + i, ns);
-                    if (row != nullptr && ns.energy > kFullEps) {
-                        row[b * OBS + i] = (float)ns.energy;
-                        row[b * OBS + n + i] = (float)(ns.est - tn);
-                    }
+                    if (ns.energy > kFullEps) { row[i] = (float)ns.energy; row[n + i] = (float)(ns.est - tn); }
                 }
                 ++nidx;
                 ent = ent2;
                 ent2 = (int)(ent & 0x7fffu) <= tn ? __ldg(arow + nidx + 1) : 0x7fffu;
             } while ((int)(ent & 0x7fffu) <= tn);
         }
+        EV_TRACE(7);
 
         // ---------------- per-env epilogue: excess current, reward, clock ---------------------------------
-        if (live) {
+        double rew = 0.0, profit = 0.0, carbon = 0.0, excess_charge = 0.0;
+        if (mine_ok) {
             double excess = 0.0;
-            {
-                float Pf[kMC];
-#pragma unroll
-                for (int c = 0; c < kMC; ++c) Pf[c] = (float)ws.P[c][lane];
-                bool near = false;
+            if ((near >> lane) & 1u) {                                    // exact (env.py:449-452)
                 for (int j = 0; j < J; ++j) {
-                    float wr = 0.f, wi = 0.f;
+                    double wr = 0, wi = 0;
 #pragma unroll
-                    for (int c = 0; c < kMC; ++c) { wr = fmaf(ms.re[j * kMC + c], Pf[c], wr); wi = fmaf(ms.im[j * kMC + c], Pf[c], wi); }
-                    near = near || (fmaf(wr, wr, wi * wi) > ms.lim2_lo[j]);
-                }
-                if (near) {                                               // exact (env.py:449-452)
-                    for (int j = 0; j < J; ++j) {
-                        double wr = 0, wi = 0;
-#pragma unroll
-                        for (int c = 0; c < kMC; ++c) {
-                            wr = fma(sh.con_re[j * kMC + c], (double)ws.P[c][lane], wr);
-                            wi = fma(sh.con_im[j * kMC + c], (double)ws.P[c][lane], wi);
-                        }
-                        const double lim = sh.lim[j], sq = fma(wr, wr, wi * wi);
-                        if (sq > lim * lim) excess += fmax(0.0, sqrt(sq) - lim);
+                    for (int c = 0; c < kMC; ++c) {
+                        wr = fma(sh.con_re[j * kMC + c], (double)ws.P[c][lane], wr);
+                        wi = fma(sh.con_im[j * kMC + c], (double)ws.P[c][lane], wi);
                     }
+                    const double lim = sh.lim[j], sq = fma(wr, wr, wi * wi);
+                    if (sq > lim * lim) excess += fmax(0.0, sqrt(sq) - lim);
                 }
             }
-            const double profit = kProfitFactor * rate_sum;
-            const double excess_charge = excess * kViolationFactor;
-            const double carbon = kCarbonFactor * rate_sum * (double)moer0f;
-            const double rew = profit - carbon - excess_charge;
+            profit = kProfitFactor * rate_sum;
+            excess_charge = excess * kViolationFactor;
+            carbon = kCarbonFactor * rate_sum * (double)moer0f;
+            rew = profit - carbon - excess_charge;
             // cumulative reward breakdown (env.py:460-462); restarted on the first step of an episode so that
             // after an auto-reset the finished episode's totals stay readable until the next step
             double* bd = s.breakdown + b * 3;
-            bd[0] = bd0 + profit; bd[1] = bd1 + carbon; bd[2] = bd2 + excess_charge;
+            if (t == 0) { bd[0] = profit; bd[1] = carbon; bd[2] = excess_charge; }
+            else { bd[0] += profit; bd[1] += carbon; bd[2] += excess_charge; }
             int t_out = tn;
             if (autoreset) {
                 day = (day + 1) % m.n_days;                               // sequential days, event_generation.py:284-291
@@ -1123,24 +1253,122 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
             *reinterpret_cast<int4*>(s.clock + b * 4) = make_int4(t_out, day, md_out, nidx);
             reward[b] = rew;
             done[b] = dn ? 1 : 0;
-            if (status != nullptr) status[b] = (uint8_t)st;
-            if (stats != nullptr) {
-                acc.add(rew, dn, profit, carbon, excess_charge);
-                acc.n_proj += (st & SG_EV_STATUS_PROJECTED) ? 1.0 : 0.0;
-                acc.n_maxiter += (st & SG_EV_STATUS_MAXITER) ? 1.0 : 0.0;
-            }
-        } else if (env) {                                                 // finished episode, not reset: stays terminal
+            if (status != nullptr) status[b] = 0;
+        } else if (env && !live) {                                        // finished episode, not reset: stays terminal
             reward[b] = 0.0; done[b] = 1;
             if (status != nullptr) status[b] = 0;
         }
+        if (stats != nullptr) {                                           // warp-level reduction into this warp's accumulators
+            const unsigned okm = __ballot_sync(kFull, mine_ok);
+            const unsigned dnm = __ballot_sync(kFull, mine_ok && dn);
+            if (okm) {
+                const double v[5] = {rew, rew * rew, profit, carbon, excess_charge};
+                double r5[5];
+#pragma unroll
+                for (int k = 0; k < 5; ++k) r5[k] = warp_sum(v[k]);
+                const double mn = warp_min(mine_ok ? rew : 1e300), mx = warp_max(mine_ok ? rew : -1e300);
+                if (lane == 0) {
+                    ws.stat[0] += (double)__popc(okm); ws.stat[1] += r5[0]; ws.stat[2] += r5[1];
+                    ws.stat[3] = fmin(ws.stat[3], mn); ws.stat[4] = fmax(ws.stat[4], mx);
+                    ws.stat[5] += (double)__popc(dnm);
+                    ws.stat[8] += r5[2]; ws.stat[9] += r5[3]; ws.stat[10] += r5[4];
+                }
+            }
+        }
+        __syncwarp();
+        EV_TRACE(8);
+
+        // ---------------- rare path: envs that need the exact projection are queued (drained outside this loop)
+        if (bad) {
+            if (lane == 0) {
+                unsigned todo = bad;
+                while (todo) { ws.todo[n_todo++] = (int)(b0 + __ffs((int)todo) - 1); todo &= todo - 1; }
+            }
+            n_todo = __shfl_sync(kFull, n_todo, 0);
+        }
+
+        // ---------------- write-out of the staged rows --------------------------------------------------------
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // staged rows -> visible to the bulk-copy engine
+        __syncwarp();
+        const bool whole = nv == kE && live_mask == kOwnerMask && ar_mask == 0u;
+        if (SG_EV_ABL & 1) {
+        } else if (whole && bulk_rows) {
+            if (lane == 0)
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(obs + b0 * OBS),
+                             "r"((unsigned)__cvta_generic_to_shared(srows)), "r"(kE * OBS * 4) : "memory");
+        } else {
+            for (int r = 0; r < nv; ++r) {
+                if (!((live_mask >> r) & 1u)) continue;
+                const bool ar = (ar_mask >> r) & 1u;
+                float* orow = ar ? (final_obs != nullptr ? final_obs + (b0 + r) * OBS : nullptr) : obs + (b0 + r) * OBS;
+                if (orow != nullptr)
+                    for (int e2 = lane; e2 < OBS; e2 += 32) orow[e2] = srows[r * OBS + e2];
+                if (ar) {                                  // reset observation of the next episode (env.py:293-338)
+                    const int mdo_r = __shfl_sync(kFull, md_out, r);
+                    const float* r0 = moer + (long long)mdo_r * SG_EV_MOER_ROWS * SG_EV_MOER_COLS;
+                    float* o2 = obs + (b0 + r) * OBS;
+                    for (int e2 = lane; e2 < OBS; e2 += 32) o2[e2] = e2 < 2 * n ? 0.f : moer_tail(r0, e2 - 2 * n, kf, 0.f);
+                }
+            }
+        }
+        if (pilots != nullptr && !(SG_EV_ABL & 1)) {
+            if (whole && bulk_pil) {
+                if (lane == 0)
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(pilots + b0 * n),
+                                 "r"((unsigned)__cvta_generic_to_shared(spil)), "r"(kE * n) : "memory");
+            } else {
+                for (int r = 0; r < nv; ++r)
+                    if ((live_mask >> r) & 1u)
+                        for (int i = lane; i < n; i += 32) pilots[(b0 + r) * n + i] = spil[r * n + i];
+            }
+        }
+        if (lane == 0) {
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            // the staging rows are reused by the next tile; queued envs rewrite their rows in global
+            // memory afterwards, so for them the copy must have completed, not only been read
+            if (n_todo) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        }
         __syncwarp();
     }
+    // ---------------- rare path, outside the tile loop: nothing of the main path is live across the calls
+    if (n_todo) {
+        EvCtx cx;
+        cx.n = m.n_stations; cx.kf = m.moer_steps; cx.C = m.n_classes; cx.J = m.n_constraints; cx.K = m.max_sessions;
+        cx.n_days = m.n_days; cx.n_moer_days = m.n_moer_days; cx.max_day_sessions = m.max_day_sessions;
+        cx.flags = flags; cx.bins = bins; cx.B = B; cx.moer = m.moer; cx.recs = reinterpret_cast<const uint4*>(m.sessions);
+        cx.arrivals = m.arrivals; cx.action = action; cx.slots = reinterpret_cast<Slot*>(s.slots);
+        cx.clock = s.clock; cx.breakdown = s.breakdown; cx.occ = reinterpret_cast<unsigned long long*>(s.occ);
+        cx.obs = obs; cx.final_obs = final_obs; cx.reward = reward; cx.done = done; cx.pilots = pilots; cx.status = status;
+        double* wst = stats != nullptr ? wsm[warp].stat : nullptr;
+        for (int k = 0; k < n_todo; ++k) {
+            const long long bq = wsm[warp].todo[k];
+            if (!fallback_env<false>(sh, cx, bq, lane, wst)) fallback_env<true>(sh, cx, bq, lane, wst);
+        }
+    }
+  }
     if (stats != nullptr) {
         __syncthreads();
-        stats_flush_block(acc, stats, ms.stat);
+        // 11 statistics x kMainWarps partials -> one set of atomics per CTA
+        if (threadIdx.x < 11) {
+            const int i = threadIdx.x;
+            double r = wsm[0].stat[i];
+            for (int w = 1; w < kMainWarps; ++w) {
+                const double o = wsm[w].stat[i];
+                r = (i == 3) ? fmin(r, o) : (i == 4) ? fmax(r, o) : r + o;
+            }
+            if (i == 3) { if (r < 1e300) atomic_min_double(stats + 3, r); }
+            else if (i == 4) { if (r > -1e300) atomic_max_double(stats + 4, r); }
+            else if (r != 0.0) atomicAdd(stats + i, r);
+        }
     }
+#ifdef SG_EV_TRACE
+    {
+        tile = (long long)blockIdx.x * kMainWarps + warp;
+        if (tile < ntiles) EV_TRACE(9);
+    }
+#endif
 }
-
 
 __global__ void ev_reset_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
                                 const uint8_t* __restrict__ mask, const int32_t* __restrict__ day_in,
@@ -1192,8 +1420,9 @@ __global__ void __launch_bounds__(128)
 ev_project_kernel(const sg_ev_model m, const long long B, const float* __restrict__ action,
                   const float* __restrict__ demands, double* __restrict__ x_out, uint8_t* __restrict__ status,
                   int32_t* __restrict__ iters) {
-    __shared__ EvShared sh;
-    load_shared(m, sh);
+    __shared__ EvTables sh;
+    load_tables(m.tables, sh);
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const long long b = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (b >= B) return;
@@ -1252,6 +1481,12 @@ int check_model(const sg_ev_model* m) {
     return 0;
 }
 
+int check_tables(const sg_ev_model* m) {
+    SG_CHECK_ARG(m->tables != nullptr, "ev: model.tables is NULL (call sg_ev_prepare_tables once per model)");
+    SG_CHECK_ARG((reinterpret_cast<uintptr_t>(m->tables) & 15u) == 0, "ev: model.tables must be 16-byte aligned");
+    return 0;
+}
+
 int check_state(const sg_ev_state* s) {
     SG_CHECK_ARG(s != nullptr && s->slots && s->clock && s->breakdown && s->occ, "ev: NULL state array");
     SG_CHECK_ARG((reinterpret_cast<uintptr_t>(s->slots) & 31u) == 0, "ev: state.slots must be 32-byte aligned");
@@ -1262,6 +1497,13 @@ int check_state(const sg_ev_state* s) {
 }  // namespace sg
 
 extern "C" {
+
+int sg_ev_prepare_tables(const sg_ev_model* m, void* tables, void* stream) {
+    if (int rc = sg::check_model(m)) return rc;
+    SG_CHECK_ARG(tables != nullptr && (reinterpret_cast<uintptr_t>(tables) & 15u) == 0, "ev_prepare_tables: tables must be a 16-byte aligned device buffer");
+    sg::ev_prepare_kernel<<<1, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*m, reinterpret_cast<sg::EvTables*>(tables));
+    return sg::launch_status("ev_prepare_kernel");
+}
 
 int sg_ev_reset(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, const uint8_t* reset_mask,
                 const int32_t* day_in, const int32_t* moer_day_in, float* obs, void* stream) {
@@ -1285,20 +1527,30 @@ int sg_ev_step(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, con
     SG_CHECK_ARG(m->sessions && m->moer && m->arrivals && m->n_days >= 1 && m->n_moer_days >= 1 && m->max_sessions >= 1,
                  "ev_step: empty trace/MOER pool");
     SG_CHECK_ARG(m->max_sessions <= 256, "ev_step: more than 256 session slots per station per day");
+    if (int rc = sg::check_tables(m)) return rc;
+    SG_CHECK_ARG(2 * num_envs * (int64_t)m->n_stations < (1ll << 40), "ev_step: batch too large");
     SG_CHECK_ARG(!((flags & 1) == SG_EV_ACTION_I64) || discrete_bins >= 2, "ev_step: discrete_bins must be >= 2");
     if (num_envs <= 0) return 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     int sms = sg_device_sm_count();
     if (sms <= 0) sms = 148;
-    // one warp per 32-env tile; at most 8 resident CTAs per SM, larger batches loop (persistent)
-    const long long ntiles = (num_envs + 31) / 32;
-    const unsigned grid = (unsigned)std::min<long long>((ntiles + sg::kMainWarps - 1) / sg::kMainWarps, (long long)sms * 8);
-    if (m->project)
-        sg::ev_step_main_kernel<1><<<grid, sg::kMainThreads, 0, st>>>(*m, *s, num_envs, action, flags, discrete_bins, obs,
-                                                                    reward, done, pilots, final_obs, status, stats);
-    else
-        sg::ev_step_main_kernel<0><<<grid, sg::kMainThreads, 0, st>>>(*m, *s, num_envs, action, flags, discrete_bins, obs,
-                                                                    reward, done, pilots, final_obs, status, stats);
+    // one warp per kE-env tile; SG_EV_MINB resident CTAs per SM, larger batches loop (persistent)
+    const long long ntiles = (num_envs + sg::kE - 1) / sg::kE;
+    const unsigned grid = (unsigned)std::min<long long>((ntiles + sg::kMainWarps - 1) / sg::kMainWarps, (long long)sms * SG_EV_MINB);
+    // staging rows in dynamic shared memory: per warp kE observation rows + kE pilot rows
+    const int OBS = 2 * m->n_stations + m->moer_steps + 2;
+    const size_t dyn = (size_t)sg::kMainWarps * (((sg::kE * OBS * 4 + 15) & ~15) + ((sg::kE * m->n_stations + 15) & ~15));
+    if (m->project) {
+        auto kern = sg::ev_step_main_kernel<1>;
+        SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        kern<<<grid, sg::kMainThreads, dyn, st>>>(*m, *s, num_envs, action, flags, discrete_bins, obs, reward, done, pilots,
+                                                  final_obs, status, stats);
+    } else {
+        auto kern = sg::ev_step_main_kernel<0>;
+        SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+        kern<<<grid, sg::kMainThreads, dyn, st>>>(*m, *s, num_envs, action, flags, discrete_bins, obs, reward, done, pilots,
+                                                  final_obs, status, stats);
+    }
     return sg::launch_status("ev_step_main_kernel");
 }
 
@@ -1332,6 +1584,12 @@ int sg_ev_export_state(const sg_ev_model* m, const sg_ev_state* s, int64_t num_e
     return sg::launch_status("ev_export_kernel");
 }
 
+#ifdef SG_EV_TRACE
+int sg_ev_set_trace(unsigned long long* buf) {
+    return cudaMemcpyToSymbol(sg::g_trace, &buf, sizeof(buf)) == cudaSuccess ? 0 : 1;
+}
+#endif
+
 int sg_ev_agent_obs(const float* cur_obs, const float* past_obs, int64_t num_envs, int32_t n_stations,
                     int32_t obs_dim, float* out, void* stream) {
     SG_CHECK_ARG(cur_obs && past_obs && out, "ev_agent_obs: NULL argument");
@@ -1348,6 +1606,7 @@ int sg_ev_project(const sg_ev_model* m, int64_t num_envs, const float* action, c
                   double* x_out, uint8_t* status, int32_t* iters, void* stream) {
     if (int rc = sg::check_model(m)) return rc;
     SG_CHECK_ARG(action && demands && x_out, "ev_project: NULL argument");
+    if (int rc = sg::check_tables(m)) return rc;
     if (num_envs <= 0) return 0;
     const unsigned grid = (unsigned)((num_envs + 3) / 4);
     sg::ev_project_kernel<<<grid, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*m, num_envs, action, demands,

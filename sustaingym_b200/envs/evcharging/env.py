@@ -115,7 +115,12 @@ class BatchedEVChargingEnv:
             int(project_action_in_env), self._c["cls"].data_ptr(), self._c["type"].data_ptr(),
             self._c["re"].data_ptr(), self._c["im"].data_ptr(), self._c["mag"].data_ptr(),
             self._c["sessions"].data_ptr(), self._c["moer"].data_ptr(), self._c["arrivals"].data_ptr(),
-            self._c["arrivals"].shape[1] - 1, 0)
+            self._c["arrivals"].shape[1] - 1, 0, None)
+        self._c["tables"] = torch.zeros(_lib.SG_EV_TABLE_BYTES, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.sg_ev_prepare_tables(C.byref(self._model), self._c["tables"].data_ptr(),
+                                                     torch.cuda.current_stream(dev).cuda_stream), "sg_ev_prepare_tables")
+        self._model.tables = self._c["tables"].data_ptr()
 
         # ---- per-env state and outputs ---------------------------------------------------------------
         B = self.num_envs
