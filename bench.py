@@ -256,7 +256,7 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     value = world * B * args.steps / (ms_total * 1e-3)
-    launches = args.steps
+    launches = 2 * args.steps
 
     # ---- roofline: duration of the step kernel alone (ev_step_main_kernel<1>) ---------------------------
     L = 120
@@ -276,7 +276,7 @@ def main():
     kern_ms = float(np.mean(durs[L // 10: L - L // 10]))     # trimmed mean
     peak, peak_src = peaks()
     achieved = ALGO_BYTES_PER_ENV_STEP * B / (kern_ms * 1e-3) / 1e9
-    launches += L
+    launches += 2 * L
 
     # ---- e2e: public host API, pinned host actions in, obs/reward/done out, every step ---------------
     E = 30
@@ -293,7 +293,7 @@ def main():
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_value = world * B * E / float(dt.item())
-    launches += E + 3
+    launches += 2 * (E + 3)
     h2d = B * N_STATIONS * 4
     d2h = B * OBS_DIM * 4 + B * 8 + B
 
@@ -316,7 +316,7 @@ def main():
                        "parallelism": f"env-sharded x{world}", "trace_pool_days": POOL_DAYS,
                        "mean_sessions_per_day": MEAN_SESSIONS,
                        "l2_policy": f"{N_SETS} env sets stepped round-robin: ~{N_SETS * 85} MB touched between reuses (> 126 MB L2)",
-                       "launch": "one CUDA graph (1 kernel) per step"},
+                       "launch": "one CUDA graph per step: ev_step_main_kernel + ev_step_rare_kernel (work list of envs needing the interior-point solver, normally empty)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "kernel": "ev_step_main_kernel<1>",
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * B,

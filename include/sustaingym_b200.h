@@ -146,17 +146,19 @@ typedef struct sg_ev_model {
                                      once per model by sg_ev_prepare_tables (the kernels stage them in shared memory) */
 } sg_ev_model;
 
-/* Per-env state.  A plugged-in session is one 32-byte record
- *     { f64 requested kWh, f64 delivered kWh, i32 departure, i32 est_departure, i32 arrival, i32 trace slot }
- * stored per (copy, env, station); the step at clock t reads copy (t & 1) and writes the other one, and
- * only the stations whose bit is set in `occ` hold a live record (sg_ev_export_state gives dense views). */
+/* Per-env state.
+ *   slots : a plugged-in session is one 32-byte record
+ *             { f64 requested kWh, f64 delivered kWh, i32 departure, i32 est_departure, i32 arrival, i32 trace slot }
+ *           stored per (env, station) and updated in place; only the stations whose bit is set in the
+ *           env's occupancy mask hold a live record (sg_ev_export_state gives dense views).
+ *   header: one 64-byte record per env
+ *             { i32 t (0..288, env.py:168), i32 day (trace index in [0,D)), i32 moer_day (MOER table index
+ *               in [0,Dm)), i32 arrival cursor (sessions of the day with arrival <= t),
+ *               u64 occupancy mask (bit i: station i has a plugged-in session),
+ *               f64[3] cumulative profit, carbon_cost, excess_charge (env.py:460-462), 16 bytes padding } */
 typedef struct sg_ev_state {
-    void*    slots;       /* [device] [2, B, n] 32-byte session records, 32-byte aligned             */
-    int32_t* clock;       /* [device] [B, 4] {t (0..288, env.py:168), day (trace index in [0,D)),    */
-                          /*   moer_day (MOER table index in [0,Dm)), arrival cursor (sessions of    */
-                          /*   the day with arrival <= t)}                                            */
-    double*  breakdown;   /* [device] [B, 3] cumulative profit, carbon_cost, excess_charge           */
-    uint64_t* occ;        /* [device] [B] bit i set: station i has a plugged-in session now           */
+    void* slots;          /* [device] [B, n] 32-byte session records, 32-byte aligned */
+    void* header;         /* [device] [B] 64-byte env records, 64-byte aligned        */
 } sg_ev_state;
 
 /* status bits written per env by sg_ev_step */
@@ -189,21 +191,23 @@ int sg_ev_reset(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs,
  *   pilots : [B, n] u8 amps actually sent (schedule of env.py:368-378) or NULL
  *   final_obs: with AUTORESET, receives the terminal observation of envs that finished, or NULL
  *   status : [B] u8 or NULL;  stats: [16] f64 accumulators or NULL (see sg_stats_*)
- * One launch per step.  With m->project != 0 the box-clipped action is tested against the network
- * constraints per env; envs that violate them run the exact projection (single-class solve or
- * interior point) inside the same kernel and report SG_EV_STATUS_PROJECTED.
+ *   work   : [B + 2] i32 zero-initialised device scratch (work list of the exact projection); required
+ *            when m->project != 0, may be NULL otherwise.  It is re-armed by every call.
+ * With m->project != 0 the box-clipped action is tested against the network constraints per env (it
+ * is then the exact projection); the few envs that violate them are finished by a second launch of
+ * the same call (exact single-class solve, else interior point) and report SG_EV_STATUS_PROJECTED.
  */
 int sg_ev_step(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs,
                const void* action, int32_t flags, int32_t discrete_bins,
                float* obs, double* reward, uint8_t* done, uint8_t* pilots, float* final_obs,
-               uint8_t* status, double* stats, void* stream);
+               uint8_t* status, double* stats, int32_t* work, void* stream);
 
 /* Host-buffer variant: H2D(action) -> step -> D2H(obs, reward, done) -> sync. */
 int sg_ev_step_host(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs,
                     const void* h_action, int32_t flags, int32_t discrete_bins,
                     float* h_obs, double* h_reward, uint8_t* h_done,
                     void* d_action, float* d_obs, double* d_reward, uint8_t* d_done,
-                    uint8_t* d_status, double* d_stats, void* stream);
+                    uint8_t* d_status, double* d_stats, int32_t* d_work, void* stream);
 
 /* Dense views of the sparse state: delivered [B,n] f64 (kWh delivered to the session plugged in at
  * each station, 0 where empty) and sess_idx [B,n] u8 (its trace slot, 255 where empty); either may be NULL. */

@@ -26,10 +26,11 @@ lib.sg_ev_set_trace(None)
 tr = trace.cpu().numpy().astype(np.float64)
 tr = tr[tr[:, 10] > 0]                       # first tile of each warp only (persistent grids stamp entry once)
 t0 = tr[:, 10].min()
-names = {10: "cta entry", 0: "tables + prologue done", 2: "fill done", 3: "keys done (last chunk)",
+names = {10: "cta entry", 0: "tables + prologue done", 2: "fill done", 11: "scan done", 12: "keys written", 3: "keys synced (last group)",
+         13: "loads issued", 14: "loads arrived",
          4: "items done (last chunk)", 5: "owner done", 6: "checks done", 7: "arrivals done", 8: "epilogue done", 9: "fallback + stats done"}
 print(f"kernel span (first entry -> last exit): {(tr[:, 9].max() - t0) / 1e3:.2f} us; tiles {ntiles}")
-order = [10, 0, 2, 3, 4, 5, 6, 7, 8, 9]
+order = [10, 0, 2, 11, 12, 3, 13, 14, 4, 6, 7, 8, 9]
 for a, b_ in zip(order[:-1], order[1:]):
     d = (tr[:, b_] - tr[:, a]) / 1e3
     print(f"  {names[a]:30s} -> {names[b_]:28s} median {np.median(d):7.2f}  p90 {np.percentile(d, 90):7.2f}  max {d.max():7.2f} us")

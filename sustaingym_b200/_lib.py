@@ -52,7 +52,7 @@ class EVModel(C.Structure):
 
 class EVState(C.Structure):
     _fields_ = [
-        ("slots", _vp), ("clock", _vp), ("breakdown", _vp), ("occ", _vp),
+        ("slots", _vp), ("header", _vp),
     ]
 
 
@@ -89,9 +89,9 @@ SIGNATURES = {
     "sg_ev_prepare_tables": (C.c_int, [C.POINTER(EVModel), _vp, _vp]),
     "sg_ev_reset": (C.c_int, [C.POINTER(EVModel), C.POINTER(EVState), _i64, _vp, _vp, _vp, _vp, _vp]),
     "sg_ev_step": (C.c_int, [C.POINTER(EVModel), C.POINTER(EVState), _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp,
-                             _vp, _vp, _vp, _vp]),
+                             _vp, _vp, _vp, _vp, _vp]),
     "sg_ev_step_host": (C.c_int, [C.POINTER(EVModel), C.POINTER(EVState), _i64, _vp, _i32, _i32, _vp, _vp, _vp,
-                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sg_ev_export_state": (C.c_int, [C.POINTER(EVModel), C.POINTER(EVState), _i64, _vp, _vp, _vp]),
     "sg_ev_agent_obs": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "sg_cogen_plant": (C.c_int, [C.POINTER(CogenModel), _i64, _vp, _vp, _vp, _vp]),

@@ -95,6 +95,8 @@ struct __align__(16) EvTables {
     float re[SG_EV_MAX_CONSTRAINTS * kMC], im[SG_EV_MAX_CONSTRAINTS * kMC];   // f32 copies for the pre-checks
     float r_in[SG_EV_MAX_CONSTRAINTS];               // (limit/32 - margin)^2 in normalised action units
     float lim2_lo[SG_EV_MAX_CONSTRAINTS];            // 0.999 * limit^2 (A^2): below it the rounded schedule has no excess
+    double simple_R[SG_EV_MAX_CONSTRAINTS];          // single-class constraints: limit on the normalised class sum
+    int8_t simple_cls[SG_EV_MAX_CONSTRAINTS];        // class of a constraint with ONE non-zero coefficient (a pod), else -1
     uint8_t cls[SG_EV_MAX_STATIONS];                 // class of each station, 255 = padding
     uint8_t type[SG_EV_MAX_STATIONS];
 };
@@ -112,6 +114,13 @@ __global__ void ev_prepare_kernel(const sg_ev_model m, EvTables* __restrict__ tb
         tb->lim[i] = lim;
         tb->r_in[i] = r > 0.0 ? (float)(r * r * 0.99999) : -1.f;
         tb->lim2_lo[i] = (float)(lim * lim * 0.999);
+        int nz = 0, cstar = -1;
+        for (int c = 0; c < kMC; ++c)
+            if (m.con_re[i * kMC + c] != 0.0 || m.con_im[i * kMC + c] != 0.0) { nz++; cstar = c; }
+        tb->simple_cls[i] = (int8_t)(nz == 1 && i < m.n_constraints ? cstar : -1);
+        double kappa = 1.0;
+        if (nz == 1) kappa = sqrt(m.con_re[i * kMC + cstar] * m.con_re[i * kMC + cstar] + m.con_im[i * kMC + cstar] * m.con_im[i * kMC + cstar]);
+        tb->simple_R[i] = lim * (1.0 / kActionScale) / kappa;
     }
     for (int i = threadIdx.x; i < 40; i += blockDim.x) tb->ppilot[i] = div_c((double)i * kVoltage, 1000.0, kInv1000);
     for (int i = threadIdx.x; i < SG_EV_MAX_STATIONS; i += blockDim.x) {
@@ -580,11 +589,13 @@ __device__ __forceinline__ bool network_feasible_tol(const EvShared& sh, int C, 
 // Per-env state (include/sustaingym_b200.h, sg_ev_state).  A plugged-in session is one 32-byte
 // record = one DRAM/L2 sector, read and written with single 256-bit accesses:
 //     { f64 requested kWh, f64 delivered kWh, i32 departure, i32 est_departure, i32 arrival, i32 slot }
-// kept per (env, station) in two copies: step t reads copy (t & 1) and writes copy (1 - t & 1).
-// Only the occupied stations (bit set in the env's 64-bit occupancy mask) hold live records, so one
-// step touches ~occupancy x 64 B of state instead of a dense [n] row, and because a step never
-// overwrites its own inputs it can be re-executed for an env (the projection fallback below does
-// that) without an undo log.
+// kept per (env, station) and updated IN PLACE: a record is written back right after it was read,
+// while its line is still in L2 (measured on B200: writing the records to a second, not yet cached
+// copy of the state cost 22 us per 65 536-env step, in place it is free).  Only the occupied
+// stations (bit set in the env's 64-bit occupancy mask) hold live records, so one step touches
+// ~occupancy x 32 B of state instead of a dense [n] row.  The records of an env are written only
+// after its clipped action passed the constraint check, so the rare exact-projection path finds
+// the state of the other envs untouched and needs no undo log.
 // =================================================================================================
 struct __align__(32) Slot {
     double energy, delivered;
@@ -621,11 +632,43 @@ __device__ __forceinline__ void st_slot_2x16(Slot* p, const Slot& s) {
     reinterpret_cast<uint4*>(p)[1] = hi;
 }
 
+// Per-env scalars, one 64-byte record (= one DRAM access granule) per env, read at the start of a
+// step and written back in place at its end: clock, occupancy mask, cumulative reward breakdown.
+struct __align__(16) EnvHeader {
+    int t, day, moer_day, nidx;                      // env.py:168 t; trace / MOER table index; arrival cursor
+    unsigned long long occ;                          // bit i: station i has a plugged-in session
+    double bd[3];                                    // cumulative profit, carbon_cost, excess_charge (env.py:460-462)
+    unsigned long long pad[2];
+};
+static_assert(sizeof(EnvHeader) == 64, "EnvHeader must be 64 bytes");
+
+__device__ __forceinline__ EnvHeader ld_header(const EnvHeader* p) {
+    union { EnvHeader h; uint4 v[4]; } u;
+    const uint4* g = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) u.v[i] = g[i];       // (the padding is not read)
+    u.v[3] = make_uint4(0u, 0u, 0u, 0u);
+    return u.h;
+}
+__device__ __forceinline__ void st_header(EnvHeader* p, const EnvHeader& h) {
+    union { EnvHeader h; uint4 v[4]; } u;
+    u.h = h;
+    uint4* g = reinterpret_cast<uint4*>(p);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) g[i] = u.v[i];       // whole record: a full 64-byte granule
+}
+__device__ __forceinline__ EnvHeader empty_header() {
+    EnvHeader h;
+    h.t = kEpisode; h.day = 0; h.moer_day = 0; h.nidx = 0; h.occ = 0ull;
+    h.bd[0] = h.bd[1] = h.bd[2] = 0.0; h.pad[0] = h.pad[1] = 0ull;
+    return h;
+}
+
 #ifndef SG_EV_KE
 #define SG_EV_KE 16
 #endif
 #ifndef SG_EV_MINB
-#define SG_EV_MINB 4
+#define SG_EV_MINB 3     // resident CTAs per SM the kernel is compiled for (3 x 128 threads -> <= 168 registers, no spills)
 #endif
 #ifndef SG_EV_KV
 #define SG_EV_KV 3
@@ -650,7 +693,8 @@ struct WarpShared {
     int S[kMC][kE];                                  // per-env class sums of the clipped action, 2^-20 fixed point
     int P[kMC][kE];                                  // per-env class sums of the integer pilots
     unsigned occ_clr[kE][2];                         // occupancy bits cleared by Unplug events
-    int todo[32];                                    // envs (index within the batch) left to the rare path
+    float xa[kItemCap];                              // rare path: action of item j (its upper bound goes to rate[j])
+    double Sx[kMC], nu[kMC];                         // rare path: exact class sums / class multipliers of one env
     double stat[12];                                 // this warp's reward statistics (SG_STATS layout)
 };
 
@@ -663,9 +707,7 @@ struct EvCtx {
     const unsigned* arrivals;
     const void* action;
     Slot* slots;
-    int32_t* clock;
-    double* breakdown;
-    unsigned long long* occ;
+    EnvHeader* header;
     float* obs;
     float* final_obs;
     double* reward;
@@ -732,16 +774,15 @@ __device__ __noinline__ bool fallback_env(const EvTables& sh, const EvCtx cx, co
                                            double* wstat) {
     const int n = cx.n, kf = cx.kf, OBS = 2 * n + kf + 2, C = cx.C, J = cx.J;
     const bool i64 = (cx.flags & 1) == SG_EV_ACTION_I64;
-    const int4 clk = *reinterpret_cast<const int4*>(cx.clock + b * 4);
-    const unsigned long long occ = cx.occ[b];
-    const int t = clk.x, tn = t + 1, md = clk.z;
-    int day = clk.y, nidx = clk.w;
-    const int par = t & 1;
+    const EnvHeader hd = cx.header[b];
+    const unsigned long long occ = hd.occ;
+    const int t = hd.t, tn = t + 1, md = hd.moer_day;
+    int day = hd.day, nidx = hd.nidx;
     const bool dn = tn >= kEpisode;
     const bool autoreset = dn && (cx.flags & SG_EV_FLAG_AUTORESET);
     const int md_out = autoreset ? (md + 1) % cx.n_moer_days : md;
-    const Slot* cur = cx.slots + ((long long)par * cx.B + b) * n;
-    Slot* nxt = cx.slots + ((long long)(par ^ 1) * cx.B + b) * n;
+    Slot* cur = cx.slots + b * n;
+    Slot* nxt = cur;                                   // records are updated in place
     const int i0 = 2 * lane;
     const bool valid[2] = {i0 < n, i0 + 1 < n};
     double a[2], u[2], x[2];
@@ -865,14 +906,14 @@ __device__ __noinline__ bool fallback_env(const EvTables& sh, const EvCtx cx, co
         const double excess_charge = excess * kViolationFactor;
         const double carbon = kCarbonFactor * total_rate * moer0;
         const double rew = profit - carbon - excess_charge;
-        double* bd = cx.breakdown + b * 3;
-        if (t == 0) { bd[0] = profit; bd[1] = carbon; bd[2] = excess_charge; }
-        else { bd[0] += profit; bd[1] += carbon; bd[2] += excess_charge; }
-        int t_out = tn;
-        unsigned long long occ_new = ((unsigned long long)occ_hi << 32) | occ_lo;
-        if (autoreset) { day = (day + 1) % cx.n_days; t_out = 0; nidx = 0; occ_new = 0ull; }
-        cx.occ[b] = occ_new;
-        *reinterpret_cast<int4*>(cx.clock + b * 4) = make_int4(t_out, day, md_out, nidx);
+        EnvHeader ho;
+        ho.bd[0] = (t == 0 ? 0.0 : hd.bd[0]) + profit;
+        ho.bd[1] = (t == 0 ? 0.0 : hd.bd[1]) + carbon;
+        ho.bd[2] = (t == 0 ? 0.0 : hd.bd[2]) + excess_charge;
+        ho.t = tn; ho.occ = ((unsigned long long)occ_hi << 32) | occ_lo;
+        if (autoreset) { day = (day + 1) % cx.n_days; ho.t = 0; nidx = 0; ho.occ = 0ull; }
+        ho.day = day; ho.moer_day = md_out; ho.nidx = nidx; ho.pad[0] = ho.pad[1] = 0ull;
+        cx.header[b] = ho;
         cx.reward[b] = rew;
         cx.done[b] = dn ? 1 : 0;
         if (cx.status != nullptr) cx.status[b] = (uint8_t)st;
@@ -887,6 +928,75 @@ __device__ __noinline__ bool fallback_env(const EvTables& sh, const EvCtx cx, co
     }
     __syncwarp();
     return true;
+}
+
+// Thread-serial exact projection of ONE env when only single-class constraints (the pods) are
+// violated — the same algorithm as simple_project above, run by the owner lane on the env's items
+// j in [lo, hi) of the warp's work list: action ws.xa[j], upper bound ws.rate[j], class from the
+// station in ws.key[j].  Returns 0: the clipped action is feasible (exact test), nothing to do;
+// 1: projected, x_i = clip(a_i - ws.nu[class_i], 0, u_i); 2: a coupled constraint is (or became)
+// violated -> interior point (rare kernel).
+__device__ __forceinline__ int pod_solve(const EvTables& sh, WarpShared& ws, const int lo, const int hi, const int J) {
+#pragma unroll
+    for (int c = 0; c < kMC; ++c) { ws.Sx[c] = 0.0; ws.nu[c] = 0.0; }
+    for (int j = lo; j < hi; ++j) {
+        const int c = sh.cls[ws.key[j] & 0xff];
+        ws.Sx[c] += fmin(fmax((double)ws.xa[j], 0.0), ws.rate[j]);
+    }
+    bool any = false;
+    for (int jc = 0; jc < J; ++jc) {
+        double wr = 0, wi = 0;
+#pragma unroll
+        for (int c = 0; c < kMC; ++c) { wr = fma(sh.con_re[jc * kMC + c], ws.Sx[c], wr); wi = fma(sh.con_im[jc * kMC + c], ws.Sx[c], wi); }
+        const double r = sh.lim[jc] * (1.0 / kActionScale);
+        if (!(sqrt(wr * wr + wi * wi) > r)) continue;        // satisfied
+        const int cs = sh.simple_cls[jc];
+        if (cs < 0) return 2;                                // a coupled constraint is violated
+        const double R = sh.simple_R[jc];
+        double amax = 0.0;
+        for (int j = lo; j < hi; ++j)
+            if (sh.cls[ws.key[j] & 0xff] == cs && ws.rate[j] > 0.0) amax = fmax(amax, (double)ws.xa[j]);
+        double lo_n = 0.0, hi_n = amax, nu = 0.0;
+        unsigned sig_prev = 0xffffffffu;
+        for (int it = 0; it < 100; ++it) {
+            double s_mid = 0.0, s_up = 0.0;
+            int n_mid = 0;
+            unsigned sig = 0u;
+            for (int j = lo; j < hi; ++j) {
+                if (sh.cls[ws.key[j] & 0xff] != cs) continue;
+                const double a = (double)ws.xa[j], ub = ws.rate[j];
+                if (!(ub > 0.0)) continue;
+                const double v = a - nu;
+                unsigned code = 0u;
+                if (v >= ub) { s_up += ub; code = 2u; }
+                else if (v > 0.0) { s_mid += a; ++n_mid; code = 1u; }
+                sig = sig * 3u + code + 1u;
+            }
+            const double phi = s_mid - n_mid * nu + s_up;
+            if (sig == sig_prev && n_mid > 0) break;          // same linear piece twice: nu is its exact root
+            sig_prev = sig;
+            if (phi > R) lo_n = nu; else hi_n = nu;
+            double nn = n_mid > 0 ? (s_mid + s_up - R) / n_mid : 0.5 * (lo_n + hi_n);
+            if (!(nn > lo_n && nn < hi_n)) { nn = 0.5 * (lo_n + hi_n); sig_prev = 0xffffffffu; }
+            if (nn == nu) break;
+            nu = nn;
+        }
+        ws.nu[cs] = nu;
+        double sc = 0.0;
+        for (int j = lo; j < hi; ++j)
+            if (sh.cls[ws.key[j] & 0xff] == cs) sc += fmin(fmax((double)ws.xa[j] - nu, 0.0), ws.rate[j]);
+        ws.Sx[cs] = sc;
+        any = true;
+    }
+    if (!any) return 0;
+    for (int jc = 0; jc < J; ++jc) {                          // all constraints again, with a relative slack
+        double wr = 0, wi = 0;
+#pragma unroll
+        for (int c = 0; c < kMC; ++c) { wr = fma(sh.con_re[jc * kMC + c], ws.Sx[c], wr); wi = fma(sh.con_im[jc * kMC + c], ws.Sx[c], wi); }
+        const double r = sh.lim[jc] * (1.0 / kActionScale);
+        if (sqrt(wr * wr + wi * wi) > r * (1.0 + 1e-12)) return 2;
+    }
+    return 1;
 }
 
 // =================================================================================================
@@ -914,8 +1024,9 @@ __device__ __noinline__ bool fallback_env(const EvTables& sh, const EvCtx cx, co
 //            rounded schedule); an env that is not certainly feasible is left to fallback_env;
 //   arrivals Plugin events with timestamp <= t+1 from the day's arrival-sorted list;
 //   epilogue reward, cumulative breakdown, clock, mask, statistics.
-// The kernel contains no function call on its main path (the rare path is entered at the very end
-// of a tile, when nothing but the tile index is live).
+// The kernel contains no function call: envs that need the exact projection are appended to a work
+// list and finished by ev_step_rare_kernel (second launch of the step), so the rare path's register
+// and stack needs (interior-point solver) do not burden this kernel.
 // =================================================================================================
 #ifdef SG_EV_TRACE
 __device__ unsigned long long* g_trace = nullptr;     // [ntiles][16] phase timestamps (diagnostic builds only)
@@ -936,7 +1047,7 @@ __global__ void __launch_bounds__(kMainThreads, SG_EV_MINB)
 ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B, const void* __restrict__ action,
                     const int flags, const int bins, float* __restrict__ obs, double* __restrict__ reward,
                     uint8_t* __restrict__ done, uint8_t* __restrict__ pilots, float* __restrict__ final_obs,
-                    uint8_t* __restrict__ status, double* __restrict__ stats) {
+                    uint8_t* __restrict__ status, double* __restrict__ stats, int32_t* __restrict__ work) {
     __shared__ EvTables sh;
     __shared__ WarpShared wsm[kMainWarps];
     extern __shared__ __align__(128) unsigned char stage_raw[];       // per warp: kE observation rows | kE pilot rows
@@ -945,13 +1056,11 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
     const long long wstride = (long long)gridDim.x * kMainWarps;
     long long tile = (long long)blockIdx.x * kMainWarps + warp;
     EV_TRACE(10);
-    // the first tile's clock / occupancy rows are requested before the table copy
-    int4 clk_next = make_int4(kEpisode, 0, 0, 0);
-    unsigned long long occ_next = 0ull;
-    if (tile < ntiles && tile * kE + lane < B && lane < kE) {
-        clk_next = *reinterpret_cast<const int4*>(s.clock + (tile * kE + lane) * 4);
-        occ_next = s.occ[tile * kE + lane];
-    }
+    // the first tile's env headers are requested before the table copy
+    EnvHeader* __restrict__ headers = reinterpret_cast<EnvHeader*>(s.header);
+    EnvHeader hd = empty_header();
+    if (tile < ntiles && tile * kE + lane < B && lane < kE) hd = ld_header(headers + tile * kE + lane);
+    bool first_tile = true;
     load_tables(m.tables, sh);
     WarpShared& ws = wsm[warp];
     if (lane < 12) ws.stat[lane] = lane == 3 ? 1e300 : (lane == 4 ? -1e300 : 0.0);
@@ -972,28 +1081,21 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
     const bool bulk_rows = ((kE * OBS) & 3) == 0 && (reinterpret_cast<uintptr_t>(obs) & 15u) == 0;
     const bool bulk_pil = pilots != nullptr && ((kE * n) & 15) == 0 && (reinterpret_cast<uintptr_t>(pilots) & 15u) == 0;
 
-  while (tile < ntiles) {
-    int n_todo = 0;                                   // rare-path queue of this warp (ws.todo)
-    for (; tile < ntiles && n_todo <= 32 - kE; tile += wstride) {
+    for (; tile < ntiles; tile += wstride) {
         const long long b0 = tile * kE;
         const int nv = (int)min((long long)kE, B - b0);
         const long long b = b0 + lane;
         const bool env = lane < nv;                    // owner lanes
-        const int4 clk = clk_next;
-        const unsigned long long occ_ld = occ_next;
-        {   // next tile's rows (persistent grids only)
-            const long long tb = (tile + wstride) * kE + lane;
-            clk_next = make_int4(kEpisode, 0, 0, 0); occ_next = 0ull;
-            if (tile + wstride < ntiles && tb < B && lane < kE) {
-                clk_next = *reinterpret_cast<const int4*>(s.clock + tb * 4);
-                occ_next = s.occ[tb];
-            }
+        if (!first_tile) {
+            hd = empty_header();
+            if (env) hd = ld_header(headers + b);
         }
-        const int t = clk.x, tn = t + 1;
-        int day = clk.y, nidx = clk.w;
-        const int md = clk.z;
+        first_tile = false;
+        const int t = hd.t, tn = t + 1;
+        int day = hd.day, nidx = hd.nidx;
+        const int md = hd.moer_day;
         const bool live = env && t < kEpisode;
-        const unsigned long long occ = live ? occ_ld : 0ull;
+        const unsigned long long occ = live ? hd.occ : 0ull;
         const bool dn = tn >= kEpisode;
         const bool autoreset = live && dn && (flags & SG_EV_FLAG_AUTORESET);
         const int md_out = autoreset ? (md + 1) % m.n_moer_days : md;
@@ -1010,35 +1112,15 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
             ent = __ldg(arow + nidx);
             if (nidx < m.max_day_sessions) ent2 = __ldg(arow + nidx + 1);
         }
-        const int par = t & 1;
-        const int info = tn | (par << 16);
         EV_TRACE(0);
 
         // ---------------- stage: zeroed rows, MOER + timestep tails, dense pilots (projection off) -------
         {
-            // tails first (their loads are the only dependency of this phase): kQ lanes per env
-            const float* p = moer + __shfl_sync(kFull, moff, eq);
-            const float ts_e = __shfl_sync(kFull, tsf, eq);
-            float tv[2 * kTailPerLane];
-#pragma unroll
-            for (int k = 0; k < kTailPerLane; ++k) {
-                const int q0 = 2 * (sub + k * kQ);
-                tv[2 * k] = q0 < kf + 2 ? moer_tail(p, q0, kf, ts_e) : 0.f;
-                tv[2 * k + 1] = q0 + 1 < kf + 2 ? moer_tail(p, q0 + 1, kf, ts_e) : 0.f;
-            }
             for (int i = lane; i < kMC * kE; i += 32) { (&ws.S[0][0])[i] = 0; (&ws.P[0][0])[i] = 0; }
             if (lane < kE) { ws.occ_clr[lane][0] = 0u; ws.occ_clr[lane][1] = 0u; }
             uint4* z = reinterpret_cast<uint4*>(srows);
-            if (!(SG_EV_ABL & 8))
             for (int i = lane; i < (row_bytes + pil_bytes) >> 4; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
             __syncwarp();
-            float* dst = srows + eq * OBS + 2 * n;
-#pragma unroll
-            for (int k = 0; k < kTailPerLane; ++k) {
-                const int q0 = 2 * (sub + k * kQ);
-                if (q0 < kf + 2) dst[q0] = tv[2 * k];
-                if (q0 + 1 < kf + 2) dst[q0 + 1] = tv[2 * k + 1];
-            }
             (void)tp;
         }
         if constexpr (MODE == 0) {
@@ -1070,6 +1152,10 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
         EV_TRACE(2);
 
         // ---------------- items: one (env, occupied station) per lane ------------------------------------
+        // The tile's envs are processed in groups of consecutive envs holding at most kItemCap items
+        // (usually one group): load + arithmetic for the whole group, then the constraint checks, then
+        // the session records go back IN PLACE (their lines are in L2: no write-allocate traffic) — only
+        // for envs that passed the check, so the rare path finds the state of the others untouched.
         const int cnt = __popcll(occ);
         int off = cnt;                                                 // inclusive scan over the owner lanes
 #pragma unroll
@@ -1077,29 +1163,37 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
             const int v = __shfl_up_sync(kFull, off, d);
             if (lane >= d) off += v;
         }
-        const int total = (SG_EV_ABL & 4) ? 0 : __shfl_sync(kFull, off, kE - 1);
         off -= cnt;
         double rate_sum = 0.0;
+        unsigned bad = 0u, near = 0u;
         // this lane's segment of env eq's occupancy bits, and the list position of its first item
         const unsigned long long occ_e = __shfl_sync(kFull, occ, eq);
         const unsigned long long seg = kQ == 1 ? occ_e : (occ_e >> (sub * kSegBits)) & ((1ull << (kSegBits & 63)) - 1ull);
         const int j0 = __shfl_sync(kFull, off, eq) +
                        (kQ == 1 ? 0 : __popcll(occ_e & ((1ull << ((sub * kSegBits) & 63)) - 1ull)));
-        for (int c0 = 0; c0 < total; c0 += kItemCap) {
-            const int nitems = min(kItemCap, total - c0);
-            {   // keys of this chunk
-                int j = j0 - c0;
+        EV_TRACE(11);
+        unsigned redo_all = 0u;                                       // envs whose action was projected here (status)
+        for (int g0 = 0; g0 < kE;) {
+            const int base = __shfl_sync(kFull, off, g0);
+            const unsigned fit = __ballot_sync(kFull, lane >= g0 && lane < kE && off + cnt - base <= kItemCap);
+            int g1 = g0 + __ffs((int)~(fit >> g0)) - 1;                // first env that does not fit any more
+            g1 = min(max(g1, g0 + 1), kE);
+            const int nitems = (SG_EV_ABL & 4) ? 0 : __shfl_sync(kFull, off + cnt, g1 - 1) - base;
+            const unsigned gmask = ((g1 >= 32 ? 0u : (1u << g1)) - 1u) & ~((1u << g0) - 1u);
+            if (nitems > 0 && eq >= g0 && eq < g1) {                   // keys of this group
+                int j = j0 - base;
                 if (kSegBits <= 32) {
                     for (unsigned m2 = (unsigned)seg; m2; m2 &= m2 - 1, ++j)
-                        if (j >= 0 && j < kItemCap) ws.key[j] = (unsigned short)((eq << 8) | (sub * kSegBits + __ffs((int)m2) - 1));
+                        ws.key[j] = (unsigned short)((eq << 8) | (sub * kSegBits + __ffs((int)m2) - 1));
                 } else {
                     for (unsigned long long m2 = seg; m2; m2 &= m2 - 1, ++j)
-                        if (j >= 0 && j < kItemCap) ws.key[j] = (unsigned short)((eq << 8) | (__ffsll((long long)m2) - 1));
+                        ws.key[j] = (unsigned short)((eq << 8) | (__ffsll((long long)m2) - 1));
                 }
             }
+            EV_TRACE(12);
             __syncwarp();
             EV_TRACE(3);
-            int e[kV], si[kV], inf[kV];
+            int e[kV], si[kV], tne[kV];
             Slot q[kV];
             float af[kV];
             bool on[kV];
@@ -1109,7 +1203,7 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
                 on[u] = j < nitems;
                 const unsigned key = on[u] ? ws.key[j] : 0u;
                 e[u] = (int)(key >> 8); si[u] = (int)(key & 0xffu);
-                inf[u] = __shfl_sync(kFull, info, e[u]);
+                tne[u] = __shfl_sync(kFull, tn, e[u]);
             }
 #pragma unroll
             for (int u = 0; u < kV; ++u) {
@@ -1117,15 +1211,42 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
                 q[u].energy = 0.0; q[u].delivered = 0.0; q[u].dep = q[u].est = q[u].arr = q[u].k = 0;
                 if (on[u]) {
                     const long long be = b0 + e[u];
-                    q[u] = ld_slot(slots + ((long long)((inf[u] >> 16) & 1) * B + be) * n + si[u]);
+                    q[u] = ld_slot(slots + be * n + si[u]);
                     af[u] = act_value(action, i64, bins, be * n + si[u]);
                 }
             }
+            if (g0 == 0) {
+                // MOER + timestep tails of the staged rows, kQ lanes per env: placed here so that their loads
+                // (L2, sometimes DRAM) are in flight together with the session-record loads above
+                const float* p = moer + __shfl_sync(kFull, moff, eq);
+                const float ts_e = __shfl_sync(kFull, tsf, eq);
+                float tv[2 * kTailPerLane];
+#pragma unroll
+                for (int k = 0; k < kTailPerLane; ++k) {
+                    const int q0 = 2 * (sub + k * kQ);
+                    tv[2 * k] = q0 < kf + 2 ? moer_tail(p, q0, kf, ts_e) : 0.f;
+                    tv[2 * k + 1] = q0 + 1 < kf + 2 ? moer_tail(p, q0 + 1, kf, ts_e) : 0.f;
+                }
+                float* dst = srows + eq * OBS + 2 * n;
+#pragma unroll
+                for (int k = 0; k < kTailPerLane; ++k) {
+                    const int q0 = 2 * (sub + k * kQ);
+                    if (q0 < kf + 2) dst[q0] = tv[2 * k];
+                    if (q0 + 1 < kf + 2) dst[q0 + 1] = tv[2 * k + 1];
+                }
+            }
+#ifdef SG_EV_TRACE
+            EV_TRACE(13);
+            if (q[0].dep + q[kV - 1].dep + (int)af[0] == -123456) return;   // wait for the loads here
+            EV_TRACE(14);
+#endif
+            bool keep[kV];
+            double del0[kV], rt[kV];                                   // delivered before / rate after the first pass
 #pragma unroll
             for (int u = 0; u < kV; ++u) {
+                keep[u] = false; del0[u] = q[u].delivered; rt[u] = 0.0;
                 if (!on[u]) continue;
-                const int i = si[u], tn_e = inf[u] & 0xffff, par_e = (inf[u] >> 16) & 1;
-                const long long be = b0 + e[u];
+                const int i = si[u];
                 const int type = sh.type[i], cls = sh.cls[i];
                 int pi;
                 if (MODE == 0) {
@@ -1139,55 +1260,125 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
                     atomicAdd(&ws.P[cls][e[u]], pi);
                     spil[e[u] * n + i] = (uint8_t)pi;
                 }
-                ws.rate[u * 32 + lane] = charge_period(q[u].energy, q[u].delivered, sh.ppilot[pi]);
-                if (q[u].dep <= tn_e) {                                                   // Unplug event (timestamp = departure)
+                rt[u] = charge_period(q[u].energy, q[u].delivered, sh.ppilot[pi]);
+                ws.rate[u * 32 + lane] = rt[u];
+                if (q[u].dep <= tne[u]) {                                                 // Unplug event (timestamp = departure)
                     atomicOr(&ws.occ_clr[e[u]][i >> 5], 1u << (i & 31));
                 } else {
-                    if (!(SG_EV_ABL & 2)) st_slot(slots + ((long long)(par_e ^ 1) * B + be) * n + i, q[u]);
+                    keep[u] = true;
                     const double rem = q[u].energy - q[u].delivered;
                     if (rem > kFullEps) {                                                 // Interface.active_sessions()
                         srows[e[u] * OBS + i] = (float)rem;
-                        srows[e[u] * OBS + n + i] = (float)(q[u].est - tn_e);
+                        srows[e[u] * OBS + n + i] = (float)(q[u].est - tne[u]);
                     }
                 }
             }
             __syncwarp();
             EV_TRACE(4);
+            // network constraints: one (env, constraint) pair per lane and iteration.  bad: the clipped action
+            // is not certainly feasible (projection needed); near: the rounded schedule is close to or over
+            // a limit (exact excess current needed)
+            unsigned gbad = 0u, gnear = 0u;
+            auto pair_checks = [&]() {
+                bool mybad = false, mynear = false;
+                for (int idx = lane; idx < ((SG_EV_ABL & 16) ? 0 : kE * J); idx += 32) {   // pair (env idx % kE, constraint idx / kE)
+                    const int j = idx / kE, e2 = idx & (kE - 1);
+                    float wr = 0.f, wi = 0.f, vr = 0.f, vi = 0.f;
+#pragma unroll
+                    for (int c = 0; c < kMC; ++c) {
+                        const float cre = sh.re[j * kMC + c], cim = sh.im[j * kMC + c];
+                        const float pv = (float)ws.P[c][e2];
+                        vr = fmaf(cre, pv, vr); vi = fmaf(cim, pv, vi);
+                        if (MODE != 0) { const float sv = (float)ws.S[c][e2] * (1.f / 1048576.f); wr = fmaf(cre, sv, wr); wi = fmaf(cim, sv, wi); }
+                    }
+                    if (MODE != 0) mybad = mybad || !(fmaf(wr, wr, wi * wi) <= sh.r_in[j]);
+                    mynear = mynear || (fmaf(vr, vr, vi * vi) > sh.lim2_lo[j]);
+                }
+                gbad = __ballot_sync(kFull, mybad);
+                gnear = __ballot_sync(kFull, mynear);
+#pragma unroll
+                for (int shf = kE; shf < 32; shf <<= 1) { gbad |= gbad >> shf; gnear |= gnear >> shf; }
+                gbad &= gmask & live_mask;
+                gnear &= gmask;
+            };
+            pair_checks();
+            // ---- envs whose clipped action is not certainly feasible (rare): the exact test and the exact
+            // single-class (pod) projection run here, thread-serial on the owner lane; envs that need the
+            // interior-point solver go to the work list of ev_step_rare_kernel (gfail)
+            unsigned gfail = 0u;
+            if (MODE != 0 && gbad) {
+                unsigned gredo = 0u;
+                for (unsigned todo = gbad; todo; todo &= todo - 1) {
+                    const int r = __ffs((int)todo) - 1;
+#pragma unroll
+                    for (int u = 0; u < kV; ++u)
+                        if (on[u] && e[u] == r) {                        // publish (action, upper bound) of env r's items
+                            const double rem = q[u].energy - del0[u];
+                            ws.rate[u * 32 + lane] = upper_bound(rem > kFullEps ? (float)rem : 0.f);
+                            ws.xa[u * 32 + lane] = af[u];
+                        }
+                    __syncwarp();
+                    int res = 0;
+                    if (lane == r) {
+                        res = pod_solve(sh, ws, off - base, off - base + cnt, J);
+                        if (res == 1) {
+#pragma unroll
+                            for (int c = 0; c < kMC; ++c) ws.P[c][r] = 0;
+                        }
+                    }
+                    res = __shfl_sync(kFull, res, r);
+                    __syncwarp();
+                    if (res == 2) gfail |= 1u << r;
+                    if (res == 1) gredo |= 1u << r;
+#pragma unroll
+                    for (int u = 0; u < kV; ++u) {
+                        if (!(on[u] && e[u] == r)) continue;
+                        if (res != 1) { ws.rate[u * 32 + lane] = rt[u]; continue; }   // first-pass results stand
+                        // re-do the item with x = clip(a - nu_class, 0, u)  (KKT point of the projection)
+                        const int i = si[u];
+                        const int type = sh.type[i], cls = sh.cls[i];
+                        const double rem0 = q[u].energy - del0[u];
+                        const double ub = upper_bound(rem0 > kFullEps ? (float)rem0 : 0.f);
+                        const double x = fmin(fmax((double)af[u] - ws.nu[cls], 0.0), ub);
+                        const int pi = min(max(__double2int_rn(to_pilot(x, type)), 0), 32);
+                        atomicAdd(&ws.P[cls][r], pi);
+                        spil[r * n + i] = (uint8_t)pi;
+                        q[u].delivered = del0[u];
+                        ws.rate[u * 32 + lane] = charge_period(q[u].energy, q[u].delivered, sh.ppilot[pi]);
+                        if (keep[u]) {
+                            const double rem = q[u].energy - q[u].delivered;
+                            const bool active = rem > kFullEps;
+                            srows[r * OBS + i] = active ? (float)rem : 0.f;
+                            srows[r * OBS + n + i] = active ? (float)(q[u].est - tne[u]) : 0.f;
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (gredo) {                                            // pilots changed: excess-current pre-check again
+                    const unsigned keep_bad = gbad;
+                    pair_checks();
+                    gbad = keep_bad;
+                    redo_all |= gredo;
+                }
+            }
+            bad |= gfail;
+            near |= gnear;
             // owner: lane e sums the rates of env e in station order
-            {
-                const int lo = max(off - c0, 0), hi = min(off + cnt - c0, nitems);
+            if (nitems > 0) {
+                const bool mine = lane >= g0 && lane < g1;
+                const int lo = off - base, hi = mine ? lo + cnt : lo;
                 for (int j = lo; __any_sync(kFull, j < hi); ++j)
                     if (j < hi) rate_sum += ws.rate[j];
             }
+            // session records back in place, for the envs of the group that are finished here
+#pragma unroll
+            for (int u = 0; u < kV; ++u)
+                if (keep[u] && !((gfail >> e[u]) & 1u) && !(SG_EV_ABL & 2)) st_slot(slots + (b0 + e[u]) * n + si[u], q[u]);
             __syncwarp();
+            g0 = g1;
         }
-        EV_TRACE(5);
+        EV_TRACE(6);
 
-        // ---------------- network constraints: one (env, constraint) pair per lane and iteration ---------
-        // bad: the clipped action is not certainly feasible (projection needed); near: the rounded
-        // schedule is close to or over a limit (exact excess current needed)
-        unsigned bad = 0u, near = 0u;
-        {
-            bool mybad = false, mynear = false;
-            for (int idx = lane; idx < ((SG_EV_ABL & 16) ? 0 : kE * J); idx += 32) {   // pair (env idx % kE, constraint idx / kE)
-                const int j = idx / kE, e = idx & (kE - 1);
-                float wr = 0.f, wi = 0.f, vr = 0.f, vi = 0.f;
-#pragma unroll
-                for (int c = 0; c < kMC; ++c) {
-                    const float cre = sh.re[j * kMC + c], cim = sh.im[j * kMC + c];
-                    const float pv = (float)ws.P[c][e];
-                    vr = fmaf(cre, pv, vr); vi = fmaf(cim, pv, vi);
-                    if (MODE != 0) { const float sv = (float)ws.S[c][e] * (1.f / 1048576.f); wr = fmaf(cre, sv, wr); wi = fmaf(cim, sv, wi); }
-                }
-                if (MODE != 0) mybad = mybad || !(fmaf(wr, wr, wi * wi) <= sh.r_in[j]);
-                mynear = mynear || (fmaf(vr, vr, vi * vi) > sh.lim2_lo[j]);
-            }
-            bad = __ballot_sync(kFull, mybad);
-            near = __ballot_sync(kFull, mynear);
-#pragma unroll
-            for (int shf = kE; shf < 32; shf <<= 1) { bad |= bad >> shf; near |= near >> shf; }
-            bad &= live_mask & kOwnerMask;
-        }
         const bool mine_ok = live && !((bad >> lane) & 1u);              // this owner lane finishes its env here
         EV_TRACE(6);
 
@@ -1196,7 +1387,7 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
                                              ws.occ_clr[lane & (kE - 1)][0]);
         if (mine_ok && (int)(ent & 0x7fffu) <= tn) {
             float* row = srows + lane * OBS;
-            Slot* nxt = slots + ((long long)(par ^ 1) * B + b) * n;
+            Slot* nxt = slots + b * n;
             do {
                 const int i = (ent >> 16) & 0xff, k = ent >> 24;
                 const uint4 rr = __ldg(recs + ((long long)day * m.max_sessions + k) * n + i);
@@ -1241,19 +1432,20 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
             rew = profit - carbon - excess_charge;
             // cumulative reward breakdown (env.py:460-462); restarted on the first step of an episode so that
             // after an auto-reset the finished episode's totals stay readable until the next step
-            double* bd = s.breakdown + b * 3;
-            if (t == 0) { bd[0] = profit; bd[1] = carbon; bd[2] = excess_charge; }
-            else { bd[0] += profit; bd[1] += carbon; bd[2] += excess_charge; }
-            int t_out = tn;
+            EnvHeader ho;
+            ho.bd[0] = (t == 0 ? 0.0 : hd.bd[0]) + profit;
+            ho.bd[1] = (t == 0 ? 0.0 : hd.bd[1]) + carbon;
+            ho.bd[2] = (t == 0 ? 0.0 : hd.bd[2]) + excess_charge;
+            ho.t = tn;
             if (autoreset) {
                 day = (day + 1) % m.n_days;                               // sequential days, event_generation.py:284-291
-                t_out = 0; nidx = 0; occ_new = 0ull;
+                ho.t = 0; nidx = 0; occ_new = 0ull;
             }
-            s.occ[b] = occ_new;
-            *reinterpret_cast<int4*>(s.clock + b * 4) = make_int4(t_out, day, md_out, nidx);
+            ho.day = day; ho.moer_day = md_out; ho.nidx = nidx; ho.occ = occ_new; ho.pad[0] = ho.pad[1] = 0ull;
+            if (!(SG_EV_ABL & 128)) st_header(headers + b, ho);           // in place: the line is in L2
             reward[b] = rew;
             done[b] = dn ? 1 : 0;
-            if (status != nullptr) status[b] = 0;
+            if (status != nullptr) status[b] = (uint8_t)(((redo_all >> lane) & 1u) ? SG_EV_STATUS_PROJECTED : 0);
         } else if (env && !live) {                                        // finished episode, not reset: stays terminal
             reward[b] = 0.0; done[b] = 1;
             if (status != nullptr) status[b] = 0;
@@ -1271,6 +1463,7 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
                     ws.stat[0] += (double)__popc(okm); ws.stat[1] += r5[0]; ws.stat[2] += r5[1];
                     ws.stat[3] = fmin(ws.stat[3], mn); ws.stat[4] = fmax(ws.stat[4], mx);
                     ws.stat[5] += (double)__popc(dnm);
+                    ws.stat[6] += (double)__popc(redo_all & okm);
                     ws.stat[8] += r5[2]; ws.stat[9] += r5[3]; ws.stat[10] += r5[4];
                 }
             }
@@ -1278,21 +1471,18 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
         __syncwarp();
         EV_TRACE(8);
 
-        // ---------------- rare path: envs that need the exact projection are queued (drained outside this loop)
-        if (bad) {
-            if (lane == 0) {
-                unsigned todo = bad;
-                while (todo) { ws.todo[n_todo++] = (int)(b0 + __ffs((int)todo) - 1); todo &= todo - 1; }
-            }
-            n_todo = __shfl_sync(kFull, n_todo, 0);
+        // ---------------- rare path: envs that need the exact projection go to the work list of ev_step_rare_kernel
+        if (bad && lane == 0) {
+            const int first = atomicAdd(work, __popc(bad));
+            int k = 0;
+            for (unsigned todo = bad; todo; todo &= todo - 1, ++k) work[2 + first + k] = (int)(b0 + __ffs((int)todo) - 1);
         }
 
         // ---------------- write-out of the staged rows --------------------------------------------------------
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // staged rows -> visible to the bulk-copy engine
         __syncwarp();
         const bool whole = nv == kE && live_mask == kOwnerMask && ar_mask == 0u;
-        if (SG_EV_ABL & 1) {
-        } else if (whole && bulk_rows) {
+        if (whole && bulk_rows) {
             if (lane == 0)
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(obs + b0 * OBS),
                              "r"((unsigned)__cvta_generic_to_shared(srows)), "r"(kE * OBS * 4) : "memory");
@@ -1311,7 +1501,7 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
                 }
             }
         }
-        if (pilots != nullptr && !(SG_EV_ABL & 1)) {
+        if (pilots != nullptr) {
             if (whole && bulk_pil) {
                 if (lane == 0)
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(pilots + b0 * n),
@@ -1324,29 +1514,10 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
         }
         if (lane == 0) {
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            // the staging rows are reused by the next tile; queued envs rewrite their rows in global
-            // memory afterwards, so for them the copy must have completed, not only been read
-            if (n_todo) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the staging rows are reused by the next tile
         }
         __syncwarp();
     }
-    // ---------------- rare path, outside the tile loop: nothing of the main path is live across the calls
-    if (n_todo) {
-        EvCtx cx;
-        cx.n = m.n_stations; cx.kf = m.moer_steps; cx.C = m.n_classes; cx.J = m.n_constraints; cx.K = m.max_sessions;
-        cx.n_days = m.n_days; cx.n_moer_days = m.n_moer_days; cx.max_day_sessions = m.max_day_sessions;
-        cx.flags = flags; cx.bins = bins; cx.B = B; cx.moer = m.moer; cx.recs = reinterpret_cast<const uint4*>(m.sessions);
-        cx.arrivals = m.arrivals; cx.action = action; cx.slots = reinterpret_cast<Slot*>(s.slots);
-        cx.clock = s.clock; cx.breakdown = s.breakdown; cx.occ = reinterpret_cast<unsigned long long*>(s.occ);
-        cx.obs = obs; cx.final_obs = final_obs; cx.reward = reward; cx.done = done; cx.pilots = pilots; cx.status = status;
-        double* wst = stats != nullptr ? wsm[warp].stat : nullptr;
-        for (int k = 0; k < n_todo; ++k) {
-            const long long bq = wsm[warp].todo[k];
-            if (!fallback_env<false>(sh, cx, bq, lane, wst)) fallback_env<true>(sh, cx, bq, lane, wst);
-        }
-    }
-  }
     if (stats != nullptr) {
         __syncthreads();
         // 11 statistics x kMainWarps partials -> one set of atomics per CTA
@@ -1370,6 +1541,54 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
 #endif
 }
 
+// Second launch of a step: the envs the main kernel could not certify (work list), one warp per env.
+__global__ void __launch_bounds__(128)
+ev_step_rare_kernel(const sg_ev_model m, const sg_ev_state s, const long long B, const void* __restrict__ action,
+                    const int flags, const int bins, float* __restrict__ obs, double* __restrict__ reward,
+                    uint8_t* __restrict__ done, uint8_t* __restrict__ pilots, float* __restrict__ final_obs,
+                    uint8_t* __restrict__ status, double* __restrict__ stats, int32_t* __restrict__ work) {
+    __shared__ EvTables sh;
+    __shared__ double wstat[4][12];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int count = work[0];
+    if (count > 0) {
+        load_tables(m.tables, sh);
+        if (lane < 12) wstat[warp][lane] = lane == 3 ? 1e300 : (lane == 4 ? -1e300 : 0.0);
+        __syncthreads();
+        EvCtx cx;
+        cx.n = m.n_stations; cx.kf = m.moer_steps; cx.C = m.n_classes; cx.J = m.n_constraints; cx.K = m.max_sessions;
+        cx.n_days = m.n_days; cx.n_moer_days = m.n_moer_days; cx.max_day_sessions = m.max_day_sessions;
+        cx.flags = flags; cx.bins = bins; cx.B = B; cx.moer = m.moer; cx.recs = reinterpret_cast<const uint4*>(m.sessions);
+        cx.arrivals = m.arrivals; cx.action = action; cx.slots = reinterpret_cast<Slot*>(s.slots);
+        cx.header = reinterpret_cast<EnvHeader*>(s.header);
+        cx.obs = obs; cx.final_obs = final_obs; cx.reward = reward; cx.done = done; cx.pilots = pilots; cx.status = status;
+        const int nwarps = gridDim.x * (blockDim.x >> 5);
+        // warp w of CTA c takes item c + w * gridDim.x: the first items spread over different SMs
+        for (int w = blockIdx.x + warp * gridDim.x; w < count; w += nwarps) {
+            const long long bq = work[2 + w];
+            double* wst = stats != nullptr ? wstat[warp] : nullptr;
+            if (!fallback_env<false>(sh, cx, bq, lane, wst)) fallback_env<true>(sh, cx, bq, lane, wst);
+        }
+        if (stats != nullptr) {
+            __syncthreads();
+            if (threadIdx.x < 11) {
+                const int i = threadIdx.x;
+                double r = wstat[0][i];
+                for (int w = 1; w < 4; ++w) r = (i == 3) ? fmin(r, wstat[w][i]) : (i == 4) ? fmax(r, wstat[w][i]) : r + wstat[w][i];
+                if (i == 3) { if (r < 1e300) atomic_min_double(stats + 3, r); }
+                else if (i == 4) { if (r > -1e300) atomic_max_double(stats + 4, r); }
+                else if (r != 0.0) atomicAdd(stats + i, r);
+            }
+        }
+    }
+    // the last CTA to finish re-arms the work list for the next step
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(work + 1, 1) == (int)gridDim.x - 1) { work[0] = 0; work[1] = 0; __threadfence(); }
+    }
+}
+
 __global__ void ev_reset_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
                                 const uint8_t* __restrict__ mask, const int32_t* __restrict__ day_in,
                                 const int32_t* __restrict__ moer_day_in, float* __restrict__ obs) {
@@ -1378,19 +1597,21 @@ __global__ void ev_reset_kernel(const sg_ev_model m, const sg_ev_state s, const 
     if (b >= B) return;
     if (mask != nullptr && mask[b] == 0) return;
     const int n = m.n_stations, kf = m.moer_steps, OBS = 2 * n + kf + 2;
-    int day = day_in ? day_in[b] : s.clock[b * 4 + 1];
-    int md = moer_day_in ? moer_day_in[b] : s.clock[b * 4 + 2];
+    EnvHeader* headers = reinterpret_cast<EnvHeader*>(s.header);
+    int day = day_in ? day_in[b] : headers[b].day;
+    int md = moer_day_in ? moer_day_in[b] : headers[b].moer_day;
     day = ((day % m.n_days) + m.n_days) % m.n_days;
     md = ((md % m.n_moer_days) + m.n_moer_days) % m.n_moer_days;
     float* orow = obs + b * OBS;
     for (int i = lane; i < 2 * n; i += 32) orow[i] = 0.f;
     const float* mrow = m.moer + ((long long)md * SG_EV_MOER_ROWS) * SG_EV_MOER_COLS;
     for (int e = lane; e < kf + 2; e += 32) orow[2 * n + e] = e < kf ? mrow[1 + e] : (e == kf ? mrow[0] : 0.f);
+    __syncwarp();
     if (lane == 0) {
         // empty garage: no occupied station, so no session record is live (the records need no clearing)
-        s.clock[b * 4 + 0] = 0; s.clock[b * 4 + 1] = day; s.clock[b * 4 + 2] = md; s.clock[b * 4 + 3] = 0;
-        s.occ[b] = 0ull;
-        s.breakdown[b * 3] = s.breakdown[b * 3 + 1] = s.breakdown[b * 3 + 2] = 0.0;
+        EnvHeader h = empty_header();
+        h.t = 0; h.day = day; h.moer_day = md;
+        st_header(headers + b, h);
     }
 }
 
@@ -1401,15 +1622,15 @@ __global__ void ev_export_kernel(const sg_ev_model m, const sg_ev_state s, const
     const int n = m.n_stations;
     const long long total = B * n;
     const Slot* slots = reinterpret_cast<const Slot*>(s.slots);
+    const EnvHeader* headers = reinterpret_cast<const EnvHeader*>(s.header);
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         const long long b = idx / n;
         const int i = (int)(idx % n);
-        const int t = s.clock[b * 4];
-        const bool on = (s.occ[b] >> i) & 1ull;
+        const bool on = (headers[b].occ >> i) & 1ull;
         double d = 0.0;
         int k = 255;
-        if (on) { const Slot q = ld_slot(slots + ((long long)(t & 1) * B + b) * n + i); d = q.delivered; k = q.k; }
+        if (on) { const Slot q = ld_slot(slots + b * n + i); d = q.delivered; k = q.k; }
         if (delivered != nullptr) delivered[idx] = d;
         if (sess_idx != nullptr) sess_idx[idx] = (uint8_t)k;
     }
@@ -1488,8 +1709,9 @@ int check_tables(const sg_ev_model* m) {
 }
 
 int check_state(const sg_ev_state* s) {
-    SG_CHECK_ARG(s != nullptr && s->slots && s->clock && s->breakdown && s->occ, "ev: NULL state array");
+    SG_CHECK_ARG(s != nullptr && s->slots && s->header, "ev: NULL state array");
     SG_CHECK_ARG((reinterpret_cast<uintptr_t>(s->slots) & 31u) == 0, "ev: state.slots must be 32-byte aligned");
+    SG_CHECK_ARG((reinterpret_cast<uintptr_t>(s->header) & 63u) == 0, "ev: state.header must be 64-byte aligned");
     return 0;
 }
 
@@ -1520,7 +1742,7 @@ int sg_ev_reset(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, co
 
 int sg_ev_step(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, const void* action, int32_t flags,
                int32_t discrete_bins, float* obs, double* reward, uint8_t* done, uint8_t* pilots,
-               float* final_obs, uint8_t* status, double* stats, void* stream) {
+               float* final_obs, uint8_t* status, double* stats, int32_t* work, void* stream) {
     if (int rc = sg::check_model(m)) return rc;
     if (int rc = sg::check_state(s)) return rc;
     SG_CHECK_ARG(action && obs && reward && done, "ev_step: NULL argument");
@@ -1530,6 +1752,7 @@ int sg_ev_step(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, con
     if (int rc = sg::check_tables(m)) return rc;
     SG_CHECK_ARG(2 * num_envs * (int64_t)m->n_stations < (1ll << 40), "ev_step: batch too large");
     SG_CHECK_ARG(!((flags & 1) == SG_EV_ACTION_I64) || discrete_bins >= 2, "ev_step: discrete_bins must be >= 2");
+    SG_CHECK_ARG(!m->project || work != nullptr, "ev_step: the projection needs the work-list scratch buffer");
     if (num_envs <= 0) return 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     int sms = sg_device_sm_count();
@@ -1544,12 +1767,18 @@ int sg_ev_step(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, con
         auto kern = sg::ev_step_main_kernel<1>;
         SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         kern<<<grid, sg::kMainThreads, dyn, st>>>(*m, *s, num_envs, action, flags, discrete_bins, obs, reward, done, pilots,
-                                                  final_obs, status, stats);
+                                                  final_obs, status, stats, work);
+        if (int rc = sg::launch_status("ev_step_main_kernel")) return rc;
+        // second launch: the envs on the work list (exact projection), one warp each
+        const unsigned rgrid = (unsigned)std::min<long long>((num_envs + 3) / 4, (long long)sms * 2);
+        sg::ev_step_rare_kernel<<<rgrid, 128, 0, st>>>(*m, *s, num_envs, action, flags, discrete_bins, obs, reward, done,
+                                                       pilots, final_obs, status, stats, work);
+        return sg::launch_status("ev_step_rare_kernel");
     } else {
         auto kern = sg::ev_step_main_kernel<0>;
         SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         kern<<<grid, sg::kMainThreads, dyn, st>>>(*m, *s, num_envs, action, flags, discrete_bins, obs, reward, done, pilots,
-                                                  final_obs, status, stats);
+                                                  final_obs, status, stats, work);
     }
     return sg::launch_status("ev_step_main_kernel");
 }
@@ -1557,7 +1786,7 @@ int sg_ev_step(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, con
 int sg_ev_step_host(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, const void* h_action,
                     int32_t flags, int32_t discrete_bins, float* h_obs, double* h_reward, uint8_t* h_done,
                     void* d_action, float* d_obs, double* d_reward, uint8_t* d_done, uint8_t* d_status,
-                    double* d_stats, void* stream) {
+                    double* d_stats, int32_t* d_work, void* stream) {
     SG_CHECK_ARG(m && h_action && h_obs && h_reward && h_done && d_action && d_obs && d_reward && d_done,
                  "ev_step_host: NULL argument");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -1565,7 +1794,7 @@ int sg_ev_step_host(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs
     const size_t abytes = B * n * (((flags & 1) == SG_EV_ACTION_I64) ? 8 : 4);
     SG_CUDA(cudaMemcpyAsync(d_action, h_action, abytes, cudaMemcpyHostToDevice, st));
     if (int rc = sg_ev_step(m, s, num_envs, d_action, flags, discrete_bins, d_obs, d_reward, d_done, nullptr,
-                            nullptr, d_status, d_stats, stream)) return rc;
+                            nullptr, d_status, d_stats, d_work, stream)) return rc;
     SG_CUDA(cudaMemcpyAsync(h_obs, d_obs, B * OBS * 4, cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaMemcpyAsync(h_reward, d_reward, B * 8, cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaMemcpyAsync(h_done, d_done, B, cudaMemcpyDeviceToHost, st));

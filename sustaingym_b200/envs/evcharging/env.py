@@ -125,21 +125,23 @@ class BatchedEVChargingEnv:
         # ---- per-env state and outputs ---------------------------------------------------------------
         B = self.num_envs
         z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)  # noqa: E731
-        # session records of the plugged-in EVs: [2 copies, B, n] x 32 bytes (see sg_ev_state); torch
-        # allocations are 512-byte aligned, which the 256-bit record accesses need
-        self.slots = z(2, B, n, 4, dtype=torch.float64)
-        self.clock = z(B, 4, dtype=torch.int32)          # columns: t, day, moer_day, arrival cursor
+        # session records of the plugged-in EVs: [B, n] x 32 bytes, and one 64-byte header per env
+        # {t, day, moer_day, arrival cursor | occupancy mask | profit, carbon_cost, excess_charge | pad}
+        # (see sg_ev_state); torch allocations are 512-byte aligned, which the vector accesses need
+        self.slots = z(B, n, 4, dtype=torch.float64)
+        self.header = z(B, 8, dtype=torch.float64)
+        self.clock = self.header.view(torch.int32)[:, 0:4]        # columns: t, day, moer_day, arrival cursor
         self.t, self.day, self.moer_day = self.clock[:, 0], self.clock[:, 1], self.clock[:, 2]
-        self.breakdown = z(B, 3, dtype=torch.float64)
-        self.occ = z(B, dtype=torch.int64)                # bit i: station i has a plugged-in session
-        self._state = _lib.EVState(self.slots.data_ptr(), self.clock.data_ptr(), self.breakdown.data_ptr(),
-                                   self.occ.data_ptr())
+        self.occ = self.header.view(torch.int64)[:, 2]            # bit i: station i has a plugged-in session
+        self.breakdown = self.header[:, 3:6]
+        self._state = _lib.EVState(self.slots.data_ptr(), self.header.data_ptr())
         self.obs = z(B, self.obs_dim, dtype=torch.float32)
         self.final_obs = z(B, self.obs_dim, dtype=torch.float32) if auto_reset else None
         self.reward = z(B, dtype=torch.float64)
         self.done = z(B, dtype=torch.uint8)
         self.status = z(B, dtype=torch.uint8)
         self.pilots = z(B, n, dtype=torch.uint8)
+        self.work = z(B + 2, dtype=torch.int32)           # work list of the exact projection (rare path)
         self.stats = z(_lib.SG_STATS_LEN, dtype=torch.float64) if collect_stats else None
         if self.stats is not None:
             self.reset_stats()
@@ -226,8 +228,8 @@ class BatchedEVChargingEnv:
                     max(self.discrete_bins, 0), self._h_obs.data_ptr(), self._h_reward.data_ptr(),
                     self._h_done.data_ptr(), self._d_action.data_ptr(), self.obs.data_ptr(),
                     self.reward.data_ptr(), self.done.data_ptr(), self.status.data_ptr(),
-                    _lib.ptr(self.stats), self._stream()), "sg_ev_step_host")
-            self.kernel_launches += 1
+                    _lib.ptr(self.stats), self.work.data_ptr(), self._stream()), "sg_ev_step_host")
+            self.kernel_launches += 2 if self.project_action_in_env else 1
             if host_np:
                 done = self._h_done.numpy().astype(bool)
                 return (self._h_obs.numpy().copy(), self._h_reward.numpy().copy(), done,
@@ -248,8 +250,8 @@ class BatchedEVChargingEnv:
                 C.byref(self._model), C.byref(self._state), self.num_envs, actions.data_ptr(), self._flags,
                 max(self.discrete_bins, 0), self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
                 self.pilots.data_ptr(), _lib.ptr(self.final_obs), self.status.data_ptr(), _lib.ptr(self.stats),
-                self._stream()), "sg_ev_step")
-        self.kernel_launches += 1
+                self.work.data_ptr(), self._stream()), "sg_ev_step")
+        self.kernel_launches += 2 if self.project_action_in_env else 1
 
     def export_state(self):
         """Dense views of the sparse per-station state: (delivered kWh f64 [B,n], trace slot u8 [B,n],
