@@ -8,8 +8,9 @@ A *step* is one ``env.step()`` of the whole batch (one pass of the hot path: pro
 pilot rounding -> acnsim period -> observation -> reward).  Reported on ONE JSON line:
 
   value      env-steps/s, whole job, actions already resident in HBM, CUDA-event timed, max over ranks
-  e2e        the same through the public host API ``env.step(pinned host actions)`` with the H2D copy
-             of the actions and the D2H copy of obs/reward/done inside the timed region
+  e2e        the same through the public host API ``env.step_async(pinned host actions)`` /
+             ``env.step_wait()`` with the H2D copy of the actions and the D2H copy of obs/reward/done of
+             every step inside the timed region (two env batches in flight so both PCIe directions work)
   roofline   the step kernel (ev_step_main_kernel<1>): algorithmic bytes per launch (1709 B/env-step,
              SURVEY.md 8d) / its CUDA-event duration, against MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the NumPy oracle port timed on this box's host cores on a bounded sample
@@ -279,27 +280,33 @@ def main():
     launches += 2 * L
 
     # ---- e2e: public host API, pinned host actions in, obs/reward/done out, every step ---------------
-    E = 30
-    env = envs[0]
+    # SB3 VecEnv-style step_async / step_wait on two env batches: while one batch's observations are
+    # copied to the host, the other batch's actions are copied to the device and its kernel runs.
+    E = 40
+    pipe = envs[:2]
     h_act = torch.rand(4, B, N_STATIONS, dtype=torch.float32).pin_memory()
-    for i in range(3):
-        env.step(h_act[i % 4])
+    torch.cuda.synchronize()
+    for i in range(4):
+        pipe[i % 2].step_async(h_act[i % 4]); pipe[i % 2].step_wait()
     barrier()
     t0 = time.perf_counter()
+    pipe[0].step_async(h_act[0])
     for i in range(E):
-        obs_h, rew_h, done_h, _, _ = env.step(h_act[i % 4])
+        pipe[(i + 1) % 2].step_async(h_act[(i + 1) % 4])
+        obs_h, rew_h, done_h, _, _ = pipe[i % 2].step_wait()
+    obs_h, rew_h, done_h, _, _ = pipe[E % 2].step_wait()
     torch.cuda.synchronize()
     dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * E / float(dt.item())
-    launches += 2 * (E + 3)
+    e2e_value = world * B * (E + 1) / float(dt.item())
+    launches += 2 * (E + 5)
     h2d = B * N_STATIONS * 4
     d2h = B * OBS_DIM * 4 + B * 8 + B
 
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        Bc, Sc = 2048, 100
+        Bc, Sc = 4096, 1200                      # ~10 s of single-core CPU work
         t0 = time.perf_counter()
         rate = cpu_oracle_rate(1, Bc, Sc)
         cpu_base = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
@@ -323,7 +330,9 @@ def main():
                          "peak_source": peak_src},
             "cpu_baseline": cpu_base,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": E, "api": "BatchedEVChargingEnv.step(pinned host tensor) -> sg_ev_step_host"},
+                    "steps": E + 1,
+                    "api": "BatchedEVChargingEnv.step_async(pinned host actions) / step_wait() -> sg_ev_step_host_async, "
+                           "two env batches in flight (H2D of one overlaps D2H of the other)"},
             "gpu_launches": launches, "clocks": clocks,
             "reward_stats": {"count": st[0], "mean": st[1] / max(st[0], 1), "n_done": st[5], "n_projected": st[6],
                              "n_maxiter": st[7]},

@@ -209,6 +209,15 @@ int sg_ev_step_host(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs
                     void* d_action, float* d_obs, double* d_reward, uint8_t* d_done,
                     uint8_t* d_status, double* d_stats, int32_t* d_work, void* stream);
 
+/* Same without the final synchronisation (SB3 VecEnv.step_async): the host buffers must be pinned and
+ * are valid after the caller synchronises `stream`.  Several env batches stepped this way on different
+ * streams overlap their host->device and device->host copies. */
+int sg_ev_step_host_async(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs,
+                          const void* h_action, int32_t flags, int32_t discrete_bins,
+                          float* h_obs, double* h_reward, uint8_t* h_done,
+                          void* d_action, float* d_obs, double* d_reward, uint8_t* d_done,
+                          uint8_t* d_status, double* d_stats, int32_t* d_work, void* stream);
+
 /* Dense views of the sparse state: delivered [B,n] f64 (kWh delivered to the session plugged in at
  * each station, 0 where empty) and sess_idx [B,n] u8 (its trace slot, 255 where empty); either may be NULL. */
 int sg_ev_export_state(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs,

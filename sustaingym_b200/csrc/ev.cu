@@ -1783,10 +1783,10 @@ int sg_ev_step(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, con
     return sg::launch_status("ev_step_main_kernel");
 }
 
-int sg_ev_step_host(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, const void* h_action,
-                    int32_t flags, int32_t discrete_bins, float* h_obs, double* h_reward, uint8_t* h_done,
-                    void* d_action, float* d_obs, double* d_reward, uint8_t* d_done, uint8_t* d_status,
-                    double* d_stats, int32_t* d_work, void* stream) {
+static int ev_step_host_impl(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, const void* h_action,
+                             int32_t flags, int32_t discrete_bins, float* h_obs, double* h_reward, uint8_t* h_done,
+                             void* d_action, float* d_obs, double* d_reward, uint8_t* d_done, uint8_t* d_status,
+                             double* d_stats, int32_t* d_work, void* stream, bool sync) {
     SG_CHECK_ARG(m && h_action && h_obs && h_reward && h_done && d_action && d_obs && d_reward && d_done,
                  "ev_step_host: NULL argument");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -1798,8 +1798,24 @@ int sg_ev_step_host(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs
     SG_CUDA(cudaMemcpyAsync(h_obs, d_obs, B * OBS * 4, cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaMemcpyAsync(h_reward, d_reward, B * 8, cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaMemcpyAsync(h_done, d_done, B, cudaMemcpyDeviceToHost, st));
-    SG_CUDA(cudaStreamSynchronize(st));
+    if (sync) SG_CUDA(cudaStreamSynchronize(st));
     return 0;
+}
+
+int sg_ev_step_host(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, const void* h_action,
+                    int32_t flags, int32_t discrete_bins, float* h_obs, double* h_reward, uint8_t* h_done,
+                    void* d_action, float* d_obs, double* d_reward, uint8_t* d_done, uint8_t* d_status,
+                    double* d_stats, int32_t* d_work, void* stream) {
+    return ev_step_host_impl(m, s, num_envs, h_action, flags, discrete_bins, h_obs, h_reward, h_done, d_action, d_obs,
+                             d_reward, d_done, d_status, d_stats, d_work, stream, true);
+}
+
+int sg_ev_step_host_async(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, const void* h_action,
+                          int32_t flags, int32_t discrete_bins, float* h_obs, double* h_reward, uint8_t* h_done,
+                          void* d_action, float* d_obs, double* d_reward, uint8_t* d_done, uint8_t* d_status,
+                          double* d_stats, int32_t* d_work, void* stream) {
+    return ev_step_host_impl(m, s, num_envs, h_action, flags, discrete_bins, h_obs, h_reward, h_done, d_action, d_obs,
+                             d_reward, d_done, d_status, d_stats, d_work, stream, false);
 }
 
 int sg_ev_export_state(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, double* delivered,

@@ -156,6 +156,7 @@ class BatchedEVChargingEnv:
             (_lib.SG_EV_FLAG_AUTORESET if auto_reset else 0)
         self.kernel_launches = 0
         self._needs_reset = True
+        self._async_stream = None
 
     # ------------------------------------------------------------------------------------------
     def __repr__(self) -> str:
@@ -241,6 +242,35 @@ class BatchedEVChargingEnv:
         actions = actions.contiguous()
         self.launch_step(actions)
         return self.obs, self.reward, self.done.bool(), torch.zeros_like(self.done, dtype=torch.bool), self._infos()
+
+    def step_async(self, actions: torch.Tensor) -> None:
+        """SB3 ``VecEnv.step_async``: enqueue H2D(actions) -> step -> D2H(obs, reward, done) on this env's
+        own stream and return immediately.  ``actions`` must be a pinned, contiguous host tensor of the
+        action dtype and must stay untouched until ``step_wait``.  Several batched envs stepped this way
+        overlap their copies in both PCIe directions."""
+        if self._needs_reset:
+            raise RuntimeError("call reset() before step()")
+        if not (actions.device.type == "cpu" and actions.is_pinned() and actions.is_contiguous()
+                and actions.dtype == self._action_dtype and tuple(actions.shape) == (self.num_envs, self.num_stations)):
+            raise ValueError("step_async needs a pinned contiguous host tensor of shape (num_envs, n)")
+        if self._async_stream is None:
+            self._async_stream = torch.cuda.Stream(self.device)
+            self._async_stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.sg_ev_step_host_async(
+                C.byref(self._model), C.byref(self._state), self.num_envs, actions.data_ptr(), self._flags,
+                max(self.discrete_bins, 0), self._h_obs.data_ptr(), self._h_reward.data_ptr(),
+                self._h_done.data_ptr(), self._d_action.data_ptr(), self.obs.data_ptr(),
+                self.reward.data_ptr(), self.done.data_ptr(), self.status.data_ptr(),
+                _lib.ptr(self.stats), self.work.data_ptr(), self._async_stream.cuda_stream), "sg_ev_step_host_async")
+        self.kernel_launches += 2 if self.project_action_in_env else 1
+
+    def step_wait(self):
+        """SB3 ``VecEnv.step_wait``: wait for the step enqueued by ``step_async``; returns views of the
+        pinned result buffers (obs f32 [B, obs_dim], reward f64 [B], done bool [B], truncated, infos)."""
+        self._async_stream.synchronize()
+        return (self._h_obs, self._h_reward, self._h_done.bool(), torch.zeros(self.num_envs, dtype=torch.bool),
+                self._infos())
 
     def launch_step(self, actions: torch.Tensor) -> None:
         """Enqueues the step kernel on the current stream without building return values (used by

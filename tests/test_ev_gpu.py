@@ -132,6 +132,44 @@ def test_autoreset_sequential_days_and_host_path(native_lib):
     np.testing.assert_array_equal(env.day.cpu().numpy(), (day0 + 2) % 4)
 
 
+def test_step_async_matches_step(native_lib):
+    """step_async / step_wait (own stream, no sync inside the C call) == the synchronous host path."""
+    B = 96
+    _, env, _, _ = make(3, 60.0, 4, B, True)
+    _, env2, _, _ = make(3, 60.0, 4, B, True)
+    env.reset(seed=2); env2.reset(seed=2)
+    rng = np.random.default_rng(1)
+    for t in range(120):
+        a = torch.from_numpy(rng.uniform(0, 1, (B, 54)).astype(np.float32)).pin_memory()
+        env.step_async(a)
+        ob, r, d, _, _ = env.step_wait()
+        ob2, r2, d2, _, _ = env2.step(a.numpy())
+        np.testing.assert_array_equal(ob.numpy(), ob2)
+        np.testing.assert_array_equal(r.numpy(), r2)
+        np.testing.assert_array_equal(d.numpy(), d2)
+
+
+def test_export_state_matches_oracle(native_lib):
+    """Dense view of the sparse in-place state: delivered kWh per station vs the oracle's sessions."""
+    B = 50
+    gen, env, net, orc = make(3, 60.0, 6, B, False)
+    env.reset(seed=1)
+    days = gen.first_days(1 + np.arange(B), B)
+    orc.reset(days, gen.moer_days(days))
+    rng = np.random.default_rng(3)
+    for t in range(150):
+        a = rng.uniform(0, 1, (B, 54)).astype(np.float32)
+        env.step(torch.from_numpy(a).cuda()); orc.step(a)
+    delivered, slot = env.export_state()
+    delivered, slot = delivered.cpu().numpy(), slot.cpu().numpy()
+    want = np.zeros((B, 54))
+    bi, si = np.nonzero(orc.plugged)
+    want[bi, orc._stn[orc.day][bi, si]] = orc.delivered[bi, si]
+    occupied = np.zeros((B, 54), bool); occupied[bi, orc._stn[orc.day][bi, si]] = True
+    np.testing.assert_array_equal(slot != 255, occupied)
+    np.testing.assert_allclose(delivered, want, rtol=1e-9, atol=1e-12)
+
+
 def test_single_env_gymnasium_view(native_lib):
     from sustaingym_b200.envs.evcharging.env import EVChargingEnv
     from sustaingym_b200.envs.evcharging.event_generation import SyntheticTraceGenerator
