@@ -39,6 +39,7 @@ N_STATIONS = 54
 MOER_STEPS = 36
 OBS_DIM = 2 * N_STATIONS + MOER_STEPS + 2
 ALGO_BYTES_PER_ENV_STEP = 1709          # SURVEY.md 8(d), EV n=54 k=36
+NCU_DRAM_BYTES_PER_LAUNCH = 88118784    # 65.27 MB read + 22.85 MB written (profiles/r1, same workload)
 N_SETS = 4
 POOL_DAYS = 256
 MEAN_SESSIONS = 25.0
@@ -325,7 +326,9 @@ def main():
                        "l2_policy": f"{N_SETS} env sets stepped round-robin: ~{N_SETS * 85} MB touched between reuses (> 126 MB L2)",
                        "launch": "one CUDA graph per step: ev_step_main_kernel + ev_step_rare_kernel (work list of envs needing the interior-point solver, normally empty)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "kernel": "ev_step_main_kernel<1>",
+                         "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "kernel": "ev_step_main_kernel<1>",
+                         "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, "
+                                           "profiles/r1/ev_step_main_kernel_ncu_full_summary.txt",
                          "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * B,
                          "peak_source": peak_src},
             "cpu_baseline": cpu_base,
