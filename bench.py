@@ -191,7 +191,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     if args.impl == "reference":
-        args.steps = 40 if args.steps is None else args.steps
+        args.steps = 400 if args.steps is None else args.steps    # ~10 s of CPU work on all cores
         args.warmup = 1 if args.warmup is None else args.warmup
         run_reference(args, rank)
         return

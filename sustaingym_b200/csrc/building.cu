@@ -1,8 +1,11 @@
 // BuildingEnv batched step()/reset() for sm_100a.
 //
 // Replaces sustaingym/envs/building/env.py:205-312 (step), :314-386 (reset), :411-434
-// (_calc_occupower) of the reference.  One thread advances one env instance; a CTA owns a tile
-// of 128 consecutive envs.  The env-major rows the callers hand us (action [B,n], state
+// (_calc_occupower) of the reference.  One thread advances one env instance; a CTA (one warp) owns
+// a tile of 32 consecutive envs.  Fused rollouts (steps > 1) are software-pipelined: the action tiles of the
+// next 3 steps are in flight (cp.async ring in shared memory) and the weather rows of the next 2 steps
+// are prefetched into registers, so a step's critical path is its arithmetic, not a DRAM round trip.
+// The env-major rows the callers hand us (action [B,n], state
 // [B,n+4]) are moved global<->shared with fully coalesced accesses and transposed through
 // shared memory so that each thread reads its own row; the discretised RC model (A_d, BD_d,
 // target, ac_map) is staged once per CTA in shared memory and read as warp-uniform broadcasts.
@@ -16,7 +19,22 @@
 namespace sg {
 namespace {
 
-constexpr int kTile = 128;  // envs per CTA
+#ifndef SG_BLD_TILE
+#define SG_BLD_TILE 32     // one warp per CTA: tiles advance independently (measured +9 % over 128 on the fused rollout)
+#endif
+constexpr int kTile = SG_BLD_TILE;  // envs per CTA
+constexpr int kPre = 3;     // rollout software pipeline: action tiles of the next kPre steps are in flight (cp.async)
+constexpr int kRing = kPre + 1;
+
+__device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __constant__ double kOccu[8] = {6.461927, 0.946892, 0.0000255737, 0.0627909,
                                 0.0000589172, 0.19855, 0.000940018, 0.00000149532};
@@ -136,20 +154,41 @@ building_step_kernel(const sg_building_model m, const long long B, const int ste
     StatsAcc acc;
     float tail[4] = {0.f, 0.f, 0.f, 0.f};
 
-    for (int s = 0; s < steps; ++s) {
-        // ---- stage this step's action rows -------------------------------------------------
-        if constexpr (N > 0) {
-            __syncthreads();   // previous step's readers of the tiles are done
-            if constexpr (DISCRETE) {
-                const long long* g = reinterpret_cast<const long long*>(action_v) + ((long long)s * B + b0) * n;
-                long long* t = reinterpret_cast<long long*>(act_tile_raw);
-                for (int i = tid; i < nvalid * n; i += kTile) t[i] = g[i];
+    // action tile ring (N > 0): slot (s % kRing) holds step s; every call commits one group (maybe empty)
+    constexpr int esz = DISCRETE ? 8 : 4;
+    const size_t act_tile_bytes = ((size_t)kTile * n * esz + 15) & ~(size_t)15;
+    auto stage_actions = [&](const int sp) {
+        if (sp < steps) {
+            const char* g = reinterpret_cast<const char*>(action_v) + ((long long)sp * B + b0) * n * esz;
+            unsigned char* t = act_tile_raw + (size_t)(sp % kRing) * act_tile_bytes;
+            const int nbytes = nvalid * n * esz;
+            if ((nbytes & 15) == 0 && (reinterpret_cast<uintptr_t>(g) & 15u) == 0) {
+                for (int i = tid * 16; i < nbytes; i += kTile * 16) cp_async_16(t + i, g + i);
             } else {
-                const float* g = reinterpret_cast<const float*>(action_v) + ((long long)s * B + b0) * n;
-                float* t = reinterpret_cast<float*>(act_tile_raw);
-                for (int i = tid; i < nvalid * n; i += kTile) t[i] = g[i];
+                for (int i = tid * 4; i < nbytes; i += kTile * 4) cp_async_4(t + i, g + i);
             }
-            __syncthreads();
+        }
+        cp_async_commit();
+    };
+    if constexpr (N > 0) {
+#pragma unroll
+        for (int d = 0; d < kPre; ++d) stage_actions(d);
+    }
+    // weather rows of this step and the next one (the cursor advances by one row per step)
+    Weather4 w_cur = {0, 0, 0, 0}, w_nxt = {0, 0, 0, 0};
+    if (valid) {
+        w_cur = load_weather(m.weather, e);
+        w_nxt = load_weather(m.weather, (e + 1) % m.T);
+    }
+
+    for (int s = 0; s < steps; ++s) {
+        // ---- this step's action rows: landed in the ring (issued kPre steps ago) --------------------
+        const unsigned char* act_tile = act_tile_raw;
+        if constexpr (N > 0) {
+            cp_async_wait<kPre - 1>();   // this thread's copies for step s
+            __syncthreads();             // everyone's copies landed; previous step's readers of the tiles are done
+            stage_actions(s + kPre);     // refills the slot step s-1 used
+            act_tile = act_tile_raw + (size_t)(s % kRing) * act_tile_bytes;
         }
         double rew = 0.0;
         bool dn = false;
@@ -163,14 +202,14 @@ building_step_kernel(const sg_building_model m, const long long B, const int ste
                 {
                     if constexpr (DISCRETE) {
                         long long ai;
-                        if constexpr (N > 0) ai = reinterpret_cast<const long long*>(act_tile_raw)[tid * n + j];
+                        if constexpr (N > 0) ai = reinterpret_cast<const long long*>(act_tile)[tid * n + j];
                         else ai = reinterpret_cast<const long long*>(action_v)[((long long)s * B + b) * n + j];
                         const float qlow100 = __fmul_rn(-(float)sAc[j], 100.f);
                         act[j] = ((double)ai + (double)qlow100) / 100.0;
                         a_dot64 = fma(act[j], act[j], a_dot64);
                     } else {
                         float af;
-                        if constexpr (N > 0) af = reinterpret_cast<const float*>(act_tile_raw)[tid * n + j];
+                        if constexpr (N > 0) af = reinterpret_cast<const float*>(act_tile)[tid * n + j];
                         else af = reinterpret_cast<const float*>(action_v)[((long long)s * B + b) * n + j];
                         act[j] = (double)af;
                         a_dot = __fmaf_rn(af, af, a_dot);
@@ -179,7 +218,11 @@ building_step_kernel(const sg_building_model m, const long long B, const int ste
                 }
             }
             // ---- exogenous inputs + occupancy heat: env.py:244-263 --------------------------
-            const Weather4 w = load_weather(m.weather, e);
+            const Weather4 w = w_cur;
+            w_cur = w_nxt;
+            {   // row the step after next will read
+                w_nxt = load_weather(m.weather, (e + 2) % m.T);
+            }
             const float avg_temp = __fdiv_rn(numpy_sum_f32<MAXN>(x, n), (float)n);
             const double occ = occupower_f32temp(avg_temp, w.meta);
             // ---- X_new = A_d X + BD_d Y: env.py:266 ; error/reward: env.py:272-276 -----------
@@ -230,7 +273,7 @@ building_step_kernel(const sg_building_model m, const long long B, const int ste
                 r = 0;
                 double sum = 0.0;
                 for (int j = 0; j < n; ++j) sum += sTarget[j];
-                const Weather4 w2 = load_weather(m.weather, e);
+                const Weather4 w2 = w_cur;                       // (row e: already prefetched)
                 const double occ0 = occupower_f64temp(sum / n, w2.meta);
 #pragma unroll
                 for (int j = 0; j < n; ++j) x[j] = (float)sTarget[j];
@@ -311,7 +354,7 @@ int launch_building(const sg_building_model* m, long long B, int steps, const vo
                     int flags, double* stats, cudaStream_t st) {
     const int n = m->n, row = n + 4;
     size_t smem = sizeof(double) * (n * n + n * row + 2 * n + 44);
-    if (N > 0) smem += sizeof(float) * kTile * row + 16 + (DISCRETE ? 8 : 4) * kTile * n;
+    if (N > 0) smem += sizeof(float) * kTile * row + 16 + (size_t)kRing * ((((DISCRETE ? 8 : 4) * (size_t)kTile * n) + 15) & ~(size_t)15);
     auto kern = building_step_kernel<N, DISCRETE>;
     if (smem > 48 * 1024) {
         cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
