@@ -936,20 +936,28 @@ __device__ __noinline__ bool fallback_env(const EvTables& sh, const EvCtx cx, co
 // station in ws.key[j].  Returns 0: the clipped action is feasible (exact test), nothing to do;
 // 1: projected, x_i = clip(a_i - ws.nu[class_i], 0, u_i); 2: a coupled constraint is (or became)
 // violated -> interior point (rare kernel).
-__device__ __forceinline__ int pod_solve(const EvTables& sh, WarpShared& ws, const int lo, const int hi, const int J) {
+__device__ __forceinline__ int pod_solve(const EvTables& sh, WarpShared& ws, const int lo, const int hi, const int J,
+                                         const unsigned suspects) {
 #pragma unroll
     for (int c = 0; c < kMC; ++c) { ws.Sx[c] = 0.0; ws.nu[c] = 0.0; }
     for (int j = lo; j < hi; ++j) {
         const int c = sh.cls[ws.key[j] & 0xff];
         ws.Sx[c] += fmin(fmax((double)ws.xa[j], 0.0), ws.rate[j]);
     }
-    bool any = false;
-    for (int jc = 0; jc < J; ++jc) {
+    // exact magnitude of constraint jc at the class sums ws.Sx
+    auto magnitude = [&](const int jc) {
         double wr = 0, wi = 0;
 #pragma unroll
         for (int c = 0; c < kMC; ++c) { wr = fma(sh.con_re[jc * kMC + c], ws.Sx[c], wr); wi = fma(sh.con_im[jc * kMC + c], ws.Sx[c], wi); }
+        return sqrt(wr * wr + wi * wi);
+    };
+    bool any = false;
+    // only the constraints the f32 margin test flagged can be violated by the clipped action
+    for (unsigned todo = suspects; todo; todo &= todo - 1) {
+        const int jc = __ffs((int)todo) - 1;
+        if (jc >= J) break;
         const double r = sh.lim[jc] * (1.0 / kActionScale);
-        if (!(sqrt(wr * wr + wi * wi) > r)) continue;        // satisfied
+        if (!(magnitude(jc) > r)) continue;                  // satisfied
         const int cs = sh.simple_cls[jc];
         if (cs < 0) return 2;                                // a coupled constraint is violated
         const double R = sh.simple_R[jc];
@@ -989,12 +997,17 @@ __device__ __forceinline__ int pod_solve(const EvTables& sh, WarpShared& ws, con
         any = true;
     }
     if (!any) return 0;
-    for (int jc = 0; jc < J; ++jc) {                          // all constraints again, with a relative slack
-        double wr = 0, wi = 0;
+    // all constraints again at the projected point (relative slack 1e-12): f32 screen with a margin first,
+    // the exact f64 magnitude only for the ones close to their limit
+    float Sf[kMC];
 #pragma unroll
-        for (int c = 0; c < kMC; ++c) { wr = fma(sh.con_re[jc * kMC + c], ws.Sx[c], wr); wi = fma(sh.con_im[jc * kMC + c], ws.Sx[c], wi); }
-        const double r = sh.lim[jc] * (1.0 / kActionScale);
-        if (sqrt(wr * wr + wi * wi) > r * (1.0 + 1e-12)) return 2;
+    for (int c = 0; c < kMC; ++c) Sf[c] = (float)ws.Sx[c];
+    for (int jc = 0; jc < J; ++jc) {
+        float wr = 0.f, wi = 0.f;
+#pragma unroll
+        for (int c = 0; c < kMC; ++c) { wr = fmaf(sh.re[jc * kMC + c], Sf[c], wr); wi = fmaf(sh.im[jc * kMC + c], Sf[c], wi); }
+        if (fmaf(wr, wr, wi * wi) <= sh.r_in[jc]) continue;   // certainly inside
+        if (magnitude(jc) > sh.lim[jc] * (1.0 / kActionScale) * (1.0 + 1e-12)) return 2;
     }
     return 1;
 }
@@ -1279,9 +1292,11 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
             // is not certainly feasible (projection needed); near: the rounded schedule is close to or over
             // a limit (exact excess current needed)
             unsigned gbad = 0u, gnear = 0u;
+            unsigned jsus = 0u;                                         // owner lane: constraints its env may violate
             auto pair_checks = [&]() {
                 bool mybad = false, mynear = false;
-                for (int idx = lane; idx < ((SG_EV_ABL & 16) ? 0 : kE * J); idx += 32) {   // pair (env idx % kE, constraint idx / kE)
+                jsus = 0u;
+                for (int idx = lane, k = 0; idx < ((SG_EV_ABL & 16) ? 0 : kE * J); idx += 32, ++k) {   // pair (env idx % kE, constraint idx / kE)
                     const int j = idx / kE, e2 = idx & (kE - 1);
                     float wr = 0.f, wi = 0.f, vr = 0.f, vi = 0.f;
 #pragma unroll
@@ -1291,8 +1306,14 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
                         vr = fmaf(cre, pv, vr); vi = fmaf(cim, pv, vi);
                         if (MODE != 0) { const float sv = (float)ws.S[c][e2] * (1.f / 1048576.f); wr = fmaf(cre, sv, wr); wi = fmaf(cim, sv, wi); }
                     }
-                    if (MODE != 0) mybad = mybad || !(fmaf(wr, wr, wi * wi) <= sh.r_in[j]);
+                    const bool b1 = MODE != 0 && !(fmaf(wr, wr, wi * wi) <= sh.r_in[j]);
+                    mybad = mybad || b1;
                     mynear = mynear || (fmaf(vr, vr, vi * vi) > sh.lim2_lo[j]);
+                    if (MODE != 0) {                                    // lane q*kE + e tested constraint k*kQ + q of env e
+                        const unsigned bb = __ballot_sync(__activemask(), b1);
+#pragma unroll
+                        for (int qq = 0; qq < kQ; ++qq) jsus |= ((bb >> (qq * kE + (lane & (kE - 1)))) & 1u) << (k * kQ + qq);
+                    }
                 }
                 gbad = __ballot_sync(kFull, mybad);
                 gnear = __ballot_sync(kFull, mynear);
@@ -1320,7 +1341,7 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
                     __syncwarp();
                     int res = 0;
                     if (lane == r) {
-                        res = pod_solve(sh, ws, off - base, off - base + cnt, J);
+                        res = pod_solve(sh, ws, off - base, off - base + cnt, J, jsus);
                         if (res == 1) {
 #pragma unroll
                             for (int c = 0; c < kMC; ++c) ws.P[c][r] = 0;
