@@ -285,6 +285,11 @@ int sg_cogen_step(const sg_cogen_model* m, int64_t num_envs, const float* action
                   uint8_t* done, float* Y_out, float* scratch /* [B,23] */, int32_t flags, double* stats,
                   void* stream);
 
+/* Unit test of the tensor-core path of the plant model: D[128,N] = A[128,K] * Bm[N,K]^T through 3xTF32
+ * tcgen05.mma (operands split in shared memory, fp32 accumulator in tensor memory). N in {128, 256},
+ * K a multiple of 8, <= 64.  All pointers [device], row-major. */
+int sg_tc_gemm_selftest(const float* A, const float* Bm, float* D, int32_t N, int32_t K, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * ElectricityMarketEnv  —  SPEC-DEFINED: the reference snapshot has no source for it (only
  *   docs/electricitymarketenv.md:9-27).  Spec: sustaingym_b200/envs/electricitymarket/SPEC.md.

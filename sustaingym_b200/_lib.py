@@ -100,6 +100,7 @@ SIGNATURES = {
     "sg_cogen_reset": (C.c_int, [C.POINTER(CogenModel), _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sg_cogen_step": (C.c_int, [C.POINTER(CogenModel), _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                 _i32, _vp, _vp]),
+    "sg_tc_gemm_selftest": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
     "sg_market_reset": (C.c_int, [C.POINTER(MarketModel), _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sg_market_step": (C.c_int, [C.POINTER(MarketModel), _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sg_ev_project": (C.c_int, [C.POINTER(EVModel), _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
