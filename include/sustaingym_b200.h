@@ -265,7 +265,15 @@ typedef struct sg_cogen_model {
     const float*   b3;       /* [device] [23]                                                           */
     const double*  ambient;  /* [device] [n_days, 96, 7]: TAMB, PAMB, RHAMB, Target_Power, Target_Steam,
                                 Energy_Price, Gas_Price (load_ambients.construct_df columns)            */
+    const float*   tc_blob;    /* [device] pre-split (3xTF32) layer-2 weights for the tensor-core kernel, filled
+                                  by sg_cogen_prepare_tc; NULL selects the fp32 FFMA kernel                    */
+    const int64_t* tc_offsets; /* [device] [23] float offset of each sub-model in tc_blob:
+                                  cumulative (H1/16) * (272 + 32*H2) floats                                   */
 } sg_cogen_model;
+
+/* Fills tc_blob (m->tc_offsets must be set; sized by its last offset + last sub-model) from the fp32
+ * weights: per 16-unit chunk W1 | b1 | W2 hi | W2 lo in the tcgen05 K-major operand layout. */
+int sg_cogen_prepare_tc(const sg_cogen_model* m, float* tc_blob, void* stream);
 
 /* The plant model alone: X [B,18] f32 -> Y [B,29] f32 (model.json order). scratch: [B,23] f32. */
 int sg_cogen_plant(const sg_cogen_model* m, int64_t num_envs, const float* X, float* Y, float* scratch,

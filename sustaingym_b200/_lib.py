@@ -61,7 +61,7 @@ class CogenModel(C.Structure):
         ("n_sub", _i32), ("forecast_horizon", _i32), ("n_days", _i32), ("reserved", _i32),
         ("ramp_penalty", _f64), ("supply_imbalance_penalty", _f64), ("constraint_violation_penalty", _f64),
         ("blob", _vp), ("offsets", _vp), ("meta", _vp), ("feats", _vp), ("mu", _vp), ("sinv", _vp), ("b3", _vp),
-        ("ambient", _vp),
+        ("ambient", _vp), ("tc_blob", _vp), ("tc_offsets", _vp),
     ]
 
 
@@ -97,6 +97,7 @@ SIGNATURES = {
     "sg_ev_export_state": (C.c_int, [C.POINTER(EVModel), C.POINTER(EVState), _i64, _vp, _vp, _vp]),
     "sg_ev_agent_obs": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "sg_cogen_plant": (C.c_int, [C.POINTER(CogenModel), _i64, _vp, _vp, _vp, _vp]),
+    "sg_cogen_prepare_tc": (C.c_int, [C.POINTER(CogenModel), _vp, _vp]),
     "sg_cogen_reset": (C.c_int, [C.POINTER(CogenModel), _i64, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sg_cogen_step": (C.c_int, [C.POINTER(CogenModel), _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                 _i32, _vp, _vp]),

@@ -5,9 +5,19 @@
 // (step) and sustaingym/envs/cogen/multiagent_env.py:97-101 (per-agent reward split).
 //
 // The plant model is 23 independent 3-layer MLPs (1.84 M MAC per env-step)
-// — a dense contraction, the one compute-bound piece of the whole engine.  Round-1 kernel:
-// fp32 FFMA (3xTF32 tensor-core variant is the follow-up; a single TF32/BF16 pass cannot meet the
-// 1e-5 tolerance).  One CTA = 64 envs x one sub-model:
+// — a dense contraction, the one compute-bound piece of the whole engine.  Two kernels:
+//
+// cogen_mlp_tc_kernel (default): layer 2 (>95% of the FLOPs) on the 5th-generation tensor cores.  One
+//   CTA = 128 envs x one sub-model; per chunk of 16 hidden-1 units the threads compute layer 1 in fp32
+//   (one env per thread), split the activations into tf32 (hi, lo) pairs and store them as the K-major
+//   A operand; the pre-split W2 chunk (hi, lo) together with the chunk's W1/b1 arrives by ONE bulk
+//   asynchronous copy (TMA) into a 2-stage ring; one thread issues 3 tcgen05.mma kind::tf32 per K=8
+//   (lo*hi, hi*lo, hi*hi: 3xTF32, because a single TF32/BF16 pass cannot meet the 1e-5 tolerance,
+//   SURVEY.md H4) accumulating a 128 x H2 fp32 tile in tensor memory; tcgen05.commit -> mbarrier frees
+//   the stage; the epilogue reads the accumulator rows with tcgen05.ld and fuses bias, activation and
+//   layer 3.
+// cogen_mlp_kernel (fallback when the model carries no pre-split weights): fp32 FFMA.  One CTA = 64
+//   envs x one sub-model:
 //   layer 1 (K = d <= 14) is recomputed per 32-wide chunk of hidden-1 units straight into shared
 //   memory (transposed, so the layer-2 A operand is one float4 broadcast per thread);
 //   layer 2 (256x128 or 512x256, >95% of the FLOPs) streams its weight rows global->shared with
@@ -17,6 +27,7 @@
 // (one thread per env) applies the gates, derived outputs, constraint hinges, rewards and writes
 // the flattened observation.
 #include "common.cuh"
+#include "tc.cuh"
 
 namespace sg {
 namespace {
@@ -184,6 +195,184 @@ cogen_mlp_kernel(const sg_cogen_model m, const long long B, const float* __restr
     else mlp_tile<128>(m, j, b0, nvalid, X_in, action, day_t, raw, smem);
 }
 
+// =================================================================================================
+// Tensor-core path (tcgen05 + TMEM).  Pre-split weight blob, per sub-model j at tc_offsets[j] (floats):
+// H1/16 chunks of  [ W1 chunk [16 inputs][16 units] | b1 chunk [16] | W2 chunk hi | W2 chunk lo ],
+// the W2 parts in the K-major no-swizzle UMMA layout [4 K-groups][H2][4]: element (n, k) = W2[k][n].
+// =================================================================================================
+constexpr int kTcM = 128;      // envs per CTA = UMMA M
+constexpr int kTcKC = 16;      // hidden-1 units per chunk (two K=8 instructions)
+__host__ __device__ constexpr int tc_chunk_floats(const int H2) { return kDPad * kTcKC + kTcKC + 2 * kTcKC * H2; }
+
+__global__ void cogen_tc_pack_kernel(const sg_cogen_model m, float* __restrict__ out) {
+    const int j = blockIdx.x;
+    const int d = m.meta[j * 6 + 0], H1 = m.meta[j * 6 + 1], H2 = m.meta[j * 6 + 2];
+    const float* W1 = m.blob + m.offsets[j * 5 + 0];
+    const float* b1 = m.blob + m.offsets[j * 5 + 1];
+    const float* W2 = m.blob + m.offsets[j * 5 + 2];
+    float* dst = out + m.tc_offsets[j];
+    const int chf = tc_chunk_floats(H2), nch = H1 / kTcKC;
+    for (long long idx = threadIdx.x; idx < (long long)nch * chf; idx += blockDim.x) {
+        const int c = (int)(idx / chf), r = (int)(idx % chf);
+        float v;
+        if (r < kDPad * kTcKC) {                                  // W1 chunk [dd][kk]
+            const int dd = r / kTcKC, kk = r % kTcKC;
+            v = dd < d ? W1[dd * H1 + c * kTcKC + kk] : 0.f;
+        } else if (r < kDPad * kTcKC + kTcKC) {                   // b1 chunk
+            v = b1[c * kTcKC + (r - kDPad * kTcKC)];
+        } else {                                                  // W2 chunk, hi then lo
+            int q = r - (kDPad * kTcKC + kTcKC);
+            const bool lo_part = q >= kTcKC * H2;
+            if (lo_part) q -= kTcKC * H2;
+            const int kg = q / (H2 * 4), nn = (q / 4) % H2, ki = q & 3;
+            float hi, lo;
+            tc::split_tf32(W2[(long long)(c * kTcKC + kg * 4 + ki) * H2 + nn], hi, lo);
+            v = lo_part ? lo : hi;
+        }
+        dst[idx] = v;
+    }
+}
+
+struct TcSync {
+    uint64_t full[2];      // stage s: the chunk's W1 | b1 | W2 bulk copy has landed
+    uint64_t freed[2];     // stage s: the MMAs that read it have completed
+    uint64_t done;         // all MMAs of the tile have completed
+    uint32_t tmem;         // TMEM base address of the accumulator
+};
+
+template <int H2>
+__device__ __forceinline__ void mlp_tile_tc(const sg_cogen_model& m, const int j, const long long b0, const int nvalid,
+                                            const float* X_in, const float* action, const int32_t* day_t,
+                                            float* __restrict__ raw, unsigned char* smem, TcSync& sy) {
+    constexpr int CHF = tc_chunk_floats(H2);                    // floats of one chunk in the blob
+    constexpr int STAGE_F = CHF + 2 * kTcM * kTcKC;             // + A operand hi | lo
+    constexpr uint32_t LBO_A = kTcM * 16, LBO_B = H2 * 16, SBO = 128;
+    float* stage[2] = {reinterpret_cast<float*>(smem), reinterpret_cast<float*>(smem) + STAGE_F};
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int d = m.meta[j * 6 + 0], H1 = m.meta[j * 6 + 1], act = m.meta[j * 6 + 3];
+    const int nch = H1 / kTcKC;
+    const float* blob = m.tc_blob + m.tc_offsets[j];
+    if (warp == 0) tc::tmem_alloc(&sy.tmem, H2);
+    if (tid == 0) {
+        tc::mbar_init(&sy.full[0], 1); tc::mbar_init(&sy.full[1], 1);
+        tc::mbar_init(&sy.freed[0], 1); tc::mbar_init(&sy.freed[1], 1);
+        tc::mbar_init(&sy.done, 1);
+        tc::mbar_fence_init();
+    }
+    // normalised inputs of this sub-model for my env (one env per thread)
+    float xr[kDPad];
+#pragma unroll
+    for (int dd = 0; dd < kDPad; ++dd) xr[dd] = 0.f;
+    if (tid < nvalid) {
+        float x[18];
+        build_x(m, X_in, action, day_t, b0 + tid, x);
+        for (int dd = 0; dd < d; ++dd)
+            xr[dd] = (ext_feature(x, m.feats[j * kDPad + dd]) - m.mu[j * kDPad + dd]) * m.sinv[j * kDPad + dd];
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem_d = sy.tmem;
+    const uint32_t idesc = tc::make_idesc_tf32(kTcM, H2);
+    auto issue_load = [&](const int c, const int s) {           // (thread 0) chunk c -> stage s, one bulk copy
+        const uint32_t bytes = CHF * 4, mb = tc::smem_u32(&sy.full[s]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         tc::smem_u32(stage[s])), "l"(blob + (long long)c * CHF), "r"(bytes), "r"(mb) : "memory");
+    };
+    if (tid == 0) issue_load(0, 0);
+    for (int c = 0; c < nch; ++c) {
+        const int s = c & 1;
+        if (c + 1 < nch && tid == 0) {                          // prefetch the next chunk into the other stage
+            if (c >= 1) tc::mbar_wait(&sy.freed[s ^ 1], ((c - 1) >> 1) & 1);
+            issue_load(c + 1, s ^ 1);
+        }
+        tc::mbar_wait(&sy.full[s], (c >> 1) & 1);               // W1 | b1 | W2 of chunk c are in stage s
+        if (c >= 2) tc::mbar_wait(&sy.freed[s], ((c - 2) >> 1) & 1);   // the A operand of stage s is free again
+        const float* w1s = stage[s];                            // [16][16]
+        const float* b1s = stage[s] + kDPad * kTcKC;
+        float h[kTcKC];
+#pragma unroll
+        for (int u = 0; u < kTcKC; ++u) h[u] = b1s[u];
+#pragma unroll
+        for (int dd = 0; dd < kDPad; ++dd) {
+#pragma unroll
+            for (int q = 0; q < kTcKC / 4; ++q) {
+                const float4 w = *reinterpret_cast<const float4*>(w1s + dd * kTcKC + q * 4);
+                h[q * 4 + 0] = fmaf(xr[dd], w.x, h[q * 4 + 0]);
+                h[q * 4 + 1] = fmaf(xr[dd], w.y, h[q * 4 + 1]);
+                h[q * 4 + 2] = fmaf(xr[dd], w.z, h[q * 4 + 2]);
+                h[q * 4 + 3] = fmaf(xr[dd], w.w, h[q * 4 + 3]);
+            }
+        }
+        float4* a_hi = reinterpret_cast<float4*>(stage[s] + CHF);
+        float4* a_lo = a_hi + kTcM * (kTcKC / 4);
+#pragma unroll
+        for (int kg = 0; kg < kTcKC / 4; ++kg) {
+            float hi[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) tc::split_tf32(act_fn(h[kg * 4 + i], act), hi[i], lo[i]);
+            a_hi[kg * kTcM + tid] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            a_lo[kg * kTcM + tid] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        tc::fence_async_smem();                                 // A operand -> visible to the tensor core
+        tc::fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+            const uint32_t ah = tc::smem_u32(stage[s] + CHF), al = ah + kTcM * kTcKC * 4;
+            const uint32_t bh = tc::smem_u32(stage[s] + kDPad * kTcKC + kTcKC), bl = bh + kTcKC * H2 * 4;
+#pragma unroll
+            for (int kk = 0; kk < kTcKC / 8; ++kk) {
+                const uint64_t dah = tc::make_smem_desc(ah + kk * 2 * LBO_A, LBO_A, SBO);
+                const uint64_t dal = tc::make_smem_desc(al + kk * 2 * LBO_A, LBO_A, SBO);
+                const uint64_t dbh = tc::make_smem_desc(bh + kk * 2 * LBO_B, LBO_B, SBO);
+                const uint64_t dbl = tc::make_smem_desc(bl + kk * 2 * LBO_B, LBO_B, SBO);
+                tc::mma_tf32(tmem_d, dal, dbh, idesc, (c | kk) != 0);   // small terms first
+                tc::mma_tf32(tmem_d, dah, dbl, idesc, 1u);
+                tc::mma_tf32(tmem_d, dah, dbh, idesc, 1u);
+            }
+            tc::mma_commit(&sy.freed[s]);
+            if (c == nch - 1) tc::mma_commit(&sy.done);
+        }
+    }
+    tc::mbar_wait(&sy.done, 0);
+    tc::fence_after_sync();
+    // epilogue: my env's accumulator row; h2 = act(acc + b2); y = h2 . W3 + b3
+    const float* b2 = m.blob + m.offsets[j * 5 + 3];
+    const float* W3 = m.blob + m.offsets[j * 5 + 4];
+    float y = 0.f;
+    for (int c0 = 0; c0 < H2; c0 += 16) {
+        float v[16];
+        tc::tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + c0, v);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(b2 + c0) + q);
+            const float4 ww = __ldg(reinterpret_cast<const float4*>(W3 + c0) + q);
+            y = fmaf(act_fn(v[q * 4 + 0] + bb.x, act), ww.x, y);
+            y = fmaf(act_fn(v[q * 4 + 1] + bb.y, act), ww.y, y);
+            y = fmaf(act_fn(v[q * 4 + 2] + bb.z, act), ww.z, y);
+            y = fmaf(act_fn(v[q * 4 + 3] + bb.w, act), ww.w, y);
+        }
+    }
+    if (tid < nvalid) raw[(b0 + tid) * kNSub + j] = y + m.b3[j];
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_d, H2);
+}
+
+__global__ void __launch_bounds__(kTcM, 2)
+cogen_mlp_tc_kernel(const sg_cogen_model m, const long long B, const float* __restrict__ X_in,
+                    const float* __restrict__ action, const int32_t* __restrict__ day_t, float* __restrict__ raw) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ TcSync sy;
+    const int j = kNSub - 1 - blockIdx.y;        // big sub-models (packed last) are scheduled first
+    const long long b0 = (long long)blockIdx.x * kTcM;
+    const int nvalid = (int)min((long long)kTcM, B - b0);
+    if (m.meta[j * 6 + 2] == 256) mlp_tile_tc<256>(m, j, b0, nvalid, X_in, action, day_t, raw, smem, sy);
+    else mlp_tile_tc<128>(m, j, b0, nvalid, X_in, action, day_t, raw, smem, sy);
+}
+
 // Y[29] from the 23 raw sub-model outputs (gates + derived sums; Appendix B)
 __device__ __forceinline__ void assemble_y(const sg_cogen_model& m, const float* x, const float* raw, float* Y) {
     const float gGT[3] = {gate_fn(x[5]), gate_fn(x[8]), gate_fn(x[11])};
@@ -333,6 +522,17 @@ int check_cogen(const sg_cogen_model* m) {
 
 int launch_mlp(const sg_cogen_model* m, long long B, const float* X, const float* action, const int32_t* day_t,
                float* raw, cudaStream_t st) {
+    if (m->tc_blob != nullptr && m->tc_offsets != nullptr) {     // tensor-core path
+        const size_t smem_tc = sizeof(float) * 2 * (tc_chunk_floats(256) + 2 * kTcM * kTcKC);
+        static bool configured_tc = false;
+        if (!configured_tc) {
+            SG_CUDA(cudaFuncSetAttribute(cogen_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
+            configured_tc = true;
+        }
+        dim3 grid((unsigned)((B + kTcM - 1) / kTcM), kNSub);
+        cogen_mlp_tc_kernel<<<grid, kTcM, smem_tc, st>>>(*m, B, X, action, day_t, raw);
+        return launch_status("cogen_mlp_tc_kernel");
+    }
     const size_t smem = sizeof(float) * (kTM * kDPad + kKC * kTM + kDPad * kKC + 2 * kKC * 256);
     static bool configured = false;   // attribute is per-function and idempotent; races are benign
     if (!configured) {
@@ -357,6 +557,14 @@ int sg_cogen_plant(const sg_cogen_model* m, int64_t num_envs, const float* X, fl
     if (int rc = sg::launch_mlp(m, num_envs, X, nullptr, nullptr, scratch, st)) return rc;
     sg::cogen_plant_finish_kernel<<<(unsigned)((num_envs + 127) / 128), 128, 0, st>>>(*m, num_envs, X, scratch, Y);
     return sg::launch_status("cogen_plant_finish_kernel");
+}
+
+int sg_cogen_prepare_tc(const sg_cogen_model* m, float* tc_blob, void* stream) {
+    if (int rc = sg::check_cogen(m)) return rc;
+    SG_CHECK_ARG(tc_blob != nullptr && m->tc_offsets != nullptr, "cogen_prepare_tc: NULL argument");
+    SG_CHECK_ARG((reinterpret_cast<uintptr_t>(tc_blob) & 15u) == 0, "cogen_prepare_tc: tc_blob must be 16-byte aligned");
+    sg::cogen_tc_pack_kernel<<<sg::kNSub, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*m, tc_blob);
+    return sg::launch_status("cogen_tc_pack_kernel");
 }
 
 int sg_cogen_reset(const sg_cogen_model* m, int64_t num_envs, const int32_t* day_in, const float* init_action,

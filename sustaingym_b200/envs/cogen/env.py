@@ -50,6 +50,7 @@ class PlantWeights:
         self.mu = t(pad(z["mu"], np.float32))
         self.sinv = t(pad(z["sinv"], np.float32))
         self.b3 = t(z["b3"].astype(np.float32))
+        self.tc_blob = self.tc_offsets = None        # filled on first use (sg_cogen_prepare_tc)
 
 
 def make_spaces(weights: PlantWeights, forecast_horizon: int):
@@ -100,7 +101,8 @@ class BatchedCogenEnv:
     def __init__(self, num_envs: int = 1, ambients: np.ndarray | None = None, renewables_magnitude: float = 0.,
                  ramp_penalty: float = 2., supply_imbalance_penalty: float = 1000,
                  constraint_violation_penalty: float = 1000, forecast_horizon: int = 3,
-                 forecast_noise_std: float = 0.0, device=None, collect_stats: bool = False, keep_outputs: bool = False):
+                 forecast_noise_std: float = 0.0, device=None, collect_stats: bool = False, keep_outputs: bool = False,
+                 tensor_cores: bool = True):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedCogenEnv needs a CUDA device (no CPU fallback)")
@@ -123,7 +125,21 @@ class BatchedCogenEnv:
         self._model = _lib.CogenModel(
             23, forecast_horizon, self.n_days, 0, float(ramp_penalty), float(supply_imbalance_penalty),
             float(constraint_violation_penalty), w.blob.data_ptr(), w.offsets.data_ptr(), w.meta.data_ptr(),
-            w.feats.data_ptr(), w.mu.data_ptr(), w.sinv.data_ptr(), w.b3.data_ptr(), self._amb.data_ptr())
+            w.feats.data_ptr(), w.mu.data_ptr(), w.sinv.data_ptr(), w.b3.data_ptr(), self._amb.data_ptr(), None, None)
+        if tensor_cores:
+            # layer-2 weights pre-split into tf32 (hi, lo) pairs in the tcgen05 operand layout (3xTF32 path)
+            if w.tc_blob is None:
+                meta = w.meta.cpu().numpy()
+                sizes = (meta[:, 1] // 16) * (272 + 32 * meta[:, 2])
+                offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+                w.tc_offsets = torch.from_numpy(offs[:-1].copy()).to(dev)
+                w.tc_blob = torch.zeros(int(offs[-1]), dtype=torch.float32, device=dev)
+                self._model.tc_offsets = w.tc_offsets.data_ptr()
+                with torch.cuda.device(dev):
+                    _lib.check(self.lib.sg_cogen_prepare_tc(C.byref(self._model), w.tc_blob.data_ptr(),
+                                                            torch.cuda.current_stream(dev).cuda_stream), "sg_cogen_prepare_tc")
+            self._model.tc_offsets = w.tc_offsets.data_ptr()
+            self._model.tc_blob = w.tc_blob.data_ptr()
         z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)  # noqa: E731
         self.prev_action = z(B, 15, dtype=torch.float32)
         self.day_t = z(B, 2, dtype=torch.int32)

@@ -18,10 +18,12 @@ def out_scale():
     return np.where(np.isfinite(span) & (span > 0), span, 100.0)
 
 
-def test_plant_operator_matches_onnx_golden(native_lib):
+@pytest.mark.parametrize("tensor_cores", [True, False])
+def test_plant_operator_matches_onnx_golden(native_lib, tensor_cores):
+    """tensor_cores=True: tcgen05 3xTF32 kernel (default); False: the fp32 FFMA kernel."""
     from sustaingym_b200.envs.cogen.env import BatchedCogenEnv
     g = np.load(os.path.join(GOLDEN, "cogen_model_io.npz"))
-    env = BatchedCogenEnv(1)
+    env = BatchedCogenEnv(1, tensor_cores=tensor_cores)
     Y = env.plant(torch.from_numpy(g["X"]).cuda()).cpu().numpy()
     scale = np.maximum(np.abs(g["Y32"]), out_scale()[None])
     err = np.abs(Y - g["Y32"]) / scale
@@ -56,10 +58,13 @@ def test_step_matches_oracle(native_lib, B, k):
         o_ob, o_r, o_term, _, o_info = orc.step(a, noise)
         Y = env.Y.cpu().numpy()
         assert (np.abs(Y - o_info["Y"]) / np.maximum(np.abs(o_info["Y"]), scale)).max() < 1e-5
-        # the reward multiplies hinges max(0, Y_j - x) by 1000: a plant output that is right to
-        # 1e-5*range_j (~3e-3) moves the reward by up to ~3 units, whatever the reward's own size
-        np.testing.assert_allclose(r.cpu().numpy(), o_r, rtol=1e-5, atol=1.0)
-        np.testing.assert_allclose(info["agent_rewards"].cpu().numpy(), o_info["agent_rewards"], rtol=1e-5, atol=1.0)
+        # the reward is Lipschitz in the plant outputs: fuel terms enter with weight 1, the constraint hinges
+        # max(0, Y_j - x) and the non-delivery terms with weight 1000 (the two penalties).  So a plant output
+        # that is right to 1e-5 * range_j moves the reward by up to 1000 * |dY|_1 whatever the reward's size:
+        # the bound below is rigorous given the measured output differences.
+        bound = 1e-5 * np.abs(o_r) + 1001.0 * np.abs(Y.astype(np.float64) - o_info["Y"]).sum(axis=1) + 1e-3
+        assert (np.abs(r.cpu().numpy() - o_r) <= bound).all()
+        assert (np.abs(info["agent_rewards"].cpu().numpy() - o_info["agent_rewards"]) <= bound[:, None]).all()
         np.testing.assert_array_equal(ob.cpu().numpy(), flatten_obs(o_ob))          # obs: table look-ups, exact
         np.testing.assert_array_equal(term.cpu().numpy(), o_term)
     assert bool(term.all())
