@@ -8,8 +8,8 @@
 // — a dense contraction, the one compute-bound piece of the whole engine.  Two kernels:
 //
 // cogen_mlp_tc_kernel (default): layer 2 (>95% of the FLOPs) on the 5th-generation tensor cores.  One
-//   CTA = 128 envs x one sub-model; per chunk of 16 hidden-1 units the threads compute layer 1 in fp32
-//   (one env per thread), split the activations into tf32 (hi, lo) pairs and store them as the K-major
+//   CTA = 128 envs x one sub-model (256 threads, two per env); per chunk of 16 hidden-1 units the threads
+//   compute layer 1 in fp32, split the activations into tf32 (hi, lo) pairs and store them as the K-major
 //   A operand; the pre-split W2 chunk (hi, lo) together with the chunk's W1/b1 arrives by ONE bulk
 //   asynchronous copy (TMA) into a 2-stage ring; one thread issues 3 tcgen05.mma kind::tf32 per K=8
 //   (lo*hi, hi*lo, hi*hi: 3xTF32, because a single TF32/BF16 pass cannot meet the 1e-5 tolerance,
@@ -248,7 +248,9 @@ __device__ __forceinline__ void mlp_tile_tc(const sg_cogen_model& m, const int j
     constexpr int STAGE_F = CHF + 2 * kTcM * kTcKC;             // + A operand hi | lo
     constexpr uint32_t LBO_A = kTcM * 16, LBO_B = H2 * 16, SBO = 128;
     float* stage[2] = {reinterpret_cast<float*>(smem), reinterpret_cast<float*>(smem) + STAGE_F};
-    const int tid = threadIdx.x, warp = tid >> 5;
+    // two threads per env row: thread (row, half) computes hidden units [8 half, 8 half + 8) of every chunk
+    // and, in the epilogue, columns [half H2/2, (half+1) H2/2) of the row
+    const int tid = threadIdx.x, warp = tid >> 5, row = tid & (kTcM - 1), half = tid >> 7;
     const int d = m.meta[j * 6 + 0], H1 = m.meta[j * 6 + 1], act = m.meta[j * 6 + 3];
     const int nch = H1 / kTcKC;
     const float* blob = m.tc_blob + m.tc_offsets[j];
@@ -263,9 +265,9 @@ __device__ __forceinline__ void mlp_tile_tc(const sg_cogen_model& m, const int j
     float xr[kDPad];
 #pragma unroll
     for (int dd = 0; dd < kDPad; ++dd) xr[dd] = 0.f;
-    if (tid < nvalid) {
+    if (row < nvalid) {
         float x[18];
-        build_x(m, X_in, action, day_t, b0 + tid, x);
+        build_x(m, X_in, action, day_t, b0 + row, x);
         for (int dd = 0; dd < d; ++dd)
             xr[dd] = (ext_feature(x, m.feats[j * kDPad + dd]) - m.mu[j * kDPad + dd]) * m.sinv[j * kDPad + dd];
     }
@@ -291,14 +293,15 @@ __device__ __forceinline__ void mlp_tile_tc(const sg_cogen_model& m, const int j
         if (c >= 2) tc::mbar_wait(&sy.freed[s], ((c - 2) >> 1) & 1);   // the A operand of stage s is free again
         const float* w1s = stage[s];                            // [16][16]
         const float* b1s = stage[s] + kDPad * kTcKC;
-        float h[kTcKC];
+        constexpr int UH = kTcKC / 2;                           // units per thread
+        float h[UH];
 #pragma unroll
-        for (int u = 0; u < kTcKC; ++u) h[u] = b1s[u];
+        for (int u = 0; u < UH; ++u) h[u] = b1s[half * UH + u];
 #pragma unroll
         for (int dd = 0; dd < kDPad; ++dd) {
 #pragma unroll
-            for (int q = 0; q < kTcKC / 4; ++q) {
-                const float4 w = *reinterpret_cast<const float4*>(w1s + dd * kTcKC + q * 4);
+            for (int q = 0; q < UH / 4; ++q) {
+                const float4 w = *reinterpret_cast<const float4*>(w1s + dd * kTcKC + half * UH + q * 4);
                 h[q * 4 + 0] = fmaf(xr[dd], w.x, h[q * 4 + 0]);
                 h[q * 4 + 1] = fmaf(xr[dd], w.y, h[q * 4 + 1]);
                 h[q * 4 + 2] = fmaf(xr[dd], w.z, h[q * 4 + 2]);
@@ -308,12 +311,13 @@ __device__ __forceinline__ void mlp_tile_tc(const sg_cogen_model& m, const int j
         float4* a_hi = reinterpret_cast<float4*>(stage[s] + CHF);
         float4* a_lo = a_hi + kTcM * (kTcKC / 4);
 #pragma unroll
-        for (int kg = 0; kg < kTcKC / 4; ++kg) {
+        for (int q = 0; q < UH / 4; ++q) {
+            const int kg = half * (UH / 4) + q;
             float hi[4], lo[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) tc::split_tf32(act_fn(h[kg * 4 + i], act), hi[i], lo[i]);
-            a_hi[kg * kTcM + tid] = make_float4(hi[0], hi[1], hi[2], hi[3]);
-            a_lo[kg * kTcM + tid] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            for (int i = 0; i < 4; ++i) tc::split_tf32(act_fn(h[q * 4 + i], act), hi[i], lo[i]);
+            a_hi[kg * kTcM + row] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            a_lo[kg * kTcM + row] = make_float4(lo[0], lo[1], lo[2], lo[3]);
         }
         tc::fence_async_smem();                                 // A operand -> visible to the tensor core
         tc::fence_before_sync();
@@ -342,9 +346,9 @@ __device__ __forceinline__ void mlp_tile_tc(const sg_cogen_model& m, const int j
     const float* b2 = m.blob + m.offsets[j * 5 + 3];
     const float* W3 = m.blob + m.offsets[j * 5 + 4];
     float y = 0.f;
-    for (int c0 = 0; c0 < H2; c0 += 16) {
+    for (int c0 = half * (H2 / 2); c0 < (half + 1) * (H2 / 2); c0 += 16) {
         float v[16];
-        tc::tmem_ld16(tmem_d + ((uint32_t)(warp * 32) << 16) + c0, v);
+        tc::tmem_ld16(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + c0, v);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             const float4 bb = __ldg(reinterpret_cast<const float4*>(b2 + c0) + q);
@@ -355,13 +359,15 @@ __device__ __forceinline__ void mlp_tile_tc(const sg_cogen_model& m, const int j
             y = fmaf(act_fn(v[q * 4 + 3] + bb.w, act), ww.w, y);
         }
     }
-    if (tid < nvalid) raw[(b0 + tid) * kNSub + j] = y + m.b3[j];
+    float* ypart = stage[0];                                    // (all MMAs are done: the stages are free)
+    if (half == 1) ypart[row] = y;
     tc::fence_before_sync();
     __syncthreads();
+    if (half == 0 && row < nvalid) raw[(b0 + row) * kNSub + j] = (y + ypart[row]) + m.b3[j];
     if (warp == 0) tc::tmem_dealloc(tmem_d, H2);
 }
 
-__global__ void __launch_bounds__(kTcM, 2)
+__global__ void __launch_bounds__(2 * kTcM, 2)
 cogen_mlp_tc_kernel(const sg_cogen_model m, const long long B, const float* __restrict__ X_in,
                     const float* __restrict__ action, const int32_t* __restrict__ day_t, float* __restrict__ raw) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -530,7 +536,7 @@ int launch_mlp(const sg_cogen_model* m, long long B, const float* X, const float
             configured_tc = true;
         }
         dim3 grid((unsigned)((B + kTcM - 1) / kTcM), kNSub);
-        cogen_mlp_tc_kernel<<<grid, kTcM, smem_tc, st>>>(*m, B, X, action, day_t, raw);
+        cogen_mlp_tc_kernel<<<grid, 2 * kTcM, smem_tc, st>>>(*m, B, X, action, day_t, raw);
         return launch_status("cogen_mlp_tc_kernel");
     }
     const size_t smem = sizeof(float) * (kTM * kDPad + kKC * kTM + kDPad * kKC + 2 * kKC * 256);
