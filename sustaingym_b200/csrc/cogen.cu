@@ -51,6 +51,15 @@ __device__ __forceinline__ float act_fn(float v, int act) {
     // act 0: sigmoid evaluated as the reference graph does, 1/(1+exp(-v)); act 1: relu
     return act == 0 ? __fdividef(1.f, 1.f + expf(-v)) : fmaxf(v, 0.f);
 }
+// same with the special-function unit: ex2.approx of a pre-scaled argument + rcp.approx (4 instructions);
+// absolute error of the sigmoid <= ~4e-7, below the 3xTF32 operand representation error of the tc kernel
+__device__ __forceinline__ float act_fn_fast(float v, int act) {
+#ifdef SG_COGEN_EXACT_ACT
+    return act_fn(v, act);
+#else
+    return act == 0 ? __fdividef(1.f, 1.f + __expf(-v)) : fmaxf(v, 0.f);
+#endif
+}
 __device__ __forceinline__ float gate_fn(float v) { return v != 0.f ? 1.f : 0.f; }     // |sign(v)|
 
 // extended feature vector E[25] from the 18 model inputs (gen_cogen_pack.py docstring)
@@ -315,7 +324,7 @@ __device__ __forceinline__ void mlp_tile_tc(const sg_cogen_model& m, const int j
             const int kg = half * (UH / 4) + q;
             float hi[4], lo[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) tc::split_tf32(act_fn(h[q * 4 + i], act), hi[i], lo[i]);
+            for (int i = 0; i < 4; ++i) tc::split_tf32(act_fn_fast(h[q * 4 + i], act), hi[i], lo[i]);
             a_hi[kg * kTcM + row] = make_float4(hi[0], hi[1], hi[2], hi[3]);
             a_lo[kg * kTcM + row] = make_float4(lo[0], lo[1], lo[2], lo[3]);
         }
