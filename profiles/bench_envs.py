@@ -60,7 +60,8 @@ def bench_building():
     algo = 105 * B * S
     # single-step launches for comparison (launch-latency bound)
     env, acts = sets[0]
-    ms1 = timed(lambda: env.step(acts[0]), 200, 20)
+    g1 = env.capture_graph(acts[0])
+    ms1 = timed(g1.replay, 400, 20)
     # CPU oracle
     p = BuildingParams(n=n, A_d=g["A_d"], BD_d=g["BD_d"], target=g["target"], ac_map=g["ac_map"], out_temp=params["out_temp"],
                        ground_temp=params["ground_temp"], ghi=params["ghi"], metabolism=params["metabolism"],
@@ -140,14 +141,15 @@ def bench_market():
     for i in range(8):
         env = BatchedElectricityMarketEnv(B, load, moer, cost, cap)
         env.reset(seed=i)
-        envs.append((env, torch.rand(B, 2, device="cuda") * 120))
+        a = torch.rand(B, 2, device="cuda") * 120
+        envs.append((env, a, env.capture_graph(a)))
     it = [0]
 
     def step():
-        env, a = envs[it[0] % 8]; it[0] += 1
-        env.step(a)
-        if it[0] % (8 * 287) == 0:
-            for e, _ in envs:
+        env, a, g = envs[it[0] % 8]; it[0] += 1
+        g.replay()
+        if it[0] % (8 * 280) == 0:
+            for e, _, _ in envs:
                 e.day_t[:, 1] = 0
     ms = timed(step, 2000, 100)
     algo = (8 + 4 * 8 * 2 + 8 + 8 + 40 + 8 + 1 + 24) * B      # action, state r/w, day_t, prev_a, obs, reward, done, info
@@ -159,7 +161,7 @@ def bench_market():
         orc.step(a)
     cpu = 16384 * 50 / (time.perf_counter() - t0)
     return {"env": "ElectricityMarketEnv (spec-defined)", "metric": "env_steps_per_sec", "value": B / (ms * 1e-3), "unit": "env-steps/s",
-            "config": {"workload": "ElectricityMarketEnv spec v1, 33 generators, 1 battery, k=1, 65536 envs, one step per launch",
+            "config": {"workload": "ElectricityMarketEnv spec v1, 33 generators, 1 battery, k=1, 65536 envs, one step per CUDA-graph replay",
                        "l2_policy": "8 env sets round-robin"},
             "ms_per_step": ms,
             "roofline": {"bound": "hbm", "achieved": algo / (ms * 1e-3) / 1e9, "peak": HBM, "unit": "GB/s",

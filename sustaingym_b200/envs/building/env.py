@@ -187,6 +187,11 @@ class BatchedBuildingEnv:
         self.kernel_launches += 1
         return obs, rew, done
 
+    def capture_graph(self, actions):
+        """One ``step(actions)`` (CUDA tensor, read in place) as a CUDA graph; see ``envs/_graph.py``."""
+        from .._graph import capture_step_graph
+        return capture_step_graph(self, actions)
+
     def close(self) -> None:
         pass
 

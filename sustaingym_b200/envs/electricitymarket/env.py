@@ -121,6 +121,11 @@ class BatchedElectricityMarketEnv:
                 {k_: v.cpu().numpy() for k_, v in info.items()}
         return self.obs, self.reward, self.done.bool(), torch.zeros_like(self.done, dtype=torch.bool), info
 
+    def capture_graph(self, actions):
+        """One ``step(actions)`` (CUDA tensor, read in place) as a CUDA graph; see ``envs/_graph.py``."""
+        from .._graph import capture_step_graph
+        return capture_step_graph(self, actions)
+
     def close(self) -> None:
         pass
 
