@@ -8,10 +8,11 @@
 // — a dense contraction, the one compute-bound piece of the whole engine.  Two kernels:
 //
 // cogen_mlp_tc_kernel (default): layer 2 (>95% of the FLOPs) on the 5th-generation tensor cores.  One
-//   CTA = 128 envs x one sub-model (256 threads, two per env); per chunk of 16 hidden-1 units the threads
-//   compute layer 1 in fp32, split the activations into tf32 (hi, lo) pairs and store them as the K-major
-//   A operand; the pre-split W2 chunk (hi, lo) together with the chunk's W1/b1 arrives by ONE bulk
-//   asynchronous copy (TMA) into a 2-stage ring; one thread issues 3 tcgen05.mma kind::tf32 per K=8
+//   CTA = 128 envs x one sub-model, warp-specialised: 8 compute warps (two threads per env) + 1 producer /
+//   MMA-issuer warp; per chunk of 16 hidden-1 units the compute threads evaluate layer 1 in fp32, split the
+//   activations into tf32 (hi, lo) pairs and store them as the K-major A operand; the pre-split W2 chunk
+//   (hi, lo) and the chunk's W1/b1 arrive by bulk asynchronous copies (TMA) into mbarrier-guarded rings
+//   (W2: 2 stages tied to MMA completion, W1/b1: 4 slots); the issuer thread issues 3 tcgen05.mma kind::tf32 per K=8
 //   (lo*hi, hi*lo, hi*hi: 3xTF32, because a single TF32/BF16 pass cannot meet the 1e-5 tolerance,
 //   SURVEY.md H4) accumulating a 128 x H2 fp32 tile in tensor memory; tcgen05.commit -> mbarrier frees
 //   the stage; the epilogue reads the accumulator rows with tcgen05.ld and fuses bias, activation and
@@ -57,7 +58,11 @@ __device__ __forceinline__ float act_fn_fast(float v, int act) {
 #ifdef SG_COGEN_EXACT_ACT
     return act_fn(v, act);
 #else
-    return act == 0 ? __fdividef(1.f, 1.f + __expf(-v)) : fmaxf(v, 0.f);
+    if (act != 0) return fmaxf(v, 0.f);
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(v * -1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));      // e = +inf -> 0
+    return r;
 #endif
 }
 __device__ __forceinline__ float gate_fn(float v) { return v != 0.f ? 1.f : 0.f; }     // |sign(v)|
@@ -242,141 +247,173 @@ __global__ void cogen_tc_pack_kernel(const sg_cogen_model m, float* __restrict__
     }
 }
 
+constexpr int kTcW1Ring = 4;   // W1 | b1 chunks in flight (their slots are not tied to MMA completion)
+constexpr int kTcThreads = 2 * kTcM + 32;   // 8 compute warps (two threads per env row) + 1 producer / MMA-issuer warp
+
 struct TcSync {
-    uint64_t full[2];      // stage s: the chunk's W1 | b1 | W2 bulk copy has landed
-    uint64_t freed[2];     // stage s: the MMAs that read it have completed
-    uint64_t done;         // all MMAs of the tile have completed
-    uint32_t tmem;         // TMEM base address of the accumulator
+    uint64_t w1full[kTcW1Ring];   // slot q: the chunk's W1 | b1 bulk copy has landed
+    uint64_t full[2];             // stage s: the chunk's W2 (hi | lo) bulk copy has landed
+    uint64_t a_ready[2];          // stage s: all compute threads have written their part of the A operand
+    uint64_t freed[2];            // stage s: the MMAs that read it have completed
+    uint64_t done;                // all MMAs of the tile have completed
+    uint32_t tmem;                // TMEM base address of the accumulator
 };
 
-template <int H2>
+// Warp-specialised tile: warps 0-7 compute layer 1 -> A operand (tf32 hi | lo) and the epilogue; lane 0 of
+// warp 8 streams the weights (TMA bulk copies: W1 | b1 chunks 3 ahead, W2 chunks into the 2-stage ring as
+// soon as the MMAs that read a stage have completed) and issues the tcgen05.mma instructions.  All hand-offs
+// are mbarriers; there is no CTA-wide barrier inside the chunk loop.
+template <int H2, int ACT>
 __device__ __forceinline__ void mlp_tile_tc(const sg_cogen_model& m, const int j, const long long b0, const int nvalid,
                                             const float* X_in, const float* action, const int32_t* day_t,
                                             float* __restrict__ raw, unsigned char* smem, TcSync& sy) {
-    constexpr int CHF = tc_chunk_floats(H2);                    // floats of one chunk in the blob
-    constexpr int STAGE_F = CHF + 2 * kTcM * kTcKC;             // + A operand hi | lo
+    constexpr int W1F = kDPad * kTcKC + kTcKC;                  // floats of W1 | b1 of one chunk
+    constexpr int W2F = 2 * kTcKC * H2;                         // floats of W2 hi | lo of one chunk
+    constexpr int CHF = tc_chunk_floats(H2);                    // = W1F + W2F, one chunk in the blob
+    constexpr int AF = 2 * kTcM * kTcKC;                        // floats of the A operand hi | lo
     constexpr uint32_t LBO_A = kTcM * 16, LBO_B = H2 * 16, SBO = 128;
-    float* stage[2] = {reinterpret_cast<float*>(smem), reinterpret_cast<float*>(smem) + STAGE_F};
-    // two threads per env row: thread (row, half) computes hidden units [8 half, 8 half + 8) of every chunk
-    // and, in the epilogue, columns [half H2/2, (half+1) H2/2) of the row
-    const int tid = threadIdx.x, warp = tid >> 5, row = tid & (kTcM - 1), half = tid >> 7;
-    const int d = m.meta[j * 6 + 0], H1 = m.meta[j * 6 + 1], act = m.meta[j * 6 + 3];
+    float* const w2base = reinterpret_cast<float*>(smem);       // [2][W2F]
+    float* const abase = w2base + 2 * W2F;                      // [2][AF]
+    float* const w1r = abase + 2 * AF;                          // [kTcW1Ring][W1F]
+    const int tid = threadIdx.x, warp = tid >> 5, row = tid & (kTcM - 1), half = (tid >> 7) & 1;
+    const bool producer = warp == 8;
+    const int d = m.meta[j * 6 + 0], H1 = m.meta[j * 6 + 1];
+    constexpr int act = ACT;
     const int nch = H1 / kTcKC;
     const float* blob = m.tc_blob + m.tc_offsets[j];
     if (warp == 0) tc::tmem_alloc(&sy.tmem, H2);
     if (tid == 0) {
-        tc::mbar_init(&sy.full[0], 1); tc::mbar_init(&sy.full[1], 1);
-        tc::mbar_init(&sy.freed[0], 1); tc::mbar_init(&sy.freed[1], 1);
+        for (int q = 0; q < kTcW1Ring; ++q) tc::mbar_init(&sy.w1full[q], 1);
+        for (int s2 = 0; s2 < 2; ++s2) {
+            tc::mbar_init(&sy.full[s2], 1); tc::mbar_init(&sy.a_ready[s2], 2 * kTcM); tc::mbar_init(&sy.freed[s2], 1);
+        }
         tc::mbar_init(&sy.done, 1);
         tc::mbar_fence_init();
     }
-    // normalised inputs of this sub-model for my env (one env per thread)
+    // normalised inputs of this sub-model for my env (two threads per env row)
     float xr[kDPad];
 #pragma unroll
     for (int dd = 0; dd < kDPad; ++dd) xr[dd] = 0.f;
-    if (row < nvalid) {
+    if (!producer && row < nvalid) {
         float x[18];
         build_x(m, X_in, action, day_t, b0 + row, x);
-        for (int dd = 0; dd < d; ++dd)
-            xr[dd] = (ext_feature(x, m.feats[j * kDPad + dd]) - m.mu[j * kDPad + dd]) * m.sinv[j * kDPad + dd];
+#pragma unroll
+        for (int dd = 0; dd < kDPad; ++dd)
+            if (dd < d) xr[dd] = (ext_feature(x, m.feats[j * kDPad + dd]) - m.mu[j * kDPad + dd]) * m.sinv[j * kDPad + dd];
     }
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_d = sy.tmem;
-    const uint32_t idesc = tc::make_idesc_tf32(kTcM, H2);
-    auto issue_load = [&](const int c, const int s) {           // (thread 0) chunk c -> stage s, one bulk copy
-        const uint32_t bytes = CHF * 4, mb = tc::smem_u32(&sy.full[s]);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                         tc::smem_u32(stage[s])), "l"(blob + (long long)c * CHF), "r"(bytes), "r"(mb) : "memory");
-    };
-    if (tid == 0) issue_load(0, 0);
-    for (int c = 0; c < nch; ++c) {
-        const int s = c & 1;
-        if (c + 1 < nch && tid == 0) {                          // prefetch the next chunk into the other stage
-            if (c >= 1) tc::mbar_wait(&sy.freed[s ^ 1], ((c - 1) >> 1) & 1);
-            issue_load(c + 1, s ^ 1);
-        }
-        tc::mbar_wait(&sy.full[s], (c >> 1) & 1);               // W1 | b1 | W2 of chunk c are in stage s
-        if (c >= 2) tc::mbar_wait(&sy.freed[s], ((c - 2) >> 1) & 1);   // the A operand of stage s is free again
-        const float* w1s = stage[s];                            // [16][16]
-        const float* b1s = stage[s] + kDPad * kTcKC;
-        constexpr int UH = kTcKC / 2;                           // units per thread
-        float h[UH];
+
+    if (producer) {
+        if (tid == 2 * kTcM) {
+            const uint32_t idesc = tc::make_idesc_tf32(kTcM, H2);
+            auto bulk = [&](float* dst, const float* src, const uint32_t bytes, uint64_t* mb) {
+                const uint32_t mba = tc::smem_u32(mb);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mba), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 tc::smem_u32(dst)), "l"(src), "r"(bytes), "r"(mba) : "memory");
+            };
+            auto load_w1 = [&](const int c) { bulk(w1r + (c % kTcW1Ring) * W1F, blob + (long long)c * CHF, W1F * 4, &sy.w1full[c % kTcW1Ring]); };
+            auto load_w2 = [&](const int c) { bulk(w2base + (c & 1) * W2F, blob + (long long)c * CHF + W1F, W2F * 4, &sy.full[c & 1]); };
+            for (int c = 0; c < kTcW1Ring - 1 && c < nch; ++c) load_w1(c);
+            load_w2(0);
+            if (nch > 1) load_w2(1);
+            for (int c = 0; c < nch; ++c) {
+                const int s = c & 1;
+                tc::mbar_wait(&sy.a_ready[s], (c >> 1) & 1);        // A(c) is written: compute threads are done with W1 slot c % ring
+                if (c + kTcW1Ring - 1 < nch) load_w1(c + kTcW1Ring - 1);   // -> slot (c - 1) % ring, released one iteration ago
+                tc::mbar_wait(&sy.full[s], (c >> 1) & 1);           // W2(c) landed
+                tc::fence_after_sync();
+                const uint32_t ah = tc::smem_u32(abase + s * AF), al = ah + kTcM * kTcKC * 4;
+                const uint32_t bh = tc::smem_u32(w2base + s * W2F), bl = bh + kTcKC * H2 * 4;
 #pragma unroll
-        for (int u = 0; u < UH; ++u) h[u] = b1s[half * UH + u];
-#pragma unroll
-        for (int dd = 0; dd < kDPad; ++dd) {
-#pragma unroll
-            for (int q = 0; q < UH / 4; ++q) {
-                const float4 w = *reinterpret_cast<const float4*>(w1s + dd * kTcKC + half * UH + q * 4);
-                h[q * 4 + 0] = fmaf(xr[dd], w.x, h[q * 4 + 0]);
-                h[q * 4 + 1] = fmaf(xr[dd], w.y, h[q * 4 + 1]);
-                h[q * 4 + 2] = fmaf(xr[dd], w.z, h[q * 4 + 2]);
-                h[q * 4 + 3] = fmaf(xr[dd], w.w, h[q * 4 + 3]);
+                for (int kk = 0; kk < kTcKC / 8; ++kk) {
+                    const uint64_t dah = tc::make_smem_desc(ah + kk * 2 * LBO_A, LBO_A, SBO);
+                    const uint64_t dal = tc::make_smem_desc(al + kk * 2 * LBO_A, LBO_A, SBO);
+                    const uint64_t dbh = tc::make_smem_desc(bh + kk * 2 * LBO_B, LBO_B, SBO);
+                    const uint64_t dbl = tc::make_smem_desc(bl + kk * 2 * LBO_B, LBO_B, SBO);
+                    tc::mma_tf32(tmem_d, dal, dbh, idesc, (c | kk) != 0);   // small terms first
+                    tc::mma_tf32(tmem_d, dah, dbl, idesc, 1u);
+                    tc::mma_tf32(tmem_d, dah, dbh, idesc, 1u);
+                }
+                tc::mma_commit(&sy.freed[s]);
+                if (c == nch - 1) tc::mma_commit(&sy.done);
+                if (c + 2 < nch) {                                  // refill W2 stage s once its MMAs have completed
+                    tc::mbar_wait(&sy.freed[s], (c >> 1) & 1);
+                    load_w2(c + 2);
+                }
             }
         }
-        float4* a_hi = reinterpret_cast<float4*>(stage[s] + CHF);
-        float4* a_lo = a_hi + kTcM * (kTcKC / 4);
+    } else {
+        for (int c = 0; c < nch; ++c) {
+            const int s = c & 1, q = c % kTcW1Ring;
+            tc::mbar_wait(&sy.w1full[q], (c / kTcW1Ring) & 1);      // W1 | b1 of chunk c
+            if (c >= 2) tc::mbar_wait(&sy.freed[s], ((c - 2) >> 1) & 1);   // the A operand of stage s is free again
+            const float* w1s = w1r + q * W1F;                       // [16][16]
+            const float* b1s = w1s + kDPad * kTcKC;
+            constexpr int UH = kTcKC / 2;                           // units per thread
+            float h[UH];
 #pragma unroll
-        for (int q = 0; q < UH / 4; ++q) {
-            const int kg = half * (UH / 4) + q;
-            float hi[4], lo[4];
+            for (int u = 0; u < UH; ++u) h[u] = b1s[half * UH + u];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) tc::split_tf32(act_fn_fast(h[q * 4 + i], act), hi[i], lo[i]);
-            a_hi[kg * kTcM + row] = make_float4(hi[0], hi[1], hi[2], hi[3]);
-            a_lo[kg * kTcM + row] = make_float4(lo[0], lo[1], lo[2], lo[3]);
-        }
-        tc::fence_async_smem();                                 // A operand -> visible to the tensor core
-        tc::fence_before_sync();
-        __syncthreads();
-        if (tid == 0) {
-            tc::fence_after_sync();
-            const uint32_t ah = tc::smem_u32(stage[s] + CHF), al = ah + kTcM * kTcKC * 4;
-            const uint32_t bh = tc::smem_u32(stage[s] + kDPad * kTcKC + kTcKC), bl = bh + kTcKC * H2 * 4;
+            for (int dd = 0; dd < kDPad; ++dd) {
+                if (dd >= 6 && dd >= d) break;                      // CTA-uniform: every sub-model has 6 <= d <= 14 inputs
 #pragma unroll
-            for (int kk = 0; kk < kTcKC / 8; ++kk) {
-                const uint64_t dah = tc::make_smem_desc(ah + kk * 2 * LBO_A, LBO_A, SBO);
-                const uint64_t dal = tc::make_smem_desc(al + kk * 2 * LBO_A, LBO_A, SBO);
-                const uint64_t dbh = tc::make_smem_desc(bh + kk * 2 * LBO_B, LBO_B, SBO);
-                const uint64_t dbl = tc::make_smem_desc(bl + kk * 2 * LBO_B, LBO_B, SBO);
-                tc::mma_tf32(tmem_d, dal, dbh, idesc, (c | kk) != 0);   // small terms first
-                tc::mma_tf32(tmem_d, dah, dbl, idesc, 1u);
-                tc::mma_tf32(tmem_d, dah, dbh, idesc, 1u);
+                for (int qq = 0; qq < UH / 4; ++qq) {
+                    const float4 w = *reinterpret_cast<const float4*>(w1s + dd * kTcKC + half * UH + qq * 4);
+                    h[qq * 4 + 0] = fmaf(xr[dd], w.x, h[qq * 4 + 0]);
+                    h[qq * 4 + 1] = fmaf(xr[dd], w.y, h[qq * 4 + 1]);
+                    h[qq * 4 + 2] = fmaf(xr[dd], w.z, h[qq * 4 + 2]);
+                    h[qq * 4 + 3] = fmaf(xr[dd], w.w, h[qq * 4 + 3]);
+                }
             }
-            tc::mma_commit(&sy.freed[s]);
-            if (c == nch - 1) tc::mma_commit(&sy.done);
+            float4* a_hi = reinterpret_cast<float4*>(abase + s * AF);
+            float4* a_lo = a_hi + kTcM * (kTcKC / 4);
+#pragma unroll
+            for (int qq = 0; qq < UH / 4; ++qq) {
+                const int kg = half * (UH / 4) + qq;
+                float hi[4], lo[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) tc::split_tf32(act_fn_fast(h[qq * 4 + i], act), hi[i], lo[i]);
+                a_hi[kg * kTcM + row] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                a_lo[kg * kTcM + row] = make_float4(lo[0], lo[1], lo[2], lo[3]);
+            }
+            tc::fence_async_smem();                                 // my part of the A operand -> visible to the tensor core
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&sy.a_ready[s])) : "memory");
         }
+        tc::mbar_wait(&sy.done, 0);
+        tc::fence_after_sync();
     }
-    tc::mbar_wait(&sy.done, 0);
-    tc::fence_after_sync();
-    // epilogue: my env's accumulator row; h2 = act(acc + b2); y = h2 . W3 + b3
-    const float* b2 = m.blob + m.offsets[j * 5 + 3];
-    const float* W3 = m.blob + m.offsets[j * 5 + 4];
+    // epilogue (compute warps): my env's accumulator row, my half of the columns; h2 = act(acc + b2); y = h2 . W3 + b3
     float y = 0.f;
-    for (int c0 = half * (H2 / 2); c0 < (half + 1) * (H2 / 2); c0 += 16) {
-        float v[16];
-        tc::tmem_ld16(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + c0, v);
+    if (!producer) {
+        const float* b2 = m.blob + m.offsets[j * 5 + 3];
+        const float* W3 = m.blob + m.offsets[j * 5 + 4];
+        for (int c0 = half * (H2 / 2); c0 < (half + 1) * (H2 / 2); c0 += 16) {
+            float v[16];
+            tc::tmem_ld16(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + c0, v);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(b2 + c0) + q);
-            const float4 ww = __ldg(reinterpret_cast<const float4*>(W3 + c0) + q);
-            y = fmaf(act_fn(v[q * 4 + 0] + bb.x, act), ww.x, y);
-            y = fmaf(act_fn(v[q * 4 + 1] + bb.y, act), ww.y, y);
-            y = fmaf(act_fn(v[q * 4 + 2] + bb.z, act), ww.z, y);
-            y = fmaf(act_fn(v[q * 4 + 3] + bb.w, act), ww.w, y);
+            for (int qq = 0; qq < 4; ++qq) {
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(b2 + c0) + qq);
+                const float4 ww = __ldg(reinterpret_cast<const float4*>(W3 + c0) + qq);
+                y = fmaf(act_fn_fast(v[qq * 4 + 0] + bb.x, act), ww.x, y);
+                y = fmaf(act_fn_fast(v[qq * 4 + 1] + bb.y, act), ww.y, y);
+                y = fmaf(act_fn_fast(v[qq * 4 + 2] + bb.z, act), ww.z, y);
+                y = fmaf(act_fn_fast(v[qq * 4 + 3] + bb.w, act), ww.w, y);
+            }
         }
     }
-    float* ypart = stage[0];                                    // (all MMAs are done: the stages are free)
-    if (half == 1) ypart[row] = y;
+    float* ypart = abase;                                          // (all MMAs are done: the stages are free)
+    if (!producer && half == 1) ypart[row] = y;
     tc::fence_before_sync();
     __syncthreads();
-    if (half == 0 && row < nvalid) raw[(b0 + row) * kNSub + j] = (y + ypart[row]) + m.b3[j];
+    if (!producer && half == 0 && row < nvalid) raw[(b0 + row) * kNSub + j] = (y + ypart[row]) + m.b3[j];
     if (warp == 0) tc::tmem_dealloc(tmem_d, H2);
 }
 
-__global__ void __launch_bounds__(2 * kTcM, 2)
+__global__ void __launch_bounds__(kTcThreads, 2)
 cogen_mlp_tc_kernel(const sg_cogen_model m, const long long B, const float* __restrict__ X_in,
                     const float* __restrict__ action, const int32_t* __restrict__ day_t, float* __restrict__ raw) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -384,8 +421,14 @@ cogen_mlp_tc_kernel(const sg_cogen_model m, const long long B, const float* __re
     const int j = kNSub - 1 - blockIdx.y;        // big sub-models (packed last) are scheduled first
     const long long b0 = (long long)blockIdx.x * kTcM;
     const int nvalid = (int)min((long long)kTcM, B - b0);
-    if (m.meta[j * 6 + 2] == 256) mlp_tile_tc<256>(m, j, b0, nvalid, X_in, action, day_t, raw, smem, sy);
-    else mlp_tile_tc<128>(m, j, b0, nvalid, X_in, action, day_t, raw, smem, sy);
+    const bool relu = m.meta[j * 6 + 3] != 0;
+    if (m.meta[j * 6 + 2] == 256) {
+        if (relu) mlp_tile_tc<256, 1>(m, j, b0, nvalid, X_in, action, day_t, raw, smem, sy);
+        else mlp_tile_tc<256, 0>(m, j, b0, nvalid, X_in, action, day_t, raw, smem, sy);
+    } else {
+        if (relu) mlp_tile_tc<128, 1>(m, j, b0, nvalid, X_in, action, day_t, raw, smem, sy);
+        else mlp_tile_tc<128, 0>(m, j, b0, nvalid, X_in, action, day_t, raw, smem, sy);
+    }
 }
 
 // Y[29] from the 23 raw sub-model outputs (gates + derived sums; Appendix B)
@@ -538,14 +581,14 @@ int check_cogen(const sg_cogen_model* m) {
 int launch_mlp(const sg_cogen_model* m, long long B, const float* X, const float* action, const int32_t* day_t,
                float* raw, cudaStream_t st) {
     if (m->tc_blob != nullptr && m->tc_offsets != nullptr) {     // tensor-core path
-        const size_t smem_tc = sizeof(float) * 2 * (tc_chunk_floats(256) + 2 * kTcM * kTcKC);
+        const size_t smem_tc = sizeof(float) * (2 * (2 * kTcKC * 256 + 2 * kTcM * kTcKC) + kTcW1Ring * (kDPad * kTcKC + kTcKC));
         static bool configured_tc = false;
         if (!configured_tc) {
             SG_CUDA(cudaFuncSetAttribute(cogen_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
             configured_tc = true;
         }
         dim3 grid((unsigned)((B + kTcM - 1) / kTcM), kNSub);
-        cogen_mlp_tc_kernel<<<grid, 2 * kTcM, smem_tc, st>>>(*m, B, X, action, day_t, raw);
+        cogen_mlp_tc_kernel<<<grid, kTcThreads, smem_tc, st>>>(*m, B, X, action, day_t, raw);
         return launch_status("cogen_mlp_tc_kernel");
     }
     const size_t smem = sizeof(float) * (kTM * kDPad + kKC * kTM + kDPad * kKC + 2 * kKC * 256);
