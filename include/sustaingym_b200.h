@@ -275,7 +275,12 @@ typedef struct sg_cogen_model {
  * weights: per 16-unit chunk W1 | b1 | W2 hi | W2 lo in the tcgen05 K-major operand layout. */
 int sg_cogen_prepare_tc(const sg_cogen_model* m, float* tc_blob, void* stream);
 
-/* The plant model alone: X [B,18] f32 -> Y [B,29] f32 (model.json order). scratch: [B,23] f32. */
+/* Device scratch of the plant model, in floats, 16-byte aligned: the 23 raw sub-model outputs per env,
+ * plus (tensor-core path) the normalised, zero-padded inputs of every sub-model [23,B,16]. */
+#define SG_COGEN_SCRATCH_FLOATS(B) ((int64_t)(B) * (23 + 23 * 16) + 4)
+
+/* The plant model alone: X [B,18] f32 -> Y [B,29] f32 (model.json order).
+ * scratch: SG_COGEN_SCRATCH_FLOATS(B) f32. */
 int sg_cogen_plant(const sg_cogen_model* m, int64_t num_envs, const float* X, float* Y, float* scratch,
                    void* stream);
 
@@ -290,7 +295,7 @@ int sg_cogen_reset(const sg_cogen_model* m, int64_t num_envs, const int32_t* day
  * reward [B] f64; agent_reward [B,4] f64 (GT1, GT2, GT3, ST); done [B]; Y_out [B,29] or NULL. */
 int sg_cogen_step(const sg_cogen_model* m, int64_t num_envs, const float* action, float* prev_action,
                   int32_t* day_t, const double* noise, float* obs, double* reward, double* agent_reward,
-                  uint8_t* done, float* Y_out, float* scratch /* [B,23] */, int32_t flags, double* stats,
+                  uint8_t* done, float* Y_out, float* scratch /* SG_COGEN_SCRATCH_FLOATS(B) */, int32_t flags, double* stats,
                   void* stream);
 
 /* Unit test of the tensor-core path of the plant model: D[128,N] = A[128,K] * Bm[N,K]^T through 3xTF32

@@ -16,6 +16,12 @@ SG_EV_MOER_COLS = 37
 SG_EV_MOER_ROWS = 289
 SG_EV_EPISODE_STEPS = 288
 SG_EV_TABLE_BYTES = 4096
+
+
+def cogen_scratch_floats(B: int) -> int:
+    """SG_COGEN_SCRATCH_FLOATS(B) of include/sustaingym_b200.h."""
+    return int(B) * (23 + 23 * 16) + 4
+
 SG_EV_MAX_STATIONS = 64
 SG_EV_MAX_CLASSES = 8
 SG_EV_MAX_CONSTRAINTS = 16

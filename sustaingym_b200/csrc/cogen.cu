@@ -247,8 +247,37 @@ __global__ void cogen_tc_pack_kernel(const sg_cogen_model m, float* __restrict__
     }
 }
 
+// Normalised, padded inputs of every sub-model, once per env: xn[j][b][16].  (Building them inside the
+// tensor-core CTAs cost ~15k cycles of dependent global loads per CTA -- 40% of a small sub-model's CTA.)
+__global__ void __launch_bounds__(128)
+cogen_tc_inputs_kernel(const sg_cogen_model m, const long long B, const float* __restrict__ X_in,
+                       const float* __restrict__ action, const int32_t* __restrict__ day_t, float* __restrict__ xn) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;     // thread = (env, sub-model)
+    const int j = blockIdx.y;
+    if (b >= B) return;
+    float x[18];
+    build_x(m, X_in, action, day_t, b, x);
+    const int d = m.meta[j * 6 + 0];
+    float4* dst = reinterpret_cast<float4*>(xn + ((long long)j * B + b) * kDPad);
+#pragma unroll
+    for (int q = 0; q < kDPad / 4; ++q) {
+        float v[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int dd = q * 4 + i;
+            v[i] = dd < d ? (ext_feature(x, m.feats[j * kDPad + dd]) - m.mu[j * kDPad + dd]) * m.sinv[j * kDPad + dd] : 0.f;
+        }
+        dst[q] = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
+
 constexpr int kTcW1Ring = 4;   // W1 | b1 chunks in flight (their slots are not tied to MMA completion)
-constexpr int kTcThreads = 2 * kTcM + 32;   // 8 compute warps (two threads per env row) + 1 producer / MMA-issuer warp
+#ifndef SG_COGEN_RT
+#define SG_COGEN_RT 2
+#endif
+constexpr int kTcRT = SG_COGEN_RT;            // compute threads per env row (each owns kTcKC / kTcRT hidden units of a chunk)
+constexpr int kTcCompute = kTcRT * kTcM;      // compute threads (kTcRT * 4 warps; 2 and 4 per row time the same: the loop is bound by the shared-memory pipe)
+constexpr int kTcThreads = kTcCompute + 32;   // + 1 producer / MMA-issuer warp
 
 struct TcSync {
     uint64_t w1full[kTcW1Ring];   // slot q: the chunk's W1 | b1 bulk copy has landed
@@ -259,13 +288,13 @@ struct TcSync {
     uint32_t tmem;                // TMEM base address of the accumulator
 };
 
-// Warp-specialised tile: warps 0-7 compute layer 1 -> A operand (tf32 hi | lo) and the epilogue; lane 0 of
-// warp 8 streams the weights (TMA bulk copies: W1 | b1 chunks 3 ahead, W2 chunks into the 2-stage ring as
+// Warp-specialised tile: the compute warps evaluate layer 1 -> A operand (tf32 hi | lo) and the epilogue; lane 0 of
+// the last warp streams the weights (TMA bulk copies: W1 | b1 chunks 3 ahead, W2 chunks into the 2-stage ring as
 // soon as the MMAs that read a stage have completed) and issues the tcgen05.mma instructions.  All hand-offs
 // are mbarriers; there is no CTA-wide barrier inside the chunk loop.
 template <int H2, int ACT>
 __device__ __forceinline__ void mlp_tile_tc(const sg_cogen_model& m, const int j, const long long b0, const int nvalid,
-                                            const float* X_in, const float* action, const int32_t* day_t,
+                                            const long long B, const float* __restrict__ xn,
                                             float* __restrict__ raw, unsigned char* smem, TcSync& sy) {
     constexpr int W1F = kDPad * kTcKC + kTcKC;                  // floats of W1 | b1 of one chunk
     constexpr int W2F = 2 * kTcKC * H2;                         // floats of W2 hi | lo of one chunk
@@ -275,56 +304,78 @@ __device__ __forceinline__ void mlp_tile_tc(const sg_cogen_model& m, const int j
     float* const w2base = reinterpret_cast<float*>(smem);       // [2][W2F]
     float* const abase = w2base + 2 * W2F;                      // [2][AF]
     float* const w1r = abase + 2 * AF;                          // [kTcW1Ring][W1F]
-    const int tid = threadIdx.x, warp = tid >> 5, row = tid & (kTcM - 1), half = (tid >> 7) & 1;
-    const bool producer = warp == 8;
+    const int tid = threadIdx.x, warp = tid >> 5, row = tid & (kTcM - 1), part = (tid >> 7) & (kTcRT - 1);
+    const bool producer = tid >= kTcCompute;
     const int d = m.meta[j * 6 + 0], H1 = m.meta[j * 6 + 1];
     constexpr int act = ACT;
     const int nch = H1 / kTcKC;
     const float* blob = m.tc_blob + m.tc_offsets[j];
+#ifdef SG_COGEN_TRACE
+    const long long tp0 = clock64();
+#endif
+    // Layer-1 mapping (independent of the epilogue's TMEM-lane mapping): a thread owns the two env rows
+    // ra, ra + 64 and 4 of the chunk's 16 hidden units, so one broadcast LDS.128 of W1 feeds 8 fmas.
+    static_assert(kTcCompute == 256 && kTcKC == 16, "layer-1 mapping: 64 row pairs x 4 unit groups");
+    const int ra = tid & 63, ug = (tid >> 6) & 3;
+    float xa[kDPad], xb[kDPad];
+    {   // normalised inputs of my two rows (cogen_tc_inputs_kernel), issued before anything else
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4* pa = reinterpret_cast<const float4*>(xn + ((long long)j * B + b0 + ra) * kDPad);
+        const bool va = !producer && ra < nvalid, vb = !producer && ra + 64 < nvalid;
+#pragma unroll
+        for (int q = 0; q < kDPad / 4; ++q) {
+            const float4 a4 = va ? __ldg(pa + q) : z4, b4 = vb ? __ldg(pa + 64 * (kDPad / 4) + q) : z4;
+            xa[q * 4 + 0] = a4.x; xa[q * 4 + 1] = a4.y; xa[q * 4 + 2] = a4.z; xa[q * 4 + 3] = a4.w;
+            xb[q * 4 + 0] = b4.x; xb[q * 4 + 1] = b4.y; xb[q * 4 + 2] = b4.z; xb[q * 4 + 3] = b4.w;
+        }
+    }
     if (warp == 0) tc::tmem_alloc(&sy.tmem, H2);
-    if (tid == 0) {
+#ifdef SG_COGEN_TRACE
+    const long long tp1 = clock64();
+#endif
+    auto bulk = [&](float* dst, const float* src, const uint32_t bytes, uint64_t* mb) {
+        const uint32_t mba = tc::smem_u32(mb);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mba), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         tc::smem_u32(dst)), "l"(src), "r"(bytes), "r"(mba) : "memory");
+    };
+    auto load_w1 = [&](const int c) { bulk(w1r + (c % kTcW1Ring) * W1F, blob + (long long)c * CHF, W1F * 4, &sy.w1full[c % kTcW1Ring]); };
+    auto load_w2 = [&](const int c) { bulk(w2base + (c & 1) * W2F, blob + (long long)c * CHF + W1F, W2F * 4, &sy.full[c & 1]); };
+    if (tid == kTcCompute) {                                    // the producer thread owns the barriers: init, first loads
         for (int q = 0; q < kTcW1Ring; ++q) tc::mbar_init(&sy.w1full[q], 1);
         for (int s2 = 0; s2 < 2; ++s2) {
-            tc::mbar_init(&sy.full[s2], 1); tc::mbar_init(&sy.a_ready[s2], 2 * kTcM); tc::mbar_init(&sy.freed[s2], 1);
+            tc::mbar_init(&sy.full[s2], 1); tc::mbar_init(&sy.a_ready[s2], kTcCompute); tc::mbar_init(&sy.freed[s2], 1);
         }
         tc::mbar_init(&sy.done, 1);
         tc::mbar_fence_init();
-    }
-    // normalised inputs of this sub-model for my env (two threads per env row)
-    float xr[kDPad];
-#pragma unroll
-    for (int dd = 0; dd < kDPad; ++dd) xr[dd] = 0.f;
-    if (!producer && row < nvalid) {
-        float x[18];
-        build_x(m, X_in, action, day_t, b0 + row, x);
-#pragma unroll
-        for (int dd = 0; dd < kDPad; ++dd)
-            if (dd < d) xr[dd] = (ext_feature(x, m.feats[j * kDPad + dd]) - m.mu[j * kDPad + dd]) * m.sinv[j * kDPad + dd];
+        for (int c = 0; c < kTcW1Ring - 1 && c < nch; ++c) load_w1(c);
+        load_w2(0);
+        if (nch > 1) load_w2(1);
     }
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_d = sy.tmem;
+#ifdef SG_COGEN_TRACE
+    const long long tp2 = clock64();
+#endif
 
     if (producer) {
-        if (tid == 2 * kTcM) {
+        if (tid == kTcCompute) {
             const uint32_t idesc = tc::make_idesc_tf32(kTcM, H2);
-            auto bulk = [&](float* dst, const float* src, const uint32_t bytes, uint64_t* mb) {
-                const uint32_t mba = tc::smem_u32(mb);
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mba), "r"(bytes) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                                 tc::smem_u32(dst)), "l"(src), "r"(bytes), "r"(mba) : "memory");
-            };
-            auto load_w1 = [&](const int c) { bulk(w1r + (c % kTcW1Ring) * W1F, blob + (long long)c * CHF, W1F * 4, &sy.w1full[c % kTcW1Ring]); };
-            auto load_w2 = [&](const int c) { bulk(w2base + (c & 1) * W2F, blob + (long long)c * CHF + W1F, W2F * 4, &sy.full[c & 1]); };
-            for (int c = 0; c < kTcW1Ring - 1 && c < nch; ++c) load_w1(c);
-            load_w2(0);
-            if (nch > 1) load_w2(1);
+#ifdef SG_COGEN_TRACE
+            long long tr[32][4]; const long long tr0 = clock64();
+#define SG_TR(i) tr[c][i] = clock64() - tr0
+#else
+#define SG_TR(i)
+#endif
             for (int c = 0; c < nch; ++c) {
                 const int s = c & 1;
-                tc::mbar_wait(&sy.a_ready[s], (c >> 1) & 1);        // A(c) is written: compute threads are done with W1 slot c % ring
+                tc::mbar_wait(&sy.a_ready[s], (c >> 1) & 1);
+                SG_TR(0);        // A(c) is written: compute threads are done with W1 slot c % ring
                 if (c + kTcW1Ring - 1 < nch) load_w1(c + kTcW1Ring - 1);   // -> slot (c - 1) % ring, released one iteration ago
                 tc::mbar_wait(&sy.full[s], (c >> 1) & 1);           // W2(c) landed
+                SG_TR(1);
                 tc::fence_after_sync();
                 const uint32_t ah = tc::smem_u32(abase + s * AF), al = ah + kTcM * kTcKC * 4;
                 const uint32_t bh = tc::smem_u32(w2base + s * W2F), bl = bh + kTcKC * H2 * 4;
@@ -340,11 +391,18 @@ __device__ __forceinline__ void mlp_tile_tc(const sg_cogen_model& m, const int j
                 }
                 tc::mma_commit(&sy.freed[s]);
                 if (c == nch - 1) tc::mma_commit(&sy.done);
+                SG_TR(2);
                 if (c + 2 < nch) {                                  // refill W2 stage s once its MMAs have completed
                     tc::mbar_wait(&sy.freed[s], (c >> 1) & 1);
                     load_w2(c + 2);
                 }
+                SG_TR(3);
             }
+#ifdef SG_COGEN_TRACE
+            if (SG_COGEN_TRACE > 1 && blockIdx.x == 7 && (blockIdx.y == 0 || blockIdx.y == 22))
+                for (int c = 0; c < nch; ++c)
+                    printf("j=%d c=%2d a_ready %6lld full %6lld issued %6lld freed %6lld\n", j, c, tr[c][0], tr[c][1], tr[c][2], tr[c][3]);
+#endif
         }
     } else {
         for (int c = 0; c < nch; ++c) {
@@ -353,45 +411,43 @@ __device__ __forceinline__ void mlp_tile_tc(const sg_cogen_model& m, const int j
             if (c >= 2) tc::mbar_wait(&sy.freed[s], ((c - 2) >> 1) & 1);   // the A operand of stage s is free again
             const float* w1s = w1r + q * W1F;                       // [16][16]
             const float* b1s = w1s + kDPad * kTcKC;
-            constexpr int UH = kTcKC / 2;                           // units per thread
-            float h[UH];
-#pragma unroll
-            for (int u = 0; u < UH; ++u) h[u] = b1s[half * UH + u];
+            const float4 bb = *reinterpret_cast<const float4*>(b1s + ug * 4);
+            float ha[4] = {bb.x, bb.y, bb.z, bb.w}, hb[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
             for (int dd = 0; dd < kDPad; ++dd) {
                 if (dd >= 6 && dd >= d) break;                      // CTA-uniform: every sub-model has 6 <= d <= 14 inputs
-#pragma unroll
-                for (int qq = 0; qq < UH / 4; ++qq) {
-                    const float4 w = *reinterpret_cast<const float4*>(w1s + dd * kTcKC + half * UH + qq * 4);
-                    h[qq * 4 + 0] = fmaf(xr[dd], w.x, h[qq * 4 + 0]);
-                    h[qq * 4 + 1] = fmaf(xr[dd], w.y, h[qq * 4 + 1]);
-                    h[qq * 4 + 2] = fmaf(xr[dd], w.z, h[qq * 4 + 2]);
-                    h[qq * 4 + 3] = fmaf(xr[dd], w.w, h[qq * 4 + 3]);
-                }
+                const float4 w = *reinterpret_cast<const float4*>(w1s + dd * kTcKC + ug * 4);
+                ha[0] = fmaf(xa[dd], w.x, ha[0]); hb[0] = fmaf(xb[dd], w.x, hb[0]);
+                ha[1] = fmaf(xa[dd], w.y, ha[1]); hb[1] = fmaf(xb[dd], w.y, hb[1]);
+                ha[2] = fmaf(xa[dd], w.z, ha[2]); hb[2] = fmaf(xb[dd], w.z, hb[2]);
+                ha[3] = fmaf(xa[dd], w.w, ha[3]); hb[3] = fmaf(xb[dd], w.w, hb[3]);
             }
-            float4* a_hi = reinterpret_cast<float4*>(abase + s * AF);
+            float4* a_hi = reinterpret_cast<float4*>(abase + s * AF) + ug * kTcM + ra;   // k-group ug, row ra
             float4* a_lo = a_hi + kTcM * (kTcKC / 4);
+            float hi[4], lo[4];
 #pragma unroll
-            for (int qq = 0; qq < UH / 4; ++qq) {
-                const int kg = half * (UH / 4) + qq;
-                float hi[4], lo[4];
+            for (int i = 0; i < 4; ++i) tc::split_tf32(act_fn_fast(ha[i], act), hi[i], lo[i]);
+            a_hi[0] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            a_lo[0] = make_float4(lo[0], lo[1], lo[2], lo[3]);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) tc::split_tf32(act_fn_fast(h[qq * 4 + i], act), hi[i], lo[i]);
-                a_hi[kg * kTcM + row] = make_float4(hi[0], hi[1], hi[2], hi[3]);
-                a_lo[kg * kTcM + row] = make_float4(lo[0], lo[1], lo[2], lo[3]);
-            }
+            for (int i = 0; i < 4; ++i) tc::split_tf32(act_fn_fast(hb[i], act), hi[i], lo[i]);
+            a_hi[64] = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            a_lo[64] = make_float4(lo[0], lo[1], lo[2], lo[3]);
             tc::fence_async_smem();                                 // my part of the A operand -> visible to the tensor core
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&sy.a_ready[s])) : "memory");
         }
         tc::mbar_wait(&sy.done, 0);
         tc::fence_after_sync();
     }
-    // epilogue (compute warps): my env's accumulator row, my half of the columns; h2 = act(acc + b2); y = h2 . W3 + b3
+#ifdef SG_COGEN_TRACE
+    const long long tp3 = clock64();
+#endif
+    // epilogue (compute warps): my env's accumulator row, my share of the columns; h2 = act(acc + b2); y = h2 . W3 + b3
     float y = 0.f;
     if (!producer) {
         const float* b2 = m.blob + m.offsets[j * 5 + 3];
         const float* W3 = m.blob + m.offsets[j * 5 + 4];
-        for (int c0 = half * (H2 / 2); c0 < (half + 1) * (H2 / 2); c0 += 16) {
+        for (int c0 = part * (H2 / kTcRT); c0 < (part + 1) * (H2 / kTcRT); c0 += 16) {
             float v[16];
             tc::tmem_ld16(tmem_d + ((uint32_t)((warp & 3) * 32) << 16) + c0, v);
 #pragma unroll
@@ -405,17 +461,24 @@ __device__ __forceinline__ void mlp_tile_tc(const sg_cogen_model& m, const int j
             }
         }
     }
-    float* ypart = abase;                                          // (all MMAs are done: the stages are free)
-    if (!producer && half == 1) ypart[row] = y;
+    float* ypart = abase;                                           // [kTcRT - 1][kTcM] (all MMAs are done: the stages are free)
+    if (!producer && part != 0) ypart[(part - 1) * kTcM + row] = y;
     tc::fence_before_sync();
     __syncthreads();
-    if (!producer && half == 0 && row < nvalid) raw[(b0 + row) * kNSub + j] = (y + ypart[row]) + m.b3[j];
+    if (!producer && part == 0 && row < nvalid) {
+#pragma unroll
+        for (int pp = 0; pp < kTcRT - 1; ++pp) y += ypart[pp * kTcM + row];
+        raw[(b0 + row) * kNSub + j] = y + m.b3[j];
+    }
     if (warp == 0) tc::tmem_dealloc(tmem_d, H2);
+#ifdef SG_COGEN_TRACE
+    if (tid == 0 && blockIdx.x % 64 == 7 && (blockIdx.y == 0 || blockIdx.y == 22 || blockIdx.y == 9))
+        printf("CTA j=%d tile=%d alloc %lld prologue %lld loop %lld epilogue %lld\n", j, blockIdx.x, tp1 - tp0, tp2 - tp1, tp3 - tp2, clock64() - tp3);
+#endif
 }
 
 __global__ void __launch_bounds__(kTcThreads, 2)
-cogen_mlp_tc_kernel(const sg_cogen_model m, const long long B, const float* __restrict__ X_in,
-                    const float* __restrict__ action, const int32_t* __restrict__ day_t, float* __restrict__ raw) {
+cogen_mlp_tc_kernel(const sg_cogen_model m, const long long B, const float* __restrict__ xn, float* __restrict__ raw) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ TcSync sy;
     const int j = kNSub - 1 - blockIdx.y;        // big sub-models (packed last) are scheduled first
@@ -423,11 +486,11 @@ cogen_mlp_tc_kernel(const sg_cogen_model m, const long long B, const float* __re
     const int nvalid = (int)min((long long)kTcM, B - b0);
     const bool relu = m.meta[j * 6 + 3] != 0;
     if (m.meta[j * 6 + 2] == 256) {
-        if (relu) mlp_tile_tc<256, 1>(m, j, b0, nvalid, X_in, action, day_t, raw, smem, sy);
-        else mlp_tile_tc<256, 0>(m, j, b0, nvalid, X_in, action, day_t, raw, smem, sy);
+        if (relu) mlp_tile_tc<256, 1>(m, j, b0, nvalid, B, xn, raw, smem, sy);
+        else mlp_tile_tc<256, 0>(m, j, b0, nvalid, B, xn, raw, smem, sy);
     } else {
-        if (relu) mlp_tile_tc<128, 1>(m, j, b0, nvalid, X_in, action, day_t, raw, smem, sy);
-        else mlp_tile_tc<128, 0>(m, j, b0, nvalid, X_in, action, day_t, raw, smem, sy);
+        if (relu) mlp_tile_tc<128, 1>(m, j, b0, nvalid, B, xn, raw, smem, sy);
+        else mlp_tile_tc<128, 0>(m, j, b0, nvalid, B, xn, raw, smem, sy);
     }
 }
 
@@ -587,8 +650,10 @@ int launch_mlp(const sg_cogen_model* m, long long B, const float* X, const float
             SG_CUDA(cudaFuncSetAttribute(cogen_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
             configured_tc = true;
         }
+        float* xn = raw + ((B * kNSub + 3) & ~3LL);               // scratch = raw [B,23] | xn [23,B,16] (16-byte aligned)
+        cogen_tc_inputs_kernel<<<dim3((unsigned)((B + 127) / 128), kNSub), 128, 0, st>>>(*m, B, X, action, day_t, xn);
         dim3 grid((unsigned)((B + kTcM - 1) / kTcM), kNSub);
-        cogen_mlp_tc_kernel<<<grid, kTcThreads, smem_tc, st>>>(*m, B, X, action, day_t, raw);
+        cogen_mlp_tc_kernel<<<grid, kTcThreads, smem_tc, st>>>(*m, B, xn, raw);
         return launch_status("cogen_mlp_tc_kernel");
     }
     const size_t smem = sizeof(float) * (kTM * kDPad + kKC * kTM + kDPad * kKC + 2 * kKC * 256);

@@ -147,7 +147,7 @@ class BatchedCogenEnv:
         self.reward = z(B, dtype=torch.float64)
         self.agent_reward = z(B, 4, dtype=torch.float64)
         self.done = z(B, dtype=torch.uint8)
-        self.scratch = z(B, 23, dtype=torch.float32)
+        self.scratch = z(_lib.cogen_scratch_floats(B), dtype=torch.float32)
         self.Y = z(B, 29, dtype=torch.float32) if keep_outputs else None
         self.stats = z(_lib.SG_STATS_LEN, dtype=torch.float64) if collect_stats else None
         if self.stats is not None:
@@ -171,7 +171,7 @@ class BatchedCogenEnv:
         """The plant model alone: X [N,18] f32 -> Y [N,29] f32 (what ORT computes at cogen/env.py:305)."""
         N = X.shape[0]
         Y = torch.empty(N, 29, dtype=torch.float32, device=self.device)
-        scratch = torch.empty(N, 23, dtype=torch.float32, device=self.device)
+        scratch = torch.empty(_lib.cogen_scratch_floats(N), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.sg_cogen_plant(C.byref(self._model), N, X.contiguous().data_ptr(), Y.data_ptr(),
                                                scratch.data_ptr(), self._stream()), "sg_cogen_plant")
