@@ -235,6 +235,35 @@ int sg_ev_project(const sg_ev_model* m, int64_t num_envs, const float* action,
 int sg_ev_agent_obs(const float* cur_obs, const float* past_obs, int64_t num_envs, int32_t n_stations,
                     int32_t obs_dim, float* out, void* stream);
 
+/* GMM day-trace sampler: GMMsTraceGenerator._sample / ._create_events
+ * (sustaingym/envs/evcharging/event_generation.py:416-515) + the per-reset event packing (:149-207)
+ * for a whole pool of days, written straight into the device layouts of sg_ev_model.sessions /
+ * .arrivals.  The mixture is the reference's pickled scikit-learn model flattened by
+ * tools/export_ev_gmms.py. */
+typedef struct sg_ev_gmm {
+    int32_t n_components;        /* 30 for the packaged models; <= 64                                     */
+    int32_t n_counts;            /* length of `counts`                                                     */
+    int32_t n_stations;          /* 54 (Caltech) / 52 (JPL)                                                */
+    int32_t reserved;
+    const double*  cum_weights;  /* [device] [nc] cumulative mixture weights                               */
+    const double*  means;        /* [device] [nc, 4] arrival, departure, est. departure (fractions of a
+                                    day), requested energy / 100 kWh                                       */
+    const double*  chol;         /* [device] [nc, 4, 4] lower Cholesky factors of the covariances          */
+    const int32_t* counts;       /* [device] [n_counts] sessions per day over the period (:479-480)        */
+    const double*  station_p;    /* [device] [n] station usage / total usage (:493)                        */
+} sg_ev_gmm;
+
+/* Samples days first_day .. first_day + n_days - 1 of the stream `seed` (day d is a pure function of
+ * (seed, d): Philox4x32-10, counter = (block, d)).  Outputs, all [device]:
+ *   sessions [n_days, max_sessions, n] sg_ev_session; arrivals [n_days, max_day_sessions + 1] u32;
+ *   dropped  [n_days] i32 or NULL: sessions that found no free station (:500-501) or no table slot;
+ *   max_kwh  [n_days] f64 or NULL: sum of min(requested kWh, (departure - arrival) * kwh_per_step),
+ *            the quantity behind EVChargingEnv._calculate_max_profit (env.py:422-429). */
+int sg_ev_sample_gmm_days(const sg_ev_gmm* g, int64_t n_days, int64_t first_day, uint64_t seed,
+                          double requested_energy_cap, double kwh_per_step, int32_t max_sessions,
+                          int32_t max_day_sessions, void* sessions, uint32_t* arrivals, int32_t* dropped,
+                          double* max_kwh, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * CogenEnv  —  replaces sustaingym/envs/cogen/env.py:276-353 (_compute_reward, incl. the ONNX
  *   Runtime session.run at :305), :232-274 (_dyn_constraint_volation), :145-184 (_get_obs /

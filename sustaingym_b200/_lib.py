@@ -56,6 +56,13 @@ class EVModel(C.Structure):
     ]
 
 
+class EVGmm(C.Structure):
+    _fields_ = [
+        ("n_components", _i32), ("n_counts", _i32), ("n_stations", _i32), ("reserved", _i32),
+        ("cum_weights", _vp), ("means", _vp), ("chol", _vp), ("counts", _vp), ("station_p", _vp),
+    ]
+
+
 class EVState(C.Structure):
     _fields_ = [
         ("slots", _vp), ("header", _vp),
@@ -102,6 +109,8 @@ SIGNATURES = {
                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sg_ev_export_state": (C.c_int, [C.POINTER(EVModel), C.POINTER(EVState), _i64, _vp, _vp, _vp]),
     "sg_ev_agent_obs": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
+    "sg_ev_sample_gmm_days": (C.c_int, [C.POINTER(EVGmm), _i64, _i64, C.c_uint64, _f64, _f64, _i32, _i32, _vp, _vp,
+                                        _vp, _vp, _vp]),
     "sg_cogen_plant": (C.c_int, [C.POINTER(CogenModel), _i64, _vp, _vp, _vp, _vp]),
     "sg_cogen_prepare_tc": (C.c_int, [C.POINTER(CogenModel), _vp, _vp]),
     "sg_cogen_reset": (C.c_int, [C.POINTER(CogenModel), _i64, _vp, _vp, _vp, _vp, _vp, _vp]),

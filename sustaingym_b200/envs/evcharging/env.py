@@ -91,10 +91,20 @@ class BatchedEVChargingEnv:
         cls, coef = self.cn.class_reduce()
         if coef.shape[1] > _lib.SG_EV_MAX_CLASSES or coef.shape[0] > _lib.SG_EV_MAX_CONSTRAINTS:
             raise ValueError("network has more station classes/constraints than the kernels support")
-        t = data_generator.tables
-        rec = np.zeros(t.arrival.shape, dtype=np.dtype([("arr", "<i2"), ("dep", "<i2"), ("est", "<i2"),
-                                                         ("res", "<i2"), ("energy", "<f8")]))
-        rec["arr"], rec["dep"], rec["est"], rec["energy"] = t.arrival, t.departure, t.est_departure, t.energy
+        pool = getattr(data_generator, "device_pool", None)     # GMMsTraceGenerator: tables sampled on the GPU
+        if pool is not None:
+            if pool["sessions"].device != dev:
+                raise ValueError("the generator's device pool lives on another device than the env")
+            sessions_dev, arrivals_dev = pool["sessions"], pool["arrivals"]
+            K_slots, n_trace_days = data_generator._K, data_generator.num_days
+        else:
+            t = data_generator.tables
+            rec = np.zeros(t.arrival.shape, dtype=np.dtype([("arr", "<i2"), ("dep", "<i2"), ("est", "<i2"),
+                                                             ("res", "<i2"), ("energy", "<f8")]))
+            rec["arr"], rec["dep"], rec["est"], rec["energy"] = t.arrival, t.departure, t.est_departure, t.energy
+            sessions_dev = torch.from_numpy(rec.view(np.uint8).reshape(-1)).to(dev)
+            arrivals_dev = torch.from_numpy(t.arrival_table().view(np.int32)).to(dev)
+            K_slots, n_trace_days = t.max_sessions, t.num_days
         J, Cn = coef.shape
         re = np.zeros((_lib.SG_EV_MAX_CONSTRAINTS, _lib.SG_EV_MAX_CLASSES)); re[:J, :Cn] = coef.real
         im = np.zeros((_lib.SG_EV_MAX_CONSTRAINTS, _lib.SG_EV_MAX_CLASSES)); im[:J, :Cn] = coef.imag
@@ -105,13 +115,15 @@ class BatchedEVChargingEnv:
             "re": torch.from_numpy(re).to(dev),
             "im": torch.from_numpy(im).to(dev),
             "mag": torch.from_numpy(mag).to(dev),
-            "sessions": torch.from_numpy(rec.view(np.uint8).reshape(-1)).to(dev),
+            "sessions": sessions_dev,
             "moer": torch.from_numpy(data_generator.moer).to(dev),
-            "arrivals": torch.from_numpy(t.arrival_table().view(np.int32)).to(dev),
+            "arrivals": arrivals_dev,
         }
-        self._max_profit_per_day = t.max_profit(self.MARGINAL_PROFIT_PER_KWH, self.A_PERS_TO_KWH, self.ACTION_SCALE_FACTOR)
+        self._pool = pool
+        self._max_profit_host = None if pool is not None else t.max_profit(
+            self.MARGINAL_PROFIT_PER_KWH, self.A_PERS_TO_KWH, self.ACTION_SCALE_FACTOR)
         self._model = _lib.EVModel(
-            n, coef.shape[1], coef.shape[0], k, t.max_sessions, t.num_days, data_generator.moer.shape[0],
+            n, coef.shape[1], coef.shape[0], k, K_slots, n_trace_days, data_generator.moer.shape[0],
             int(project_action_in_env), self._c["cls"].data_ptr(), self._c["type"].data_ptr(),
             self._c["re"].data_ptr(), self._c["im"].data_ptr(), self._c["mag"].data_ptr(),
             self._c["sessions"].data_ptr(), self._c["moer"].data_ptr(), self._c["arrivals"].data_ptr(),
@@ -271,6 +283,13 @@ class BatchedEVChargingEnv:
         self._async_stream.synchronize()
         return (self._h_obs, self._h_reward, self._h_done.bool(), torch.zeros(self.num_envs, dtype=torch.bool),
                 self._infos())
+
+    @property
+    def _max_profit_per_day(self) -> np.ndarray:
+        """``_calculate_max_profit`` (env.py:422-429) of every day of the pool: [D] f64 on the host."""
+        if self._pool is None:
+            return self._max_profit_host
+        return self._pool["max_kwh"].cpu().numpy() * self.MARGINAL_PROFIT_PER_KWH
 
     def launch_step(self, actions: torch.Tensor) -> None:
         """Enqueues the step kernel on the current stream without building return values (used by
