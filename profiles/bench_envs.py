@@ -2,7 +2,7 @@
 GPU at their per-GPU batch, CUDA-event timed, with the roofline each kernel is bound by and the NumPy
 oracle timed beside it.  The headline (config 2, EV) is bench.py.  One JSON line per env.
 
-    python profiles/bench_envs.py [building] [cogen] [market]
+    python profiles/bench_envs.py [building] [cogen] [cogen32k] [market] [ev_gmm]
 """
 import json
 import os
@@ -83,11 +83,11 @@ def bench_building():
                              "sample": "NumPy oracle, 4096 envs x 100 steps (reference class under shim measured 14557 steps/s in the build container, BASELINE.md)"}}
 
 
-def bench_cogen():
+def bench_cogen(B=4096):
     from oracle.cogen import CogenOracle
     from sustaingym_b200.data.cogen_ambients import synthetic_ambients
     from sustaingym_b200.envs.cogen.env import BatchedCogenEnv
-    B = 4096                               # config 5: 32768 envs over 8 GPUs
+    # config 5: 32768 envs over 8 GPUs = 4096 per GPU; 'cogen32k' runs the whole config on one GPU
     amb = synthetic_ambients(256, seed=0)
     env = BatchedCogenEnv(B, amb, forecast_horizon=12, forecast_noise_std=0.0)
     rng = np.random.default_rng(0)
@@ -99,7 +99,7 @@ def bench_cogen():
         env.step(acts[it[0] % 4]); it[0] += 1
         if it[0] % 96 == 0:
             env.day_t[:, 1] = 0
-    ms = timed(step, 300, 30)
+    ms = timed(step, 300 if B <= 4096 else 60, 30 if B <= 4096 else 10)
     flops = 3684096 * B
     # the FFMA kernel on the same workload, for the record
     env_f = BatchedCogenEnv(B, amb, forecast_horizon=12, forecast_noise_std=0.0, tensor_cores=False)
@@ -109,7 +109,7 @@ def bench_cogen():
         env_f.step(acts[it[0] % 4]); it[0] += 1
         if it[0] % 96 == 0:
             env_f.day_t[:, 1] = 0
-    ms_f = timed(step_f, 100, 10)
+    ms_f = timed(step_f, 100 if B <= 4096 else 20, 10 if B <= 4096 else 4)
     tf32_peak = float(PEAKS.get("bf16_tflops", 1590.0)) / 2.0        # dense TF32 = half the measured bf16 rate
     orc = CogenOracle(amb, 1024, forecast_horizon=12)
     a = env.sample_actions(rng)[:1024]
@@ -119,7 +119,7 @@ def bench_cogen():
         orc.step(a)
     cpu = 1024 * 5 / (time.perf_counter() - t0)
     return {"env": "CogenEnv", "metric": "env_steps_per_sec", "value": B / (ms * 1e-3), "unit": "env-steps/s",
-            "config": {"workload": "CogenEnv 4 agents k=12, 4096 envs/GPU (32768 over 8), one step per launch pair"},
+            "config": {"workload": f"CogenEnv 4 agents k=12, {B} envs on one GPU (config 5: 32768 over 8 GPUs), one step = inputs + plant (tcgen05) + finish kernels"},
             "ms_per_step": ms,
             "roofline": {"bound": "tensor", "achieved": flops / (ms * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
                          "frac": flops / (ms * 1e-3) / 1e12 / tf32_peak, "traffic": None, "kernel": "cogen_mlp_tc_kernel",
@@ -170,7 +170,39 @@ def bench_market():
             "cpu_baseline": {"value": cpu, "unit": "env-steps/s", "cores": 1, "kind": "port", "sample": "NumPy oracle, 16384 envs x 50 steps"}}
 
 
+def bench_ev_gmm():
+    """Reset-path operator: GMM day-trace sampler, one pool of days per launch."""
+    from oracle import ev_gmm as G
+    from sustaingym_b200.envs.evcharging.event_generation import GmmDevice, load_gmm
+    gmm = load_gmm("caltech", "Summer 2019")
+    D, K, smax = 65536, 8, 128
+    dev = GmmDevice(gmm, 54, "cuda")
+    pools = [dev.alloc_pool(D, K, smax) for _ in range(2)]      # 2 x 485 MB of tables: beyond L2
+    it = [0]
+    kwh = 32 * (5 / 60 * 0.208)
+
+    def sample():
+        dev.sample(pools[it[0] % 2], it[0] * D, 1, 100.0, kwh); it[0] += 1
+    ms = timed(sample, 10, 3)
+    algo = D * (K * 54 * 16 + (smax + 1) * 4 + 12)             # tables written per launch
+    sessions = int((pools[0]["arrivals"] != 0x7FFF).sum().item())
+    t0 = time.perf_counter()
+    G.sample_days(gmm, 1, 64, 54, 100.0, K, smax, kwh)
+    cpu = 64 / (time.perf_counter() - t0)
+    return {"env": "EVChargingEnv reset path (GMM trace sampler)", "metric": "days_per_sec", "value": D / (ms * 1e-3), "unit": "days/s",
+            "config": {"workload": "GMMsTraceGenerator caltech Summer 2019 (30 components), 65536 days per launch, K=8 slots, 128 events/day",
+                       "l2_policy": "2 pools of 485 MB round-robin"},
+            "ms_per_launch": ms, "sessions_per_launch": sessions,
+            "roofline": {"bound": "hbm", "achieved": algo / (ms * 1e-3) / 1e9, "peak": HBM, "unit": "GB/s",
+                         "frac": algo / (ms * 1e-3) / 1e9 / HBM, "traffic": None, "kernel": "ev_gmm_days_kernel",
+                         "algorithmic_bytes_per_launch": algo,
+                         "note": "thread per day, serial rejection sampling + station draw: latency bound, not a streaming kernel"},
+            "cpu_baseline": {"value": cpu, "unit": "days/s", "cores": 1, "kind": "port",
+                             "sample": "pure-Python oracle (bit-exact restatement), 64 days; the reference samples one day per reset with scikit-learn + pandas"}}
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["building", "cogen", "market"]
     for w in which:
-        print(json.dumps({"building": bench_building, "cogen": bench_cogen, "market": bench_market}[w]()), flush=True)
+        print(json.dumps({"building": bench_building, "cogen": bench_cogen, "cogen32k": lambda: bench_cogen(32768),
+                          "market": bench_market, "ev_gmm": bench_ev_gmm}[w]()), flush=True)

@@ -84,24 +84,26 @@ ev_gmm_days_kernel(const sg_ev_gmm g, const long long n_days, const long long fi
                    const double energy_cap, const double kwh_per_step, const int K, const int smax,
                    sg_ev_session* __restrict__ sessions, uint32_t* __restrict__ arrivals,
                    int32_t* __restrict__ dropped_out, double* __restrict__ max_kwh_out) {
-    const long long d = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (d >= n_days) return;
+    const long long d0 = (long long)blockIdx.x * blockDim.x;
+    const long long d = d0 + threadIdx.x;
     const int nc = g.n_components, n_st = g.n_stations;
+    {   // the block's days start empty: one contiguous range of each table, filled with coalesced stores
+        const long long nd = min((long long)blockDim.x, n_days - d0);
+        uint4 e;                                             // {arrival, departure, est_departure = 32767, reserved 0 | energy 0.0}
+        e.x = 0x7FFF7FFFu; e.y = 0x00007FFFu; e.z = 0u; e.w = 0u;
+        uint4* rec4 = reinterpret_cast<uint4*>(sessions + d0 * K * n_st);
+        for (long long i = threadIdx.x; i < nd * K * n_st; i += blockDim.x) rec4[i] = e;
+        uint32_t* rows = arrivals + d0 * (smax + 1);
+        for (long long i = threadIdx.x; i < nd * (smax + 1); i += blockDim.x) rows[i] = 0x7FFFu;
+    }
+    __syncthreads();
+    if (d >= n_days) return;
     Philox rs;
     const unsigned long long day = (unsigned long long)(first_day + d);
     rs.key0 = (uint32_t)seed; rs.key1 = (uint32_t)(seed >> 32);
     rs.day0 = (uint32_t)day; rs.day1 = (uint32_t)(day >> 32);
     rs.block = 0; rs.have = 0;
-
-    // the day's tables start empty
     sg_ev_session* rec = sessions + d * K * n_st;
-    {
-        sg_ev_session e;
-        e.arrival = e.departure = e.est_departure = 32767; e.reserved = 0; e.energy = 0.0;
-        for (int i = 0; i < K * n_st; ++i) rec[i] = e;
-        uint32_t* row = arrivals + d * (smax + 1);
-        for (int i = 0; i <= smax; ++i) row[i] = 0x7FFFu;
-    }
 
     int n = g.counts[min((int)__dmul_rn(rs.uniform(), (double)g.n_counts), g.n_counts - 1)];
     n = min(n, kCandMax);
