@@ -58,6 +58,9 @@ typedef struct sg_building_model {
  * reset(seed) with the seed that maps to the current cursor, env.py:339-378).  The observation
  * returned for a finished env is then the first observation of its next episode. */
 #define SG_BUILDING_FLAG_AUTORESET 16
+/* n >= 16, continuous actions, pnorm 2 run on the tensor-core (DMMA) cluster kernel; this flag forces the
+ * thread-per-env kernel instead (tests compare the two). */
+#define SG_BUILDING_FLAG_NO_MMA 32
 
 /* reset(): env.py:346-378 with the weather cursor already resolved by the host
  * (seed -> epoch mapping env.py:339-345 is host logic).  `T_initial` may be NULL (= target). */

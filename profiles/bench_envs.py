@@ -201,8 +201,40 @@ def bench_ev_gmm():
                              "sample": "pure-Python oracle (bit-exact restatement), 64 days; the reference samples one day per reset with scikit-learn + pandas"}}
 
 
+def bench_building_large():
+    """The reference's largest building (OutPatientHealthCare, n = 118 zones) on the generic-n kernel path."""
+    from sustaingym_b200.envs.building.env import BatchedBuildingEnv
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import load_building_fixture
+    g, params = load_building_fixture(os.path.join(ROOT, "tests", "golden", "building_outpatient_s3.npz"))
+    n, B, S = int(params["n"]), 8192, 96
+    sets = []
+    for i in range(3):
+        env = BatchedBuildingEnv(params, B, auto_reset=True)
+        env.reset(epochs=np.random.default_rng(i).integers(0, 1500, B))
+        sets.append((env, torch.rand(S, B, n, device="cuda") * 2 - 1))
+    it = [0]
+
+    def roll():
+        env, acts = sets[it[0] % 3]; it[0] += 1
+        env.rollout(acts, keep_obs=True)
+    ms = timed(roll, 6, 2)
+    algo = (4 * n + 4 * n + 4 * (n + 4) + 16 + 8 + 4 + 1) * B * S
+    flops = 2 * n * (2 * n + 4) * B * S
+    return {"env": "BuildingEnv (n=118)", "metric": "env_steps_per_sec", "value": B * S / (ms * 1e-3), "unit": "env-steps/s",
+            "config": {"workload": f"BuildingEnv OutPatientHealthCare n={n}, {B} envs, {S}-step fused rollout per launch, obs kept",
+                       "l2_policy": "3 env sets round-robin (371 MB of actions + 383 MB of obs per launch)"},
+            "ms_per_launch": ms,
+            "roofline": {"bound": "hbm", "achieved": algo / (ms * 1e-3) / 1e9, "peak": HBM, "unit": "GB/s",
+                         "frac": algo / (ms * 1e-3) / 1e9 / HBM, "traffic": None, "kernel": "building_step_kernel<0,false>",
+                         "algorithmic_bytes_per_launch": algo, "f64_gflops": flops / (ms * 1e-3) / 1e9,
+                         "note": "generic-n path: thread per env, f64 matvec from shared memory; at n=118 the arithmetic intensity is 39 flop/B, "
+                                 "so this is where a tensor-core formulation would pay (DESIGN.md section 4)"},
+            "cpu_baseline": None}
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["building", "cogen", "market"]
     for w in which:
         print(json.dumps({"building": bench_building, "cogen": bench_cogen, "cogen32k": lambda: bench_cogen(32768),
-                          "market": bench_market, "ev_gmm": bench_ev_gmm}[w]()), flush=True)
+                          "market": bench_market, "ev_gmm": bench_ev_gmm, "building118": bench_building_large}[w]()), flush=True)

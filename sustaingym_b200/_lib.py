@@ -31,6 +31,7 @@ SG_EV_ACTION_F32 = 0
 SG_EV_ACTION_I64 = 1
 SG_EV_FLAG_AUTORESET = 16
 SG_BUILDING_FLAG_AUTORESET = 16
+SG_BUILDING_FLAG_NO_MMA = 32
 
 _vp = C.c_void_p
 _i32 = C.c_int32

@@ -14,7 +14,11 @@
 // Bound: HBM (105 B per env-step at n = 5: SURVEY.md 8d).  All arithmetic is f64 except where
 // the reference itself computes in f32 (avg_temp, the NEP-50 f32 products inside
 // _calc_occupower, the f32 action norm); those are mirrored with explicit __f*_rn intrinsics.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace sg {
 namespace {
@@ -348,6 +352,300 @@ __global__ void building_reset_kernel(const sg_building_model m, const long long
     runs_g[b] = 0;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Large buildings (n >= 16, continuous actions, Euclidean reward): the zone coupling
+//     X+ = A_d X + BD_d[:, 3:3+n] a + (4 rank-1 exogenous terms)
+// is a dense f64 contraction with K = 2n, and runs on the tensor cores (DMMA, mma.sync m8n8k4 f64;
+// f64 because the reference computes this product in f64 from its f32 state, env.py:266).  The f64
+// weights of the biggest shipped building (n = 118: 2n x n x 8 B = 223 KB) do not fit one SM's shared
+// memory next to the state tile, so a CLUSTER OF TWO CTAs owns a tile of 32 envs: each CTA keeps the
+// weight columns of half of the zones resident in shared memory, computes that half of X+ for all 32
+// envs, and writes its f32 results into both CTAs' next-state tiles through distributed shared memory;
+// one cluster barrier per step.  Per-env scalar work (occupancy polynomial, action norm, reward,
+// cursors, auto-reset) is done redundantly by warp 0 of both CTAs with the thread-per-env code's exact
+// arithmetic; rank 0 writes rewards / done flags, the ranks split the observation rows.
+// Summation order inside a dot product differs from the thread-per-env kernel (and from BLAS), i.e.
+// f64 differences of ~1e-16 before the f32 rounding of the state.
+constexpr int kMmaEnvs = 32;       // envs per cluster tile: 4 m-tiles of 8
+constexpr int kMmaThreads = 256;   // 8 warps: warp -> (m-tile = warp & 3, n-tiles of parity warp >> 2)
+constexpr int kMmaMaxNT = 8;       // n-tiles of 8 zones per CTA (64 >= 59 = ceil(118 / 2))
+
+struct MmaLayout {
+    int n4, XP, NH, NT, NHp, NS;
+    size_t off_R4, off_tgt, off_ac, off_tgtAll, off_env, off_errw, off_errp, off_stat, off_tail, off_X, off_A, total;
+};
+__host__ __device__ inline MmaLayout mma_layout(const int n) {
+    MmaLayout L;
+    L.n4 = (n + 3) & ~3;
+    L.XP = (L.n4 % 8 == 4) ? L.n4 : L.n4 + 4;            // row stride of the f32 tiles: 16-byte bank groups of 8 rows distinct
+    L.NH = (n + 1) / 2;
+    L.NT = (L.NH + 7) / 8;
+    L.NHp = L.NT * 8;
+    L.NS = (L.NHp % 16 == 8) ? L.NHp : L.NHp + 8;        // row stride of W: the 4 k-rows of a fragment hit distinct banks
+    size_t o = sizeof(double) * (size_t)(2 * L.n4) * L.NS;                       // W [2 n4][NS]
+    L.off_R4 = o; o += sizeof(double) * 4 * L.NHp;
+    L.off_tgt = o; o += sizeof(double) * L.NHp;
+    L.off_ac = o; o += sizeof(double) * L.NHp;
+    L.off_tgtAll = o; o += sizeof(double) * L.n4;
+    L.off_env = o; o += sizeof(double) * 4 * kMmaEnvs;                            // occ, ground, out, ghi per env
+    L.off_errw = o; o += sizeof(double) * 2 * kMmaEnvs;
+    L.off_errp = o; o += sizeof(double) * 2 * 2 * kMmaEnvs;                       // [step parity][rank][env]
+    L.off_stat = o; o += sizeof(double) * 11 * (kMmaThreads / 32);
+    L.off_tail = o; o += sizeof(float) * 4 * kMmaEnvs;
+    L.off_X = o; o += sizeof(float) * 2 * kMmaEnvs * L.XP;
+    L.off_A = o; o += sizeof(float) * 2 * kMmaEnvs * L.XP;
+    L.total = o;
+    return L;
+}
+
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, const double a, const double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                 : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+// numpy_sum_f32 for a row in shared memory (n >= 8): same operation order
+__device__ __forceinline__ float numpy_sum_f32_row(const float* x, const int n) {
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = x[j];
+    int i = 8;
+    for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = __fadd_rn(r[j], x[i + j]);
+    }
+    float res = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                          __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+    for (; i < n; ++i) res = __fadd_rn(res, x[i]);
+    return res;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMmaThreads, 1)
+building_mma_kernel(const sg_building_model m, const long long B, const int steps, const float* __restrict__ action,
+                    float* __restrict__ state, int32_t* __restrict__ epoch_g, int32_t* __restrict__ runs_g,
+                    float* __restrict__ obs_out, double* __restrict__ reward_g, uint8_t* __restrict__ done_g,
+                    const int flags, double* __restrict__ stats) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int rank = (int)cluster.block_rank();
+    const int n = m.n, row = n + 4;
+    const MmaLayout L = mma_layout(n);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* W = reinterpret_cast<double*>(smem_raw);
+    double* R4 = reinterpret_cast<double*>(smem_raw + L.off_R4);
+    double* sTgt = reinterpret_cast<double*>(smem_raw + L.off_tgt);
+    double* sAc = reinterpret_cast<double*>(smem_raw + L.off_ac);
+    double* sTgtAll = reinterpret_cast<double*>(smem_raw + L.off_tgtAll);
+    double* sEnv = reinterpret_cast<double*>(smem_raw + L.off_env);
+    double* sErrW = reinterpret_cast<double*>(smem_raw + L.off_errw);
+    double* sErrP = reinterpret_cast<double*>(smem_raw + L.off_errp);
+    double* sStat = reinterpret_cast<double*>(smem_raw + L.off_stat);
+    float* sTail = reinterpret_cast<float*>(smem_raw + L.off_tail);
+    float* Xs = reinterpret_cast<float*>(smem_raw + L.off_X);
+    float* As = reinterpret_cast<float*>(smem_raw + L.off_A);
+    float* Xs_peer = cluster.map_shared_rank(Xs, rank ^ 1);
+    double* sErrP_peer = cluster.map_shared_rank(sErrP, rank ^ 1);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long b0 = (long long)(blockIdx.x >> 1) * kMmaEnvs;
+    const int nvalid = (int)min((long long)kMmaEnvs, B - b0);
+    const int z_lo = rank * L.NH, nz = min(L.NH, n - z_lo);
+    const int XP = L.XP, NS = L.NS, n4 = L.n4;
+
+    // ---- resident weights of my zones: W[k][z], k < n4: A_d[z][k]; k >= n4: BD_d[z][3 + k - n4] ----
+    for (int idx = tid; idx < 2 * n4 * NS; idx += kMmaThreads) {
+        const int k = idx / NS, z = idx % NS;
+        double v = 0.0;
+        if (z < nz) {
+            if (k < n) v = m.A_d[(z_lo + z) * n + k];
+            else if (k >= n4 && k - n4 < n) v = m.BD_d[(z_lo + z) * row + 3 + (k - n4)];
+        }
+        W[idx] = v;
+    }
+    for (int z = tid; z < L.NHp; z += kMmaThreads) {
+        const bool ok = z < nz;
+        const double* bd = m.BD_d + (long long)(z_lo + z) * row;
+        R4[0 * L.NHp + z] = ok ? bd[0] : 0.0;
+        R4[1 * L.NHp + z] = ok ? bd[1] : 0.0;
+        R4[2 * L.NHp + z] = ok ? bd[2] : 0.0;
+        R4[3 * L.NHp + z] = ok ? bd[n + 3] : 0.0;
+        sTgt[z] = ok ? m.target[z_lo + z] : 0.0;
+        sAc[z] = ok ? m.ac_map[z_lo + z] : 0.0;
+    }
+    for (int j = tid; j < n4; j += kMmaThreads) sTgtAll[j] = j < n ? m.target[j] : 0.0;
+    for (int i = tid; i < 2 * kMmaEnvs * XP; i += kMmaThreads) { Xs[i] = 0.f; As[i] = 0.f; }
+    __syncthreads();
+    for (int i = tid; i < nvalid * n; i += kMmaThreads) {
+        const int env = i / n, j = i % n;
+        Xs[env * XP + j] = state[(b0 + env) * row + j];
+    }
+    auto stage_actions = [&](const int sp) {       // action tile of step sp -> As[sp & 1] (one cp.async group per call)
+        if (sp < steps) {
+            const float* g = action + ((long long)sp * B + b0) * n;
+            float* t = As + (size_t)(sp & 1) * kMmaEnvs * XP;
+            for (int i = tid; i < nvalid * n; i += kMmaThreads) cp_async_4(t + (i / n) * XP + (i % n), g + i);
+        }
+        cp_async_commit();
+    };
+    stage_actions(0);
+
+    // per-env scalars live in warp 0 (lane = env)
+    const bool envthr = warp == 0 && lane < nvalid;
+    const long long b = b0 + lane;
+    int e = 0, r = 0;
+    Weather4 w_cur = {0, 0, 0, 0}, w_nxt = {0, 0, 0, 0};
+    if (envthr) {
+        e = epoch_g[b]; r = runs_g[b];
+        w_cur = load_weather(m.weather, e);
+        w_nxt = load_weather(m.weather, (e + 1) % m.T);
+    }
+    StatsAcc acc;
+    const int mt = warp & 3, nt0 = warp >> 2;
+    cluster.sync();                                  // both CTAs are initialised before any remote write
+
+    for (int s = 0; s < steps; ++s) {
+        const int cur = s & 1, nxt = cur ^ 1;
+        float* Xc = Xs + (size_t)cur * kMmaEnvs * XP;
+        float* Xn = Xs + (size_t)nxt * kMmaEnvs * XP;
+        float* Xn_peer = Xs_peer + (size_t)nxt * kMmaEnvs * XP;
+        const float* Ac = As + (size_t)cur * kMmaEnvs * XP;
+        cp_async_wait<0>();
+        __syncthreads();                             // actions of step s landed; X[cur] complete (local + remote halves)
+        stage_actions(s + 1);
+        // ---- per-env exogenous inputs (env.py:244-263) and the f32 action norm ----------------
+        Weather4 w = {0, 0, 0, 0};
+        double occ = 0.0;
+        float a_dot = 0.f;
+        if (envthr) {
+            w = w_cur; w_cur = w_nxt;
+            w_nxt = load_weather(m.weather, (e + 2) % m.T);
+            const float avg_temp = __fdiv_rn(numpy_sum_f32_row(Xc + lane * XP, n), (float)n);
+            occ = occupower_f32temp(avg_temp, w.meta);
+            sEnv[0 * kMmaEnvs + lane] = occ; sEnv[1 * kMmaEnvs + lane] = w.ground;
+            sEnv[2 * kMmaEnvs + lane] = w.out; sEnv[3 * kMmaEnvs + lane] = w.ghi;
+            const float* ar = Ac + lane * XP;
+            for (int j = 0; j < n; ++j) a_dot = __fmaf_rn(ar[j], ar[j], a_dot);
+        }
+        __syncthreads();
+        // ---- tensor-core contraction: C[env, zone] over k = (x | action) ----------------------------
+        double c[kMmaMaxNT / 2][2];
+#pragma unroll
+        for (int ti = 0; ti < kMmaMaxNT / 2; ++ti) c[ti][0] = c[ti][1] = 0.0;
+        const int arow = (mt * 8 + (lane >> 2)) * XP + (lane & 3);
+        const int bcol = (lane & 3) * NS + (lane >> 2);
+#pragma unroll 1
+        for (int part = 0; part < 2; ++part) {
+            const float* src = (part == 0 ? Xc : Ac) + arow;
+            const double* wb = W + (size_t)part * n4 * NS + bcol;
+#pragma unroll 2
+            for (int kb = 0; kb < n4 / 4; ++kb) {
+                const double a = (double)src[kb * 4];
+                const double* wk = wb + (size_t)kb * 4 * NS;
+#pragma unroll
+                for (int ti = 0; ti < kMmaMaxNT / 2; ++ti) {
+                    const int t = nt0 + 2 * ti;
+                    if (t < L.NT) dmma_m8n8k4(c[ti][0], c[ti][1], a, wk[t * 8]);
+                }
+            }
+        }
+        // ---- epilogue: exogenous rank-1 terms, comfort error, new f32 state to both CTAs -------------
+        {
+            const int env = mt * 8 + (lane >> 2);
+            const double occ_e = sEnv[0 * kMmaEnvs + env], gr_e = sEnv[1 * kMmaEnvs + env];
+            const double out_e = sEnv[2 * kMmaEnvs + env], ghi_e = sEnv[3 * kMmaEnvs + env];
+            double e2 = 0.0;
+#pragma unroll
+            for (int ti = 0; ti < kMmaMaxNT / 2; ++ti) {
+                const int t = nt0 + 2 * ti;
+                if (t < L.NT) {
+#pragma unroll
+                    for (int q = 0; q < 2; ++q) {
+                        const int z = t * 8 + 2 * (lane & 3) + q;
+                        if (z < nz) {
+                            double v = R4[0 * L.NHp + z] * occ_e;
+                            v = fma(R4[1 * L.NHp + z], gr_e, v);
+                            v = fma(R4[2 * L.NHp + z], out_e, v);
+                            v = fma(R4[3 * L.NHp + z], ghi_e, v);
+                            v += c[ti][q];
+                            const double er = v * sAc[z] - sTgt[z] * sAc[z];
+                            e2 = fma(er, er, e2);
+                            const float xf = (float)v;
+                            Xn[env * XP + z_lo + z] = xf;
+                            Xn_peer[env * XP + z_lo + z] = xf;
+                        }
+                    }
+                }
+            }
+            e2 += __shfl_xor_sync(kFull, e2, 1);
+            e2 += __shfl_xor_sync(kFull, e2, 2);
+            if ((lane & 3) == 0) sErrW[nt0 * kMmaEnvs + env] = e2;
+        }
+        __syncthreads();
+        if (warp == 0) {                             // my half's comfort error -> both CTAs
+            const double part = sErrW[lane] + sErrW[kMmaEnvs + lane];
+            sErrP[(cur * 2 + rank) * kMmaEnvs + lane] = part;
+            sErrP_peer[(cur * 2 + rank) * kMmaEnvs + lane] = part;
+        }
+        cluster.sync();                              // X[nxt] and the error partials are complete in both CTAs
+        // ---- reward, cursors, auto-reset (env.py:272-309, 346-378) ------------------------------------
+        if (envthr) {
+            const double err2 = sErrP[(cur * 2 + 0) * kMmaEnvs + lane] + sErrP[(cur * 2 + 1) * kMmaEnvs + lane];
+            const double e_term = sqrt(err2) * m.error_rate;
+            const double a_term = (double)__fmul_rn(__fsqrt_rn(a_dot), (float)m.q_rate);
+            const double rew = -(a_term + e_term);
+            float t0 = (float)w.out, t1 = (float)w.ground, t2 = (float)w.ghi, t3 = (float)(occ / 1000.0);
+            e += 1; r += 1;
+            if (e >= m.T) e = 0;
+            const bool dn = r >= m.episode_len;
+            if (dn && (flags & SG_BUILDING_FLAG_AUTORESET)) {
+                r = 0;
+                double sum = 0.0;
+                for (int j = 0; j < n; ++j) sum += sTgtAll[j];
+                const double occ0 = occupower_f64temp(sum / n, w_cur.meta);
+                for (int j = 0; j < n; ++j) Xn[lane * XP + j] = (float)sTgtAll[j];
+                t0 = (float)w_cur.out; t1 = (float)w_cur.ground; t2 = (float)w_cur.ghi; t3 = (float)(occ0 / 1000.0);
+            }
+            sTail[lane * 4 + 0] = t0; sTail[lane * 4 + 1] = t1; sTail[lane * 4 + 2] = t2; sTail[lane * 4 + 3] = t3;
+            if (rank == 0) {
+                acc.add(rew, dn, -e_term, -a_term, 0.0);
+                reward_g[(long long)s * B + b] = rew;
+                done_g[(long long)s * B + b] = dn ? 1 : 0;
+            }
+        }
+        const bool last = (s == steps - 1);
+        if (obs_out != nullptr || last) {            // the ranks split the observation rows
+            __syncthreads();
+            const int e_lo = rank * (kMmaEnvs / 2), e_hi = min(nvalid, e_lo + kMmaEnvs / 2);
+            for (int i = tid; i < (e_hi - e_lo) * row; i += kMmaThreads) {
+                const int env = e_lo + i / row, j = i % row;
+                const float v = j < n ? Xn[env * XP + j] : sTail[env * 4 + (j - n)];
+                if (obs_out != nullptr) obs_out[((long long)s * B + b0 + env) * row + j] = v;
+                if (last) state[(b0 + env) * row + j] = v;
+            }
+        }
+    }
+    if (envthr && rank == 0) { epoch_g[b] = e; runs_g[b] = r; }
+    if (stats != nullptr && rank == 0) {
+        __syncthreads();
+        stats_flush_block(acc, stats, sStat);
+    }
+    cluster.sync();                                  // nobody exits while its shared memory may still be addressed
+}
+
+int launch_building_mma(const sg_building_model* m, long long B, int steps, const void* action, float* state,
+                        int32_t* epoch, int32_t* runs, float* obs_out, double* reward, uint8_t* done,
+                        int flags, double* stats, cudaStream_t st) {
+    const MmaLayout L = mma_layout(m->n);
+    static size_t configured = 0;
+    if (L.total > configured) {
+        cudaError_t err = cudaFuncSetAttribute(building_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+        if (err != cudaSuccess) { set_error("building: %zu B of shared memory unavailable", L.total); return 2; }
+        configured = L.total;
+    }
+    const unsigned grid = 2u * (unsigned)((B + kMmaEnvs - 1) / kMmaEnvs);
+    building_mma_kernel<<<grid, kMmaThreads, L.total, st>>>(*m, B, steps, static_cast<const float*>(action), state, epoch,
+                                                            runs, obs_out, reward, done, flags, stats);
+    return launch_status("building_mma_kernel");
+}
+
 template <int N, bool DISCRETE>
 int launch_building(const sg_building_model* m, long long B, int steps, const void* action, float* state,
                     int32_t* epoch, int32_t* runs, float* obs_out, double* reward, uint8_t* done,
@@ -375,6 +673,8 @@ int dispatch_building(const sg_building_model* m, long long B, int steps, const 
     SG_CHECK_ARG(action && state && epoch && runs && reward && done, "building: NULL buffer");
     if (B == 0) return 0;
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (m->n >= 16 && (m->n + 1) / 2 <= 8 * kMmaMaxNT && !m->discrete && m->pnorm == 2.0 && !(flags & SG_BUILDING_FLAG_NO_MMA))
+        return launch_building_mma(m, B, steps, action, state, epoch, runs, obs_out, reward, done, flags, stats, st);
 #define SG_B_CASE(NN)                                                                                  \
     case NN:                                                                                           \
         return m->discrete ? launch_building<NN, true>(m, B, steps, action, state, epoch, runs, obs_out, \

@@ -40,7 +40,7 @@ def seed_to_epoch(seed: int, episode_len: int, time_res: int, length_of_weather:
 
 class BatchedBuildingEnv:
     def __init__(self, parameters: dict[str, Any], num_envs: int = 1, device=None, auto_reset: bool = False,
-                 collect_stats: bool = False):
+                 collect_stats: bool = False, tensor_cores: bool = True):
         self.lib = _lib.load()
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedBuildingEnv needs a CUDA device (no CPU fallback)")
@@ -107,6 +107,8 @@ class BatchedBuildingEnv:
         self._h_reward = torch.zeros(B, dtype=torch.float64).pin_memory()
         self._h_done = torch.zeros(B, dtype=torch.uint8).pin_memory()
         self._flags = _lib.SG_BUILDING_FLAG_AUTORESET if auto_reset else 0
+        if not tensor_cores:      # n >= 16 runs on the DMMA cluster kernel unless told otherwise (csrc/building.cu)
+            self._flags |= _lib.SG_BUILDING_FLAG_NO_MMA
         self.kernel_launches = 0
 
     def _stream(self) -> int:

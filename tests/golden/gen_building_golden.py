@@ -73,6 +73,10 @@ def run_case(name, building, seed, *, discrete=False, steps=STEPS, **pg_kwargs):
 
 
 if __name__ == "__main__":
+    only = sys.argv[1:]
+    if only:
+        _run_case = run_case
+        run_case = lambda name, *a, **k: _run_case(name, *a, **k) if name in only else None  # noqa: E731
     # seed -> epoch = int(seed/365 * 2000); 5 -> 27
     run_case("officesmall_s5", "OfficeSmall", 5)
     run_case("retail_s5", "RetailStandalone", 5)
@@ -86,3 +90,9 @@ if __name__ == "__main__":
     run_case("retail_discrete", "RetailStandalone", 77, discrete=True)
     # a mid-size building (n = 18) to exercise the 8-accumulator f32 pairwise sum of avg_temp
     run_case("officemedium_s9", "OfficeMedium", 9, steps=120)
+    # the generic-n kernel path on the reference's largest / smallest buildings (every
+    # shipped building runs on the engine): n = 118, 90, 55 and 3
+    run_case("outpatient_s3", "OutPatientHealthCare", 3, steps=100)
+    run_case("apartmenthighrise_s21", "ApartmentHighRise", 21, steps=100)
+    run_case("hospital_s6", "Hospital", 6, steps=100)
+    run_case("restaurantfastfood_s2", "RestaurantFastFood", 2, steps=100)

@@ -104,3 +104,36 @@ def test_autoreset_and_stats(native_lib):
     st = env.stats.cpu().numpy()
     assert st[0] == 25 * B and st[5] == 2 * B
     assert abs(st[1] - tot) < 1e-6 * abs(tot)
+
+
+@pytest.mark.parametrize("name,B", [("outpatient_s3", 77), ("apartmenthighrise_s21", 64), ("hospital_s6", 33),
+                                    ("officemedium_s9", 130)])
+def test_tensor_core_kernel_matches_thread_per_env_kernel(native_lib, name, B):
+    """n >= 16: DMMA cluster kernel (default) vs the thread-per-env kernel on the same inputs — fused rollout
+    with auto-reset, per-step observations and statistics.  The two sum each dot product in a different
+    order (f64), so the f32 states agree bit for bit except for rare last-bit roundings."""
+    from sustaingym_b200.envs.building.env import BatchedBuildingEnv
+    g, params = load_building_fixture([p for p in building_fixtures() if name in p][0])
+    params = dict(params, episode_len=20)
+    S = 50
+    rng = np.random.default_rng(3)
+    epochs = rng.integers(0, len(g["out_temp"]), B)
+    acts = torch.from_numpy((rng.uniform(-1, 1, (S, B, params["n"])) * np.asarray(params["ac_map"])).astype(np.float32)).cuda()
+    outs = []
+    for tc in (True, False):
+        env = BatchedBuildingEnv(params, B, auto_reset=True, collect_stats=True, tensor_cores=tc)
+        env.reset(epochs=epochs)
+        obs, rew, done = env.rollout(acts, keep_obs=True)
+        o1, r1, d1, _, _ = env.step(acts[0])                 # single-step launch after the rollout
+        torch.cuda.synchronize()
+        outs.append((obs.cpu().numpy(), rew.cpu().numpy(), done.cpu().numpy(), o1.cpu().numpy(), r1.cpu().numpy(),
+                     env.epoch.cpu().numpy(), env.runs.cpu().numpy(), env.stats.cpu().numpy()))
+    a, b = outs
+    assert (a[0] != b[0]).mean() < 1e-4 and rel_err(a[0], b[0]) < 1e-6
+    np.testing.assert_allclose(a[1], b[1], rtol=1e-9)
+    np.testing.assert_array_equal(a[2], b[2])
+    assert a[2].sum() == 2 * B                               # two episode ends per env in 50 steps
+    assert rel_err(a[3], b[3]) < 1e-6
+    np.testing.assert_allclose(a[4], b[4], rtol=1e-9)
+    np.testing.assert_array_equal(a[5], b[5]); np.testing.assert_array_equal(a[6], b[6])
+    np.testing.assert_allclose(a[7][:3], b[7][:3], rtol=1e-9)
