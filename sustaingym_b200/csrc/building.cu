@@ -17,6 +17,7 @@
 #include <cooperative_groups.h>
 
 #include "common.cuh"
+#include "tc.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -35,6 +36,9 @@ __device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
 }
 __device__ __forceinline__ void cp_async_4(void* smem, const void* gmem) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void* smem, const void* gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -367,19 +371,22 @@ __global__ void building_reset_kernel(const sg_building_model m, const long long
 // Summation order inside a dot product differs from the thread-per-env kernel (and from BLAS), i.e.
 // f64 differences of ~1e-16 before the f32 rounding of the state.
 constexpr int kMmaEnvs = 32;       // envs per cluster tile: 4 m-tiles of 8
-constexpr int kMmaThreads = 256;   // 8 warps: warp -> (m-tile = warp & 3, n-tiles of parity warp >> 2)
+constexpr int kMmaWarps = 8;        // contraction warps: warp -> (m-tile = warp & 3, n-tiles of parity warp >> 2)
+constexpr int kMmaThreads = (kMmaWarps + 2) * 32;   // + the per-env scalar warp + the copy warp
+constexpr int kBarOcc = 1, kBarErr = 2, kBarTail = 3;   // named barriers (0 is __syncthreads)
 constexpr int kMmaMaxNT = 8;       // n-tiles of 8 zones per CTA (64 >= 59 = ceil(118 / 2))
 
 struct MmaLayout {
     int n4, XP, NH, NT, NHp, NS;
-    size_t off_R4, off_tgt, off_ac, off_tgtAll, off_env, off_errw, off_errp, off_stat, off_tail, off_X, off_A, total;
+    int AB;      // floats per action buffer: 32 packed rows + 4 zeroed pad floats (fragment loads run to n4)
+    size_t off_R4, off_tgt, off_ac, off_tgtAll, off_env, off_errw, off_errp, off_stat, off_mbar, off_tail, off_X, off_A, off_O, total;
 };
 __host__ __device__ inline MmaLayout mma_layout(const int n) {
     MmaLayout L;
     L.n4 = (n + 3) & ~3;
     L.XP = (L.n4 % 8 == 4) ? L.n4 : L.n4 + 4;            // row stride of the f32 tiles: 16-byte bank groups of 8 rows distinct
     L.NH = (n + 1) / 2;
-    L.NT = (L.NH + 7) / 8;
+    L.NT = ((L.NH + 15) / 16) * 2;                       // n-tiles of 8 zones, even: the two warp groups take TI = NT / 2 each
     L.NHp = L.NT * 8;
     L.NS = (L.NHp % 16 == 8) ? L.NHp : L.NHp + 8;        // row stride of W: the 4 k-rows of a fragment hit distinct banks
     size_t o = sizeof(double) * (size_t)(2 * L.n4) * L.NS;                       // W [2 n4][NS]
@@ -387,17 +394,26 @@ __host__ __device__ inline MmaLayout mma_layout(const int n) {
     L.off_tgt = o; o += sizeof(double) * L.NHp;
     L.off_ac = o; o += sizeof(double) * L.NHp;
     L.off_tgtAll = o; o += sizeof(double) * L.n4;
-    L.off_env = o; o += sizeof(double) * 4 * kMmaEnvs;                            // occ, ground, out, ghi per env
+    L.off_env = o; o += sizeof(double) * 5 * kMmaEnvs;                            // occ, ground, out, ghi, episode-ends flag per env
     L.off_errw = o; o += sizeof(double) * 2 * kMmaEnvs;
     L.off_errp = o; o += sizeof(double) * 2 * 2 * kMmaEnvs;                       // [step parity][rank][env]
     L.off_stat = o; o += sizeof(double) * 11 * (kMmaThreads / 32);
+    L.off_mbar = o; o += 16;
     L.off_tail = o; o += sizeof(float) * 4 * kMmaEnvs;
     L.off_X = o; o += sizeof(float) * 2 * kMmaEnvs * L.XP;
-    L.off_A = o; o += sizeof(float) * 2 * kMmaEnvs * L.XP;
+    L.AB = kMmaEnvs * n + 4;
+    L.off_A = o; o += sizeof(float) * 2 * L.AB;                                   // action tiles, packed [32][n] (one bulk copy each)
+    L.off_O = o; o += (sizeof(float) * (kMmaEnvs / 2) * (n + 4) + 15) & ~(size_t)15;   // my half of the observation rows, packed
     L.total = o;
     return L;
 }
 
+__device__ __forceinline__ void named_bar_sync(const int id, const int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(const int id, const int count) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
 __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, const double a, const double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
                  : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
@@ -419,6 +435,7 @@ __device__ __forceinline__ float numpy_sum_f32_row(const float* x, const int n) 
     return res;
 }
 
+template <int TI>       // n-tiles per warp (NT = 2 TI); tiles beyond the real zones multiply zero weight columns
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kMmaThreads, 1)
 building_mma_kernel(const sg_building_model m, const long long B, const int steps, const float* __restrict__ action,
                     float* __restrict__ state, int32_t* __restrict__ epoch_g, int32_t* __restrict__ runs_g,
@@ -441,6 +458,8 @@ building_mma_kernel(const sg_building_model m, const long long B, const int step
     float* sTail = reinterpret_cast<float*>(smem_raw + L.off_tail);
     float* Xs = reinterpret_cast<float*>(smem_raw + L.off_X);
     float* As = reinterpret_cast<float*>(smem_raw + L.off_A);
+    float* Obuf = reinterpret_cast<float*>(smem_raw + L.off_O);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem_raw + L.off_mbar);     // [2]: action tile s & 1 has landed
     float* Xs_peer = cluster.map_shared_rank(Xs, rank ^ 1);
     double* sErrP_peer = cluster.map_shared_rank(sErrP, rank ^ 1);
 
@@ -471,24 +490,50 @@ building_mma_kernel(const sg_building_model m, const long long B, const int step
         sAc[z] = ok ? m.ac_map[z_lo + z] : 0.0;
     }
     for (int j = tid; j < n4; j += kMmaThreads) sTgtAll[j] = j < n ? m.target[j] : 0.0;
-    for (int i = tid; i < 2 * kMmaEnvs * XP; i += kMmaThreads) { Xs[i] = 0.f; As[i] = 0.f; }
+    for (int i = tid; i < 2 * kMmaEnvs * XP; i += kMmaThreads) Xs[i] = 0.f;
+    for (int i = tid; i < 2 * L.AB; i += kMmaThreads) As[i] = 0.f;
+    if (tid == 0) { tc::mbar_init(&mbar[0], 1); tc::mbar_init(&mbar[1], 1); tc::mbar_fence_init(); }
     __syncthreads();
-    for (int i = tid; i < nvalid * n; i += kMmaThreads) {
-        const int env = i / n, j = i % n;
-        Xs[env * XP + j] = state[(b0 + env) * row + j];
-    }
-    auto stage_actions = [&](const int sp) {       // action tile of step sp -> As[sp & 1] (one cp.async group per call)
-        if (sp < steps) {
-            const float* g = action + ((long long)sp * B + b0) * n;
-            float* t = As + (size_t)(sp & 1) * kMmaEnvs * XP;
-            for (int i = tid; i < nvalid * n; i += kMmaThreads) cp_async_4(t + (i / n) * XP + (i % n), g + i);
+    for (int env = warp; env < nvalid; env += kMmaThreads / 32)
+        for (int j = lane; j < n; j += 32) Xs[env * XP + j] = state[(b0 + env) * row + j];
+    // The action tile of a step is one contiguous range of global memory: a single bulk asynchronous copy
+    // (TMA) when its address and size are multiples of 16 bytes, 4/8-byte cp.async otherwise.
+    const bool pair_ok = (n % 2 == 0) && ((reinterpret_cast<uintptr_t>(action) & 7u) == 0);
+    const bool bulk_ok = nvalid == kMmaEnvs && ((B * n) % 4 == 0) && ((reinterpret_cast<uintptr_t>(action) & 15u) == 0);
+    auto stage_actions = [&](const int sp) {       // copy warp: action tile of step sp -> As[sp & 1]
+        if (sp >= steps) return;
+        const float* g = action + ((long long)sp * B + b0) * n;
+        float* t = As + (size_t)(sp & 1) * L.AB;
+        if (bulk_ok) {
+            if (lane == 0) {
+                const uint32_t bytes = (uint32_t)(kMmaEnvs * n * sizeof(float)), mba = tc::smem_u32(&mbar[sp & 1]);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mba), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                                 tc::smem_u32(t)), "l"(g), "r"(bytes), "r"(mba) : "memory");
+            }
+        } else {
+            for (int env = 0; env < nvalid; ++env) {
+                if (pair_ok) {
+                    for (int j = 2 * lane; j < n; j += 64) cp_async_8(t + env * n + j, g + env * n + j);
+                } else {
+                    for (int j = lane; j < n; j += 32) cp_async_4(t + env * n + j, g + env * n + j);
+                }
+            }
+            cp_async_commit();
         }
-        cp_async_commit();
     };
-    stage_actions(0);
-
-    // per-env scalars live in warp 0 (lane = env)
-    const bool envthr = warp == 0 && lane < nvalid;
+    auto wait_actions = [&](const int sp) {        // copy warp: the tile of step sp is in shared memory
+        if (sp >= steps) return;
+        if (bulk_ok) tc::mbar_wait(&mbar[sp & 1], (uint32_t)((sp >> 1) & 1));
+        else cp_async_wait<0>();
+    };
+    // Roles: warps 0-7 tensor-core contraction + epilogue; warp 8 (lane = env) per-env scalars: occupancy,
+    // weather, action norm, reward, cursors; warp 9 copies: action tiles in, observation rows out.  Hand-offs
+    // inside a step are named barriers; the step boundary is the cluster barrier (every thread of both CTAs).
+    const bool is_mma = warp < kMmaWarps, is_scalar = warp == kMmaWarps, is_copy = warp == kMmaWarps + 1;
+    __syncthreads();                                 // zero fill and mbarrier init precede the first copy
+    if (is_copy) { stage_actions(0); wait_actions(0); }
+    const bool envthr = is_scalar && lane < nvalid;
     const long long b = b0 + lane;
     int e = 0, r = 0;
     Weather4 w_cur = {0, 0, 0, 0}, w_nxt = {0, 0, 0, 0};
@@ -498,64 +543,101 @@ building_mma_kernel(const sg_building_model m, const long long B, const int step
         w_nxt = load_weather(m.weather, (e + 1) % m.T);
     }
     StatsAcc acc;
-    const int mt = warp & 3, nt0 = warp >> 2;
-    cluster.sync();                                  // both CTAs are initialised before any remote write
+    const int mt = warp & 3, nt0 = (warp >> 2) & 1;
+    const bool autoreset = (flags & SG_BUILDING_FLAG_AUTORESET) != 0;
+    auto write_obs_rows = [&](const int s, const float* Xrow_src) {      // copy warp: my half of the rows of step s
+        const bool last = (s == steps - 1);
+        if (obs_out == nullptr && !last) return;
+        const int e_lo = rank * (kMmaEnvs / 2), e_hi = min(nvalid, e_lo + kMmaEnvs / 2);
+        if (e_hi <= e_lo) return;
+        float* og = obs_out != nullptr ? obs_out + ((long long)s * B + b0 + e_lo) * row : nullptr;
+        float* sg_ = last ? state + (b0 + e_lo) * row : nullptr;
+        const uint32_t bytes = (uint32_t)((e_hi - e_lo) * row * sizeof(float));
+        const bool bulk = (bytes % 16 == 0) && ((reinterpret_cast<uintptr_t>(og) & 15u) == 0) && ((reinterpret_cast<uintptr_t>(sg_) & 15u) == 0);
+        if (bulk) {   // rows assembled in shared memory, then ONE bulk asynchronous store per destination
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the previous store has read Obuf
+            __syncwarp();
+            for (int env = e_lo; env < e_hi; ++env)
+                for (int j = lane; j < row; j += 32)
+                    Obuf[(env - e_lo) * row + j] = j < n ? Xrow_src[env * XP + j] : sTail[env * 4 + (j - n)];
+            tc::fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                if (og != nullptr)
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(og), "r"(tc::smem_u32(Obuf)), "r"(bytes) : "memory");
+                if (sg_ != nullptr)
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(sg_), "r"(tc::smem_u32(Obuf)), "r"(bytes) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        } else {
+            for (int env = e_lo; env < e_hi; ++env)
+                for (int j = lane; j < row; j += 32) {
+                    const float v = j < n ? Xrow_src[env * XP + j] : sTail[env * 4 + (j - n)];
+                    if (og != nullptr) og[(env - e_lo) * row + j] = v;
+                    if (sg_ != nullptr) sg_[(env - e_lo) * row + j] = v;
+                }
+        }
+    };
+    cluster.sync();                                  // both CTAs initialised, action tile 0 landed
+#ifdef SG_BLD_TRACE
+    long long tph[6] = {0, 0, 0, 0, 0, 0}, tq = clock64(), tq2;
+#define SG_PH(i) tq2 = clock64(); tph[i] += tq2 - tq; tq = tq2
+#else
+#define SG_PH(i)
+#endif
 
     for (int s = 0; s < steps; ++s) {
         const int cur = s & 1, nxt = cur ^ 1;
         float* Xc = Xs + (size_t)cur * kMmaEnvs * XP;
         float* Xn = Xs + (size_t)nxt * kMmaEnvs * XP;
         float* Xn_peer = Xs_peer + (size_t)nxt * kMmaEnvs * XP;
-        const float* Ac = As + (size_t)cur * kMmaEnvs * XP;
-        cp_async_wait<0>();
-        __syncthreads();                             // actions of step s landed; X[cur] complete (local + remote halves)
-        stage_actions(s + 1);
-        // ---- per-env exogenous inputs (env.py:244-263) and the f32 action norm ----------------
-        Weather4 w = {0, 0, 0, 0};
-        double occ = 0.0;
-        float a_dot = 0.f;
-        if (envthr) {
-            w = w_cur; w_cur = w_nxt;
-            w_nxt = load_weather(m.weather, (e + 2) % m.T);
-            const float avg_temp = __fdiv_rn(numpy_sum_f32_row(Xc + lane * XP, n), (float)n);
-            occ = occupower_f32temp(avg_temp, w.meta);
-            sEnv[0 * kMmaEnvs + lane] = occ; sEnv[1 * kMmaEnvs + lane] = w.ground;
-            sEnv[2 * kMmaEnvs + lane] = w.out; sEnv[3 * kMmaEnvs + lane] = w.ghi;
-            const float* ar = Ac + lane * XP;
-            for (int j = 0; j < n; ++j) a_dot = __fmaf_rn(ar[j], ar[j], a_dot);
-        }
-        __syncthreads();
-        // ---- tensor-core contraction: C[env, zone] over k = (x | action) ----------------------------
-        double c[kMmaMaxNT / 2][2];
+        const float* Ac = As + (size_t)cur * L.AB;      // packed rows of n floats
+        if (is_mma) {
+            // ---- tensor-core contraction: C[env, zone] over k = (x | action) ----------------------------
+            // two accumulator sets (even / odd k-blocks): 8 independent DMMA chains per warp hide the pipe latency
+            double c[TI][2], c2[TI][2];
 #pragma unroll
-        for (int ti = 0; ti < kMmaMaxNT / 2; ++ti) c[ti][0] = c[ti][1] = 0.0;
-        const int arow = (mt * 8 + (lane >> 2)) * XP + (lane & 3);
-        const int bcol = (lane & 3) * NS + (lane >> 2);
+            for (int ti = 0; ti < TI; ++ti) c[ti][0] = c[ti][1] = c2[ti][0] = c2[ti][1] = 0.0;
+            const int xrow = (mt * 8 + (lane >> 2)) * XP + (lane & 3), acrow = (mt * 8 + (lane >> 2)) * n + (lane & 3);
+            const int bcol = (lane & 3) * NS + (lane >> 2);
 #pragma unroll 1
-        for (int part = 0; part < 2; ++part) {
-            const float* src = (part == 0 ? Xc : Ac) + arow;
-            const double* wb = W + (size_t)part * n4 * NS + bcol;
-#pragma unroll 2
-            for (int kb = 0; kb < n4 / 4; ++kb) {
-                const double a = (double)src[kb * 4];
-                const double* wk = wb + (size_t)kb * 4 * NS;
+            for (int part = 0; part < 2; ++part) {
+                const float* src = part == 0 ? Xc + xrow : Ac + acrow;
+                const double* wb = W + (size_t)part * n4 * NS + bcol;
+                int kb = 0;
+#pragma unroll 1
+                for (; kb + 1 < n4 / 4; kb += 2) {
+                    const double a0 = (double)src[kb * 4], a1 = (double)src[kb * 4 + 4];
+                    const double* wk = wb + (size_t)kb * 4 * NS;
 #pragma unroll
-                for (int ti = 0; ti < kMmaMaxNT / 2; ++ti) {
-                    const int t = nt0 + 2 * ti;
-                    if (t < L.NT) dmma_m8n8k4(c[ti][0], c[ti][1], a, wk[t * 8]);
+                    for (int ti = 0; ti < TI; ++ti) {
+                        const int t = nt0 + 2 * ti;
+                        dmma_m8n8k4(c[ti][0], c[ti][1], a0, wk[t * 8]);
+                        dmma_m8n8k4(c2[ti][0], c2[ti][1], a1, wk[4 * NS + t * 8]);
+                    }
+                }
+                if (kb < n4 / 4) {
+                    const double a0 = (double)src[kb * 4];
+                    const double* wk = wb + (size_t)kb * 4 * NS;
+#pragma unroll
+                    for (int ti = 0; ti < TI; ++ti) dmma_m8n8k4(c[ti][0], c[ti][1], a0, wk[(nt0 + 2 * ti) * 8]);
                 }
             }
-        }
-        // ---- epilogue: exogenous rank-1 terms, comfort error, new f32 state to both CTAs -------------
-        {
-            const int env = mt * 8 + (lane >> 2);
-            const double occ_e = sEnv[0 * kMmaEnvs + env], gr_e = sEnv[1 * kMmaEnvs + env];
-            const double out_e = sEnv[2 * kMmaEnvs + env], ghi_e = sEnv[3 * kMmaEnvs + env];
-            double e2 = 0.0;
 #pragma unroll
-            for (int ti = 0; ti < kMmaMaxNT / 2; ++ti) {
-                const int t = nt0 + 2 * ti;
-                if (t < L.NT) {
+            for (int ti = 0; ti < TI; ++ti) { c[ti][0] += c2[ti][0]; c[ti][1] += c2[ti][1]; }
+            SG_PH(0);
+            named_bar_sync(kBarOcc, (kMmaWarps + 1) * 32);
+            SG_PH(1);      // the scalar warp has published this step's exogenous inputs
+            // ---- epilogue: exogenous rank-1 terms, comfort error, new f32 state to both CTAs -------------
+            {
+                const int env = mt * 8 + (lane >> 2);
+                const double occ_e = sEnv[0 * kMmaEnvs + env], gr_e = sEnv[1 * kMmaEnvs + env];
+                const double out_e = sEnv[2 * kMmaEnvs + env], ghi_e = sEnv[3 * kMmaEnvs + env];
+                const bool ends = sEnv[4 * kMmaEnvs + env] != 0.0;    // episode ends with this step and auto-reset is on
+                double e2 = 0.0;
+#pragma unroll
+                for (int ti = 0; ti < TI; ++ti) {
+                    const int t = nt0 + 2 * ti;
 #pragma unroll
                     for (int q = 0; q < 2; ++q) {
                         const int z = t * 8 + 2 * (lane & 3) + q;
@@ -567,60 +649,102 @@ building_mma_kernel(const sg_building_model m, const long long B, const int step
                             v += c[ti][q];
                             const double er = v * sAc[z] - sTgt[z] * sAc[z];
                             e2 = fma(er, er, e2);
-                            const float xf = (float)v;
+                            const float xf = ends ? (float)sTgt[z] : (float)v;    // env.py:346-378: next episode starts at the targets
                             Xn[env * XP + z_lo + z] = xf;
                             Xn_peer[env * XP + z_lo + z] = xf;
                         }
                     }
                 }
+                e2 += __shfl_xor_sync(kFull, e2, 1);
+                e2 += __shfl_xor_sync(kFull, e2, 2);
+                if ((lane & 3) == 0) sErrW[nt0 * kMmaEnvs + env] = e2;
             }
-            e2 += __shfl_xor_sync(kFull, e2, 1);
-            e2 += __shfl_xor_sync(kFull, e2, 2);
-            if ((lane & 3) == 0) sErrW[nt0 * kMmaEnvs + env] = e2;
-        }
-        __syncthreads();
-        if (warp == 0) {                             // my half's comfort error -> both CTAs
-            const double part = sErrW[lane] + sErrW[kMmaEnvs + lane];
-            sErrP[(cur * 2 + rank) * kMmaEnvs + lane] = part;
-            sErrP_peer[(cur * 2 + rank) * kMmaEnvs + lane] = part;
-        }
-        cluster.sync();                              // X[nxt] and the error partials are complete in both CTAs
-        // ---- reward, cursors, auto-reset (env.py:272-309, 346-378) ------------------------------------
-        if (envthr) {
-            const double err2 = sErrP[(cur * 2 + 0) * kMmaEnvs + lane] + sErrP[(cur * 2 + 1) * kMmaEnvs + lane];
-            const double e_term = sqrt(err2) * m.error_rate;
-            const double a_term = (double)__fmul_rn(__fsqrt_rn(a_dot), (float)m.q_rate);
-            const double rew = -(a_term + e_term);
-            float t0 = (float)w.out, t1 = (float)w.ground, t2 = (float)w.ghi, t3 = (float)(occ / 1000.0);
-            e += 1; r += 1;
-            if (e >= m.T) e = 0;
-            const bool dn = r >= m.episode_len;
-            if (dn && (flags & SG_BUILDING_FLAG_AUTORESET)) {
-                r = 0;
-                double sum = 0.0;
-                for (int j = 0; j < n; ++j) sum += sTgtAll[j];
-                const double occ0 = occupower_f64temp(sum / n, w_cur.meta);
-                for (int j = 0; j < n; ++j) Xn[lane * XP + j] = (float)sTgtAll[j];
-                t0 = (float)w_cur.out; t1 = (float)w_cur.ground; t2 = (float)w_cur.ghi; t3 = (float)(occ0 / 1000.0);
+            SG_PH(2);
+            named_bar_sync(kBarErr, kMmaWarps * 32);
+            if (warp == 0) {                         // my half's comfort error -> both CTAs
+                const double part = sErrW[lane] + sErrW[kMmaEnvs + lane];
+                sErrP[(cur * 2 + rank) * kMmaEnvs + lane] = part;
+                sErrP_peer[(cur * 2 + rank) * kMmaEnvs + lane] = part;
             }
-            sTail[lane * 4 + 0] = t0; sTail[lane * 4 + 1] = t1; sTail[lane * 4 + 2] = t2; sTail[lane * 4 + 3] = t3;
-            if (rank == 0) {
-                acc.add(rew, dn, -e_term, -a_term, 0.0);
-                reward_g[(long long)s * B + b] = rew;
-                done_g[(long long)s * B + b] = dn ? 1 : 0;
+            SG_PH(3);
+            cluster.sync();                          // X[nxt] and the error partials are complete in both CTAs
+            SG_PH(4);
+        } else if (is_scalar) {
+            // ---- per-env exogenous inputs (env.py:244-263) -> MMA epilogue; the f32 action norm -----------
+            Weather4 w = {0, 0, 0, 0};
+            double occ = 0.0;
+            float a_dot = 0.f;
+            bool dn = false;
+            if (envthr) {
+                w = w_cur; w_cur = w_nxt;
+                w_nxt = load_weather(m.weather, (e + 2) % m.T);
+                const float avg_temp = __fdiv_rn(numpy_sum_f32_row(Xc + lane * XP, n), (float)n);
+                occ = occupower_f32temp(avg_temp, w.meta);
+                dn = r + 1 >= m.episode_len;
+                sEnv[0 * kMmaEnvs + lane] = occ; sEnv[1 * kMmaEnvs + lane] = w.ground;
+                sEnv[2 * kMmaEnvs + lane] = w.out; sEnv[3 * kMmaEnvs + lane] = w.ghi;
+                sEnv[4 * kMmaEnvs + lane] = (dn && autoreset) ? 1.0 : 0.0;
             }
-        }
-        const bool last = (s == steps - 1);
-        if (obs_out != nullptr || last) {            // the ranks split the observation rows
-            __syncthreads();
-            const int e_lo = rank * (kMmaEnvs / 2), e_hi = min(nvalid, e_lo + kMmaEnvs / 2);
-            for (int i = tid; i < (e_hi - e_lo) * row; i += kMmaThreads) {
-                const int env = e_lo + i / row, j = i % row;
-                const float v = j < n ? Xn[env * XP + j] : sTail[env * 4 + (j - n)];
-                if (obs_out != nullptr) obs_out[((long long)s * B + b0 + env) * row + j] = v;
-                if (last) state[(b0 + env) * row + j] = v;
+            __threadfence_block();
+            named_bar_arrive(kBarOcc, (kMmaWarps + 1) * 32);
+            SG_PH(0);
+            if (envthr) {
+                const float* ar = Ac + lane * n;
+                for (int j = 0; j < n; ++j) a_dot = __fmaf_rn(ar[j], ar[j], a_dot);
             }
+            SG_PH(1);
+            cluster.sync();
+            SG_PH(2);
+            // ---- reward, cursors, auto-reset bookkeeping (env.py:272-309, 346-378) -------------------------
+            if (envthr) {
+                const double err2 = sErrP[(cur * 2 + 0) * kMmaEnvs + lane] + sErrP[(cur * 2 + 1) * kMmaEnvs + lane];
+                const double e_term = sqrt(err2) * m.error_rate;
+                const double a_term = (double)__fmul_rn(__fsqrt_rn(a_dot), (float)m.q_rate);
+                const double rew = -(a_term + e_term);
+                float t0 = (float)w.out, t1 = (float)w.ground, t2 = (float)w.ghi, t3 = (float)(occ / 1000.0);
+                e += 1; r += 1;
+                if (e >= m.T) e = 0;
+                if (dn && autoreset) {
+                    r = 0;
+                    double sum = 0.0;
+                    for (int j = 0; j < n; ++j) sum += sTgtAll[j];
+                    const double occ0 = occupower_f64temp(sum / n, w_cur.meta);
+                    t0 = (float)w_cur.out; t1 = (float)w_cur.ground; t2 = (float)w_cur.ghi; t3 = (float)(occ0 / 1000.0);
+                }
+                sTail[lane * 4 + 0] = t0; sTail[lane * 4 + 1] = t1; sTail[lane * 4 + 2] = t2; sTail[lane * 4 + 3] = t3;
+                if (rank == 0) {
+                    acc.add(rew, dn, -e_term, -a_term, 0.0);
+                    reward_g[(long long)s * B + b] = rew;
+                    done_g[(long long)s * B + b] = dn ? 1 : 0;
+                }
+            }
+            __threadfence_block();
+            named_bar_arrive(kBarTail, 64);          // -> copy warp: tails of step s are in place
+            SG_PH(3);
+        } else {
+            // ---- copy warp: next action tile in, observation rows of the previous step out -------------------
+            stage_actions(s + 1);
+            SG_PH(0);
+            if (s > 0) {
+                named_bar_sync(kBarTail, 64);
+                SG_PH(1);
+                write_obs_rows(s - 1, Xc);           // X[cur] of step s is the state step s-1 produced
+            }
+            SG_PH(2);
+            wait_actions(s + 1);
+            SG_PH(3);
+            cluster.sync();
+            SG_PH(4);
         }
+    }
+#ifdef SG_BLD_TRACE
+    if (blockIdx.x == 6 && lane == 0 && (warp == 0 || warp == 5 || warp >= kMmaWarps))
+        printf("warp %d: %lld %lld %lld %lld %lld %lld (cycles/step)\n", warp, tph[0] / steps, tph[1] / steps, tph[2] / steps, tph[3] / steps, tph[4] / steps, tph[5] / steps);
+#endif
+    if (is_copy) {
+        named_bar_sync(kBarTail, 64);
+        write_obs_rows(steps - 1, Xs + (size_t)(steps & 1) * kMmaEnvs * XP);
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");      // bulk stores complete before the CTA exits
     }
     if (envthr && rank == 0) { epoch_g[b] = e; runs_g[b] = r; }
     if (stats != nullptr && rank == 0) {
@@ -634,15 +758,30 @@ int launch_building_mma(const sg_building_model* m, long long B, int steps, cons
                         int32_t* epoch, int32_t* runs, float* obs_out, double* reward, uint8_t* done,
                         int flags, double* stats, cudaStream_t st) {
     const MmaLayout L = mma_layout(m->n);
-    static size_t configured = 0;
-    if (L.total > configured) {
-        cudaError_t err = cudaFuncSetAttribute(building_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
-        if (err != cudaSuccess) { set_error("building: %zu B of shared memory unavailable", L.total); return 2; }
-        configured = L.total;
-    }
     const unsigned grid = 2u * (unsigned)((B + kMmaEnvs - 1) / kMmaEnvs);
-    building_mma_kernel<<<grid, kMmaThreads, L.total, st>>>(*m, B, steps, static_cast<const float*>(action), state, epoch,
-                                                            runs, obs_out, reward, done, flags, stats);
+    const float* act = static_cast<const float*>(action);
+#define SG_MMA_CASE(TI_)                                                                                              \
+    case TI_: {                                                                                                       \
+        static size_t configured = 0;                                                                                 \
+        if (L.total > configured) {                                                                                   \
+            cudaError_t err = cudaFuncSetAttribute(building_mma_kernel<TI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total); \
+            if (err != cudaSuccess) { set_error("building: %zu B of shared memory unavailable", L.total); return 2; } \
+            configured = L.total;                                                                                     \
+        }                                                                                                             \
+        building_mma_kernel<TI_><<<grid, kMmaThreads, L.total, st>>>(*m, B, steps, act, state, epoch, runs, obs_out,  \
+                                                                     reward, done, flags, stats);                     \
+        break;                                                                                                        \
+    }
+    switch (L.NT / 2) {
+        SG_MMA_CASE(1)
+        SG_MMA_CASE(2)
+        SG_MMA_CASE(3)
+        SG_MMA_CASE(4)
+        default:
+            set_error("building: n=%d too large for the tensor-core kernel", m->n);
+            return 1;
+    }
+#undef SG_MMA_CASE
     return launch_status("building_mma_kernel");
 }
 
