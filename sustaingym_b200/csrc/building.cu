@@ -605,7 +605,7 @@ building_mma_kernel(const sg_building_model m, const long long B, const int step
                 const float* src = part == 0 ? Xc + xrow : Ac + acrow;
                 const double* wb = W + (size_t)part * n4 * NS + bcol;
                 int kb = 0;
-#pragma unroll 1
+#pragma unroll 3
                 for (; kb + 1 < n4 / 4; kb += 2) {
                     const double a0 = (double)src[kb * 4], a1 = (double)src[kb * 4 + 4];
                     const double* wk = wb + (size_t)kb * 4 * NS;
