@@ -128,6 +128,8 @@ def _cpu_worker(args):
         orc.step(acts[t % 8])
     t0 = time.perf_counter()
     for t in range(steps):
+        if (60 + t) % 288 == 0:                           # end of the day: next episode (the GPU arm auto-resets in-kernel)
+            orc.reset((np.arange(B) + t) % 32, (np.arange(B) + t + 1) % 32)
         orc.step(acts[t % 8])
     return B * steps, time.perf_counter() - t0
 
