@@ -262,22 +262,32 @@ def main():
     value = world * B * args.steps / (ms_total * 1e-3)
     launches = 2 * args.steps
 
-    # ---- roofline: duration of the step kernel alone (ev_step_main_kernel<1>) ---------------------------
-    L = 120
+    # ---- roofline: duration of the step kernels alone (ev_step_main_kernel<1> + the normally empty rare kernel) ----
+    # The cost of a step follows the garage's occupancy over the day, so the sample covers one whole episode of
+    # every env set (288 x N_SETS launches), in chunks queued behind ~20 ms of filler work so that the host is
+    # always ahead and no launch gap leaks into an event pair.
+    CH = 96
+    L = 288 * N_SETS
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(L)]
     filler = torch.empty(1 << 28, dtype=torch.float32, device=dev)
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(); filler.normal_(); f1.record()
     torch.cuda.synchronize()
-    for _ in range(6):
-        filler.normal_()                         # ~ms of GPU work so the CPU can queue the loop behind it
-    for i in range(L):
-        env, a = envs[i % N_SETS], acts[i % N_SETS]
-        evs[i][0].record()
-        env.launch_step(a)
-        evs[i][1].record()
-    torch.cuda.synchronize()
+    n_fill = int(np.ceil(20.0 / max(f0.elapsed_time(f1), 0.05)))
+    for c0 in range(0, L, CH):
+        for _ in range(n_fill):
+            filler.normal_()
+        for i in range(c0, c0 + CH):
+            env, a = envs[i % N_SETS], acts[i % N_SETS]
+            evs[i][0].record()
+            env.launch_step(a)
+            evs[i][1].record()
+        torch.cuda.synchronize()
     del filler
     durs = sorted(a_.elapsed_time(b_) for a_, b_ in evs)
-    kern_ms = float(np.mean(durs[L // 10: L - L // 10]))     # trimmed mean
+    kern_events_ms = float(np.mean(durs[L // 20: L - L // 20]))     # 5 % trimmed mean over one episode
+    # an event pair also times two event records; the graph step holds the same two kernels, so it bounds them
+    kern_ms = min(kern_events_ms, ms_total / args.steps)
     peak, peak_src = peaks()
     achieved = ALGO_BYTES_PER_ENV_STEP * B / (kern_ms * 1e-3) / 1e9
     launches += 2 * L
@@ -331,7 +341,10 @@ def main():
                          "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "kernel": "ev_step_main_kernel<1>",
                          "traffic_source": "ncu --set full dram__bytes_read.sum + dram__bytes_write.sum, "
                                            "profiles/r1/ev_step_main_kernel_ncu_full_summary.txt",
-                         "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * B,
+                         "kernel_ms": kern_ms, "kernel_ms_event_pairs": kern_events_ms,
+                         "kernel_ms_note": "main + (normally empty) rare kernel, mean over one whole episode of every env set "
+                                           "(the step cost follows the garage occupancy over the day); min(event pairs, graph step)",
+                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * B,
                          "peak_source": peak_src},
             "cpu_baseline": cpu_base,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

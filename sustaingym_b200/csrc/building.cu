@@ -388,7 +388,8 @@ __host__ __device__ inline MmaLayout mma_layout(const int n) {
     L.NH = (n + 1) / 2;
     L.NT = ((L.NH + 15) / 16) * 2;                       // n-tiles of 8 zones, even: the two warp groups take TI = NT / 2 each
     L.NHp = L.NT * 8;
-    L.NS = (L.NHp % 16 == 8) ? L.NHp : L.NHp + 8;        // row stride of W: the 4 k-rows of a fragment hit distinct banks
+    L.NS = L.NHp + 4;                                    // row stride of W (NHp % 16 == 0): 32 bytes mod 128, so the 4 k-rows x 4 zones
+                                                         // a half-warp reads in one LDS.64 wavefront fall into distinct banks
     size_t o = sizeof(double) * (size_t)(2 * L.n4) * L.NS;                       // W [2 n4][NS]
     L.off_R4 = o; o += sizeof(double) * 4 * L.NHp;
     L.off_tgt = o; o += sizeof(double) * L.NHp;
