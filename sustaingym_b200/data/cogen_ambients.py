@@ -9,6 +9,8 @@ table inside the observation-space bounds (cogen/env.py:136-142) for tests and b
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 AMBIENT_COLS = ("TAMB", "PAMB", "RHAMB", "Target_Power", "Target_Steam", "Energy_Price", "Gas_Price")
@@ -20,6 +22,21 @@ STEPS_PER_DAY = 96
 def from_dataframes(dfs) -> np.ndarray:
     """``load_ambients.construct_df()`` output -> [n_days, 96, 7] float64."""
     return np.stack([np.asarray(df[list(REFERENCE_COLUMNS)], np.float64) for df in dfs])
+
+
+_REAL = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cogen_ambients_real.npz")
+
+
+def real_ambients(renewables_magnitude: float = 0.0) -> np.ndarray:
+    """The reference's own ambient table (253 days from 2021-05 on; built once from its raw xlsx / csv files by
+    ``python -m sustaingym_b200.data.load_ambients``, which restates ``load_ambients.construct_df``), for any
+    ``renewables_magnitude``: target power = max(raw target - magnitude * wind capacity factor, 0)
+    (load_ambients.py:120-126)."""
+    with np.load(_REAL) as z:
+        tab, cf = z["ambients"].copy(), z["wind_cf"]
+    if renewables_magnitude:
+        tab[..., 3] = np.maximum(tab[..., 3] - float(renewables_magnitude) * cf, 0.0)
+    return tab
 
 
 def synthetic_ambients(n_days: int = 64, seed: int = 0) -> np.ndarray:

@@ -16,7 +16,7 @@ import numpy as np
 import torch
 
 from ... import _lib, spaces
-from ...data.cogen_ambients import AMBIENT_COLS, synthetic_ambients
+from ...data.cogen_ambients import AMBIENT_COLS, real_ambients, synthetic_ambients  # noqa: F401
 
 PLANT_NPZ = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))),
                          "data", "cogen_plant.npz")
@@ -95,8 +95,8 @@ def action_row_to_dict(row: np.ndarray) -> dict:
 
 
 class BatchedCogenEnv:
-    """Constructor mirrors cogen/env.py:75-82; ``ambients`` replaces the xlsx-derived table
-    (``renewables_magnitude`` only affects how that table is built, load_ambients.py:120-126)."""
+    """Constructor mirrors cogen/env.py:75-82.  ``ambients`` ([days, 96, 7]) overrides the table; by default it
+    is the reference's own xlsx-derived table for ``renewables_magnitude`` (packaged, ``data/cogen_ambients.py``)."""
 
     def __init__(self, num_envs: int = 1, ambients: np.ndarray | None = None, renewables_magnitude: float = 0.,
                  ramp_penalty: float = 2., supply_imbalance_penalty: float = 1000,
@@ -111,8 +111,8 @@ class BatchedCogenEnv:
         self.ramp_penalty, self.supply_imbalance_penalty = ramp_penalty, supply_imbalance_penalty
         self.constraint_violation_penalty = constraint_violation_penalty
         self.forecast_horizon, self.forecast_noise_std = forecast_horizon, forecast_noise_std
-        if ambients is None:
-            ambients = synthetic_ambients(64)
+        if ambients is None:      # the reference's table for this renewables_magnitude (cogen/env.py:89)
+            ambients = real_ambients(renewables_magnitude)
         self.ambients = np.ascontiguousarray(ambients, np.float64)
         self.n_days, self.timesteps_per_day = self.ambients.shape[0], self.ambients.shape[1]
         assert self.timesteps_per_day == 96 and self.ambients.shape[2] == 7

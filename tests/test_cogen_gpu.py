@@ -95,3 +95,16 @@ def test_single_and_multiagent_views(native_lib):
     # seed reproducibility (parallel_seed_test): same seed -> same first observation
     o1, _ = ma.reset(seed=5); o2, _ = ma.reset(seed=5)
     np.testing.assert_array_equal(o1["ST"], o2["ST"])
+
+
+def test_default_env_runs_on_the_reference_ambient_table(native_lib):
+    """CogenEnv() without arguments uses the reference's own 253-day ambient table (packaged), like cogen/env.py:89."""
+    from sustaingym_b200.envs.cogen.env import CogenEnv
+    env = CogenEnv(renewables_magnitude=50.0)
+    assert env._b.n_days == 253
+    obs, _ = env.reset(seed=7)
+    assert env.current_day == 7 and env.observation_space.contains(obs)
+    for t in range(96):
+        obs, r, term, trunc, info = env.step(env.action_space.sample())
+        assert env.observation_space.contains(obs) and np.isfinite(r)
+    assert term
