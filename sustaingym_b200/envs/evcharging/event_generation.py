@@ -232,7 +232,10 @@ class RealTraceGenerator(ArrayTraceGenerator):
     ``data/evcharging/acn_data/<site>/<begin> <end>.csv.gz`` files under ``data_dir`` (a checkout of the
     reference's ``sustaingym/data``; the files are data, not shipped here).  Filters follow
     ``_create_events`` (:293-328): claimed sessions only unless ``use_unclaimed``, stations of the network,
-    departure and estimated departure on the arrival's calendar day, estimated departure after arrival."""
+    departure and estimated departure on the arrival's calendar day, estimated departure after arrival.  MOER tables
+    come from ``data_dir/moer`` (``data/load_moer.py``; day d+1's table goes with day d's sessions and the last day
+    wraps to the first, as the reference's day cursor does).  Not reproduced: the reference's pytz LMT day stamp makes
+    its session window run 00:53-00:53 local, which drops the rare sessions that arrive before 00:53."""
 
     def __init__(self, site="caltech", date_period="Summer 2019", data_dir: str | None = None,
                  sequential: bool = True, use_unclaimed: bool = False, requested_energy_cap: float = 100,
@@ -271,7 +274,13 @@ class RealTraceGenerator(ArrayTraceGenerator):
                 continue
             days[d].append((arr, dep, est, float(r.kwh), index[r.station_id]))
         self.date_period, self.use_unclaimed = date_period, use_unclaimed
-        moer = synthetic_moer(n_days + 1, 1) if moer is None else moer
+        if moer is None:
+            moer_dir = os.path.join(data_dir, "moer")
+            if os.path.isdir(moer_dir):     # the reference's MOERLoader tables of the same days (get_moer, :209-218)
+                from ...data.load_moer import load_moer_days
+                moer = load_moer_days(moer_dir, begin, n_days)
+            else:
+                moer = synthetic_moer(n_days + 1, 1)
         super().__init__(days, moer, net, requested_energy_cap, sequential=sequential, seed=seed, **kw)
 
     def __repr__(self) -> str:
