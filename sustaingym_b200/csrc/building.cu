@@ -189,6 +189,12 @@ building_step_kernel(const sg_building_model m, const long long B, const int ste
         w_nxt = load_weather(m.weather, (e + 1) % m.T);
     }
 
+#ifdef SG_BLD_TRACE2
+    long long tp[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tq = clock64(), tq2;
+#define SG_P2(i) tq2 = clock64(); tp[i] += tq2 - tq; tq = tq2
+#else
+#define SG_P2(i)
+#endif
     for (int s = 0; s < steps; ++s) {
         // ---- this step's action rows: landed in the ring (issued kPre steps ago) --------------------
         const unsigned char* act_tile = act_tile_raw;
@@ -198,6 +204,7 @@ building_step_kernel(const sg_building_model m, const long long B, const int ste
             stage_actions(s + kPre);     // refills the slot step s-1 used
             act_tile = act_tile_raw + (size_t)(s % kRing) * act_tile_bytes;
         }
+        SG_P2(0);
         double rew = 0.0;
         bool dn = false;
         if (valid) {
@@ -225,6 +232,7 @@ building_step_kernel(const sg_building_model m, const long long B, const int ste
                     }
                 }
             }
+            SG_P2(1);
             // ---- exogenous inputs + occupancy heat: env.py:244-263 --------------------------
             const Weather4 w = w_cur;
             w_cur = w_nxt;
@@ -233,6 +241,7 @@ building_step_kernel(const sg_building_model m, const long long B, const int ste
             }
             const float avg_temp = __fdiv_rn(numpy_sum_f32<MAXN>(x, n), (float)n);
             const double occ = occupower_f32temp(avg_temp, w.meta);
+            SG_P2(2);
             // ---- X_new = A_d X + BD_d Y: env.py:266 ; error/reward: env.py:272-276 -----------
             double err2 = 0.0, errp = 0.0;
             float xn[MAXN];
@@ -256,6 +265,7 @@ building_step_kernel(const sg_building_model m, const long long B, const int ste
                     xn[i] = (float)v;
                 }
             }
+            SG_P2(3);
             double a_term, e_term;
             if (p2) {
                 e_term = sqrt(err2) * m.error_rate;
@@ -291,6 +301,7 @@ building_step_kernel(const sg_building_model m, const long long B, const int ste
             reward_g[(long long)s * B + b] = rew;
             done_g[(long long)s * B + b] = dn ? 1 : 0;
         }
+        SG_P2(4);
         // ---- emit the observation row (per step for rollouts, final state always) ------------
         const bool last = (s == steps - 1);
         if (obs_out != nullptr || last) {
@@ -323,7 +334,11 @@ building_step_kernel(const sg_building_model m, const long long B, const int ste
                 }
             }
         }
+        SG_P2(5);
     }
+#ifdef SG_BLD_TRACE2
+    if (blockIdx.x == 5 && tid == 0) printf("steps %d: top %lld act %lld occ %lld matvec %lld reward %lld emit %lld (cycles/step)\n", steps, tp[0] / steps, tp[1] / steps, tp[2] / steps, tp[3] / steps, tp[4] / steps, tp[5] / steps);
+#endif
     if (valid) { epoch_g[b] = e; runs_g[b] = r; }
     if (stats != nullptr) {
         __syncthreads();
