@@ -120,6 +120,7 @@ class BatchedEVChargingEnv:
             "arrivals": arrivals_dev,
         }
         self._pool = pool
+        self._max_profit_version = -1
         self._max_profit_host = None if pool is not None else t.max_profit(
             self.MARGINAL_PROFIT_PER_KWH, self.A_PERS_TO_KWH, self.ACTION_SCALE_FACTOR)
         self._model = _lib.EVModel(
@@ -286,10 +287,25 @@ class BatchedEVChargingEnv:
 
     @property
     def _max_profit_per_day(self) -> np.ndarray:
-        """``_calculate_max_profit`` (env.py:422-429) of every day of the pool: [D] f64 on the host."""
+        """``_calculate_max_profit`` (env.py:422-429) of every day of the pool: [D] f64 on the host (cached; a
+        device-sampled pool is read back once per ``resample()``)."""
         if self._pool is None:
             return self._max_profit_host
-        return self._pool["max_kwh"].cpu().numpy() * self.MARGINAL_PROFIT_PER_KWH
+        version = getattr(self.data_generator, "pool_version", 0)
+        if self._max_profit_host is None or self._max_profit_version != version:
+            self._max_profit_host = self._pool["max_kwh"].cpu().numpy() * self.MARGINAL_PROFIT_PER_KWH
+            self._max_profit_version = version
+        return self._max_profit_host
+
+    def episode_info(self) -> dict:
+        """Per-env ``info`` of the reference at the end of an episode (env.py:403-406), as columns:
+        ``max_profit`` [B] and ``reward_breakdown`` (list of dicts) — what ``BaseAlgorithm.run`` tabulates."""
+        bd = self.breakdown.cpu().numpy()
+        day = self.day.cpu().numpy()
+        mp = self._max_profit_per_day
+        return {"max_profit": [float(mp[d]) for d in day],
+                "reward_breakdown": [{"profit": float(r[0]), "carbon_cost": float(r[1]), "excess_charge": float(r[2])}
+                                     for r in bd]}
 
     def launch_step(self, actions: torch.Tensor) -> None:
         """Enqueues the step kernel on the current stream without building return values (used by

@@ -205,6 +205,7 @@ class GMMsTraceGenerator(AbstractTraceGenerator):
                              32 * self.A_PERS_TO_KWH)
         self._next_day += self._num_days
         self._tables = None
+        self.pool_version = getattr(self, "pool_version", 0) + 1
 
     @property
     def tables(self) -> TraceTables:
