@@ -3,7 +3,7 @@
 The reference builds the dict with ``ParameterGenerator`` (sustaingym/envs/building/utils.py:462-779) from
 EnergyPlus HTM tables and EPW weather files at construction time.  The engine only needs its numeric
 content — the RC matrices, per-zone vectors and the four 5-minute weather tables — so an offline export
-(``tools/export_building_params.py``, which runs the reference's generator) is enough to run any shipped
+(``tests/golden/export_building_params.py``, which runs the reference's generator) is enough to run any shipped
 building / climate without the reference tree.
 """
 from __future__ import annotations

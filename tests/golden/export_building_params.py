@@ -3,7 +3,7 @@ shipped buildings / climates and writes one ``.npz`` per setting that ``load_par
 (sustaingym_b200/envs/building/params.py) turns back into the ``parameters`` dict BuildingEnv takes —
 so every shipped building runs on the engine where the reference tree is not present (the GPU box).
 
-    python tools/export_building_params.py OUT_DIR [--buildings OfficeSmall,Hospital] [--weather Hot_Dry] [--location Tucson]
+    python tests/golden/export_building_params.py OUT_DIR [--buildings OfficeSmall,Hospital] [--weather Hot_Dry] [--location Tucson]
 
 Needs /root/reference (imported under oracle/ref_shim.py: gymnasium / pvlib stubs).  Without --buildings all 16
 ASHRAE 90.1 prototypes are exported (n = 3 ... 118 zones).  Weather tables are stored as float32 (they are
@@ -17,7 +17,7 @@ import sys
 
 import numpy as np
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 
 BUILDINGS = ["ApartmentHighRise", "ApartmentMidRise", "Hospital", "HotelLarge", "HotelSmall", "OfficeLarge",
              "OfficeMedium", "OfficeSmall", "OutPatientHealthCare", "RestaurantFastFood", "RestaurantSitDown",
