@@ -9,7 +9,6 @@ fewer launches.
 """
 from __future__ import annotations
 
-from collections import defaultdict
 from collections.abc import Sequence
 from copy import deepcopy
 from typing import Any, Callable
@@ -18,6 +17,8 @@ import numpy as np
 
 
 class BaseAlgorithm:
+    """A controller bound to one env.  Subclasses provide ``get_action``; ``reset`` is called between episodes."""
+
     def __init__(self, env, multiagent: bool = False):
         self.env = env
         self.multiagent = multiagent
@@ -26,37 +27,34 @@ class BaseAlgorithm:
         raise NotImplementedError
 
     def reset(self) -> None:
-        """Resets the algorithm at the end of each episode."""
+        return None
+
+    def _episode(self, seed: int) -> tuple[float, dict]:
+        """Plays the episode ``seed`` selects to its end: (sum of rewards, last info)."""
+        obs, info = self.env.reset(seed=seed)
+        self.reset()
+        total, finished = 0.0, False
+        while not finished:
+            obs, rew, term, trunc, info = self.env.step(self.get_action(obs))
+            if self.multiagent:          # PettingZoo dicts: team reward, any agent ending ends the episode
+                total += sum(rew.values())
+                finished = any(term.values()) or any(trunc.values())
+            else:
+                total += rew
+                finished = bool(term or trunc)
+        if self.multiagent and info:
+            info = next(iter(info.values()))   # all agents carry the same info
+        return total, info
 
     def run(self, seeds: Sequence[int] | int):
-        """base.py:35-97: one episode per seed; DataFrame with ``seed``, ``return`` and the final info entries."""
+        """One row per seed: ``seed``, ``return`` and the entries of the episode's final ``info``
+        (the table of sustaingym/algorithms/base.py:35-97)."""
         import pandas as pd
-        if isinstance(seeds, int):
-            seeds = list(range(seeds))
-        results: dict[str, list] = defaultdict(list)
-        for seed in seeds:
-            results["seed"].append(seed)
-            ep_return = 0.0
-            obs, _ = self.env.reset(seed=seed)
-            self.reset()
-            done = False
-            info: dict = {}
-            while not done:
-                action = self.get_action(obs)
-                obs, reward, terminated, truncated, info = self.env.step(action)
-                assert isinstance(reward, dict) == self.multiagent
-                if self.multiagent:
-                    reward = sum(reward.values())
-                    done = any(terminated.values()) or any(truncated.values())
-                else:
-                    done = terminated or truncated
-                ep_return += reward
-            results["return"].append(ep_return)
-            if self.multiagent:
-                info = info[list(info.keys())[0]]
-            for key, value in info.items():
-                results[key].append(deepcopy(value))
-        return pd.DataFrame(results)
+        rows = []
+        for seed in (range(seeds) if isinstance(seeds, int) else seeds):
+            total, info = self._episode(int(seed))
+            rows.append({"seed": int(seed), "return": total, **{k: deepcopy(v) for k, v in info.items()}})
+        return pd.DataFrame(rows, columns=list(rows[0]) if rows else ["seed", "return"])
 
 
 def run_batched(batched_env, policy: Callable, seeds: Sequence[int] | int, max_steps: int | None = None):
