@@ -89,12 +89,13 @@ int sg_building_rollout(const sg_building_model* m, int64_t num_envs, int32_t st
                         float* obs_out, double* reward, uint8_t* done,
                         int32_t flags, double* stats, void* stream);
 
-/* Host-buffer variant of sg_building_step: copies `h_action` to `d_action`, steps, copies
- * state/reward/done back, synchronises. d_* are caller-owned device scratch of the same shapes. */
+/* Host-buffer variant of sg_building_step: copies `h_action` to `d_action`, steps (same `flags` / `d_stats`
+ * as sg_building_step), copies state/reward/done back, synchronises. d_* are caller-owned device
+ * scratch of the same shapes. */
 int sg_building_step_host(const sg_building_model* m, int64_t num_envs,
                           const void* h_action, float* h_obs, double* h_reward, uint8_t* h_done,
                           void* d_action, float* d_state, int32_t* d_epoch, int32_t* d_runs,
-                          double* d_reward, uint8_t* d_done, void* stream);
+                          double* d_reward, uint8_t* d_done, int32_t flags, double* d_stats, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * EVChargingEnv  —  replaces sustaingym/envs/evcharging/env.py:229-291 (step), :200-221 +

@@ -99,7 +99,7 @@ SIGNATURES = {
     "sg_building_rollout": (C.c_int, [C.POINTER(BuildingModel), _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                       _i32, _vp, _vp]),
     "sg_building_step_host": (C.c_int, [C.POINTER(BuildingModel), _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                        _vp, _vp, _vp]),
+                                        _vp, _vp, _i32, _vp, _vp]),
     "sg_ev_prepare_tables": (C.c_int, [C.POINTER(EVModel), _vp, _vp]),
     "sg_ev_reset": (C.c_int, [C.POINTER(EVModel), C.POINTER(EVState), _i64, _vp, _vp, _vp, _vp, _vp]),
     "sg_ev_step": (C.c_int, [C.POINTER(EVModel), C.POINTER(EVState), _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp,

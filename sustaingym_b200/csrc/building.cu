@@ -778,12 +778,9 @@ int launch_building_mma(const sg_building_model* m, long long B, int steps, cons
     const float* act = static_cast<const float*>(action);
 #define SG_MMA_CASE(TI_)                                                                                              \
     case TI_: {                                                                                                       \
-        static size_t configured = 0;                                                                                 \
-        if (L.total > configured) {                                                                                   \
-            cudaError_t err = cudaFuncSetAttribute(building_mma_kernel<TI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total); \
-            if (err != cudaSuccess) { set_error("building: %zu B of shared memory unavailable", L.total); return 2; } \
-            configured = L.total;                                                                                     \
-        }                                                                                                             \
+        /* per-device attribute: set on every launch (a process may drive several GPUs) */                            \
+        cudaError_t err = cudaFuncSetAttribute(building_mma_kernel<TI_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total); \
+        if (err != cudaSuccess) { set_error("building: %zu B of shared memory unavailable", L.total); return 2; }     \
         building_mma_kernel<TI_><<<grid, kMmaThreads, L.total, st>>>(*m, B, steps, act, state, epoch, runs, obs_out,  \
                                                                      reward, done, flags, stats);                     \
         break;                                                                                                        \
@@ -883,13 +880,13 @@ int sg_building_rollout(const sg_building_model* m, int64_t num_envs, int32_t st
 int sg_building_step_host(const sg_building_model* m, int64_t num_envs, const void* h_action, float* h_obs,
                           double* h_reward, uint8_t* h_done, void* d_action, float* d_state,
                           int32_t* d_epoch, int32_t* d_runs, double* d_reward, uint8_t* d_done,
-                          void* stream) {
+                          int32_t flags, double* d_stats, void* stream) {
     SG_CHECK_ARG(m && h_action && h_obs && h_reward && h_done && d_action, "building_step_host: NULL argument");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     const size_t B = (size_t)num_envs, n = (size_t)m->n;
     SG_CUDA(cudaMemcpyAsync(d_action, h_action, B * n * (m->discrete ? 8 : 4), cudaMemcpyHostToDevice, st));
     int rc = sg::dispatch_building(m, num_envs, 1, d_action, d_state, d_epoch, d_runs, nullptr, d_reward,
-                                   d_done, 0, nullptr, stream);
+                                   d_done, flags, d_stats, stream);
     if (rc) return rc;
     SG_CUDA(cudaMemcpyAsync(h_obs, d_state, B * (n + 4) * 4, cudaMemcpyDeviceToHost, st));
     SG_CUDA(cudaMemcpyAsync(h_reward, d_reward, B * 8, cudaMemcpyDeviceToHost, st));

@@ -645,11 +645,8 @@ int launch_mlp(const sg_cogen_model* m, long long B, const float* X, const float
                float* raw, cudaStream_t st) {
     if (m->tc_blob != nullptr && m->tc_offsets != nullptr) {     // tensor-core path
         const size_t smem_tc = sizeof(float) * (2 * (2 * kTcKC * 256 + 2 * kTcM * kTcKC) + kTcW1Ring * (kDPad * kTcKC + kTcKC));
-        static bool configured_tc = false;
-        if (!configured_tc) {
-            SG_CUDA(cudaFuncSetAttribute(cogen_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
-            configured_tc = true;
-        }
+        // per-device attribute: set on every launch (a process may drive several GPUs)
+        SG_CUDA(cudaFuncSetAttribute(cogen_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tc));
         float* xn = raw + ((B * kNSub + 3) & ~3LL);               // scratch = raw [B,23] | xn [23,B,16] (16-byte aligned)
         cogen_tc_inputs_kernel<<<dim3((unsigned)((B + 127) / 128), kNSub), 128, 0, st>>>(*m, B, X, action, day_t, xn);
         dim3 grid((unsigned)((B + kTcM - 1) / kTcM), kNSub);
@@ -657,11 +654,7 @@ int launch_mlp(const sg_cogen_model* m, long long B, const float* X, const float
         return launch_status("cogen_mlp_tc_kernel");
     }
     const size_t smem = sizeof(float) * (kTM * kDPad + kKC * kTM + kDPad * kKC + 2 * kKC * 256);
-    static bool configured = false;   // attribute is per-function and idempotent; races are benign
-    if (!configured) {
-        SG_CUDA(cudaFuncSetAttribute(cogen_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
+    SG_CUDA(cudaFuncSetAttribute(cogen_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((unsigned)((B + kTM - 1) / kTM), kNSub);
     cogen_mlp_kernel<<<grid, kThreadsC, smem, st>>>(*m, B, X, action, day_t, raw);
     return launch_status("cogen_mlp_kernel");

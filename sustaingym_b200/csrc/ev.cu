@@ -28,6 +28,7 @@
 //
 // Bound: HBM.  Algorithmic bytes per env-step: SURVEY.md 8d (1709 B at n=54, k=36).
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -1780,7 +1781,13 @@ int sg_ev_step(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, con
     if (sms <= 0) sms = 148;
     // one warp per kE-env tile; SG_EV_MINB resident CTAs per SM, larger batches loop (persistent)
     const long long ntiles = (num_envs + sg::kE - 1) / sg::kE;
-    const unsigned grid = (unsigned)std::min<long long>((ntiles + sg::kMainWarps - 1) / sg::kMainWarps, (long long)sms * SG_EV_MINB);
+    unsigned grid = (unsigned)std::min<long long>((ntiles + sg::kMainWarps - 1) / sg::kMainWarps, (long long)sms * SG_EV_MINB);
+    // SG_EV_MAX_CTAS=<n> caps the grid (test hook): every warp then loops over many tiles, which is the code path
+    // the BASELINE batch runs on, at any batch size
+    if (const char* cap = getenv("SG_EV_MAX_CTAS")) {
+        const long v = atol(cap);
+        if (v >= 1) grid = (unsigned)std::min<long long>(grid, v);
+    }
     // staging rows in dynamic shared memory: per warp kE observation rows + kE pilot rows
     const int OBS = 2 * m->n_stations + m->moer_steps + 2;
     const size_t dyn = (size_t)sg::kMainWarps * (((sg::kE * OBS * 4 + 15) & ~15) + ((sg::kE * m->n_stations + 15) & ~15));

@@ -158,7 +158,7 @@ class BatchedBuildingEnv:
                     C.byref(self._model), B, self._h_action.data_ptr(), self._h_obs.data_ptr(),
                     self._h_reward.data_ptr(), self._h_done.data_ptr(), self._d_action.data_ptr(),
                     self.state.data_ptr(), self.epoch.data_ptr(), self.runs.data_ptr(), self.reward.data_ptr(),
-                    self.done.data_ptr(), self._stream()), "sg_building_step_host")
+                    self.done.data_ptr(), self._flags, _lib.ptr(self.stats), self._stream()), "sg_building_step_host")
             self.kernel_launches += 1
             d = self._h_done.numpy().astype(bool)
             return self._h_obs.numpy().copy(), self._h_reward.numpy().copy(), d, d.copy(), {}
@@ -235,8 +235,15 @@ class BuildingEnv:
 
     def step(self, action):
         dt = np.float32 if self.is_continuous_action else np.int64
-        obs, rew, done, _, _ = self._b.step(np.asarray(action, dt).reshape(1, self.n))
+        action = np.asarray(action, dt).reshape(self.n)
+        obs, rew, done, _, _ = self._b.step(action.reshape(1, self.n))
         self.state = obs[0]
+        # reward breakdown (env.py:276-280): the power term is the reference's own expression on the action, the
+        # comfort term is the rest of the reward the kernel returned (reward = -(power + comfort))
+        a = action if self.is_continuous_action else (action + self.Qlow * DISCRETE_LENGTH) / DISCRETE_LENGTH   # env.py:234-235
+        power = float(np.linalg.norm(a, self.reward_pnorm) * self.q_rate)
+        self._reward_breakdown["power_consumption"] -= power
+        self._reward_breakdown["comfort_level"] -= -float(rew[0]) - power
         return self.state, float(rew[0]), bool(done[0]), bool(done[0]), self._info()
 
     def close(self) -> None:

@@ -11,7 +11,12 @@ from .env import BuildingEnv
 
 
 class MultiAgentBuildingEnv:
-    def __init__(self, parameters: dict[str, Any], device=None) -> None:
+    def __init__(self, parameters: dict[str, Any], device=None, positional_keys: bool = False) -> None:
+        """``positional_keys``: the reference reads ``actions[i]`` with i the ENUMERATION index of the agent
+        (multiagent_env.py:84-85), which equals the agent id only when every zone has an AC unit.  Default here:
+        the PettingZoo convention (the dict is keyed by agent id, as ``parallel_api_test`` drives it);
+        ``positional_keys=True`` reproduces the reference's indexing."""
+        self.positional_keys = positional_keys
         self.single_env = BuildingEnv(parameters, device)
         self.possible_agents = np.nonzero(self.single_env.ac_map)[0].tolist()      # multiagent_env.py:53
         self.agents = self.possible_agents[:]
@@ -29,9 +34,7 @@ class MultiAgentBuildingEnv:
         dt = np.float32 if self.single_env.is_continuous_action else np.int64
         action = np.zeros(self.single_env.n, dtype=dt)
         for i, agent in enumerate(self.agents):
-            # the reference indexes the mapping by enumeration index (multiagent_env.py:84-85); accept
-            # agent ids as well so that dicts keyed the PettingZoo way work
-            v = actions[i] if i in actions else actions[agent]
+            v = actions[i] if self.positional_keys else actions[agent]
             action[agent] = np.asarray(v).reshape(-1)[0]
         obs, reward, terminated, truncated, info = self.single_env.step(action)
         self._state = obs

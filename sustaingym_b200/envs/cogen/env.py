@@ -52,6 +52,16 @@ class PlantWeights:
         self.b3 = t(z["b3"].astype(np.float32))
         self.tc_blob = self.tc_offsets = None        # filled on first use (sg_cogen_prepare_tc)
 
+    _cache: dict = {}
+
+    @classmethod
+    def shared(cls, device) -> "PlantWeights":
+        """One copy per device: every env instance (and every CTA) reads the same L2-resident weights."""
+        key = str(device)
+        if key not in cls._cache:
+            cls._cache[key] = cls(device)
+        return cls._cache[key]
+
 
 def make_spaces(weights: PlantWeights, forecast_horizon: int):
     """Action / observation spaces exactly as cogen/env.py:114-143 builds them."""
@@ -117,7 +127,7 @@ class BatchedCogenEnv:
         self.n_days, self.timesteps_per_day = self.ambients.shape[0], self.ambients.shape[1]
         assert self.timesteps_per_day == 96 and self.ambients.shape[2] == 7
         assert 0 <= forecast_horizon < self.timesteps_per_day - 1       # cogen/env.py:92
-        self.weights = PlantWeights(dev)
+        self.weights = PlantWeights.shared(dev)
         self.single_action_space, self.single_observation_space = make_spaces(self.weights, forecast_horizon)
         self.obs_dim = 7 * (forecast_horizon + 1) + 33
         self._amb = torch.from_numpy(self.ambients).to(dev)
@@ -273,7 +283,9 @@ class CogenEnv:
                  constraint_violation_penalty: float = 1000, forecast_horizon: int = 3, forecast_noise_std: float = 0.0,
                  ambients: np.ndarray | None = None, device=None):
         self._b = BatchedCogenEnv(1, ambients, renewables_magnitude, ramp_penalty, supply_imbalance_penalty,
-                                  constraint_violation_penalty, forecast_horizon, forecast_noise_std, device)
+                                  constraint_violation_penalty, forecast_horizon, forecast_noise_std, device,
+                                  keep_outputs=True)
+        self.ramp_penalty, self.supply_imbalance_penalty = ramp_penalty, supply_imbalance_penalty
         self.action_space = self._b.single_action_space
         self.observation_space = self._b.single_observation_space
         self.forecast_horizon, self.forecast_noise_std = forecast_horizon, forecast_noise_std
@@ -296,12 +308,33 @@ class CogenEnv:
         noise = None
         if self.forecast_noise_std > 0 and self.forecast_horizon > 0:        # cogen/env.py:161 (env's own RNG)
             noise = torch.from_numpy(self.np_random.normal(size=(1, self.forecast_horizon, 7)))
+        prev_obs = self.obs
         obs, rew, done, _, info = self._b.step(action_dict_to_row(action)[None], noise)
         self.t += 1
         self.obs = _unflatten_obs(obs[0], self.forecast_horizon)
         ar = info["agent_rewards"][0]
         self.current_info = {"agent_rewards": {a: float(ar[i]) for i, a in enumerate(AGENTS)}}
+        self.current_info.update(self._reward_breakdown(prev_obs, action, ar))
         return self.obs, float(rew[0]), bool(done[0]), False, self.current_info
+
+    def _reward_breakdown(self, prev_obs: dict, action: dict, agent_rewards: np.ndarray) -> dict:
+        """The reference's info dict (cogen/env.py:309-352) from what the kernels emit: fuel costs are plant outputs
+        6..8, ramp and non-delivery costs are the reference's own f32 expressions on the action / previous observation
+        / plant outputs 27, 28, and each unit's constraint-violation cost is what is left of its reward share
+        (multiagent_env.py:97-101: reward_i = -(fuel_i + ramp_i + dyn_cv_i + non_delivery / 4))."""
+        Y = self._b.Y[0].cpu().numpy()
+        rp = np.float32(self.ramp_penalty)
+        fuel = {"GT1": Y[6], "GT2": Y[7], "GT3": Y[8], "ST": 0}
+        prev = prev_obs["Prev_Action"]
+        pw = {"GT1": "GT1_PWR", "GT2": "GT2_PWR", "GT3": "GT3_PWR", "ST": "ST_PWR"}
+        ramp = {a: rp * np.abs(np.float32(np.asarray(action[k]).reshape(-1)[0]) - np.float32(np.asarray(prev[k]).reshape(-1)[0]))
+                for a, k in pw.items()}
+        steam_penalty = np.maximum(np.float32(0), prev_obs["Target_Steam"][0] - Y[28])
+        energy_penalty = np.maximum(np.float32(0), prev_obs["Target_Power"][0] - Y[27])
+        non_delivery = np.float32(self.supply_imbalance_penalty) * (steam_penalty + energy_penalty)
+        dyn = {a: max(0.0, -float(agent_rewards[i]) - float(fuel[a]) - float(ramp[a]) - float(non_delivery) / 4)
+               for i, a in enumerate(AGENTS)}
+        return {"fuel_costs": fuel, "ramp_costs": ramp, "dyn_cv_costs": dyn, "non_delivery_cost": non_delivery}
 
     def close(self) -> None:
         pass

@@ -47,6 +47,17 @@ class BatchedEVChargingEnv:
     VIOLATION_FACTOR = A_PERS_TO_KWH * VIOLATION_WEIGHT
     CARBON_COST_FACTOR = A_PERS_TO_KWH * (CO2_COST_PER_METRIC_TON / 1000)
 
+    HOST_PATH_NOTE = ("BatchedEVChargingEnv.step_async(pinned host actions) / step_wait() -> sg_ev_step_host_async, "
+                      "two env batches in flight (H2D of one overlaps D2H of the other)")
+
+    @property
+    def h2d_bytes_per_step(self) -> int:
+        return self.num_envs * self.num_stations * (8 if self.discrete_bins > 0 else 4)
+
+    @property
+    def d2h_bytes_per_step(self) -> int:
+        return self.num_envs * (self.obs_dim * 4 + 8 + 1)
+
     def __init__(self, data_generator: AbstractTraceGenerator, num_envs: int = 1,
                  moer_forecast_steps: int = 36, project_action_in_env: bool = True, verbose: int = 0,
                  device: str | torch.device | None = None, auto_reset: bool = False,
@@ -67,6 +78,7 @@ class BatchedEVChargingEnv:
         self.cn: ChargingNetworkSpec = data_generator.network
         self.num_stations = n = self.cn.num_stations
         self.obs_dim = 2 * n + moer_forecast_steps + 2
+        self._async_stream = None
 
         # ---- spaces (env.py:143-150, 171-172; wrappers.py:36-41 for the discrete variant) ---------
         k = moer_forecast_steps
@@ -178,7 +190,10 @@ class BatchedEVChargingEnv:
                 f"x {self.num_envs} envs on {self.device}")
 
     def _stream(self) -> int:
-        return torch.cuda.current_stream(self.device).cuda_stream
+        cur = torch.cuda.current_stream(self.device)
+        if self._async_stream is not None:      # work queued by step_async() touches the same state: order after it
+            cur.wait_stream(self._async_stream)
+        return cur.cuda_stream
 
     def reset_stats(self) -> None:
         _lib.check(self.lib.sg_stats_reset(self.stats.data_ptr(), self._stream()), "sg_stats_reset")
@@ -268,7 +283,8 @@ class BatchedEVChargingEnv:
             raise ValueError("step_async needs a pinned contiguous host tensor of shape (num_envs, n)")
         if self._async_stream is None:
             self._async_stream = torch.cuda.Stream(self.device)
-            self._async_stream.wait_stream(torch.cuda.current_stream(self.device))
+        # order this step after everything queued on the caller's stream (reset(), step(), graph replays ...)
+        self._async_stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.device(self.device):
             _lib.check(self.lib.sg_ev_step_host_async(
                 C.byref(self._model), C.byref(self._state), self.num_envs, actions.data_ptr(), self._flags,

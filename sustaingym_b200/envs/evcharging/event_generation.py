@@ -60,6 +60,12 @@ class AbstractTraceGenerator:
         return np.array([np.random.default_rng(int(s)).integers(0, D) for s in np.asarray(seeds)], np.int32)
 
     def moer_days(self, days: np.ndarray) -> np.ndarray:
+        """MOER table index that goes with each trace index.  Sequential generators: the day after the events' day
+        (see the module docstring).  Non-sequential generators: the reference draws the events' day at random and
+        fetches THAT day's MOER (event_generation.py:479-480, env.py:321-323) — with an i.i.d. pool of synthetic
+        days the equivalent is an independent random calendar day of the period."""
+        if not self.sequential and getattr(self, "moer_source", "") == "real":
+            return self.rng.integers(0, self.moer.shape[0], len(np.asarray(days))).astype(np.int32)
         return ((np.asarray(days, np.int64) + self.moer_day_offset) % self.moer.shape[0]).astype(np.int32)
 
     def __repr__(self) -> str:
@@ -102,6 +108,35 @@ DEFAULT_PERIOD_TO_RANGE = {
     "Summer 2021": DEFAULT_DATE_RANGES[3], "Post-COVID-19": DEFAULT_DATE_RANGES[3],
 }
 _GMM_FILE = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "data", "ev_gmms.npz")
+
+
+def _resolve_moer(moer, data_dir: str | None, date_period, synthetic_seed: int):
+    """MOER tables of a generator: an explicit ``[days, 289, 37]`` array; ``"synthetic"`` (explicit opt-in: smooth
+    random-walk tables, NOT the reference's data); or ``None`` = the reference's SGIP tables of the period's calendar
+    days, read from ``data_dir/moer`` (``$SUSTAINGYM_DATA_DIR``) through ``data/load_moer.py`` — and an error when
+    they are not there, because the carbon term of the reward and two observation fields depend on them
+    (``MOERLoader.retrieve(self.day)``, event_generation.py:209-218).  Returns (array f32, source tag)."""
+    if isinstance(moer, str):
+        if moer != "synthetic":
+            raise ValueError("moer must be an array, None (real SGIP tables) or 'synthetic'")
+        import pandas as pd
+        begin, end = _date_range(date_period)
+        n_days = (pd.Timestamp(end) - pd.Timestamp(begin)).days + 1
+        return np.ascontiguousarray(synthetic_moer(n_days + 1, synthetic_seed), dtype=np.float32), "synthetic"
+    if moer is not None:
+        return np.ascontiguousarray(moer, dtype=np.float32), "array"
+    data_dir = data_dir or os.environ.get("SUSTAINGYM_DATA_DIR")
+    moer_dir = os.path.join(data_dir, "moer") if data_dir else None
+    if moer_dir is None or not os.path.isdir(moer_dir):
+        raise FileNotFoundError(
+            "no MOER tables: pass data_dir (or set $SUSTAINGYM_DATA_DIR) to the reference's sustaingym/data so that "
+            "data_dir/moer/SGIP_CAISO_*.csv.gz can be read, pass moer=<[days,289,37] array>, or opt in to "
+            "moer='synthetic' (random-walk tables that do NOT match the reference's carbon costs)")
+    import pandas as pd
+    from ...data.load_moer import load_moer_days
+    begin, end = _date_range(date_period)
+    n_days = (pd.Timestamp(end) - pd.Timestamp(begin)).days + 1
+    return np.ascontiguousarray(load_moer_days(moer_dir, begin, n_days), dtype=np.float32), "real"
 
 
 def _date_range(date_period) -> tuple[str, str]:
@@ -176,8 +211,8 @@ class GMMsTraceGenerator(AbstractTraceGenerator):
 
     def __init__(self, site="caltech", date_period="Summer 2019", n_components: int = 30,
                  requested_energy_cap: float = 100, seed: int | None = None, num_days: int = 1024,
-                 max_sessions: int = 8, max_day_sessions: int = 128, moer: np.ndarray | None = None,
-                 gmm: dict | None = None, device="cuda", **kw):
+                 max_sessions: int = 8, max_day_sessions: int = 128, moer: np.ndarray | str | None = None,
+                 gmm: dict | None = None, device="cuda", data_dir: str | None = None, **kw):
         import torch
         kw.setdefault("sequential", False)           # the reference draws i.i.d. days (:479-480)
         super().__init__(site, requested_energy_cap, seed=seed, **kw)
@@ -191,7 +226,7 @@ class GMMsTraceGenerator(AbstractTraceGenerator):
         self.device = torch.device(device)
         self._gmm_dev = GmmDevice(self.gmm, self.num_stations, self.device)
         self.device_pool = self._gmm_dev.alloc_pool(self._num_days, self._K, self._smax)
-        self.moer = np.ascontiguousarray(synthetic_moer(64, self.seed + 1) if moer is None else moer, dtype=np.float32)
+        self.moer, self.moer_source = _resolve_moer(moer, data_dir, date_period, self.seed + 1)
         self._next_day = 0
         self.resample()
 
@@ -224,7 +259,7 @@ class GMMsTraceGenerator(AbstractTraceGenerator):
     def __repr__(self) -> str:
         begin, end = _date_range(self.date_period)
         return (f"{self.n_components}-component GMM-based trace generator for {self.site} ({begin} to {end}), "
-                f"pool of {self._num_days} days on {self.device}")
+                f"pool of {self._num_days} days on {self.device}, MOER: {self.moer_source}")
 
 
 class RealTraceGenerator(ArrayTraceGenerator):
@@ -240,7 +275,7 @@ class RealTraceGenerator(ArrayTraceGenerator):
 
     def __init__(self, site="caltech", date_period="Summer 2019", data_dir: str | None = None,
                  sequential: bool = True, use_unclaimed: bool = False, requested_energy_cap: float = 100,
-                 moer: np.ndarray | None = None, seed: int | None = None, **kw):
+                 moer: np.ndarray | str | None = None, seed: int | None = None, **kw):
         import pandas as pd
         net = site_str_to_site(site) if isinstance(site, str) else site
         begin, end = _date_range(date_period)
@@ -275,15 +310,10 @@ class RealTraceGenerator(ArrayTraceGenerator):
                 continue
             days[d].append((arr, dep, est, float(r.kwh), index[r.station_id]))
         self.date_period, self.use_unclaimed = date_period, use_unclaimed
-        if moer is None:
-            moer_dir = os.path.join(data_dir, "moer")
-            if os.path.isdir(moer_dir):     # the reference's MOERLoader tables of the same days (get_moer, :209-218)
-                from ...data.load_moer import load_moer_days
-                moer = load_moer_days(moer_dir, begin, n_days)
-            else:
-                moer = synthetic_moer(n_days + 1, 1)
+        # the reference's MOERLoader tables of the same days (get_moer, :209-218); synthetic tables only on request
+        moer, self.moer_source = _resolve_moer(moer, data_dir, date_period, 1)
         super().__init__(days, moer, net, requested_energy_cap, sequential=sequential, seed=seed, **kw)
 
     def __repr__(self) -> str:
         begin, end = _date_range(self.date_period)
-        return f"Real trace generator for {self.site} ({begin} to {end}), {self.num_days} days"
+        return f"Real trace generator for {self.site} ({begin} to {end}), {self.num_days} days, MOER: {self.moer_source}"

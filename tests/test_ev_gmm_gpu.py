@@ -49,7 +49,7 @@ def test_env_steps_on_device_sampled_pool(native_lib):
     from sustaingym_b200.envs.evcharging.env import BatchedEVChargingEnv
     from sustaingym_b200.envs.evcharging.event_generation import GMMsTraceGenerator
     B = 96
-    gen = GMMsTraceGenerator("caltech", "Summer 2019", seed=4, num_days=16, sequential=True)
+    gen = GMMsTraceGenerator("caltech", "Summer 2019", seed=4, num_days=16, sequential=True, moer="synthetic")
     env = BatchedEVChargingEnv(gen, B, project_action_in_env=False)
     net = O.caltech_acn()
 
