@@ -515,7 +515,14 @@ def main():
     side = torch.cuda.Stream(dev)
     main_stream = torch.cuda.current_stream(dev)
     tick = torch.cuda.Event()
-    job_stats = [all_reduce_stats(shared_stats)]            # also warms the NCCL communicator up
+    stats_buf = torch.zeros(shared_stats.numel() + 2, dtype=torch.float64, device=dev)   # no allocation in the timed region
+    job_stats = [None]
+    for _ in range(2):                                      # warms the side stream, the event and the NCCL communicator up
+        tick.record(main_stream)
+        side.wait_event(tick)
+        with torch.cuda.stream(side):
+            job_stats[0] = all_reduce_stats(shared_stats, out=stats_buf)
+        main_stream.wait_stream(side)
     ctx.barrier()
     sampler = ClockSampler(physical_gpu_index(local_rank))
     sampler.start()
@@ -529,7 +536,7 @@ def main():
             tick.record(main_stream)
             side.wait_event(tick)
             with torch.cuda.stream(side):
-                job_stats[0] = all_reduce_stats(shared_stats)
+                job_stats[0] = all_reduce_stats(shared_stats, out=stats_buf)
             n_collectives += 1
     main_stream.wait_stream(side)
     e1.record()
@@ -566,11 +573,12 @@ def main():
     durs = sorted(a_.elapsed_time(b_) for a_, b_ in evs)
     kern_events_ms = float(np.mean(durs[L // 20: L - L // 20]))     # 5 % trimmed mean over one episode
 
-    # ---- e2e: public host API, pinned host actions in, obs/reward/done out, every step ---------------
-    # SB3 VecEnv-style step_async / step_wait on two env batches: while one batch's observations are
-    # copied to the host, the other batch's actions are copied to the device and its kernel runs.
-    E = 40
-    pipe = envs[1:3]                             # the two mid-day sets (t ~ 108 / 180 + what ran so far)
+    # ---- e2e: the public host API (the SB3 VecEnv adapter INTEGRATION.md tells users to use), pinned host actions in,
+    # host obs/reward/done out, every step.  step_async / step_wait on two env batches: while one batch's results are
+    # copied to the host and expanded, the other batch's actions are copied to the device and its kernel runs.
+    from sustaingym_b200.envs.vector import SB3VecEnv
+    E = 200
+    pipe = [SB3VecEnv(e, dict_obs=False, copy=False) for e in envs[1:3]]   # the two mid-day sets
     h_act = torch.rand(4, B, N_STATIONS, dtype=torch.float32).pin_memory()
     torch.cuda.synchronize()
     for i in range(4):
@@ -580,13 +588,15 @@ def main():
     pipe[0].step_async(h_act[0])
     for i in range(E):
         pipe[(i + 1) % 2].step_async(h_act[(i + 1) % 4])
-        obs_h, rew_h, done_h, _, _ = pipe[i % 2].step_wait()
-    obs_h, rew_h, done_h, _, _ = pipe[E % 2].step_wait()
+        obs_h, rew_h, done_h, _ = pipe[i % 2].step_wait()
+    obs_h, rew_h, done_h, _ = pipe[E % 2].step_wait()
     torch.cuda.synchronize()
     dt = ctx.max_over_ranks(time.perf_counter() - t0)
     e2e_value = world * B * (E + 1) / dt
-    h2d = pipe[0].h2d_bytes_per_step
-    d2h = pipe[0].d2h_bytes_per_step
+    assert obs_h.shape == (B, OBS_DIM) and rew_h.shape == (B,)
+    h2d = pipe[0].env.h2d_bytes_per_step
+    d2h = pipe[0].env.d2h_bytes_per_step
+    e2e_threads = pipe[0].env.host_threads
 
     cpu_base = None
     want_cpu = rank == 0 and world == 1 and not args.no_cpu_baseline
@@ -634,7 +644,8 @@ def main():
                          "peak_source": peak_src},
             "cpu_baseline": cpu_base,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": E + 1, "api": pipe_api_note()},
+                    "steps": E + 1, "host_threads_per_rank": e2e_threads,
+                    "api": "SB3VecEnv(BatchedEVChargingEnv).step_async / step_wait -> " + pipe_api_note()},
             "gpu_launches": launches, "clocks": clocks,
             "reward_stats": {"count": st[0], "mean": st[1] / max(st[0], 1), "min": st[3], "max": st[4], "n_done": st[5],
                              "n_projected": st[6], "n_maxiter": st[7]},

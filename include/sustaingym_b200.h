@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define SG_ABI_VERSION 1
+#define SG_ABI_VERSION 2
 
 int         sg_abi_version(void);
 const char* sg_last_error(void);
@@ -148,7 +148,13 @@ typedef struct sg_ev_model {
     int32_t reserved;
     const void* tables;           /* [device] SG_EV_TABLE_BYTES, 16-byte aligned: derived constant tables filled
                                      once per model by sg_ev_prepare_tables (the kernels stage them in shared memory) */
+    const float* obs_tail;        /* [device] [Dm, 289, SG_EV_TAIL_FLOATS(k)] or NULL: the last k+2 entries of the
+                                     observation for every (MOER day, t) — forecasted_moer[k] | prev_moer | t/288 —
+                                     laid out as they appear in the row (filled by sg_ev_prepare_obs_tail), so the step
+                                     kernel copies them with asynchronous 8-byte copies instead of 39 scalar loads;
+                                     NULL: the kernel reads `moer` directly                                        */
 } sg_ev_model;
+#define SG_EV_TAIL_FLOATS(k) (((k) + 3) & ~1)   /* k + 2 rounded up to an even count */
 
 /* Per-env state.
  *   slots : a plugged-in session is one 32-byte record
@@ -173,12 +179,24 @@ typedef struct sg_ev_state {
 #define SG_EV_ACTION_F32      0
 #define SG_EV_ACTION_I64      1   /* DiscreteActionWrapper input (wrappers.py:43-45)          */
 #define SG_EV_FLAG_AUTORESET  16  /* on done: advance day (mod D), reset state, obs = reset obs */
+#define SG_EV_FLAG_STATIC_TILES 32 /* sg_ev_step: grid-stride tile assignment instead of the dynamic scheduler
+                                     (diagnostic; results are identical)                           */
+
+/* `work` scratch of sg_ev_step: SG_EV_WORK_INTS(B) int32, zero-initialised once by the caller; every call leaves
+ * it zeroed again.  [0] entries of the exact-projection work list, [1] finished CTAs of the second launch,
+ * [2] tiles handed out by the dynamic tile scheduler, [3] warps that left the tile loop, [8...] the work list. */
+#define SG_EV_WORK_HEADER_INTS 8
+#define SG_EV_WORK_INTS(B)     ((B) + SG_EV_WORK_HEADER_INTS)
 
 /* Fills the derived constant tables of a model (f32 copies of the constraint coefficients, squared
  * limits, the pilot -> kW table, padded class / EVSE-type maps) into `tables`; call once per model,
  * then store the pointer in m->tables.  Replaces EVChargingEnv.__init__ / _init_action_projection
  * bookkeeping (env.py:131-134, 178-198). */
 int sg_ev_prepare_tables(const sg_ev_model* m, void* tables /* [device] [SG_EV_TABLE_BYTES] */, void* stream);
+
+/* Fills the observation-tail table of a model from m->moer (env.py:389-392: prev_moer = moer[t,0],
+ * forecasted_moer = moer[t,1:k+1], timestep = t/288); store the pointer in m->obs_tail afterwards. */
+int sg_ev_prepare_obs_tail(const sg_ev_model* m, float* obs_tail /* [device] [Dm, 289, SG_EV_TAIL_FLOATS(k)] */, void* stream);
 
 /* reset(): env.py:293-338 for envs whose `reset_mask` byte is non-zero (NULL = all).
  * `day_in`/`moer_day_in` pick the trace/MOER table (the seed->day map is host logic,
@@ -195,8 +213,9 @@ int sg_ev_reset(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs,
  *   pilots : [B, n] u8 amps actually sent (schedule of env.py:368-378) or NULL
  *   final_obs: with AUTORESET, receives the terminal observation of envs that finished, or NULL
  *   status : [B] u8 or NULL;  stats: [16] f64 accumulators or NULL (see sg_stats_*)
- *   work   : [B + 2] i32 zero-initialised device scratch (work list of the exact projection); required
- *            when m->project != 0, may be NULL otherwise.  It is re-armed by every call.
+ *   work   : [SG_EV_WORK_INTS(B)] i32 zero-initialised device scratch (tile scheduler + work list of the exact
+ *            projection); required when m->project != 0, may be NULL otherwise (tiles are then assigned by a
+ *            grid stride).  It is re-armed by every call.
  * With m->project != 0 the box-clipped action is tested against the network constraints per env (it
  * is then the exact projection); the few envs that violate them are finished by a second launch of
  * the same call (exact single-class solve, else interior point) and report SG_EV_STATUS_PROJECTED.
@@ -221,6 +240,57 @@ int sg_ev_step_host_async(const sg_ev_model* m, const sg_ev_state* s, int64_t nu
                           float* h_obs, double* h_reward, uint8_t* h_done,
                           void* d_action, float* d_obs, double* d_reward, uint8_t* d_done,
                           uint8_t* d_status, double* d_stats, int32_t* d_work, void* stream);
+
+/* ---- compact host path -------------------------------------------------------------------------------------
+ * A caller that keeps its observations in host memory (SB3 VecEnv, examples/evcharging/train_stable_baselines.py:264-275)
+ * does not need the dense [B, 2n+k+2] row to cross PCIe: ~6 of 54 stations hold an active session and the MOER
+ * row is a table look-up.  After a step the device packs one 120-byte record per env, the records are copied to
+ * the host and sg_ev_expand_obs rebuilds the observation there, bit-identical to the dense copy. */
+#define SG_EV_COMPACT_ENTRIES      16   /* active sessions held in a record                                       */
+#define SG_EV_COMPACT_OVERFLOW     1    /* flags bit: more active sessions than entries -> rows in the overflow area */
+#define SG_EV_COMPACT_HEADER_BYTES 16   /* the compact buffer starts with { i32 n_overflow, 12 bytes padding }     */
+#define SG_EV_COMPACT_BYTES(B)     (SG_EV_COMPACT_HEADER_BYTES + (size_t)(B) * 120)
+typedef struct sg_ev_compact_obs {
+    uint64_t active;       /* bit i: station i has an active session (non-zero demand / est_departure entries)  */
+    double   reward;
+    int16_t  t;            /* env clock after the step (0..288): timestep = t / 288, MOER row t                  */
+    int16_t  moer_day;     /* MOER table index the observation reads                                             */
+    uint8_t  done;
+    uint8_t  flags;        /* SG_EV_COMPACT_OVERFLOW                                                             */
+    uint8_t  n_active;
+    uint8_t  status;       /* SG_EV_STATUS_* of the step                                                         */
+    float    demand[SG_EV_COMPACT_ENTRIES];   /* active stations in ascending station order                       */
+    int16_t  est[SG_EV_COMPACT_ENTRIES];      /* est_departure - t (integer-valued in the observation)            */
+} sg_ev_compact_obs;
+
+/* Packs the observation / reward / done / status of every env (as written by sg_ev_step or sg_ev_reset) into
+ * `compact` ([device] SG_EV_COMPACT_BYTES(B), 16-byte aligned).  Envs with more than SG_EV_COMPACT_ENTRIES active
+ * sessions set SG_EV_COMPACT_OVERFLOW and append their index to ovf_idx and their demand | est_departure rows
+ * ([2n] f32) to ovf_rows (at most ovf_cap of them; the counter in the buffer header keeps counting). */
+int sg_ev_pack_obs(int64_t num_envs, int32_t n_stations, int32_t obs_dim, const float* obs, const double* reward,
+                   const uint8_t* done, const uint8_t* status /* or NULL */, const void* header /* sg_ev_state.header */,
+                   void* compact, int32_t* ovf_idx /* [device] [ovf_cap] */, float* ovf_rows /* [device] [ovf_cap, 2n] */,
+                   int32_t ovf_cap, void* stream);
+
+/* H2D(action) -> step -> pack -> D2H(compact records), no synchronisation: h_action / h_compact must be pinned;
+ * after the caller synchronises `stream`, h_compact holds SG_EV_COMPACT_BYTES(B) bytes for sg_ev_expand_obs. */
+int sg_ev_step_host_compact_async(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs,
+                                  const void* h_action, int32_t flags, int32_t discrete_bins, void* h_compact,
+                                  void* d_action, float* d_obs, double* d_reward, uint8_t* d_done, uint8_t* d_status,
+                                  double* d_stats, int32_t* d_work, void* d_compact, int32_t* d_ovf_idx,
+                                  float* d_ovf_rows, int32_t ovf_cap, void* stream);
+
+/* HOST function (no CUDA call): rebuilds obs [B, 2n+k+2] f32, reward [B] f64, done [B] u8 (and status [B] u8 unless
+ * NULL) from the compact records with `n_threads` threads of a persistent pool.  `h_moer` is the host copy of
+ * sg_ev_model.moer.  incremental != 0: `h_obs` still holds the previous expansion of the same envs and
+ * `h_prev_active` ([B] u64, zero-initialised together with h_obs) its activity masks — only entries that changed
+ * are written; incremental == 0 rewrites every row (h_prev_active may be NULL).  h_ovf_idx / h_ovf_rows: host
+ * copies of the first n_ovf overflow entries (n_ovf = min(counter, ovf_cap); the caller falls back to a dense
+ * copy when the counter exceeds ovf_cap). */
+int sg_ev_expand_obs(const void* h_compact, int64_t num_envs, int32_t n_stations, int32_t moer_steps,
+                     const float* h_moer, int32_t n_moer_days, uint64_t* h_prev_active, int32_t incremental,
+                     const int32_t* h_ovf_idx, const float* h_ovf_rows, int32_t n_ovf,
+                     float* h_obs, double* h_reward, uint8_t* h_done, uint8_t* h_status, int32_t n_threads);
 
 /* Dense views of the sparse state: delivered [B,n] f64 (kWh delivered to the session plugged in at
  * each station, 0 where empty) and sess_idx [B,n] u8 (its trace slot, 255 where empty); either may be NULL. */

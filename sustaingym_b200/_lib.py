@@ -11,6 +11,7 @@ import os
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SG_LIB_PATH", os.path.join(_PKG_DIR, "libsustaingym_b200.so"))
 
+ABI_VERSION = 2
 SG_STATS_LEN = 16
 SG_EV_MOER_COLS = 37
 SG_EV_MOER_ROWS = 289
@@ -30,6 +31,11 @@ SG_EV_STATUS_MAXITER = 2
 SG_EV_ACTION_F32 = 0
 SG_EV_ACTION_I64 = 1
 SG_EV_FLAG_AUTORESET = 16
+SG_EV_FLAG_STATIC_TILES = 32
+SG_EV_WORK_HEADER_INTS = 8
+SG_EV_COMPACT_ENTRIES = 16
+SG_EV_COMPACT_HEADER_BYTES = 16
+SG_EV_COMPACT_RECORD_BYTES = 120
 SG_BUILDING_FLAG_AUTORESET = 16
 SG_BUILDING_FLAG_NO_MMA = 32
 
@@ -53,7 +59,7 @@ class EVModel(C.Structure):
         ("max_sessions", _i32), ("n_days", _i32), ("n_moer_days", _i32), ("project", _i32),
         ("station_class", _vp), ("station_type", _vp), ("con_re", _vp), ("con_im", _vp),
         ("magnitudes", _vp), ("sessions", _vp), ("moer", _vp), ("arrivals", _vp),
-        ("max_day_sessions", _i32), ("reserved", _i32), ("tables", _vp),
+        ("max_day_sessions", _i32), ("reserved", _i32), ("tables", _vp), ("obs_tail", _vp),
     ]
 
 
@@ -101,6 +107,7 @@ SIGNATURES = {
     "sg_building_step_host": (C.c_int, [C.POINTER(BuildingModel), _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                         _vp, _vp, _i32, _vp, _vp]),
     "sg_ev_prepare_tables": (C.c_int, [C.POINTER(EVModel), _vp, _vp]),
+    "sg_ev_prepare_obs_tail": (C.c_int, [C.POINTER(EVModel), _vp, _vp]),
     "sg_ev_reset": (C.c_int, [C.POINTER(EVModel), C.POINTER(EVState), _i64, _vp, _vp, _vp, _vp, _vp]),
     "sg_ev_step": (C.c_int, [C.POINTER(EVModel), C.POINTER(EVState), _i64, _vp, _i32, _i32, _vp, _vp, _vp, _vp,
                              _vp, _vp, _vp, _vp, _vp]),
@@ -108,6 +115,10 @@ SIGNATURES = {
                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sg_ev_step_host_async": (C.c_int, [C.POINTER(EVModel), C.POINTER(EVState), _i64, _vp, _i32, _i32, _vp, _vp, _vp,
                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "sg_ev_pack_obs": (C.c_int, [_i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "sg_ev_step_host_compact_async": (C.c_int, [C.POINTER(EVModel), C.POINTER(EVState), _i64, _vp, _i32, _i32, _vp, _vp,
+                                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+    "sg_ev_expand_obs": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32]),
     "sg_ev_export_state": (C.c_int, [C.POINTER(EVModel), C.POINTER(EVState), _i64, _vp, _vp, _vp]),
     "sg_ev_agent_obs": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),
     "sg_ev_sample_gmm_days": (C.c_int, [C.POINTER(EVGmm), _i64, _i64, C.c_uint64, _f64, _f64, _i32, _i32, _vp, _vp,
@@ -147,7 +158,7 @@ def load() -> C.CDLL:
             raise NativeLibraryError(f"{LIB_PATH} does not export {name}; rebuild it") from e
         fn.restype = res
         fn.argtypes = args
-    if lib.sg_abi_version() != 1:
+    if lib.sg_abi_version() != ABI_VERSION:
         raise NativeLibraryError("ABI version mismatch between _lib.py and the shared library")
     _lib = lib
     return lib

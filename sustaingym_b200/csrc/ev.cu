@@ -57,6 +57,13 @@ constexpr double kInvOMT = 1.0 / kOneMinusTrans, kInvPeriodH = 1.0 / kPeriodH, k
 // fixed-point scale and safety margin of the fast-path feasibility test (normalised units)
 constexpr double kFixScale = 1048576.0, kFixInv = 1.0 / 1048576.0, kFeasMargin = 1e-4;
 
+// layout of the `work` scratch buffer (SG_EV_WORK_INTS(B) int32, zero-initialised once, re-armed by every step)
+constexpr int kWorkCount = 0;        // entries of the exact-projection work list
+constexpr int kWorkRareDone = 1;     // CTAs of ev_step_rare_kernel that have finished
+constexpr int kWorkNextTile = 2;     // dynamic tile scheduler of ev_step_main_kernel: tiles handed out so far
+constexpr int kWorkRetired = 3;      // ... and warps that have left its tile loop (the last one re-arms both)
+constexpr int kWorkList = SG_EV_WORK_HEADER_INTS;   // first entry of the work list
+
 constexpr int kWarpsPerBlock = 8;
 constexpr int kThreads = kWarpsPerBlock * 32;
 constexpr int kMC = SG_EV_MAX_CLASSES;
@@ -100,6 +107,15 @@ struct __align__(16) EvTables {
     int8_t simple_cls[SG_EV_MAX_CONSTRAINTS];        // class of a constraint with ONE non-zero coefficient (a pod), else -1
     uint8_t cls[SG_EV_MAX_STATIONS];                 // class of each station, 255 = padding
     uint8_t type[SG_EV_MAX_STATIONS];
+    // Integer screens of the per-env constraint pre-checks (owner lane, see env_checks).  Class sums are kept as
+    // integers (clipped action: 2^-20 fixed point; pilots: A), so the common case is a handful of compares:
+    //   single-class constraint q (a pod): certainly satisfied iff the class sum <= simple_S_fix[q] / simple_P_lim[q];
+    //   coupled constraints: |sum_c coef_c S_c| <= max_c|coef_c| * sum_c S_c, so all of them are certainly satisfied
+    //   iff the sum over ALL classes <= scr_S_fix / scr_P_lim; only otherwise they are evaluated (f32, with margin).
+    int simple_S_fix[SG_EV_MAX_CONSTRAINTS];
+    int simple_P_lim[SG_EV_MAX_CONSTRAINTS];
+    uint8_t simple_j[SG_EV_MAX_CONSTRAINTS];         // the single-class constraints, n_simple of them
+    int n_simple, scr_S_fix, scr_P_lim, pad_;
 };
 static_assert(sizeof(EvTables) % 16 == 0 && sizeof(EvTables) <= SG_EV_TABLE_BYTES, "table block size");
 using EvShared = EvTables;
@@ -123,11 +139,58 @@ __global__ void ev_prepare_kernel(const sg_ev_model m, EvTables* __restrict__ tb
         if (nz == 1) kappa = sqrt(m.con_re[i * kMC + cstar] * m.con_re[i * kMC + cstar] + m.con_im[i * kMC + cstar] * m.con_im[i * kMC + cstar]);
         tb->simple_R[i] = lim * (1.0 / kActionScale) / kappa;
     }
+    if (threadIdx.x == 0) {
+        int ns = 0;
+        double scrS = 1e30, scrP = 1e30;
+        for (int j = 0; j < SG_EV_MAX_CONSTRAINTS; ++j) { tb->simple_j[j] = 0; tb->simple_S_fix[j] = 0; tb->simple_P_lim[j] = 0; }
+        for (int j = 0; j < m.n_constraints; ++j) {
+            int nz = 0;
+            double kmax = 0.0;
+            for (int c = 0; c < kMC; ++c) {
+                const double mag = sqrt(m.con_re[j * kMC + c] * m.con_re[j * kMC + c] + m.con_im[j * kMC + c] * m.con_im[j * kMC + c]);
+                if (mag != 0.0) nz++;
+                kmax = fmax(kmax, mag);
+            }
+            const double lim = m.magnitudes[j];
+            // thresholds mirror the f32 tests they stand in for: (limit/32 - margin) for the clipped action,
+            // sqrt(0.999) * limit for the rounded schedule; both scaled down a little more, rounded down
+            const double rS = (lim * (1.0 / kActionScale) - (double)kPreMargin) * 0.99999;
+            const double rP = sqrt(0.999) * lim * 0.99999;
+            if (nz == 0) continue;                        // empty row: never violated
+            if (nz == 1) {
+                tb->simple_j[ns] = (uint8_t)j;
+                tb->simple_S_fix[ns] = rS > 0.0 ? (int)fmin(floor(rS / kmax * kFixScale), 2.0e9) : -1;
+                tb->simple_P_lim[ns] = (int)fmin(floor(rP / kmax), 2.0e9);
+                ns++;
+            } else {
+                scrS = fmin(scrS, rS > 0.0 ? rS / kmax : -1.0);
+                scrP = fmin(scrP, rP / kmax);
+            }
+        }
+        tb->n_simple = ns;
+        tb->scr_S_fix = scrS < 0.0 ? -1 : (int)fmin(floor(scrS * kFixScale), 2.0e9);
+        tb->scr_P_lim = (int)fmin(floor(scrP), 2.0e9);
+        tb->pad_ = 0;
+    }
     for (int i = threadIdx.x; i < 40; i += blockDim.x) tb->ppilot[i] = div_c((double)i * kVoltage, 1000.0, kInv1000);
     for (int i = threadIdx.x; i < SG_EV_MAX_STATIONS; i += blockDim.x) {
         const bool in = i < m.n_stations;
         tb->cls[i] = in ? m.station_class[i] : 255;
         tb->type[i] = in ? m.station_type[i] : 0;
+    }
+}
+
+// Observation-tail table: row (md, t) = forecasted_moer[k] | prev_moer | t / 288 (| padding), env.py:389-392
+__global__ void ev_prepare_tail_kernel(const float* __restrict__ moer, const int n_moer_days, const int kf,
+                                       float* __restrict__ tail) {
+    const int TL = SG_EV_TAIL_FLOATS(kf);
+    const long long rows = (long long)n_moer_days * SG_EV_MOER_ROWS;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < rows * TL;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long r = idx / TL;
+        const int q = (int)(idx % TL), t = (int)(r % SG_EV_MOER_ROWS);
+        const float* row = moer + r * SG_EV_MOER_COLS;
+        tail[idx] = q < kf ? row[1 + q] : (q == kf ? row[0] : (q == kf + 1 ? (float)((double)t * (1.0 / (double)kEpisode)) : 0.f));
     }
 }
 
@@ -686,7 +749,7 @@ constexpr int kV = SG_EV_KV;                         // work items per lane and 
 constexpr int kItemCap = 32 * kV;                    // (env, station) work items staged per warp and chunk
 constexpr int kTailMax = (SG_EV_MOER_COLS + 1) / 2;  // float2 pairs in the longest MOER + timestep tail
 constexpr int kTailPerLane = (kTailMax + kQ - 1) / kQ;
-static_assert(kE == 8 || kE == 16 || kE == 32, "tile size");
+static_assert(kE == 4 || kE == 8 || kE == 16 || kE == 32, "tile size");
 
 struct WarpShared {
     double rate[kItemCap];                           // charging rate (A) of item j
@@ -1068,6 +1131,11 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long ntiles = (B + kE - 1) / kE;
     const long long wstride = (long long)gridDim.x * kMainWarps;
+    // Tile scheduling.  Every warp starts on the tile of its own index; further tiles come from a global counter
+    // (work[kWorkNextTile]) when the scratch buffer is there, else from a grid stride.  Static strides leave the
+    // SMs unevenly loaded — B200 places consecutive CTAs on the same SM, so with 2.3 tiles per warp the SMs that
+    // hold the low-numbered CTAs run 9 tile rounds against 6 elsewhere (ncu: SMs busy 62 % of the launch).
+    int32_t* sched = (work != nullptr && !(flags & SG_EV_FLAG_STATIC_TILES)) ? work + kWorkNextTile : nullptr;
     long long tile = (long long)blockIdx.x * kMainWarps + warp;
     EV_TRACE(10);
     // the first tile's env headers are requested before the table copy
@@ -1094,8 +1162,18 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
     // the bulk copies need 16-byte aligned, 16-byte multiple global ranges
     const bool bulk_rows = ((kE * OBS) & 3) == 0 && (reinterpret_cast<uintptr_t>(obs) & 15u) == 0;
     const bool bulk_pil = pilots != nullptr && ((kE * n) & 15) == 0 && (reinterpret_cast<uintptr_t>(pilots) & 15u) == 0;
+    // 8-byte asynchronous copies of the observation tails need an even row length (8-byte aligned tails)
+    const int tail_floats = SG_EV_TAIL_FLOATS(kf);
+    const bool tail_async = m.obs_tail != nullptr && (OBS & 1) == 0 && !(SG_EV_ABL & 512);
 
-    for (; tile < ntiles; tile += wstride) {
+    while (tile < ntiles) {
+        // the next tile is requested now and picked up at the end of this one (the atomic's latency is hidden)
+        int next_ticket = 0;
+        if (sched != nullptr && lane == 0) next_ticket = atomicAdd(sched, 1);
+        EV_TRACE(5);
+#ifdef SG_EV_TRACE
+        if (g_trace != nullptr && lane == 0) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); g_trace[tile * 16 + 1] = sm; }
+#endif
         const long long b0 = tile * kE;
         const int nv = (int)min((long long)kE, B - b0);
         const long long b = b0 + lane;
@@ -1132,10 +1210,24 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
         {
             for (int i = lane; i < kMC * kE; i += 32) { (&ws.S[0][0])[i] = 0; (&ws.P[0][0])[i] = 0; }
             if (lane < kE) { ws.occ_clr[lane][0] = 0u; ws.occ_clr[lane][1] = 0u; }
+            // the previous tile's bulk copies must have read the staging rows before they are cleared; the wait sits
+            // here, behind this tile's header / MOER / arrival loads, instead of at the end of the previous tile
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncwarp();
             uint4* z = reinterpret_cast<uint4*>(srows);
             for (int i = lane; i < (row_bytes + pil_bytes) >> 4; i += 32) z[i] = make_uint4(0u, 0u, 0u, 0u);
             __syncwarp();
             (void)tp;
+            if (tail_async) {
+                // MOER + timestep tails straight from the observation-tail table into the staged rows: kQ lanes per
+                // env issue 8-byte asynchronous copies (no registers, nothing waits on them until the write-out)
+                const float* src = m.obs_tail + ((long long)__shfl_sync(kFull, md, eq) * SG_EV_MOER_ROWS +
+                                                 min(__shfl_sync(kFull, tn, eq), SG_EV_MOER_ROWS - 1)) * tail_floats;
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(srows + eq * OBS + 2 * n);
+                if (eq < nv)
+                    for (int q2 = sub; q2 < (kf + 2) >> 1; q2 += kQ)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * q2), "l"(src + 2 * q2) : "memory");
+            }
         }
         if constexpr (MODE == 0) {
             // every EVSE receives a pilot, occupied or not (env.py:368-378); class sums for the excess current
@@ -1229,7 +1321,7 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
                     af[u] = act_value(action, i64, bins, be * n + si[u]);
                 }
             }
-            if (g0 == 0) {
+            if (g0 == 0 && !tail_async) {
                 // MOER + timestep tails of the staged rows, kQ lanes per env: placed here so that their loads
                 // (L2, sometimes DRAM) are in flight together with the session-record loads above
                 const float* p = moer + __shfl_sync(kFull, moff, eq);
@@ -1238,8 +1330,8 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
 #pragma unroll
                 for (int k = 0; k < kTailPerLane; ++k) {
                     const int q0 = 2 * (sub + k * kQ);
-                    tv[2 * k] = q0 < kf + 2 ? moer_tail(p, q0, kf, ts_e) : 0.f;
-                    tv[2 * k + 1] = q0 + 1 < kf + 2 ? moer_tail(p, q0 + 1, kf, ts_e) : 0.f;
+                    tv[2 * k] = (q0 < kf + 2 && !(SG_EV_ABL & 512)) ? moer_tail(p, q0, kf, ts_e) : 0.f;
+                    tv[2 * k + 1] = (q0 + 1 < kf + 2 && !(SG_EV_ABL & 512)) ? moer_tail(p, q0 + 1, kf, ts_e) : 0.f;
                 }
                 float* dst = srows + eq * OBS + 2 * n;
 #pragma unroll
@@ -1294,34 +1386,39 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
             // a limit (exact excess current needed)
             unsigned gbad = 0u, gnear = 0u;
             unsigned jsus = 0u;                                         // owner lane: constraints its env may violate
+            // Owner lane e tests its env: integer screens first (a few compares: the pods' class sums against their
+            // limits, the total current against the tightest coupled limit), the coupled constraints in f32 with a
+            // margin only when the total is large enough for one of them to be violated at all.
             auto pair_checks = [&]() {
                 bool mybad = false, mynear = false;
                 jsus = 0u;
-                for (int idx = lane, k = 0; idx < ((SG_EV_ABL & 16) ? 0 : kE * J); idx += 32, ++k) {   // pair (env idx % kE, constraint idx / kE)
-                    const int j = idx / kE, e2 = idx & (kE - 1);
-                    float wr = 0.f, wi = 0.f, vr = 0.f, vi = 0.f;
+                if (lane < kE && !(SG_EV_ABL & 16)) {
+                    int St = 0, Pt = 0;
 #pragma unroll
-                    for (int c = 0; c < kMC; ++c) {
-                        const float cre = sh.re[j * kMC + c], cim = sh.im[j * kMC + c];
-                        const float pv = (float)ws.P[c][e2];
-                        vr = fmaf(cre, pv, vr); vi = fmaf(cim, pv, vi);
-                        if (MODE != 0) { const float sv = (float)ws.S[c][e2] * (1.f / 1048576.f); wr = fmaf(cre, sv, wr); wi = fmaf(cim, sv, wi); }
+                    for (int c = 0; c < kMC; ++c) { St += ws.S[c][lane]; Pt += ws.P[c][lane]; }
+                    for (int q = 0; q < sh.n_simple; ++q) {
+                        const int j = sh.simple_j[q], c = sh.simple_cls[j];
+                        if (MODE != 0 && ws.S[c][lane] > sh.simple_S_fix[q]) { mybad = true; jsus |= 1u << j; }
+                        mynear = mynear || ws.P[c][lane] > sh.simple_P_lim[q];
                     }
-                    const bool b1 = MODE != 0 && !(fmaf(wr, wr, wi * wi) <= sh.r_in[j]);
-                    mybad = mybad || b1;
-                    mynear = mynear || (fmaf(vr, vr, vi * vi) > sh.lim2_lo[j]);
-                    if (MODE != 0) {                                    // lane q*kE + e tested constraint k*kQ + q of env e
-                        const unsigned bb = __ballot_sync(__activemask(), b1);
+                    if ((MODE != 0 && St > sh.scr_S_fix) || Pt > sh.scr_P_lim) {
+                        for (int j = 0; j < J; ++j) {
+                            if (sh.simple_cls[j] >= 0) continue;
+                            float wr = 0.f, wi = 0.f, vr = 0.f, vi = 0.f;
 #pragma unroll
-                        for (int qq = 0; qq < kQ; ++qq) jsus |= ((bb >> (qq * kE + (lane & (kE - 1)))) & 1u) << (k * kQ + qq);
+                            for (int c = 0; c < kMC; ++c) {
+                                const float cre = sh.re[j * kMC + c], cim = sh.im[j * kMC + c];
+                                const float pv = (float)ws.P[c][lane];
+                                vr = fmaf(cre, pv, vr); vi = fmaf(cim, pv, vi);
+                                if (MODE != 0) { const float sv = (float)ws.S[c][lane] * (1.f / 1048576.f); wr = fmaf(cre, sv, wr); wi = fmaf(cim, sv, wi); }
+                            }
+                            if (MODE != 0 && !(fmaf(wr, wr, wi * wi) <= sh.r_in[j])) { mybad = true; jsus |= 1u << j; }
+                            mynear = mynear || (fmaf(vr, vr, vi * vi) > sh.lim2_lo[j]);
+                        }
                     }
                 }
-                gbad = __ballot_sync(kFull, mybad);
-                gnear = __ballot_sync(kFull, mynear);
-#pragma unroll
-                for (int shf = kE; shf < 32; shf <<= 1) { gbad |= gbad >> shf; gnear |= gnear >> shf; }
-                gbad &= gmask & live_mask;
-                gnear &= gmask;
+                gbad = __ballot_sync(kFull, mybad) & gmask & live_mask;
+                gnear = __ballot_sync(kFull, mynear) & gmask;
             };
             pair_checks();
             // ---- envs whose clipped action is not certainly feasible (rare): the exact test and the exact
@@ -1495,15 +1592,18 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
 
         // ---------------- rare path: envs that need the exact projection go to the work list of ev_step_rare_kernel
         if (bad && lane == 0) {
-            const int first = atomicAdd(work, __popc(bad));
+            const int first = atomicAdd(work + kWorkCount, __popc(bad));
             int k = 0;
-            for (unsigned todo = bad; todo; todo &= todo - 1, ++k) work[2 + first + k] = (int)(b0 + __ffs((int)todo) - 1);
+            for (unsigned todo = bad; todo; todo &= todo - 1, ++k) work[kWorkList + first + k] = (int)(b0 + __ffs((int)todo) - 1);
         }
 
         // ---------------- write-out of the staged rows --------------------------------------------------------
+        if (tail_async) asm volatile("cp.async.wait_all;" ::: "memory");  // the tails have landed in the staged rows
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // staged rows -> visible to the bulk-copy engine
         __syncwarp();
         const bool whole = nv == kE && live_mask == kOwnerMask && ar_mask == 0u;
+        if (SG_EV_ABL & 256) {                          // (ablation: no observation / pilot rows written)
+        } else
         if (whole && bulk_rows) {
             if (lane == 0)
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(obs + b0 * OBS),
@@ -1523,7 +1623,7 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
                 }
             }
         }
-        if (pilots != nullptr) {
+        if (pilots != nullptr && !(SG_EV_ABL & 256)) {
             if (whole && bulk_pil) {
                 if (lane == 0)
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(pilots + b0 * n),
@@ -1534,11 +1634,18 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
                         for (int i = lane; i < n; i += 32) pilots[(b0 + r) * n + i] = spil[r * n + i];
             }
         }
-        if (lane == 0) {
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // the staging rows are reused by the next tile
-        }
+        if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");   // (waited for before the rows are cleared again)
         __syncwarp();
+        EV_TRACE(15);
+        tile = sched != nullptr ? wstride + (long long)__shfl_sync(kFull, next_ticket, 0) : tile + wstride;
+    }
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging rows stay valid until read
+    if (sched != nullptr && lane == 0) {
+        // the last warp to leave the loop re-arms the scheduler (every other warp has made its last request)
+        if (atomicAdd(sched + (kWorkRetired - kWorkNextTile), 1) == (int)wstride - 1) {
+            sched[0] = 0;
+            sched[kWorkRetired - kWorkNextTile] = 0;
+        }
     }
     if (stats != nullptr) {
         __syncthreads();
@@ -1572,7 +1679,7 @@ ev_step_rare_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
     __shared__ EvTables sh;
     __shared__ double wstat[4][12];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int count = work[0];
+    const int count = work[kWorkCount];
     if (count > 0) {
         load_tables(m.tables, sh);
         if (lane < 12) wstat[warp][lane] = lane == 3 ? 1e300 : (lane == 4 ? -1e300 : 0.0);
@@ -1587,7 +1694,7 @@ ev_step_rare_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
         const int nwarps = gridDim.x * (blockDim.x >> 5);
         // warp w of CTA c takes item c + w * gridDim.x: the first items spread over different SMs
         for (int w = blockIdx.x + warp * gridDim.x; w < count; w += nwarps) {
-            const long long bq = work[2 + w];
+            const long long bq = work[kWorkList + w];
             double* wst = stats != nullptr ? wstat[warp] : nullptr;
             if (!fallback_env<false>(sh, cx, bq, lane, wst)) fallback_env<true>(sh, cx, bq, lane, wst);
         }
@@ -1607,7 +1714,7 @@ ev_step_rare_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
-        if (atomicAdd(work + 1, 1) == (int)gridDim.x - 1) { work[0] = 0; work[1] = 0; __threadfence(); }
+        if (atomicAdd(work + kWorkRareDone, 1) == (int)gridDim.x - 1) { work[kWorkCount] = 0; work[kWorkRareDone] = 0; __threadfence(); }
     }
 }
 
@@ -1727,6 +1834,7 @@ int check_model(const sg_ev_model* m) {
 int check_tables(const sg_ev_model* m) {
     SG_CHECK_ARG(m->tables != nullptr, "ev: model.tables is NULL (call sg_ev_prepare_tables once per model)");
     SG_CHECK_ARG((reinterpret_cast<uintptr_t>(m->tables) & 15u) == 0, "ev: model.tables must be 16-byte aligned");
+    SG_CHECK_ARG((reinterpret_cast<uintptr_t>(m->obs_tail) & 7u) == 0, "ev: model.obs_tail must be 8-byte aligned");
     return 0;
 }
 
@@ -1747,6 +1855,16 @@ int sg_ev_prepare_tables(const sg_ev_model* m, void* tables, void* stream) {
     SG_CHECK_ARG(tables != nullptr && (reinterpret_cast<uintptr_t>(tables) & 15u) == 0, "ev_prepare_tables: tables must be a 16-byte aligned device buffer");
     sg::ev_prepare_kernel<<<1, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(*m, reinterpret_cast<sg::EvTables*>(tables));
     return sg::launch_status("ev_prepare_kernel");
+}
+
+int sg_ev_prepare_obs_tail(const sg_ev_model* m, float* obs_tail, void* stream) {
+    if (int rc = sg::check_model(m)) return rc;
+    SG_CHECK_ARG(obs_tail != nullptr && m->moer != nullptr && m->n_moer_days >= 1, "ev_prepare_obs_tail: NULL argument / empty MOER pool");
+    SG_CHECK_ARG((reinterpret_cast<uintptr_t>(obs_tail) & 7u) == 0, "ev_prepare_obs_tail: the table must be 8-byte aligned");
+    const long long total = (long long)m->n_moer_days * SG_EV_MOER_ROWS * SG_EV_TAIL_FLOATS(m->moer_steps);
+    const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148ll * 8);
+    sg::ev_prepare_tail_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(m->moer, m->n_moer_days, m->moer_steps, obs_tail);
+    return sg::launch_status("ev_prepare_tail_kernel");
 }
 
 int sg_ev_reset(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, const uint8_t* reset_mask,

@@ -22,17 +22,26 @@ def shard_range(num_envs: int, rank: int, world_size: int) -> tuple[int, int]:
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def all_reduce_stats(stats: torch.Tensor, group=None) -> torch.Tensor:
-    """Returns the job-wide statistics vector (the input is left untouched)."""
-    out = stats.clone()
+def all_reduce_stats(stats: torch.Tensor, group=None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """Returns the job-wide statistics vector (the input is left untouched).  ``out``: optional preallocated
+    ``[SG_STATS_LEN + 2]`` buffer of the same dtype/device (result in ``out[:SG_STATS_LEN]``, the last two
+    entries are the MIN / MAX scratch), so that the call allocates nothing — needed when it is issued on a side
+    stream inside a timed region (a caching-allocator miss on a new stream costs a cudaMalloc)."""
+    n = stats.numel()
+    if out is None:
+        out = torch.empty(n + 2, dtype=stats.dtype, device=stats.device)
+    res, mn, mx = out[:n], out[n:n + 1], out[n + 1:n + 2]
+    res.copy_(stats)
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return out
-    mn, mx = out[STATS_MIN:STATS_MIN + 1].clone(), out[STATS_MAX:STATS_MAX + 1].clone()
-    dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+        return res
+    mn.copy_(stats[STATS_MIN:STATS_MIN + 1])
+    mx.copy_(stats[STATS_MAX:STATS_MAX + 1])
+    dist.all_reduce(res, op=dist.ReduceOp.SUM, group=group)
     dist.all_reduce(mn, op=dist.ReduceOp.MIN, group=group)
     dist.all_reduce(mx, op=dist.ReduceOp.MAX, group=group)
-    out[STATS_MIN], out[STATS_MAX] = mn[0], mx[0]
-    return out
+    res[STATS_MIN:STATS_MIN + 1].copy_(mn)
+    res[STATS_MAX:STATS_MAX + 1].copy_(mx)
+    return res
 
 
 def summarize(stats: torch.Tensor) -> dict:

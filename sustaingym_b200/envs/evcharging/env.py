@@ -47,8 +47,9 @@ class BatchedEVChargingEnv:
     VIOLATION_FACTOR = A_PERS_TO_KWH * VIOLATION_WEIGHT
     CARBON_COST_FACTOR = A_PERS_TO_KWH * (CO2_COST_PER_METRIC_TON / 1000)
 
-    HOST_PATH_NOTE = ("BatchedEVChargingEnv.step_async(pinned host actions) / step_wait() -> sg_ev_step_host_async, "
-                      "two env batches in flight (H2D of one overlaps D2H of the other)")
+    HOST_PATH_NOTE = ("BatchedEVChargingEnv.step_async(pinned host actions) / step_wait(): sg_ev_step_host_compact_async "
+                      "(H2D actions -> step -> pack 120-byte records -> D2H) + sg_ev_expand_obs (host thread pool rebuilds "
+                      "the dense [B,146] f32 observation, bit-identical to a dense copy); two env batches in flight")
 
     @property
     def h2d_bytes_per_step(self) -> int:
@@ -56,12 +57,15 @@ class BatchedEVChargingEnv:
 
     @property
     def d2h_bytes_per_step(self) -> int:
+        if self.host_obs == "compact":
+            return _lib.SG_EV_COMPACT_HEADER_BYTES + self.num_envs * _lib.SG_EV_COMPACT_RECORD_BYTES
         return self.num_envs * (self.obs_dim * 4 + 8 + 1)
 
     def __init__(self, data_generator: AbstractTraceGenerator, num_envs: int = 1,
                  moer_forecast_steps: int = 36, project_action_in_env: bool = True, verbose: int = 0,
                  device: str | torch.device | None = None, auto_reset: bool = False,
-                 discrete_bins: int = -1, collect_stats: bool = False):
+                 discrete_bins: int = -1, collect_stats: bool = False, host_obs: str = "compact",
+                 host_threads: int | None = None):
         assert 1 <= moer_forecast_steps <= 36                                   # env.py:120
         self.lib = _lib.load()                                                  # fails loudly if not built
         if not torch.cuda.is_available():
@@ -79,6 +83,17 @@ class BatchedEVChargingEnv:
         self.num_stations = n = self.cn.num_stations
         self.obs_dim = 2 * n + moer_forecast_steps + 2
         self._async_stream = None
+        if host_obs not in ("compact", "dense"):
+            raise ValueError("host_obs must be 'compact' (120-byte records over PCIe, expanded on the host) or 'dense'")
+        self.host_obs = host_obs
+        import os
+        if host_threads is None:
+            host_threads = int(os.environ.get("SG_HOST_THREADS", 0)) or max(
+                1, min(16, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))))
+        self.host_threads = int(host_threads)
+        # host expansion mode: False = every row rewritten with streaming stores (default: no read-for-ownership of the
+        # 38 MB observation batch); True = only the entries that changed, with ordinary stores (cache-resident batches)
+        self.host_incremental = os.environ.get("SG_HOST_INCREMENTAL", "0") == "1"
 
         # ---- spaces (env.py:143-150, 171-172; wrappers.py:36-41 for the discrete variant) ---------
         k = moer_forecast_steps
@@ -140,12 +155,20 @@ class BatchedEVChargingEnv:
             int(project_action_in_env), self._c["cls"].data_ptr(), self._c["type"].data_ptr(),
             self._c["re"].data_ptr(), self._c["im"].data_ptr(), self._c["mag"].data_ptr(),
             self._c["sessions"].data_ptr(), self._c["moer"].data_ptr(), self._c["arrivals"].data_ptr(),
-            self._c["arrivals"].shape[1] - 1, 0, None)
+            self._c["arrivals"].shape[1] - 1, 0, None, None)
         self._c["tables"] = torch.zeros(_lib.SG_EV_TABLE_BYTES, dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
             _lib.check(self.lib.sg_ev_prepare_tables(C.byref(self._model), self._c["tables"].data_ptr(),
                                                      torch.cuda.current_stream(dev).cuda_stream), "sg_ev_prepare_tables")
         self._model.tables = self._c["tables"].data_ptr()
+        # observation-tail table (forecasted_moer | prev_moer | timestep of every (MOER day, t)), see sg_ev_model.obs_tail
+        tail_floats = (k + 3) & ~1
+        self._c["obs_tail"] = torch.zeros(data_generator.moer.shape[0], _lib.SG_EV_MOER_ROWS, tail_floats,
+                                          dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(self.lib.sg_ev_prepare_obs_tail(C.byref(self._model), self._c["obs_tail"].data_ptr(),
+                                                       torch.cuda.current_stream(dev).cuda_stream), "sg_ev_prepare_obs_tail")
+        self._model.obs_tail = self._c["obs_tail"].data_ptr()
 
         # ---- per-env state and outputs ---------------------------------------------------------------
         B = self.num_envs
@@ -166,22 +189,29 @@ class BatchedEVChargingEnv:
         self.done = z(B, dtype=torch.uint8)
         self.status = z(B, dtype=torch.uint8)
         self.pilots = z(B, n, dtype=torch.uint8)
-        self.work = z(B + 2, dtype=torch.int32)           # work list of the exact projection (rare path)
+        self.work = z(B + _lib.SG_EV_WORK_HEADER_INTS, dtype=torch.int32)   # tile scheduler + work list of the exact projection
         self.stats = z(_lib.SG_STATS_LEN, dtype=torch.float64) if collect_stats else None
         if self.stats is not None:
             self.reset_stats()
         self._action_dtype = torch.int64 if discrete_bins > 0 else torch.float32
         self._d_action = z(B, n, dtype=self._action_dtype)
-        # pinned host staging for the host-buffer path
+        # host staging for the host-buffer path.  Pinned where the DMA engines touch it: the actions always, the
+        # results only on the dense path — on the compact path they are written by the expansion threads, and
+        # ordinary (first-touch, NUMA-local) memory is ~2.5x faster for them than cudaHostAlloc memory (measured)
+        pin = (lambda t: t.pin_memory()) if host_obs == "dense" else (lambda t: t)
         self._h_action = torch.zeros(B, n, dtype=self._action_dtype).pin_memory()
-        self._h_obs = torch.zeros(B, self.obs_dim, dtype=torch.float32).pin_memory()
-        self._h_reward = torch.zeros(B, dtype=torch.float64).pin_memory()
-        self._h_done = torch.zeros(B, dtype=torch.uint8).pin_memory()
+        self._h_obs = pin(torch.zeros(B, self.obs_dim, dtype=torch.float32))
+        self._h_reward = pin(torch.zeros(B, dtype=torch.float64))
+        self._h_done = pin(torch.zeros(B, dtype=torch.uint8))
+        self._h_trunc = torch.zeros(B, dtype=torch.bool)                       # truncated is always False (env.py:291)
         self._flags = (_lib.SG_EV_ACTION_I64 if discrete_bins > 0 else _lib.SG_EV_ACTION_F32) | \
             (_lib.SG_EV_FLAG_AUTORESET if auto_reset else 0)
         self.kernel_launches = 0
         self._needs_reset = True
-        self._async_stream = None
+        # compact host path (allocated on first use): records, overflow area, host MOER table, activity masks
+        self._compact = None
+        self._host_obs_valid = False          # _h_obs holds the expansion of the previous host-path step
+        self._pending = None                  # "compact" / "dense": what step_async enqueued
 
     # ------------------------------------------------------------------------------------------
     def __repr__(self) -> str:
@@ -230,6 +260,7 @@ class BatchedEVChargingEnv:
                                             self.obs.data_ptr(), self._stream()), "sg_ev_reset")
         self.kernel_launches += 1
         self._needs_reset = False
+        self._host_obs_valid = False
         return self.obs, self._infos()
 
     def step(self, actions):
@@ -251,14 +282,18 @@ class BatchedEVChargingEnv:
             else:
                 self._h_action.copy_(actions)
                 h_act = self._h_action
-            with torch.cuda.device(self.device):
-                _lib.check(self.lib.sg_ev_step_host(
-                    C.byref(self._model), C.byref(self._state), B, h_act.data_ptr(), self._flags,
-                    max(self.discrete_bins, 0), self._h_obs.data_ptr(), self._h_reward.data_ptr(),
-                    self._h_done.data_ptr(), self._d_action.data_ptr(), self.obs.data_ptr(),
-                    self.reward.data_ptr(), self.done.data_ptr(), self.status.data_ptr(),
-                    _lib.ptr(self.stats), self.work.data_ptr(), self._stream()), "sg_ev_step_host")
-            self.kernel_launches += 2 if self.project_action_in_env else 1
+            if self.host_obs == "compact":
+                self._enqueue_host(h_act, self._stream())
+                obs, rew, done, trunc, infos = self._finish_host(torch.cuda.current_stream(self.device))
+            else:
+                with torch.cuda.device(self.device):
+                    _lib.check(self.lib.sg_ev_step_host(
+                        C.byref(self._model), C.byref(self._state), B, h_act.data_ptr(), self._flags,
+                        max(self.discrete_bins, 0), self._h_obs.data_ptr(), self._h_reward.data_ptr(),
+                        self._h_done.data_ptr(), self._d_action.data_ptr(), self.obs.data_ptr(),
+                        self.reward.data_ptr(), self.done.data_ptr(), self.status.data_ptr(),
+                        _lib.ptr(self.stats), self.work.data_ptr(), self._stream()), "sg_ev_step_host")
+                self.kernel_launches += 2 if self.project_action_in_env else 1
             if host_np:
                 done = self._h_done.numpy().astype(bool)
                 return (self._h_obs.numpy().copy(), self._h_reward.numpy().copy(), done,
@@ -285,21 +320,77 @@ class BatchedEVChargingEnv:
             self._async_stream = torch.cuda.Stream(self.device)
         # order this step after everything queued on the caller's stream (reset(), step(), graph replays ...)
         self._async_stream.wait_stream(torch.cuda.current_stream(self.device))
-        with torch.cuda.device(self.device):
-            _lib.check(self.lib.sg_ev_step_host_async(
-                C.byref(self._model), C.byref(self._state), self.num_envs, actions.data_ptr(), self._flags,
-                max(self.discrete_bins, 0), self._h_obs.data_ptr(), self._h_reward.data_ptr(),
-                self._h_done.data_ptr(), self._d_action.data_ptr(), self.obs.data_ptr(),
-                self.reward.data_ptr(), self.done.data_ptr(), self.status.data_ptr(),
-                _lib.ptr(self.stats), self.work.data_ptr(), self._async_stream.cuda_stream), "sg_ev_step_host_async")
-        self.kernel_launches += 2 if self.project_action_in_env else 1
+        self._enqueue_host(actions, self._async_stream.cuda_stream)
 
     def step_wait(self):
         """SB3 ``VecEnv.step_wait``: wait for the step enqueued by ``step_async``; returns views of the
         pinned result buffers (obs f32 [B, obs_dim], reward f64 [B], done bool [B], truncated, infos)."""
-        self._async_stream.synchronize()
-        return (self._h_obs, self._h_reward, self._h_done.bool(), torch.zeros(self.num_envs, dtype=torch.bool),
-                self._infos())
+        return self._finish_host(self._async_stream)
+
+    # ---- host-buffer path ---------------------------------------------------------------------------------------
+    def _ensure_compact(self) -> dict:
+        if self._compact is None:
+            B, n, dev = self.num_envs, self.num_stations, self.device
+            nbytes = _lib.SG_EV_COMPACT_HEADER_BYTES + B * _lib.SG_EV_COMPACT_RECORD_BYTES
+            cap = max(256, B // 64)                     # envs with > 16 active sessions per step before the dense fallback
+            self._compact = {
+                "cap": cap,
+                "d": torch.zeros(nbytes, dtype=torch.uint8, device=dev),
+                "h": torch.zeros(nbytes, dtype=torch.uint8).pin_memory(),
+                "d_idx": torch.zeros(cap, dtype=torch.int32, device=dev),
+                "d_rows": torch.zeros(cap, 2 * n, dtype=torch.float32, device=dev),
+                "h_idx": torch.zeros(cap, dtype=torch.int32).pin_memory(),
+                "h_rows": torch.zeros(cap, 2 * n, dtype=torch.float32).pin_memory(),
+                "prev": torch.zeros(B, dtype=torch.int64),
+                "moer": np.ascontiguousarray(self.data_generator.moer, dtype=np.float32),
+                "h_status": torch.zeros(B, dtype=torch.uint8),
+            }
+        return self._compact
+
+    def _enqueue_host(self, h_act: torch.Tensor, stream: int) -> None:
+        """H2D(actions) -> step -> [pack ->] D2H on ``stream``, no synchronisation."""
+        args = (C.byref(self._model), C.byref(self._state), self.num_envs, h_act.data_ptr(), self._flags,
+                max(self.discrete_bins, 0))
+        dev_out = (self._d_action.data_ptr(), self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
+                   self.status.data_ptr(), _lib.ptr(self.stats), self.work.data_ptr())
+        with torch.cuda.device(self.device):
+            if self.host_obs == "compact":
+                c = self._ensure_compact()
+                _lib.check(self.lib.sg_ev_step_host_compact_async(
+                    *args, c["h"].data_ptr(), *dev_out, c["d"].data_ptr(), c["d_idx"].data_ptr(),
+                    c["d_rows"].data_ptr(), c["cap"], stream), "sg_ev_step_host_compact_async")
+                self.kernel_launches += 1
+            else:
+                _lib.check(self.lib.sg_ev_step_host_async(
+                    *args, self._h_obs.data_ptr(), self._h_reward.data_ptr(), self._h_done.data_ptr(), *dev_out,
+                    stream), "sg_ev_step_host_async")
+        self._pending = self.host_obs
+        self.kernel_launches += 2 if self.project_action_in_env else 1
+
+    def _finish_host(self, stream: "torch.cuda.Stream"):
+        stream.synchronize()
+        B = self.num_envs
+        if self._pending == "compact":
+            c = self._compact
+            n_ovf = int(c["h"][:4].view(torch.int32)[0])
+            dense_fallback = n_ovf > c["cap"]
+            n_rows = 0 if dense_fallback else n_ovf
+            if n_rows:                                   # rare: rows of the envs with more than 16 active sessions
+                c["h_idx"][:n_rows].copy_(c["d_idx"][:n_rows]); c["h_rows"][:n_rows].copy_(c["d_rows"][:n_rows])
+                torch.cuda.current_stream(self.device).synchronize()
+            _lib.check(self.lib.sg_ev_expand_obs(
+                c["h"].data_ptr(), B, self.num_stations, self.moer_forecast_steps, c["moer"].ctypes.data,
+                c["moer"].shape[0], c["prev"].data_ptr(), int(self._host_obs_valid and self.host_incremental),
+                c["h_idx"].data_ptr(),
+                c["h_rows"].data_ptr(), n_rows, self._h_obs.data_ptr(), self._h_reward.data_ptr(),
+                self._h_done.data_ptr(), c["h_status"].data_ptr(), self.host_threads), "sg_ev_expand_obs")
+            if dense_fallback:
+                self._h_obs.copy_(self.obs)
+                torch.cuda.current_stream(self.device).synchronize()
+            self._host_obs_valid = True
+        self._pending = None
+        # zero-copy results: no torch CPU op (and none of its OpenMP threads) on the per-step path
+        return (self._h_obs, self._h_reward, self._h_done.view(torch.bool), self._h_trunc, self._infos())
 
     @property
     def _max_profit_per_day(self) -> np.ndarray:
@@ -333,6 +424,7 @@ class BatchedEVChargingEnv:
                 self.pilots.data_ptr(), _lib.ptr(self.final_obs), self.status.data_ptr(), _lib.ptr(self.stats),
                 self.work.data_ptr(), self._stream()), "sg_ev_step")
         self.kernel_launches += 2 if self.project_action_in_env else 1
+        self._host_obs_valid = False          # the next host-path step rewrites every observation row
 
     def export_state(self):
         """Dense views of the sparse per-station state: (delivered kWh f64 [B,n], trace slot u8 [B,n],

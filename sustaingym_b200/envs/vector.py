@@ -64,13 +64,29 @@ class _Base:
         self.env.close()
 
 
-class SB3VecEnv(_Base):
-    """stable_baselines3.common.vec_env.VecEnv protocol."""
+_NO_INFO: dict = {}       # shared by every env that has nothing to report this step (treat as read-only)
 
-    def __init__(self, env, dict_obs=None, seed: int = 0):
+
+class SB3VecEnv(_Base):
+    """stable_baselines3.common.vec_env.VecEnv protocol.
+
+    With an engine that steps asynchronously and resets in-kernel (``BatchedEVChargingEnv(auto_reset=True)``),
+    ``step_async`` only enqueues H2D(actions) -> step -> D2H on the env's own stream and returns; ``step_wait``
+    waits for it, so two adapters stepped alternately overlap their copies (what SubprocVecEnv's worker processes
+    do in the reference, examples/evcharging/train_stable_baselines.py:264-275).  ``actions`` may be a NumPy
+    array (copied into the env's pinned staging buffer) or a pinned torch tensor (DMA straight from it).
+    ``infos`` is ONE list reused between steps whose entries are the shared empty dict except for envs that
+    finished (``terminal_observation``, ``TimeLimit.truncated``) — no per-env allocation per step.
+    ``copy=False`` returns views of the pinned result buffers (valid until the next ``step_wait``)."""
+
+    def __init__(self, env, dict_obs=None, seed: int = 0, copy: bool = True):
         super().__init__(env, dict_obs)
         self._seed = seed
         self._actions = None
+        self._copy = copy
+        self._fast = bool(getattr(env, "auto_reset", False)) and hasattr(env, "step_async") and hasattr(env, "final_obs")
+        self._infos = [_NO_INFO] * self.num_envs
+        self._dirty = ()
 
     def seed(self, seed=None):
         self._seed = 0 if seed is None else seed
@@ -79,20 +95,50 @@ class SB3VecEnv(_Base):
     def reset(self):
         return self._fmt(self._reset_all(self._seed))
 
+    def _fmt(self, flat: np.ndarray):
+        if self._dict and self._slices is not None:
+            return {k: (flat[:, s].copy() if self._copy else flat[:, s]) for k, s in self._slices.items()}
+        return flat.copy() if self._copy else flat
+
     def step_async(self, actions):
-        self._actions = np.asarray(actions)
+        if self._fast:
+            env = self.env
+            if isinstance(actions, np.ndarray):
+                env._h_action.numpy()[...] = actions.reshape(env._h_action.shape)
+                actions = env._h_action
+            env.step_async(actions)
+        else:
+            self._actions = np.asarray(actions)
 
     def step_wait(self):
+        infos = self._infos
+        for i in self._dirty:                              # entries filled by the previous step
+            infos[i] = _NO_INFO
+        self._dirty = ()
+        if self._fast:
+            obs, rew, term, trunc, _ = self.env.step_wait()
+            obs, done = obs.numpy(), term.numpy()
+            if done.any():                                 # the kernel already reset them: obs holds the reset observation
+                idx = np.nonzero(done)[0]
+                import torch
+                terminal = self.env.final_obs[torch.from_numpy(idx).to(self.env.device)].cpu().numpy()
+                for j, i in enumerate(idx):
+                    infos[i] = {"terminal_observation": self._fmt_one(terminal[j]), "TimeLimit.truncated": False}
+                self._dirty = idx
+                self._episode += 1
+            rew = rew.numpy().astype(np.float32)
+            return self._fmt(obs), rew, (done.copy() if self._copy else done), infos
         obs, rew, term, trunc, _ = self.env.step(self._actions)
         obs = np.asarray(obs)
         done = np.asarray(term) | np.asarray(trunc)
-        infos = [{} for _ in range(self.num_envs)]
         if done.any():
             terminal = obs.copy()
             obs = self._reset_done(done, self._seed + self._episode * self.num_envs)
-            for i in np.nonzero(done)[0]:
-                infos[i]["terminal_observation"] = self._fmt_one(terminal[i])
-                infos[i]["TimeLimit.truncated"] = bool(np.asarray(trunc)[i] and not np.asarray(term)[i])
+            idx = np.nonzero(done)[0]
+            for i in idx:
+                infos[i] = {"terminal_observation": self._fmt_one(terminal[i]),
+                            "TimeLimit.truncated": bool(np.asarray(trunc)[i] and not np.asarray(term)[i])}
+            self._dirty = idx
         return self._fmt(obs), np.asarray(rew, np.float32), done, infos
 
     def step(self, actions):

@@ -25,7 +25,7 @@ def test_ctypes_signatures_cover_header(native_lib):
 
 
 def test_abi_version_and_error_string(native_lib):
-    assert native_lib.sg_abi_version() == 1
+    assert native_lib.sg_abi_version() == 2
     assert isinstance(native_lib.sg_last_error(), bytes)
 
 

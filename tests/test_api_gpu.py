@@ -127,3 +127,45 @@ def test_discrete_action_wrapper(native_lib):
         o1, r1, *_ = e1.step(a)
         o2, r2, *_ = e2.step(a)
         assert r1 == r2 and all(np.array_equal(o1[k], o2[k]) for k in o1)
+
+
+def test_sb3_adapter_pipelined_path_matches_generic_path(native_lib):
+    """SB3VecEnv over an auto-resetting engine (step_async enqueues on the env's stream, the kernel resets, compact
+    records cross PCIe) returns what the generic adapter path (synchronous step + host-driven reset) returns; the
+    infos list is reused and only finished envs get a dict."""
+    import torch
+    from sustaingym_b200.envs.evcharging.env import BatchedEVChargingEnv
+    from sustaingym_b200.envs.vector import SB3VecEnv
+    N = 40
+    fast = SB3VecEnv(BatchedEVChargingEnv(ev_gen(), N, project_action_in_env=True, auto_reset=True), copy=False)
+    slow = SB3VecEnv(BatchedEVChargingEnv(ev_gen(), N, project_action_in_env=True, host_obs="dense"))
+    assert fast._fast and not slow._fast
+    o_f, o_s = fast.reset(), slow.reset()
+    rng = np.random.default_rng(1)
+    pinned = torch.zeros(N, 54).pin_memory()
+    infos_id = None
+    for t in range(288 + 20):
+        a = rng.uniform(0, 1, (N, 54)).astype(np.float32)
+        if t % 2:
+            pinned.numpy()[...] = a
+            fast.step_async(pinned)                       # pinned torch tensor: no staging copy
+        else:
+            fast.step_async(a)
+        o_f, r_f, d_f, i_f = fast.step_wait()
+        infos_id = infos_id or id(i_f)
+        assert id(i_f) == infos_id                        # one list, reused
+        if t > 287:       # second episode: the kernel moved every env to its next day (the generic path re-seeds instead)
+            assert not d_f.any() and all(len(x) == 0 for x in i_f) and np.all(o_f["timestep"] == np.float32((t - 287) / 288))
+            continue
+        slow.step_async(a)
+        o_s, r_s, d_s, i_s = slow.step_wait()
+        np.testing.assert_array_equal(r_f, r_s)
+        np.testing.assert_array_equal(d_f, d_s)
+        if t == 287:
+            assert d_f.all() and np.all(o_f["timestep"] == 0) and np.all(o_f["demands"] == 0)
+            for k in o_s:
+                np.testing.assert_array_equal(i_f[3]["terminal_observation"][k], i_s[3]["terminal_observation"][k])
+        else:
+            for k in o_s:
+                np.testing.assert_array_equal(o_f[k], o_s[k], err_msg=f"{k} at step {t}")
+            assert not d_f.any() and all(len(x) == 0 for x in i_f)

@@ -189,3 +189,38 @@ def test_single_env_gymnasium_view(native_lib):
     obs_b, _ = env.reset(seed=1)
     for k in obs_a:
         np.testing.assert_array_equal(obs_a[k], obs_b[k])
+
+
+@pytest.mark.parametrize("mean,cap", [(30.0, None), (110.0, None), (110.0, 3)])
+def test_compact_host_path_is_bit_identical(native_lib, mean, cap):
+    """Host-buffer path through 120-byte records + host expansion (sg_ev_step_host_compact_async, sg_ev_expand_obs)
+    against the dense device->host copy: observations, rewards, done flags bit for bit, through an auto-reset;
+    mean = 110 sessions/day puts more than 16 active sessions into many envs (overflow rows), cap = 3 forces the
+    dense fallback of a step whose overflow area is too small."""
+    B = 300
+    gen, env_c, _, _ = make(4, mean, 8, B, True, auto_reset=True, host_obs="compact", host_threads=3)
+    _, env_d, _, _ = make(4, mean, 8, B, True, auto_reset=True, host_obs="dense")
+    env_c.reset(seed=0); env_d.reset(seed=0)
+    if cap is not None:
+        env_c._ensure_compact()["cap"] = cap
+    rng = np.random.default_rng(0)
+    n_over = 0
+    for t in range(288 + 40):
+        a = torch.from_numpy(rng.uniform(0, 1, (B, 54)).astype(np.float32)).pin_memory()
+        if t % 3 == 0:
+            env_c.step_async(a); oc, rc, dc, _, _ = env_c.step_wait()
+            env_d.step_async(a); od, rd, dd, _, _ = env_d.step_wait()
+            oc, rc, dc, od, rd, dd = (x.numpy() for x in (oc, rc, dc, od, rd, dd))
+        else:
+            oc, rc, dc, _, _ = env_c.step(a.numpy())
+            od, rd, dd, _, _ = env_d.step(a.numpy())
+        np.testing.assert_array_equal(oc, od, err_msg=f"step {t}")
+        np.testing.assert_array_equal(rc, rd)
+        np.testing.assert_array_equal(dc, dd)
+        n_over += int(((od[:, :54] != 0).sum(1) > 16).sum())
+        if t == 100:                      # a device-path step in between: the next host step must rewrite every row
+            g = a.cuda()
+            env_c.step(g); env_d.step(g)
+    assert torch.equal(env_c.obs, env_d.obs)
+    if mean > 100:
+        assert n_over > 100               # the overflow rows were really used
