@@ -159,13 +159,14 @@ typedef struct sg_ev_model {
 /* Per-env state.
  *   slots : a plugged-in session is one 32-byte record
  *             { f64 requested kWh, f64 delivered kWh, i32 departure, i32 est_departure, i32 arrival, i32 trace slot }
- *           stored per (env, station) and updated in place; only the stations whose bit is set in the
- *           env's occupancy mask hold a live record (sg_ev_export_state gives dense views).
- *   header: one 64-byte record per env
+ *           Each env owns a block of n records holding its live sessions as a PACKED LIST in station order: the
+ *           record of station i is entry popcount(occupancy & ((1 << i) - 1)); the list is updated in place
+ *           (sg_ev_export_state gives dense per-station views).
+ *   header: one 64-byte record per env, two 32-byte halves
  *             { i32 t (0..288, env.py:168), i32 day (trace index in [0,D)), i32 moer_day (MOER table index
  *               in [0,Dm)), i32 arrival cursor (sessions of the day with arrival <= t),
- *               u64 occupancy mask (bit i: station i has a plugged-in session),
- *               f64[3] cumulative profit, carbon_cost, excess_charge (env.py:460-462), 16 bytes padding } */
+ *               u64 occupancy mask (bit i: station i has a plugged-in session), 8 bytes padding }
+ *             { f64[3] cumulative profit, carbon_cost, excess_charge (env.py:460-462), 8 bytes padding } */
 typedef struct sg_ev_state {
     void* slots;          /* [device] [B, n] 32-byte session records, 32-byte aligned */
     void* header;         /* [device] [B] 64-byte env records, 64-byte aligned        */
@@ -278,7 +279,9 @@ int sg_ev_step_host_compact_async(const sg_ev_model* m, const sg_ev_state* s, in
                                   const void* h_action, int32_t flags, int32_t discrete_bins, void* h_compact,
                                   void* d_action, float* d_obs, double* d_reward, uint8_t* d_done, uint8_t* d_status,
                                   double* d_stats, int32_t* d_work, void* d_compact, int32_t* d_ovf_idx,
-                                  float* d_ovf_rows, int32_t ovf_cap, void* stream);
+                                  float* d_ovf_rows, int32_t ovf_cap,
+                                  float* d_final_obs /* [device] [B, 2n+k+2] or NULL: terminal observations (AUTORESET) */,
+                                  void* stream);
 
 /* HOST function (no CUDA call): rebuilds obs [B, 2n+k+2] f32, reward [B] f64, done [B] u8 (and status [B] u8 unless
  * NULL) from the compact records with `n_threads` threads of a persistent pool.  `h_moer` is the host copy of

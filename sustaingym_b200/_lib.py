@@ -117,7 +117,7 @@ SIGNATURES = {
                                         _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "sg_ev_pack_obs": (C.c_int, [_i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "sg_ev_step_host_compact_async": (C.c_int, [C.POINTER(EVModel), C.POINTER(EVState), _i64, _vp, _i32, _i32, _vp, _vp,
-                                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
+                                                _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "sg_ev_expand_obs": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32]),
     "sg_ev_export_state": (C.c_int, [C.POINTER(EVModel), C.POINTER(EVState), _i64, _vp, _vp, _vp]),
     "sg_ev_agent_obs": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),

@@ -653,7 +653,10 @@ __device__ __forceinline__ bool network_feasible_tol(const EvShared& sh, int C, 
 // Per-env state (include/sustaingym_b200.h, sg_ev_state).  A plugged-in session is one 32-byte
 // record = one DRAM/L2 sector, read and written with single 256-bit accesses:
 //     { f64 requested kWh, f64 delivered kWh, i32 departure, i32 est_departure, i32 arrival, i32 slot }
-// kept per (env, station) and updated IN PLACE: a record is written back right after it was read,
+// kept per env as a PACKED LIST in station order — the record of station i is entry popc(occ & ((1 << i) - 1)) of
+// the env's [n]-entry block — so the ~6 live records of an env are contiguous (2-3 cache lines instead of 6
+// scattered sectors: the kernel is bound by the NUMBER of memory requests, profiles/r2/dram_random.cu), and
+// updated IN PLACE: a record is written back right after it was read,
 // while its line is still in L2 (measured on B200: writing the records to a second, not yet cached
 // copy of the state cost 22 us per 65 536-env step, in place it is free).  Only the occupied
 // stations (bit set in the env's 64-bit occupancy mask) hold live records, so one step touches
@@ -696,36 +699,56 @@ __device__ __forceinline__ void st_slot_2x16(Slot* p, const Slot& s) {
     reinterpret_cast<uint4*>(p)[1] = hi;
 }
 
-// Per-env scalars, one 64-byte record (= one DRAM access granule) per env, read at the start of a
-// step and written back in place at its end: clock, occupancy mask, cumulative reward breakdown.
-struct __align__(16) EnvHeader {
+// Per-env scalars, one 64-byte record per env, read at the start of a step and written back in place at its
+// end.  Two 32-byte halves, each moved with ONE 256-bit access per owner lane (a tile's 16 headers are then 4 + 4
+// line requests instead of 3 x 8 with 16-byte loads; the step kernel is bound by the number of memory requests):
+//   hot  { i32 t, day, moer_day, arrival cursor | u64 occupancy mask | pad }
+//   cold { f64 cumulative profit, carbon_cost, excess_charge | pad }
+struct __align__(32) EnvHeader {
     int t, day, moer_day, nidx;                      // env.py:168 t; trace / MOER table index; arrival cursor
     unsigned long long occ;                          // bit i: station i has a plugged-in session
+    unsigned long long pad0;
     double bd[3];                                    // cumulative profit, carbon_cost, excess_charge (env.py:460-462)
-    unsigned long long pad[2];
+    unsigned long long pad1;
 };
 static_assert(sizeof(EnvHeader) == 64, "EnvHeader must be 64 bytes");
 
+__device__ __forceinline__ void ld_v4u64(const void* p, unsigned long long (&v)[4]) {
+    asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v[0]), "=l"(v[1]), "=l"(v[2]), "=l"(v[3]) : "l"(p));
+}
+__device__ __forceinline__ void st_v4u64(void* p, const unsigned long long (&v)[4]) {
+    asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(v[0]), "l"(v[1]), "l"(v[2]), "l"(v[3]) : "memory");
+}
 __device__ __forceinline__ EnvHeader ld_header(const EnvHeader* p) {
-    union { EnvHeader h; uint4 v[4]; } u;
-    const uint4* g = reinterpret_cast<const uint4*>(p);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) u.v[i] = g[i];       // (the padding is not read)
-    u.v[3] = make_uint4(0u, 0u, 0u, 0u);
-    return u.h;
+    unsigned long long a[4], c[4];
+    ld_v4u64(p, a);
+    ld_v4u64(reinterpret_cast<const unsigned char*>(p) + 32, c);
+    EnvHeader h;
+    h.t = (int)(unsigned)(a[0] & 0xffffffffull); h.day = (int)(unsigned)(a[0] >> 32);
+    h.moer_day = (int)(unsigned)(a[1] & 0xffffffffull); h.nidx = (int)(unsigned)(a[1] >> 32);
+    h.occ = a[2]; h.pad0 = 0ull;
+    h.bd[0] = __longlong_as_double((long long)c[0]); h.bd[1] = __longlong_as_double((long long)c[1]);
+    h.bd[2] = __longlong_as_double((long long)c[2]); h.pad1 = 0ull;
+    return h;
 }
 __device__ __forceinline__ void st_header(EnvHeader* p, const EnvHeader& h) {
-    union { EnvHeader h; uint4 v[4]; } u;
-    u.h = h;
-    uint4* g = reinterpret_cast<uint4*>(p);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) g[i] = u.v[i];       // whole record: a full 64-byte granule
+    const unsigned long long a[4] = {(unsigned long long)(unsigned)h.t | ((unsigned long long)(unsigned)h.day << 32),
+                                     (unsigned long long)(unsigned)h.moer_day | ((unsigned long long)(unsigned)h.nidx << 32),
+                                     h.occ, 0ull};
+    const unsigned long long c[4] = {(unsigned long long)__double_as_longlong(h.bd[0]), (unsigned long long)__double_as_longlong(h.bd[1]),
+                                     (unsigned long long)__double_as_longlong(h.bd[2]), 0ull};
+    st_v4u64(p, a);
+    st_v4u64(reinterpret_cast<unsigned char*>(p) + 32, c);
 }
 __device__ __forceinline__ EnvHeader empty_header() {
     EnvHeader h;
     h.t = kEpisode; h.day = 0; h.moer_day = 0; h.nidx = 0; h.occ = 0ull;
-    h.bd[0] = h.bd[1] = h.bd[2] = 0.0; h.pad[0] = h.pad[1] = 0ull;
+    h.bd[0] = h.bd[1] = h.bd[2] = 0.0; h.pad0 = h.pad1 = 0ull;
     return h;
+}
+// position of station i's record in the env's packed list: the occupied stations below it
+__device__ __forceinline__ int slot_rank(const unsigned long long occ, const int i) {
+    return __popcll(occ & ((1ull << i) - 1ull));
 }
 
 #ifndef SG_EV_KE
@@ -757,6 +780,7 @@ struct WarpShared {
     int S[kMC][kE];                                  // per-env class sums of the clipped action, 2^-20 fixed point
     int P[kMC][kE];                                  // per-env class sums of the integer pilots
     unsigned occ_clr[kE][2];                         // occupancy bits cleared by Unplug events
+    unsigned long long occ_fin[kE];                  // occupancy after this step's Unplug and Plugin events (list ranks)
     float xa[kItemCap];                              // rare path: action of item j (its upper bound goes to rate[j])
     double Sx[kMC], nu[kMC];                         // rare path: exact class sums / class multipliers of one env
     double stat[12];                                 // this warp's reward statistics (SG_STATS layout)
@@ -863,7 +887,7 @@ __device__ __noinline__ bool fallback_env(const EvTables& sh, const EvCtx cx, co
             a[p] = (double)act_value(cx.action, i64, cx.bins, b * n + i);
             cls[p] = sh.cls[i]; type[p] = sh.type[i];
             if (occd[p]) {
-                q[p] = ld_slot(cur + i);
+                q[p] = ld_slot(cur + slot_rank(occ, i));
                 const double rem = q[p].energy - q[p].delivered;
                 const float dem = rem > kFullEps ? (float)rem : 0.f;          // obs 'demands', env.py:388
                 u[p] = upper_bound(dem);
@@ -887,6 +911,7 @@ __device__ __noinline__ bool fallback_env(const EvTables& sh, const EvCtx cx, co
     float dem_o[2] = {0.f, 0.f}, est_o[2] = {0.f, 0.f};
     double rate_part = 0.0;
     unsigned long long mine = 0ull;
+    bool wr[2] = {false, false};                       // q[p] is live after this step (written once the final mask is known)
 #pragma unroll
     for (int p = 0; p < 2; ++p) {
         if (!valid[p]) continue;
@@ -896,7 +921,7 @@ __device__ __noinline__ bool fallback_env(const EvTables& sh, const EvCtx cx, co
         if (occd[p]) {
             rate_part += charge_period(q[p].energy, q[p].delivered, sh.ppilot[pi]);
             if (q[p].dep > tn) {
-                st_slot_2x16(nxt + i, q[p]);
+                wr[p] = true;
                 mine |= 1ull << i;
                 const double rem = q[p].energy - q[p].delivered;
                 if (rem > kFullEps) { dem_o[p] = (float)rem; est_o[p] = (float)(q[p].est - tn); }   // Interface.active_sessions()
@@ -917,9 +942,9 @@ __device__ __noinline__ bool fallback_env(const EvTables& sh, const EvCtx cx, co
                 ns.est = (int)(short)(rr.y & 0xffffu); ns.k = k;
                 ns.energy = __hiloint2double((int)rr.w, (int)rr.z); ns.delivered = 0.0;
                 if (ns.dep > tn) {
-                    st_slot_2x16(nxt + i, ns);
                     mine |= 1ull << i;
                     const int p = i & 1;
+                    if (p == 0) { q[0] = ns; wr[0] = true; } else { q[1] = ns; wr[1] = true; }
                     if (ns.energy > kFullEps) { dem_o[p] = (float)ns.energy; est_o[p] = (float)(ns.est - tn); }
                 }
             }
@@ -929,6 +954,12 @@ __device__ __noinline__ bool fallback_env(const EvTables& sh, const EvCtx cx, co
     }
     const unsigned occ_lo = __reduce_or_sync(kFull, (unsigned)(mine & 0xffffffffull));
     const unsigned occ_hi = __reduce_or_sync(kFull, (unsigned)(mine >> 32));
+    {   // the packed list of the new occupancy (every record of the old list was read above, by all lanes)
+        const unsigned long long occ_fin = ((unsigned long long)occ_hi << 32) | occ_lo;
+#pragma unroll
+        for (int p = 0; p < 2; ++p)
+            if (wr[p]) st_slot_2x16(nxt + slot_rank(occ_fin, i0 + p), q[p]);
+    }
     // excess current from the rounded schedule (env.py:449-452)
     double excess = 0.0;
     {
@@ -976,7 +1007,7 @@ __device__ __noinline__ bool fallback_env(const EvTables& sh, const EvCtx cx, co
         ho.bd[2] = (t == 0 ? 0.0 : hd.bd[2]) + excess_charge;
         ho.t = tn; ho.occ = ((unsigned long long)occ_hi << 32) | occ_lo;
         if (autoreset) { day = (day + 1) % cx.n_days; ho.t = 0; nidx = 0; ho.occ = 0ull; }
-        ho.day = day; ho.moer_day = md_out; ho.nidx = nidx; ho.pad[0] = ho.pad[1] = 0ull;
+        ho.day = day; ho.moer_day = md_out; ho.nidx = nidx; ho.pad0 = ho.pad1 = 0ull;
         cx.header[b] = ho;
         cx.reward[b] = rew;
         cx.done[b] = dn ? 1 : 0;
@@ -1279,6 +1310,7 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
                        (kQ == 1 ? 0 : __popcll(occ_e & ((1ull << ((sub * kSegBits) & 63)) - 1ull)));
         EV_TRACE(11);
         unsigned redo_all = 0u;                                       // envs whose action was projected here (status)
+        unsigned long long arr_mask = 0ull;                           // owner lane: stations that get a new session now
         for (int g0 = 0; g0 < kE;) {
             const int base = __shfl_sync(kFull, off, g0);
             const unsigned fit = __ballot_sync(kFull, lane >= g0 && lane < kE && off + cnt - base <= kItemCap);
@@ -1299,7 +1331,7 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
             EV_TRACE(12);
             __syncwarp();
             EV_TRACE(3);
-            int e[kV], si[kV], tne[kV];
+            int e[kV], si[kV], tne[kV], rk[kV];
             Slot q[kV];
             float af[kV];
             bool on[kV];
@@ -1310,6 +1342,7 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
                 const unsigned key = on[u] ? ws.key[j] : 0u;
                 e[u] = (int)(key >> 8); si[u] = (int)(key & 0xffu);
                 tne[u] = __shfl_sync(kFull, tn, e[u]);
+                rk[u] = base + j - __shfl_sync(kFull, off, e[u]);        // items are listed in station order: list rank
             }
 #pragma unroll
             for (int u = 0; u < kV; ++u) {
@@ -1317,9 +1350,23 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
                 q[u].energy = 0.0; q[u].delivered = 0.0; q[u].dep = q[u].est = q[u].arr = q[u].k = 0;
                 if (on[u]) {
                     const long long be = b0 + e[u];
-                    q[u] = ld_slot(slots + be * n + si[u]);
+                    q[u] = ld_slot(slots + be * n + rk[u]);
                     af[u] = act_value(action, i64, bins, be * n + si[u]);
                 }
+            }
+            if (g0 == 0 && live && (int)(ent & 0x7fffu) <= tn) {
+                // Plugin events of this step, first pass (their trace-record loads overlap the session-record loads
+                // above): which stations get a new session, i.e. the occupancy the packed lists are written for
+                unsigned en = ent, en2 = ent2;
+                int ni = nidx;
+                do {
+                    const int i = (en >> 16) & 0xff, k = en >> 24;
+                    const unsigned rx = __ldg(reinterpret_cast<const unsigned*>(recs + ((long long)day * m.max_sessions + k) * n + i));
+                    if ((int)(short)(rx >> 16) > tn) arr_mask |= 1ull << i;      // (zero-length sessions never charge)
+                    ++ni;
+                    en = en2;
+                    en2 = (int)(en & 0x7fffu) <= tn ? __ldg(arow + ni + 1) : 0x7fffu;
+                } while ((int)(en & 0x7fffu) <= tn);
             }
             if (g0 == 0 && !tail_async) {
                 // MOER + timestep tails of the staged rows, kQ lanes per env: placed here so that their loads
@@ -1489,10 +1536,16 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
                 for (int j = lo; __any_sync(kFull, j < hi); ++j)
                     if (j < hi) rate_sum += ws.rate[j];
             }
-            // session records back in place, for the envs of the group that are finished here
+            // session records back into the env's packed list of the NEW occupancy (Unplug events of the items
+            // phase removed, this step's Plugin events included), for the envs of the group that are finished here;
+            // every record of these envs was read at the top of the group
+            if (lane >= g0 && lane < g1)
+                ws.occ_fin[lane] = (occ & ~(((unsigned long long)ws.occ_clr[lane][1] << 32) | ws.occ_clr[lane][0])) | arr_mask;
+            __syncwarp();
 #pragma unroll
             for (int u = 0; u < kV; ++u)
-                if (keep[u] && !((gfail >> e[u]) & 1u) && !(SG_EV_ABL & 2)) st_slot(slots + (b0 + e[u]) * n + si[u], q[u]);
+                if (keep[u] && !((gfail >> e[u]) & 1u) && !(SG_EV_ABL & 2))
+                    st_slot(slots + (b0 + e[u]) * n + slot_rank(ws.occ_fin[e[u]], si[u]), q[u]);
             __syncwarp();
             g0 = g1;
         }
@@ -1502,8 +1555,8 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
         EV_TRACE(6);
 
         // ---------------- arrivals: Plugin events with timestamp <= t+1 (after the Unplug events) -------
-        unsigned long long occ_new = occ & ~(((unsigned long long)ws.occ_clr[lane & (kE - 1)][1] << 32) |
-                                             ws.occ_clr[lane & (kE - 1)][0]);
+        unsigned long long occ_new = (occ & ~(((unsigned long long)ws.occ_clr[lane & (kE - 1)][1] << 32) |
+                                              ws.occ_clr[lane & (kE - 1)][0])) | arr_mask;
         if (mine_ok && (int)(ent & 0x7fffu) <= tn) {
             float* row = srows + lane * OBS;
             Slot* nxt = slots + b * n;
@@ -1518,8 +1571,7 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
                 ns.energy = __hiloint2double((int)rr.w, (int)rr.z);
                 ns.delivered = 0.0;
                 if (ns.dep > tn) {                                        // (zero-length sessions never charge)
-                    occ_new |= 1ull << i;
-                    st_slot(nxt + i, ns);
+                    st_slot(nxt + slot_rank(occ_new, i), ns);
                     if (ns.energy > kFullEps) { row[i] = (float)ns.energy; row[n + i] = (float)(ns.est - tn); }
                 }
                 ++nidx;
@@ -1560,7 +1612,7 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
                 day = (day + 1) % m.n_days;                               // sequential days, event_generation.py:284-291
                 ho.t = 0; nidx = 0; occ_new = 0ull;
             }
-            ho.day = day; ho.moer_day = md_out; ho.nidx = nidx; ho.occ = occ_new; ho.pad[0] = ho.pad[1] = 0ull;
+            ho.day = day; ho.moer_day = md_out; ho.nidx = nidx; ho.occ = occ_new; ho.pad0 = ho.pad1 = 0ull;
             if (!(SG_EV_ABL & 128)) st_header(headers + b, ho);           // in place: the line is in L2
             reward[b] = rew;
             done[b] = dn ? 1 : 0;
@@ -1759,7 +1811,7 @@ __global__ void ev_export_kernel(const sg_ev_model m, const sg_ev_state s, const
         const bool on = (headers[b].occ >> i) & 1ull;
         double d = 0.0;
         int k = 255;
-        if (on) { const Slot q = ld_slot(slots + b * n + i); d = q.delivered; k = q.k; }
+        if (on) { const Slot q = ld_slot(slots + b * n + slot_rank(headers[b].occ, i)); d = q.delivered; k = q.k; }
         if (delivered != nullptr) delivered[idx] = d;
         if (sess_idx != nullptr) sess_idx[idx] = (uint8_t)k;
     }

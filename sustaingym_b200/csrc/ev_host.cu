@@ -177,7 +177,8 @@ int sg_ev_pack_obs(int64_t num_envs, int32_t n_stations, int32_t obs_dim, const 
 int sg_ev_step_host_compact_async(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, const void* h_action,
                                   int32_t flags, int32_t discrete_bins, void* h_compact, void* d_action, float* d_obs,
                                   double* d_reward, uint8_t* d_done, uint8_t* d_status, double* d_stats, int32_t* d_work,
-                                  void* d_compact, int32_t* d_ovf_idx, float* d_ovf_rows, int32_t ovf_cap, void* stream) {
+                                  void* d_compact, int32_t* d_ovf_idx, float* d_ovf_rows, int32_t ovf_cap,
+                                  float* d_final_obs, void* stream) {
     SG_CHECK_ARG(m && s && h_action && h_compact && d_action && d_obs && d_reward && d_done && d_compact,
                  "ev_step_host_compact: NULL argument");
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
@@ -185,7 +186,7 @@ int sg_ev_step_host_compact_async(const sg_ev_model* m, const sg_ev_state* s, in
     const int obs_dim = 2 * m->n_stations + m->moer_steps + 2;
     const size_t abytes = B * n * (((flags & 1) == SG_EV_ACTION_I64) ? 8 : 4);
     SG_CUDA(cudaMemcpyAsync(d_action, h_action, abytes, cudaMemcpyHostToDevice, st));
-    if (int rc = sg_ev_step(m, s, num_envs, d_action, flags, discrete_bins, d_obs, d_reward, d_done, nullptr, nullptr,
+    if (int rc = sg_ev_step(m, s, num_envs, d_action, flags, discrete_bins, d_obs, d_reward, d_done, nullptr, d_final_obs,
                             d_status, d_stats, d_work, stream)) return rc;
     if (int rc = sg_ev_pack_obs(num_envs, m->n_stations, obs_dim, d_obs, d_reward, d_done, d_status, s->header, d_compact,
                                 d_ovf_idx, d_ovf_rows, ovf_cap, stream)) return rc;

@@ -174,14 +174,14 @@ class BatchedEVChargingEnv:
         B = self.num_envs
         z = lambda *shape, dtype: torch.zeros(*shape, dtype=dtype, device=dev)  # noqa: E731
         # session records of the plugged-in EVs: [B, n] x 32 bytes, and one 64-byte header per env
-        # {t, day, moer_day, arrival cursor | occupancy mask | profit, carbon_cost, excess_charge | pad}
+        # {t, day, moer_day, arrival cursor | occupancy mask | pad || profit, carbon_cost, excess_charge | pad}
         # (see sg_ev_state); torch allocations are 512-byte aligned, which the vector accesses need
         self.slots = z(B, n, 4, dtype=torch.float64)
         self.header = z(B, 8, dtype=torch.float64)
         self.clock = self.header.view(torch.int32)[:, 0:4]        # columns: t, day, moer_day, arrival cursor
         self.t, self.day, self.moer_day = self.clock[:, 0], self.clock[:, 1], self.clock[:, 2]
         self.occ = self.header.view(torch.int64)[:, 2]            # bit i: station i has a plugged-in session
-        self.breakdown = self.header[:, 3:6]
+        self.breakdown = self.header[:, 4:7]
         self._state = _lib.EVState(self.slots.data_ptr(), self.header.data_ptr())
         self.obs = z(B, self.obs_dim, dtype=torch.float32)
         self.final_obs = z(B, self.obs_dim, dtype=torch.float32) if auto_reset else None
@@ -358,7 +358,7 @@ class BatchedEVChargingEnv:
                 c = self._ensure_compact()
                 _lib.check(self.lib.sg_ev_step_host_compact_async(
                     *args, c["h"].data_ptr(), *dev_out, c["d"].data_ptr(), c["d_idx"].data_ptr(),
-                    c["d_rows"].data_ptr(), c["cap"], stream), "sg_ev_step_host_compact_async")
+                    c["d_rows"].data_ptr(), c["cap"], _lib.ptr(self.final_obs), stream), "sg_ev_step_host_compact_async")
                 self.kernel_launches += 1
             else:
                 _lib.check(self.lib.sg_ev_step_host_async(
