@@ -49,3 +49,11 @@ for lo, hi in [(0, 25), (25, 50), (50, 75), (75, 100)]:
     a, b_ = np.percentile(start, [lo, hi])
     sel = (start >= a) & (start <= b_)
     print(f"  tiles starting in [{a:5.1f},{b_:5.1f}] us: median duration {np.median(tot[sel]):.2f} us")
+ph = np.stack([(tr[:, b_] - tr[:, a]) / 1e3 for a, b_ in zip(order[:-1], order[1:])], 1)
+print("p99 per phase:", np.percentile(ph, 99, axis=0).round(2))
+print("count of tiles > 20 us:", int((tot > 20).sum()), " > 25 us:", int((tot > 25).sum()))
+occn = None
+for title, idx in (("10 longest tiles", np.argsort(-tot)[:10]), ("10 last-ending tiles", np.argsort(-fin)[:10])):
+    print(title)
+    for i in idx:
+        print(f"  tile {i:5d} sm {sm[i]:3d} start {start[i]:6.1f} end {fin[i]:6.1f} total {tot[i]:6.2f} | " + " ".join(f"{x:5.2f}" for x in ph[i]))

@@ -766,7 +766,10 @@ __device__ __forceinline__ int slot_rank(const unsigned long long occ, const int
 constexpr int kE = SG_EV_KE;                         // envs per warp tile
 constexpr int kQ = 32 / kE;                          // lanes per env in the spread phases
 constexpr int kSegBits = 64 / kQ;                    // occupancy bits enumerated by one lane
-constexpr int kMainWarps = 4;                        // warps per CTA of the main kernel
+#ifndef SG_EV_WARPS
+#define SG_EV_WARPS 4
+#endif
+constexpr int kMainWarps = SG_EV_WARPS;              // warps per CTA of the main kernel
 constexpr int kMainThreads = kMainWarps * 32;
 constexpr int kV = SG_EV_KV;                         // work items per lane and chunk (loads in flight)
 constexpr int kItemCap = 32 * kV;                    // (env, station) work items staged per warp and chunk
@@ -782,7 +785,8 @@ struct WarpShared {
     unsigned occ_clr[kE][2];                         // occupancy bits cleared by Unplug events
     unsigned long long occ_fin[kE];                  // occupancy after this step's Unplug and Plugin events (list ranks)
     float xa[kItemCap];                              // rare path: action of item j (its upper bound goes to rate[j])
-    double Sx[kMC], nu[kMC];                         // rare path: exact class sums / class multipliers of one env
+    unsigned char icls[kItemCap];                    // rare path: station class of item j
+    double nu[kMC];                                  // rare path: class multipliers of one env's projection
     double stat[12];                                 // this warp's reward statistics (SG_STATS layout)
 };
 
@@ -1025,29 +1029,36 @@ __device__ __noinline__ bool fallback_env(const EvTables& sh, const EvCtx cx, co
     return true;
 }
 
-// Thread-serial exact projection of ONE env when only single-class constraints (the pods) are
-// violated — the same algorithm as simple_project above, run by the owner lane on the env's items
-// j in [lo, hi) of the warp's work list: action ws.xa[j], upper bound ws.rate[j], class from the
-// station in ws.key[j].  Returns 0: the clipped action is feasible (exact test), nothing to do;
-// 1: projected, x_i = clip(a_i - ws.nu[class_i], 0, u_i); 2: a coupled constraint is (or became)
-// violated -> interior point (rare kernel).
+// Exact projection of ONE env when only single-class constraints (the pods) are violated — the algorithm of
+// simple_project above, run by the WHOLE warp on the env's items j in [lo, hi) of the warp's work list (action
+// ws.xa[j], upper bound ws.rate[j], class ws.icls[j]); all arguments are warp-uniform.  Lanes stand for classes
+// (exact class sums), for break points of the piecewise-linear sum phi (all evaluated at once) and for constraints
+// (checks): a thread-serial version of this took 12-17 us on one lane and, with ~60 such envs per 65 536-env step,
+// set the end of the launch.  Returns 0: the clipped action is feasible (exact test), nothing to do; 1: projected,
+// x_i = clip(a_i - ws.nu[class_i], 0, u_i); 2: a coupled constraint is (or became) violated -> interior point
+// (rare kernel).
 __device__ __forceinline__ int pod_solve(const EvTables& sh, WarpShared& ws, const int lo, const int hi, const int J,
-                                         const unsigned suspects) {
-#pragma unroll
-    for (int c = 0; c < kMC; ++c) { ws.Sx[c] = 0.0; ws.nu[c] = 0.0; }
+                                         const unsigned suspects, const int lane) {
+    // exact class sums of the clipped action: lane c < kMC sums class c over the items (broadcast reads)
+    double mine = 0.0;
     for (int j = lo; j < hi; ++j) {
-        const int c = sh.cls[ws.key[j] & 0xff];
-        ws.Sx[c] += fmin(fmax((double)ws.xa[j], 0.0), ws.rate[j]);
+        const double v = fmin(fmax((double)ws.xa[j], 0.0), ws.rate[j]);
+        mine += ws.icls[j] == lane ? v : 0.0;
     }
-    // exact magnitude of constraint jc at the class sums ws.Sx
+    double Sx[kMC];
+#pragma unroll
+    for (int c = 0; c < kMC; ++c) Sx[c] = __shfl_sync(kFull, mine, c);
+    if (lane < kMC) ws.nu[lane] = 0.0;
+    __syncwarp();
+    // exact magnitude of constraint jc at the class sums Sx (every lane evaluates the same expression)
     auto magnitude = [&](const int jc) {
         double wr = 0, wi = 0;
 #pragma unroll
-        for (int c = 0; c < kMC; ++c) { wr = fma(sh.con_re[jc * kMC + c], ws.Sx[c], wr); wi = fma(sh.con_im[jc * kMC + c], ws.Sx[c], wi); }
+        for (int c = 0; c < kMC; ++c) { wr = fma(sh.con_re[jc * kMC + c], Sx[c], wr); wi = fma(sh.con_im[jc * kMC + c], Sx[c], wi); }
         return sqrt(wr * wr + wi * wi);
     };
     bool any = false;
-    // only the constraints the f32 margin test flagged can be violated by the clipped action
+    // only the constraints the margin test flagged can be violated by the clipped action
     for (unsigned todo = suspects; todo; todo &= todo - 1) {
         const int jc = __ffs((int)todo) - 1;
         if (jc >= J) break;
@@ -1056,55 +1067,49 @@ __device__ __forceinline__ int pod_solve(const EvTables& sh, WarpShared& ws, con
         const int cs = sh.simple_cls[jc];
         if (cs < 0) return 2;                                // a coupled constraint is violated
         const double R = sh.simple_R[jc];
-        double amax = 0.0;
-        for (int j = lo; j < hi; ++j)
-            if (sh.cls[ws.key[j] & 0xff] == cs && ws.rate[j] > 0.0) amax = fmax(amax, (double)ws.xa[j]);
-        double lo_n = 0.0, hi_n = amax, nu = 0.0;
-        unsigned sig_prev = 0xffffffffu;
-        for (int it = 0; it < 100; ++it) {
-            double s_mid = 0.0, s_up = 0.0;
-            int n_mid = 0;
-            unsigned sig = 0u;
+        // phi(nu) = sum over the class of clip(a_i - nu, 0, u_i): continuous, non-increasing, linear between the
+        // break points {a_i - u_i, a_i}, phi(0) > R >= phi(max a_i)
+        auto phi = [&](const double nu, double& s_mid, int& n_mid, double& s_up) {
+            s_mid = 0.0; s_up = 0.0; n_mid = 0;
             for (int j = lo; j < hi; ++j) {
-                if (sh.cls[ws.key[j] & 0xff] != cs) continue;
                 const double a = (double)ws.xa[j], ub = ws.rate[j];
-                if (!(ub > 0.0)) continue;
+                if (ws.icls[j] != cs || !(ub > 0.0)) continue;
                 const double v = a - nu;
-                unsigned code = 0u;
-                if (v >= ub) { s_up += ub; code = 2u; }
-                else if (v > 0.0) { s_mid += a; ++n_mid; code = 1u; }
-                sig = sig * 3u + code + 1u;
+                if (v >= ub) s_up += ub;
+                else if (v > 0.0) { s_mid += a; ++n_mid; }
             }
-            const double phi = s_mid - n_mid * nu + s_up;
-            if (sig == sig_prev && n_mid > 0) break;          // same linear piece twice: nu is its exact root
-            sig_prev = sig;
-            if (phi > R) lo_n = nu; else hi_n = nu;
-            double nn = n_mid > 0 ? (s_mid + s_up - R) / n_mid : 0.5 * (lo_n + hi_n);
-            if (!(nn > lo_n && nn < hi_n)) { nn = 0.5 * (lo_n + hi_n); sig_prev = 0xffffffffu; }
-            if (nn == nu) break;
-            nu = nn;
+            return s_mid - n_mid * nu + s_up;
+        };
+        double lo_n = 0.0, hi_n = 0.0, s_mid, s_up;
+        int n_mid;
+        for (int j = lo; j < hi; ++j)
+            if (ws.icls[j] == cs && ws.rate[j] > 0.0) hi_n = fmax(hi_n, (double)ws.xa[j]);
+        // lane l evaluates phi at break point l & 1 of item lo + (l >> 1) (+ 16 per round); the bracket shrinks to
+        // the largest break point with phi > R and the smallest with phi <= R
+        for (int j0 = lo; j0 < hi; j0 += 16) {
+            const int j = j0 + (lane >> 1);
+            double bp = -1.0;
+            if (j < hi && ws.icls[j] == cs && ws.rate[j] > 0.0) bp = (lane & 1) ? (double)ws.xa[j] : (double)ws.xa[j] - ws.rate[j];
+            const bool in = bp > lo_n && bp < hi_n;
+            const double v = phi(in ? bp : 0.0, s_mid, n_mid, s_up);
+            lo_n = warp_max(in && v > R ? bp : lo_n);
+            hi_n = warp_min(in && !(v > R) ? bp : hi_n);
         }
-        ws.nu[cs] = nu;
+        phi(0.5 * (lo_n + hi_n), s_mid, n_mid, s_up);        // the linear piece that is left
+        const double nu = n_mid > 0 ? fmin(fmax((s_mid + s_up - R) / n_mid, lo_n), hi_n) : hi_n;
+        if (lane == 0) ws.nu[cs] = nu;
         double sc = 0.0;
         for (int j = lo; j < hi; ++j)
-            if (sh.cls[ws.key[j] & 0xff] == cs) sc += fmin(fmax((double)ws.xa[j] - nu, 0.0), ws.rate[j]);
-        ws.Sx[cs] = sc;
+            if (ws.icls[j] == cs) sc += fmin(fmax((double)ws.xa[j] - nu, 0.0), ws.rate[j]);
+#pragma unroll
+        for (int cc = 0; cc < kMC; ++cc) Sx[cc] = cc == cs ? sc : Sx[cc];
         any = true;
     }
     if (!any) return 0;
-    // all constraints again at the projected point (relative slack 1e-12): f32 screen with a margin first,
-    // the exact f64 magnitude only for the ones close to their limit
-    float Sf[kMC];
-#pragma unroll
-    for (int c = 0; c < kMC; ++c) Sf[c] = (float)ws.Sx[c];
-    for (int jc = 0; jc < J; ++jc) {
-        float wr = 0.f, wi = 0.f;
-#pragma unroll
-        for (int c = 0; c < kMC; ++c) { wr = fmaf(sh.re[jc * kMC + c], Sf[c], wr); wi = fmaf(sh.im[jc * kMC + c], Sf[c], wi); }
-        if (fmaf(wr, wr, wi * wi) <= sh.r_in[jc]) continue;   // certainly inside
-        if (magnitude(jc) > sh.lim[jc] * (1.0 / kActionScale) * (1.0 + 1e-12)) return 2;
-    }
-    return 1;
+    // all constraints again at the projected point (relative slack 1e-12), constraint l on lane l
+    bool viol = false;
+    if (lane < J) viol = magnitude(lane) > sh.lim[lane] * (1.0 / kActionScale) * (1.0 + 1e-12);
+    return __any_sync(kFull, viol) ? 2 : 1;
 }
 
 // =================================================================================================
@@ -1469,7 +1474,7 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
             };
             pair_checks();
             // ---- envs whose clipped action is not certainly feasible (rare): the exact test and the exact
-            // single-class (pod) projection run here, thread-serial on the owner lane; envs that need the
+            // single-class (pod) projection run here, one env at a time on the whole warp; envs that need the
             // interior-point solver go to the work list of ev_step_rare_kernel (gfail)
             unsigned gfail = 0u;
             if (MODE != 0 && gbad) {
@@ -1482,17 +1487,12 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
                             const double rem = q[u].energy - del0[u];
                             ws.rate[u * 32 + lane] = upper_bound(rem > kFullEps ? (float)rem : 0.f);
                             ws.xa[u * 32 + lane] = af[u];
+                            ws.icls[u * 32 + lane] = (unsigned char)sh.cls[si[u]];
                         }
                     __syncwarp();
-                    int res = 0;
-                    if (lane == r) {
-                        res = pod_solve(sh, ws, off - base, off - base + cnt, J, jsus);
-                        if (res == 1) {
-#pragma unroll
-                            for (int c = 0; c < kMC; ++c) ws.P[c][r] = 0;
-                        }
-                    }
-                    res = __shfl_sync(kFull, res, r);
+                    const int lo_r = __shfl_sync(kFull, off, r) - base;
+                    const int res = pod_solve(sh, ws, lo_r, lo_r + __shfl_sync(kFull, cnt, r), J, __shfl_sync(kFull, jsus, r), lane);
+                    if (res == 1 && lane < kMC) ws.P[lane][r] = 0;
                     __syncwarp();
                     if (res == 2) gfail |= 1u << r;
                     if (res == 1) gredo |= 1u << r;
@@ -1553,6 +1553,25 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
 
         const bool mine_ok = live && !((bad >> lane) & 1u);              // this owner lane finishes its env here
         EV_TRACE(6);
+
+        // ---------------- the next tile: pick up the ticket and pull its headers, the head of its session lists and its
+        // action rows into L2 while this tile finishes (checks, arrivals, epilogue, write-out).  The lists are packed, so
+        // the first two lines of an env's block hold its first 6-8 sessions — all of them for a typical garage.
+        const long long tile_next = sched != nullptr ? wstride + (long long)__shfl_sync(kFull, next_ticket, 0) : tile + wstride;
+        if (tile_next < ntiles && (tile_next + 1) * kE <= B && !(SG_EV_ABL & 1024)) {
+            const long long bn = tile_next * kE;
+            const unsigned char* hp = reinterpret_cast<const unsigned char*>(headers + bn) + lane * 128;
+            if (lane < (kE * 64 + 127) / 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(hp));
+            const int eper = lane / (32 / kE), part = lane % (32 / kE);            // 32 / kE lines per env
+            const unsigned char* sp = reinterpret_cast<const unsigned char*>(slots + (bn + eper) * n) + part * 128;
+            // a line holds ~4 records: as many lines as the env in the same position of THIS tile would need (the envs
+            // of a batch share the time of day, so its occupancy predicts the next tile's), at least one
+            if (4 * part <= __shfl_sync(kFull, cnt, eper))
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(sp));
+            const long long abytes = (long long)kE * n * (i64 ? 8 : 4);
+            const unsigned char* ap = reinterpret_cast<const unsigned char*>(action) + bn * n * (i64 ? 8 : 4);
+            for (long long o = (long long)lane * 128; o < abytes; o += 32 * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(ap + o));
+        }
 
         // ---------------- arrivals: Plugin events with timestamp <= t+1 (after the Unplug events) -------
         unsigned long long occ_new = (occ & ~(((unsigned long long)ws.occ_clr[lane & (kE - 1)][1] << 32) |
@@ -1689,7 +1708,7 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
         if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");   // (waited for before the rows are cleared again)
         __syncwarp();
         EV_TRACE(15);
-        tile = sched != nullptr ? wstride + (long long)__shfl_sync(kFull, next_ticket, 0) : tile + wstride;
+        tile = tile_next;
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging rows stay valid until read
     if (sched != nullptr && lane == 0) {
