@@ -577,26 +577,40 @@ def main():
     # host obs/reward/done out, every step.  step_async / step_wait on two env batches: while one batch's results are
     # copied to the host and expanded, the other batch's actions are copied to the device and its kernel runs.
     from sustaingym_b200.envs.vector import SB3VecEnv
-    E = 200
-    pipe = [SB3VecEnv(e, dict_obs=False, copy=False) for e in envs[1:3]]   # the two mid-day sets
+    E = 240
+    D = N_SETS                                   # env batches in flight (their day phases average the day, like `value`)
+    pipe = [SB3VecEnv(e, dict_obs=False, copy=False) for e in envs]
     h_act = torch.rand(4, B, N_STATIONS, dtype=torch.float32).pin_memory()
     torch.cuda.synchronize()
-    for i in range(4):
-        pipe[i % 2].step_async(h_act[i % 4]); pipe[i % 2].step_wait()
+    for i in range(2 * D):
+        pipe[i % D].step_async(h_act[i % 4]); pipe[i % D].step_wait()
     ctx.barrier()
+    stamps = np.zeros(E + 1)
+    for v in pipe:
+        v.env.host_timing.update(sync=0.0, expand=0.0, steps=0)
+    t_async = 0.0
     t0 = time.perf_counter()
-    pipe[0].step_async(h_act[0])
+    for i in range(D - 1):
+        pipe[i].step_async(h_act[i % 4])
     for i in range(E):
-        pipe[(i + 1) % 2].step_async(h_act[(i + 1) % 4])
-        obs_h, rew_h, done_h, _ = pipe[i % 2].step_wait()
-    obs_h, rew_h, done_h, _ = pipe[E % 2].step_wait()
+        ta = time.perf_counter()
+        if i + D - 1 < E:
+            pipe[(i + D - 1) % D].step_async(h_act[(i + D - 1) % 4])
+        t_async += time.perf_counter() - ta
+        obs_h, rew_h, done_h, _ = pipe[i % D].step_wait()
+        stamps[i + 1] = time.perf_counter() - t0
     torch.cuda.synchronize()
+    step_ms = np.diff(stamps) * 1e3
     dt = ctx.max_over_ranks(time.perf_counter() - t0)
-    e2e_value = world * B * (E + 1) / dt
+    e2e_value = world * B * E / dt
     assert obs_h.shape == (B, OBS_DIM) and rew_h.shape == (B,)
     h2d = pipe[0].env.h2d_bytes_per_step
     d2h = pipe[0].env.d2h_bytes_per_step
     e2e_threads = pipe[0].env.host_threads
+    e2e_step_ms = {"p50": float(np.median(step_ms)), "p90": float(np.percentile(step_ms, 90)), "max": float(step_ms.max()),
+                   "n_over_2ms": int((step_ms > 2.0).sum()), "step_async": 1e3 * t_async / E,
+                   "stream_sync": 1e3 * sum(v.env.host_timing["sync"] for v in pipe) / E,
+                   "after_sync": 1e3 * sum(v.env.host_timing["expand"] for v in pipe) / E}
 
     cpu_base = None
     want_cpu = rank == 0 and world == 1 and not args.no_cpu_baseline
@@ -644,7 +658,8 @@ def main():
                          "peak_source": peak_src},
             "cpu_baseline": cpu_base,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": E + 1, "host_threads_per_rank": e2e_threads,
+                    "steps": E, "batches_in_flight": D, "host_threads_per_rank": e2e_threads,
+                    "step_ms": e2e_step_ms,
                     "api": "SB3VecEnv(BatchedEVChargingEnv).step_async / step_wait -> " + pipe_api_note()},
             "gpu_launches": launches, "clocks": clocks,
             "reward_stats": {"count": st[0], "mean": st[1] / max(st[0], 1), "min": st[3], "max": st[4], "n_done": st[5],

@@ -184,9 +184,10 @@ typedef struct sg_ev_state {
                                      (diagnostic; results are identical)                           */
 
 /* `work` scratch of sg_ev_step: SG_EV_WORK_INTS(B) int32, zero-initialised once by the caller; every call leaves
- * it zeroed again.  [0] entries of the exact-projection work list, [1] finished CTAs of the second launch,
- * [2] tiles handed out by the dynamic tile scheduler, [3] warps that left the tile loop, [8...] the work list. */
-#define SG_EV_WORK_HEADER_INTS 8
+ * it zeroed again.  Three 128-byte lines of counters — [0] entries appended to the exact-projection work list, [1]
+ * entries claimed by the helper warps; [32] tiles handed out by the dynamic tile scheduler; [64] tile warps that
+ * left the tile loop, [65] helper warps that finished — then [96...] the work list (env index + 1). */
+#define SG_EV_WORK_HEADER_INTS 96
 #define SG_EV_WORK_INTS(B)     ((B) + SG_EV_WORK_HEADER_INTS)
 
 /* Fills the derived constant tables of a model (f32 copies of the constraint coefficients, squared
@@ -218,8 +219,8 @@ int sg_ev_reset(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs,
  *            projection); required when m->project != 0, may be NULL otherwise (tiles are then assigned by a
  *            grid stride).  It is re-armed by every call.
  * With m->project != 0 the box-clipped action is tested against the network constraints per env (it
- * is then the exact projection); the few envs that violate them are finished by a second launch of
- * the same call (exact single-class solve, else interior point) and report SG_EV_STATUS_PROJECTED.
+ * is then the exact projection); the few envs that violate them are finished by helper CTAs of the
+ * same launch (exact single-class solve, else interior point) and report SG_EV_STATUS_PROJECTED.
  */
 int sg_ev_step(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs,
                const void* action, int32_t flags, int32_t discrete_bins,
@@ -282,6 +283,40 @@ int sg_ev_step_host_compact_async(const sg_ev_model* m, const sg_ev_state* s, in
                                   float* d_ovf_rows, int32_t ovf_cap,
                                   float* d_final_obs /* [device] [B, 2n+k+2] or NULL: terminal observations (AUTORESET) */,
                                   void* stream);
+
+/* Host buffers of a stream-ordered expansion (sg_ev_step_host_compact_stream): everything sg_ev_expand_obs takes. */
+typedef struct sg_ev_host_expand {
+    const float* h_moer;        /* host copy of sg_ev_model.moer                                               */
+    int32_t  n_moer_days;
+    int32_t  incremental;       /* see sg_ev_expand_obs                                                         */
+    uint64_t* h_prev_active;    /* [B] or NULL                                                                  */
+    int32_t* h_ovf_idx;         /* [ovf_cap] pinned                                                             */
+    float*   h_ovf_rows;        /* [ovf_cap, 2n] pinned                                                         */
+    float*   h_obs;             /* [B, 2n+k+2]                                                                  */
+    double*  h_reward;          /* [B]                                                                          */
+    uint8_t* h_done;            /* [B]                                                                          */
+    uint8_t* h_status;          /* [B] or NULL                                                                  */
+    int32_t  n_threads;
+    int32_t  reserved;
+} sg_ev_host_expand;
+
+/* sg_ev_step_host_compact_async + the overflow area copied to x->h_ovf_idx / x->h_ovf_rows + sg_ev_expand_obs enqueued
+ * on `stream` as a host function (cudaLaunchHostFunc): the expansion runs on a driver thread as soon as the records
+ * have arrived, overlapped with the caller and with other streams' work.  After the caller synchronises `stream` the
+ * host buffers of `x` hold the step's results, unless the overflow counter (first int32 of h_compact) exceeds ovf_cap:
+ * then the rows of the overflowing envs are incomplete and the caller copies the dense observation instead.  Overflow
+ * indices are relative to the first compact env (dense_envs).  The
+ * struct `x` is copied; the buffers it points to must stay valid until the stream has been synchronised. */
+int sg_ev_step_host_compact_stream(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs,
+                                   const void* h_action, int32_t flags, int32_t discrete_bins, void* h_compact,
+                                   void* d_action, float* d_obs, double* d_reward, uint8_t* d_done, uint8_t* d_status,
+                                   double* d_stats, int32_t* d_work, void* d_compact, int32_t* d_ovf_idx,
+                                   float* d_ovf_rows, int32_t ovf_cap, float* d_final_obs,
+                                   const sg_ev_host_expand* x,
+                                   int64_t dense_envs /* the first dense_envs envs are copied as dense rows (pinned
+                                                         x->h_obs / h_reward / h_done), the rest as records: balances the
+                                                         PCIe link against the host's store bandwidth; 0 = all compact */,
+                                   void* stream);
 
 /* HOST function (no CUDA call): rebuilds obs [B, 2n+k+2] f32, reward [B] f64, done [B] u8 (and status [B] u8 unless
  * NULL) from the compact records with `n_threads` threads of a persistent pool.  `h_moer` is the host copy of

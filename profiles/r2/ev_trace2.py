@@ -18,13 +18,15 @@ for i in range(T0): env.launch_step(acts[i % 4])
 torch.cuda.synchronize()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda"); flush.zero_(); torch.cuda.synchronize()
 ntiles = (B + KE - 1) // KE
-trace = torch.zeros(ntiles, 16, dtype=torch.int64, device="cuda")
+trace = torch.zeros(ntiles + 4096, 16, dtype=torch.int64, device="cuda")
 lib = _lib.load()
 lib.sg_ev_set_trace.argtypes = [C.c_void_p]; lib.sg_ev_set_trace.restype = C.c_int
 assert lib.sg_ev_set_trace(trace.data_ptr()) == 0
 env.launch_step(acts[2]); torch.cuda.synchronize()
 lib.sg_ev_set_trace(None)
-tr = trace.cpu().numpy().astype(np.float64)
+tr_all = trace.cpu().numpy().astype(np.float64)
+tr = tr_all[:ntiles]
+hl = tr_all[ntiles:]
 t0 = tr[:, 5].min()
 end = tr[:, 15].max()
 print(f"t={T0} tiles {ntiles}; kernel span first tile start -> last tile end: {(end - t0) / 1e3:.2f} us")
@@ -57,3 +59,8 @@ for title, idx in (("10 longest tiles", np.argsort(-tot)[:10]), ("10 last-ending
     print(title)
     for i in idx:
         print(f"  tile {i:5d} sm {sm[i]:3d} start {start[i]:6.1f} end {fin[i]:6.1f} total {tot[i]:6.2f} | " + " ".join(f"{x:5.2f}" for x in ph[i]))
+
+hl = hl[hl[:, 0] > 0]
+if len(hl):
+    hs, he = (hl[:, 0] - t0) / 1e3, (hl[:, 1] - t0) / 1e3
+    print(f"helper envs {len(hl)}: start min {hs.min():.1f} median {np.median(hs):.1f} max {hs.max():.1f}; end max {he.max():.1f}; duration median {np.median(he - hs):.2f} p90 {np.percentile(he - hs, 90):.2f} max {(he - hs).max():.2f} us; helper warps used {len(np.unique(hl[:, 2]))}")

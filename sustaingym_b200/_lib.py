@@ -32,7 +32,7 @@ SG_EV_ACTION_F32 = 0
 SG_EV_ACTION_I64 = 1
 SG_EV_FLAG_AUTORESET = 16
 SG_EV_FLAG_STATIC_TILES = 32
-SG_EV_WORK_HEADER_INTS = 8
+SG_EV_WORK_HEADER_INTS = 96
 SG_EV_COMPACT_ENTRIES = 16
 SG_EV_COMPACT_HEADER_BYTES = 16
 SG_EV_COMPACT_RECORD_BYTES = 120
@@ -67,6 +67,14 @@ class EVGmm(C.Structure):
     _fields_ = [
         ("n_components", _i32), ("n_counts", _i32), ("n_stations", _i32), ("reserved", _i32),
         ("cum_weights", _vp), ("means", _vp), ("chol", _vp), ("counts", _vp), ("station_p", _vp),
+    ]
+
+
+class EVHostExpand(C.Structure):
+    _fields_ = [
+        ("h_moer", _vp), ("n_moer_days", _i32), ("incremental", _i32), ("h_prev_active", _vp), ("h_ovf_idx", _vp),
+        ("h_ovf_rows", _vp), ("h_obs", _vp), ("h_reward", _vp), ("h_done", _vp), ("h_status", _vp),
+        ("n_threads", _i32), ("reserved", _i32),
     ]
 
 
@@ -118,6 +126,9 @@ SIGNATURES = {
     "sg_ev_pack_obs": (C.c_int, [_i64, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp]),
     "sg_ev_step_host_compact_async": (C.c_int, [C.POINTER(EVModel), C.POINTER(EVState), _i64, _vp, _i32, _i32, _vp, _vp,
                                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "sg_ev_step_host_compact_stream": (C.c_int, [C.POINTER(EVModel), C.POINTER(EVState), _i64, _vp, _i32, _i32, _vp, _vp,
+                                                 _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp,
+                                                 C.POINTER(EVHostExpand), _i64, _vp]),
     "sg_ev_expand_obs": (C.c_int, [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _i32]),
     "sg_ev_export_state": (C.c_int, [C.POINTER(EVModel), C.POINTER(EVState), _i64, _vp, _vp, _vp]),
     "sg_ev_agent_obs": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _vp, _vp]),

@@ -58,11 +58,13 @@ constexpr double kInvOMT = 1.0 / kOneMinusTrans, kInvPeriodH = 1.0 / kPeriodH, k
 constexpr double kFixScale = 1048576.0, kFixInv = 1.0 / 1048576.0, kFeasMargin = 1e-4;
 
 // layout of the `work` scratch buffer (SG_EV_WORK_INTS(B) int32, zero-initialised once, re-armed by every step)
-constexpr int kWorkCount = 0;        // entries of the exact-projection work list
-constexpr int kWorkRareDone = 1;     // CTAs of ev_step_rare_kernel that have finished
-constexpr int kWorkNextTile = 2;     // dynamic tile scheduler of ev_step_main_kernel: tiles handed out so far
-constexpr int kWorkRetired = 3;      // ... and warps that have left its tile loop (the last one re-arms both)
-constexpr int kWorkList = SG_EV_WORK_HEADER_INTS;   // first entry of the work list
+// (three 128-byte lines: the helper warps poll the third while the tile warps hammer the second with ticket requests)
+constexpr int kWorkCount = 0;        // entries appended to the exact-projection work list
+constexpr int kWorkTaken = 1;        // ... and entries claimed by the helper warps
+constexpr int kWorkNextTile = 32;    // dynamic tile scheduler of ev_step_main_kernel: tiles handed out so far
+constexpr int kWorkRetired = 64;     // tile warps that have left the tile loop
+constexpr int kWorkHelpersDone = 65; // helper warps that have finished (the last one re-arms the buffer)
+constexpr int kWorkList = SG_EV_WORK_HEADER_INTS;   // first entry of the work list: env index + 1, 0 = not yet written
 
 constexpr int kWarpsPerBlock = 8;
 constexpr int kThreads = kWarpsPerBlock * 32;
@@ -770,6 +772,15 @@ constexpr int kSegBits = 64 / kQ;                    // occupancy bits enumerate
 #define SG_EV_WARPS 4
 #endif
 constexpr int kMainWarps = SG_EV_WARPS;              // warps per CTA of the main kernel
+#ifndef SG_EV_HELPER_CTAS
+#define SG_EV_HELPER_CTAS 4                          // helper CTAs of a full-size launch (exact projections, see the kernel)
+#endif
+#ifndef SG_EV_INLINE_POD
+#define SG_EV_INLINE_POD 1                           // 1: single-class (pod) projections on the tile warp itself; 0: every env that
+                                                     // fails the margin test goes to the helper warps (measured: the tile warps then
+                                                     // finish at 43 us instead of 54, but a helper needs ~25 us per env — cold code
+                                                     // on SMs it shares with tile CTAs — and the launch ends at 60-67 us)
+#endif
 constexpr int kMainThreads = kMainWarps * 32;
 constexpr int kV = SG_EV_KV;                         // work items per lane and chunk (loads in flight)
 constexpr int kItemCap = 32 * kV;                    // (env, station) work items staged per warp and chunk
@@ -861,8 +872,11 @@ __device__ __forceinline__ float moer_tail(const float* __restrict__ row, const 
 // instance (small) returns false without side effects when the interior-point solver is needed;
 // the caller then runs the WITH_IPM = true instance.
 // =================================================================================================
+__device__ __forceinline__ int pod_solve(const EvTables& sh, WarpShared& ws, const int lo, const int hi, const int J,
+                                         const unsigned suspects, const int lane);
+
 template <bool WITH_IPM>
-__device__ __noinline__ bool fallback_env(const EvTables& sh, const EvCtx cx, const long long b, const int lane,
+__device__ __noinline__ bool fallback_env(const EvTables& sh, WarpShared& ws, const EvCtx cx, const long long b, const int lane,
                                            double* wstat) {
     const int n = cx.n, kf = cx.kf, OBS = 2 * n + kf + 2, C = cx.C, J = cx.J;
     const bool i64 = (cx.flags & 1) == SG_EV_ACTION_I64;
@@ -900,15 +914,32 @@ __device__ __noinline__ bool fallback_env(const EvTables& sh, const EvCtx cx, co
         x[p] = valid[p] ? fmin(fmax(a[p], 0.0), u[p]) : 0.0;
     }
     int st = 0;
-    if (!network_feasible(sh, C, J, x, cls)) {
-        bool cap = false;
-        if (!(simple_project(sh, C, J, a, u, cls, valid, x) && network_feasible_tol(sh, C, J, x, cls))) {
-            if (!WITH_IPM) return false;                 // (warp-uniform)
+    {
+        // exact feasibility test of the clipped action and, when only single-class constraints (the pods) are violated,
+        // the exact projection: the occupied stations go to the warp's item lists, pod_solve runs on the whole warp
+        const unsigned m0 = __ballot_sync(kFull, occd[0]), m1 = __ballot_sync(kFull, occd[1]);
+        const unsigned lt = (1u << lane) - 1u;
+        const int pos0 = __popc(m0 & lt) + __popc(m1 & lt);
 #pragma unroll
-            for (int p = 0; p < 2; ++p) x[p] = valid[p] ? fmin(fmax(a[p], 0.0), u[p]) : 0.0;
+        for (int p = 0; p < 2; ++p)
+            if (occd[p]) {
+                const int pos = pos0 + (p == 1 && occd[0] ? 1 : 0);
+                ws.xa[pos] = (float)a[p]; ws.rate[pos] = u[p]; ws.icls[pos] = (unsigned char)cls[p];
+            }
+        __syncwarp();
+        const int res = pod_solve(sh, ws, 0, __popc(m0) + __popc(m1), J, J >= 32 ? 0xffffffffu : (1u << J) - 1u, lane);
+        __syncwarp();
+        if (res == 1) {
+#pragma unroll
+            for (int p = 0; p < 2; ++p) if (occd[p]) x[p] = fmin(fmax(a[p] - ws.nu[cls[p]], 0.0), u[p]);
+            st = SG_EV_STATUS_PROJECTED;
+        } else if (res == 2) {
+            if (!WITH_IPM) return false;                 // (warp-uniform)
+            bool cap = false;
             if (WITH_IPM) ipm_dispatch(sh, C, J, a, u, cls, valid, x, &cap);
+            st = SG_EV_STATUS_PROJECTED | (cap ? SG_EV_STATUS_MAXITER : 0);
         }
-        st = SG_EV_STATUS_PROJECTED | (cap ? SG_EV_STATUS_MAXITER : 0);
+        __syncwarp();
     }
     // schedule (env.py:368-378), charging, Unplug events
     unsigned pil[2] = {0u, 0u};
@@ -1160,19 +1191,80 @@ __global__ void __launch_bounds__(kMainThreads, SG_EV_MINB)
 ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B, const void* __restrict__ action,
                     const int flags, const int bins, float* __restrict__ obs, double* __restrict__ reward,
                     uint8_t* __restrict__ done, uint8_t* __restrict__ pilots, float* __restrict__ final_obs,
-                    uint8_t* __restrict__ status, double* __restrict__ stats, int32_t* __restrict__ work) {
+                    uint8_t* __restrict__ status, double* __restrict__ stats, int32_t* __restrict__ work,
+                    const int n_helpers) {
     __shared__ EvTables sh;
     __shared__ WarpShared wsm[kMainWarps];
     extern __shared__ __align__(128) unsigned char stage_raw[];       // per warp: kE observation rows | kE pilot rows
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long ntiles = (B + kE - 1) / kE;
-    const long long wstride = (long long)gridDim.x * kMainWarps;
+    const long long wstride = (long long)((int)gridDim.x - n_helpers) * kMainWarps;   // tile warps of the launch
+    if (MODE != 0 && (int)blockIdx.x < n_helpers) {
+        // ---------------- helper CTAs: the envs the tile warps could not finish (exact projection needed) --------
+        // The first n_helpers CTAs of the grid take no tiles: their warps claim entries of the work list as the tile
+        // warps append them and run the complete step of those envs (fallback_env: exact test, single-class solve,
+        // interior point), WHILE the tile warps go on.  On a tile warp that path ran on cold instruction-cache
+        // lines (~12 us per env, measured with the phase trace) and, hitting ~60 tiles of a 65 536-env step, set
+        // the end of the launch; here the code stays resident in the few SMs that run it.
+        load_tables(m.tables, sh);
+        if (lane < 12) wsm[warp].stat[lane] = lane == 3 ? 1e300 : (lane == 4 ? -1e300 : 0.0);
+        __syncthreads();
+        EvCtx cx;
+        cx.n = m.n_stations; cx.kf = m.moer_steps; cx.C = m.n_classes; cx.J = m.n_constraints; cx.K = m.max_sessions;
+        cx.n_days = m.n_days; cx.n_moer_days = m.n_moer_days; cx.max_day_sessions = m.max_day_sessions;
+        cx.flags = flags; cx.bins = bins; cx.B = B; cx.moer = m.moer; cx.recs = reinterpret_cast<const uint4*>(m.sessions);
+        cx.arrivals = m.arrivals; cx.action = action; cx.slots = reinterpret_cast<Slot*>(s.slots);
+        cx.header = reinterpret_cast<EnvHeader*>(s.header);
+        cx.obs = obs; cx.final_obs = final_obs; cx.reward = reward; cx.done = done; cx.pilots = pilots; cx.status = status;
+        volatile int32_t* vw = work;
+        for (;;) {
+            int k = 0, v = 0;
+            if (lane == 0) {
+                k = atomicAdd(work + kWorkTaken, 1);
+                const bool in_list = k < B;                   // (the list holds at most one entry per env)
+                for (int spin = 0;; ++spin) {                 // entry k: written, or never coming
+                    v = in_list ? vw[kWorkList + k] : 0;
+                    if (v != 0) break;
+                    if ((spin & 3) == 3 && vw[kWorkRetired] >= (int)wstride) { v = in_list ? vw[kWorkList + k] : 0; break; }   // (appends precede retirement)
+                    __nanosleep(500);
+                }
+                if (v != 0) vw[kWorkList + k] = 0;            // re-armed for the next step
+            }
+            v = __shfl_sync(kFull, v, 0);
+            if (v == 0) break;
+            __threadfence();                                  // the tile warp's rows of this env are complete (see append)
+            const long long bq = v - 1;
+            double* wst = stats != nullptr ? wsm[warp].stat : nullptr;
+#ifdef SG_EV_TRACE
+            k = __shfl_sync(kFull, k, 0);
+            if (g_trace != nullptr && lane == 0 && k < 4096) {
+                unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+                g_trace[(ntiles + k) * 16 + 0] = gt; g_trace[(ntiles + k) * 16 + 2] = blockIdx.x * kMainWarps + warp;
+            }
+#endif
+            if (!fallback_env<false>(sh, wsm[warp], cx, bq, lane, wst)) fallback_env<true>(sh, wsm[warp], cx, bq, lane, wst);
+#ifdef SG_EV_TRACE
+            if (g_trace != nullptr && lane == 0 && k < 4096) {
+                unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+                g_trace[(ntiles + k) * 16 + 1] = gt;
+            }
+#endif
+        }
+        if (lane == 0) {
+            const int nhw = n_helpers * kMainWarps;
+            if (atomicAdd(work + kWorkHelpersDone, 1) == nhw - 1) {     // last helper warp: every counter back to zero
+                work[kWorkCount] = 0; work[kWorkTaken] = 0; work[kWorkNextTile] = 0; work[kWorkRetired] = 0;
+                work[kWorkHelpersDone] = 0;
+            }
+        }
+    } else {
+    const int cta = (int)blockIdx.x - n_helpers;
     // Tile scheduling.  Every warp starts on the tile of its own index; further tiles come from a global counter
     // (work[kWorkNextTile]) when the scratch buffer is there, else from a grid stride.  Static strides leave the
     // SMs unevenly loaded — B200 places consecutive CTAs on the same SM, so with 2.3 tiles per warp the SMs that
     // hold the low-numbered CTAs run 9 tile rounds against 6 elsewhere (ncu: SMs busy 62 % of the launch).
     int32_t* sched = (work != nullptr && !(flags & SG_EV_FLAG_STATIC_TILES)) ? work + kWorkNextTile : nullptr;
-    long long tile = (long long)blockIdx.x * kMainWarps + warp;
+    long long tile = (long long)cta * kMainWarps + warp;
     EV_TRACE(10);
     // the first tile's env headers are requested before the table copy
     EnvHeader* __restrict__ headers = reinterpret_cast<EnvHeader*>(s.header);
@@ -1477,7 +1569,9 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
             // single-class (pod) projection run here, one env at a time on the whole warp; envs that need the
             // interior-point solver go to the work list of ev_step_rare_kernel (gfail)
             unsigned gfail = 0u;
-            if (MODE != 0 && gbad) {
+            if (!SG_EV_INLINE_POD) {
+                gfail = MODE != 0 ? gbad : 0u;        // every env that is not certainly feasible goes to the helper warps
+            } else if (MODE != 0 && gbad) {
                 unsigned gredo = 0u;
                 for (unsigned todo = gbad; todo; todo &= todo - 1) {
                     const int r = __ffs((int)todo) - 1;
@@ -1661,13 +1755,6 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
         __syncwarp();
         EV_TRACE(8);
 
-        // ---------------- rare path: envs that need the exact projection go to the work list of ev_step_rare_kernel
-        if (bad && lane == 0) {
-            const int first = atomicAdd(work + kWorkCount, __popc(bad));
-            int k = 0;
-            for (unsigned todo = bad; todo; todo &= todo - 1, ++k) work[kWorkList + first + k] = (int)(b0 + __ffs((int)todo) - 1);
-        }
-
         // ---------------- write-out of the staged rows --------------------------------------------------------
         if (tail_async) asm volatile("cp.async.wait_all;" ::: "memory");  // the tails have landed in the staged rows
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // staged rows -> visible to the bulk-copy engine
@@ -1707,17 +1794,34 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
         }
         if (lane == 0) asm volatile("cp.async.bulk.commit_group;" ::: "memory");   // (waited for before the rows are cleared again)
         __syncwarp();
+        // ---------------- rare path: envs that need the exact projection go to the helper warps' work list — once this
+        // tile's rows (which hold first-pass values for those envs) are in global memory, so that the helper's rows
+        // are the ones that stay
+        if (bad) {
+            if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            __syncwarp();
+            __threadfence();
+            if (lane == 0) {
+                const int first = atomicAdd(work + kWorkCount, __popc(bad));
+                int k = 0;
+                for (unsigned todo = bad; todo; todo &= todo - 1, ++k)
+                    atomicExch(work + kWorkList + first + k, (int)(b0 + __ffs((int)todo) - 1) + 1);
+            }
+        }
         EV_TRACE(15);
         tile = tile_next;
     }
     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // staging rows stay valid until read
-    if (sched != nullptr && lane == 0) {
-        // the last warp to leave the loop re-arms the scheduler (every other warp has made its last request)
-        if (atomicAdd(sched + (kWorkRetired - kWorkNextTile), 1) == (int)wstride - 1) {
-            sched[0] = 0;
-            sched[kWorkRetired - kWorkNextTile] = 0;
+    if (work != nullptr && lane == 0) {
+        __threadfence();                                  // this warp's appends are visible before its retirement
+        // without helper CTAs the last warp to leave re-arms the scheduler (every other warp has made its last
+        // request); with helpers the last helper warp re-arms the whole buffer
+        if (atomicAdd(work + kWorkRetired, 1) == (int)wstride - 1 && n_helpers == 0) {
+            work[kWorkNextTile] = 0;
+            work[kWorkRetired] = 0;
         }
     }
+    }   // tile CTAs
     if (stats != nullptr) {
         __syncthreads();
         // 11 statistics x kMainWarps partials -> one set of atomics per CTA
@@ -1735,58 +1839,10 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
     }
 #ifdef SG_EV_TRACE
     {
-        tile = (long long)blockIdx.x * kMainWarps + warp;
-        if (tile < ntiles) EV_TRACE(9);
+        long long tile = (long long)((int)blockIdx.x - n_helpers) * kMainWarps + warp;
+        if (tile >= 0 && tile < ntiles) EV_TRACE(9);
     }
 #endif
-}
-
-// Second launch of a step: the envs the main kernel could not certify (work list), one warp per env.
-__global__ void __launch_bounds__(128)
-ev_step_rare_kernel(const sg_ev_model m, const sg_ev_state s, const long long B, const void* __restrict__ action,
-                    const int flags, const int bins, float* __restrict__ obs, double* __restrict__ reward,
-                    uint8_t* __restrict__ done, uint8_t* __restrict__ pilots, float* __restrict__ final_obs,
-                    uint8_t* __restrict__ status, double* __restrict__ stats, int32_t* __restrict__ work) {
-    __shared__ EvTables sh;
-    __shared__ double wstat[4][12];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int count = work[kWorkCount];
-    if (count > 0) {
-        load_tables(m.tables, sh);
-        if (lane < 12) wstat[warp][lane] = lane == 3 ? 1e300 : (lane == 4 ? -1e300 : 0.0);
-        __syncthreads();
-        EvCtx cx;
-        cx.n = m.n_stations; cx.kf = m.moer_steps; cx.C = m.n_classes; cx.J = m.n_constraints; cx.K = m.max_sessions;
-        cx.n_days = m.n_days; cx.n_moer_days = m.n_moer_days; cx.max_day_sessions = m.max_day_sessions;
-        cx.flags = flags; cx.bins = bins; cx.B = B; cx.moer = m.moer; cx.recs = reinterpret_cast<const uint4*>(m.sessions);
-        cx.arrivals = m.arrivals; cx.action = action; cx.slots = reinterpret_cast<Slot*>(s.slots);
-        cx.header = reinterpret_cast<EnvHeader*>(s.header);
-        cx.obs = obs; cx.final_obs = final_obs; cx.reward = reward; cx.done = done; cx.pilots = pilots; cx.status = status;
-        const int nwarps = gridDim.x * (blockDim.x >> 5);
-        // warp w of CTA c takes item c + w * gridDim.x: the first items spread over different SMs
-        for (int w = blockIdx.x + warp * gridDim.x; w < count; w += nwarps) {
-            const long long bq = work[kWorkList + w];
-            double* wst = stats != nullptr ? wstat[warp] : nullptr;
-            if (!fallback_env<false>(sh, cx, bq, lane, wst)) fallback_env<true>(sh, cx, bq, lane, wst);
-        }
-        if (stats != nullptr) {
-            __syncthreads();
-            if (threadIdx.x < 11) {
-                const int i = threadIdx.x;
-                double r = wstat[0][i];
-                for (int w = 1; w < 4; ++w) r = (i == 3) ? fmin(r, wstat[w][i]) : (i == 4) ? fmax(r, wstat[w][i]) : r + wstat[w][i];
-                if (i == 3) { if (r < 1e300) atomic_min_double(stats + 3, r); }
-                else if (i == 4) { if (r > -1e300) atomic_max_double(stats + 4, r); }
-                else if (r != 0.0) atomicAdd(stats + i, r);
-            }
-        }
-    }
-    // the last CTA to finish re-arms the work list for the next step
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(work + kWorkRareDone, 1) == (int)gridDim.x - 1) { work[kWorkCount] = 0; work[kWorkRareDone] = 0; __threadfence(); }
-    }
 }
 
 __global__ void ev_reset_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
@@ -1968,15 +2024,22 @@ int sg_ev_step(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, con
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     int sms = sg_device_sm_count();
     if (sms <= 0) sms = 148;
-    // one warp per kE-env tile; SG_EV_MINB resident CTAs per SM, larger batches loop (persistent)
+    // one warp per kE-env tile; SG_EV_MINB resident CTAs per SM, larger batches loop (persistent).  With the
+    // projection on, the first n_helpers CTAs of the grid are helpers (exact projection of the envs the tile warps
+    // hand over, see the kernel); they come out of the same residency budget so that every CTA is resident at once
     const long long ntiles = (num_envs + sg::kE - 1) / sg::kE;
-    unsigned grid = (unsigned)std::min<long long>((ntiles + sg::kMainWarps - 1) / sg::kMainWarps, (long long)sms * SG_EV_MINB);
-    // SG_EV_MAX_CTAS=<n> caps the grid (test hook): every warp then loops over many tiles, which is the code path
-    // the BASELINE batch runs on, at any batch size
+    const long long want = (ntiles + sg::kMainWarps - 1) / sg::kMainWarps;
+    const long long resident = (long long)sms * SG_EV_MINB;
+    int n_helpers = 0;
+    if (m->project) n_helpers = (int)std::max<long long>(1, std::min<long long>(SG_EV_HELPER_CTAS, want / 64));
+    unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>(want, resident - n_helpers));
+    // SG_EV_MAX_CTAS=<n> caps the tile CTAs (test hook): every warp then loops over many tiles, which is the code
+    // path the BASELINE batch runs on, at any batch size
     if (const char* cap = getenv("SG_EV_MAX_CTAS")) {
         const long v = atol(cap);
         if (v >= 1) grid = (unsigned)std::min<long long>(grid, v);
     }
+    grid += (unsigned)n_helpers;
     // staging rows in dynamic shared memory: per warp kE observation rows + kE pilot rows
     const int OBS = 2 * m->n_stations + m->moer_steps + 2;
     const size_t dyn = (size_t)sg::kMainWarps * (((sg::kE * OBS * 4 + 15) & ~15) + ((sg::kE * m->n_stations + 15) & ~15));
@@ -1984,18 +2047,12 @@ int sg_ev_step(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, con
         auto kern = sg::ev_step_main_kernel<1>;
         SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         kern<<<grid, sg::kMainThreads, dyn, st>>>(*m, *s, num_envs, action, flags, discrete_bins, obs, reward, done, pilots,
-                                                  final_obs, status, stats, work);
-        if (int rc = sg::launch_status("ev_step_main_kernel")) return rc;
-        // second launch: the envs on the work list (exact projection), one warp each
-        const unsigned rgrid = (unsigned)std::min<long long>((num_envs + 3) / 4, (long long)sms * 2);
-        sg::ev_step_rare_kernel<<<rgrid, 128, 0, st>>>(*m, *s, num_envs, action, flags, discrete_bins, obs, reward, done,
-                                                       pilots, final_obs, status, stats, work);
-        return sg::launch_status("ev_step_rare_kernel");
+                                                  final_obs, status, stats, work, n_helpers);
     } else {
         auto kern = sg::ev_step_main_kernel<0>;
         SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         kern<<<grid, sg::kMainThreads, dyn, st>>>(*m, *s, num_envs, action, flags, discrete_bins, obs, reward, done, pilots,
-                                                  final_obs, status, stats, work);
+                                                  final_obs, status, stats, work, 0);
     }
     return sg::launch_status("ev_step_main_kernel");
 }

@@ -195,6 +195,73 @@ int sg_ev_step_host_compact_async(const sg_ev_model* m, const sg_ev_state* s, in
     return 0;
 }
 
+namespace {
+struct ExpandJob {
+    sg_ev_host_expand x;
+    const void* h_compact;
+    int64_t num_envs;
+    int32_t n, k, ovf_cap;
+};
+void CUDART_CB expand_job(void* p) {
+    ExpandJob* j = static_cast<ExpandJob*>(p);
+    const int32_t n_ovf = *static_cast<const int32_t*>(j->h_compact);
+    // (a counter beyond the overflow area: the caller falls back to the dense copy; expand what is there)
+    sg_ev_expand_obs(j->h_compact, j->num_envs, j->n, j->k, j->x.h_moer, j->x.n_moer_days, j->x.h_prev_active,
+                     j->x.incremental, j->x.h_ovf_idx, j->x.h_ovf_rows, n_ovf > j->ovf_cap ? 0 : n_ovf, j->x.h_obs,
+                     j->x.h_reward, j->x.h_done, j->x.h_status, j->x.n_threads);
+    delete j;
+}
+}  // namespace
+
+int sg_ev_step_host_compact_stream(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, const void* h_action,
+                                   int32_t flags, int32_t discrete_bins, void* h_compact, void* d_action, float* d_obs,
+                                   double* d_reward, uint8_t* d_done, uint8_t* d_status, double* d_stats, int32_t* d_work,
+                                   void* d_compact, int32_t* d_ovf_idx, float* d_ovf_rows, int32_t ovf_cap,
+                                   float* d_final_obs, const sg_ev_host_expand* x, int64_t dense_envs, void* stream) {
+    SG_CHECK_ARG(m && s && h_action && h_compact && d_action && d_obs && d_reward && d_done && d_compact,
+                 "ev_step_host_compact_stream: NULL argument");
+    SG_CHECK_ARG(x && x->h_moer && x->h_obs && x->h_reward && x->h_done, "ev_step_host_compact_stream: NULL expansion buffer");
+    SG_CHECK_ARG(ovf_cap == 0 || (x->h_ovf_idx && x->h_ovf_rows), "ev_step_host_compact_stream: NULL host overflow area");
+    SG_CHECK_ARG(dense_envs >= 0 && dense_envs <= num_envs, "ev_step_host_compact_stream: dense_envs outside [0, num_envs]");
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t B = (size_t)num_envs, n = (size_t)m->n_stations, dn = (size_t)dense_envs;
+    const int obs_dim = 2 * m->n_stations + m->moer_steps + 2;
+    const size_t abytes = B * n * (((flags & 1) == SG_EV_ACTION_I64) ? 8 : 4);
+    SG_CUDA(cudaMemcpyAsync(d_action, h_action, abytes, cudaMemcpyHostToDevice, st));
+    if (int rc = sg_ev_step(m, s, num_envs, d_action, flags, discrete_bins, d_obs, d_reward, d_done, nullptr, d_final_obs,
+                            d_status, d_stats, d_work, stream)) return rc;
+    // The first dense_envs envs travel as they are (the DMA engine writes their rows), the others as compact
+    // records expanded by the host threads: the two run side by side, so the split balances the PCIe link against
+    // the host's store bandwidth.
+    const size_t rest = B - dn;
+    if (rest > 0) {
+        if (int rc = sg_ev_pack_obs((int64_t)rest, m->n_stations, obs_dim, d_obs + dn * obs_dim, d_reward + dn, d_done + dn,
+                                    d_status ? d_status + dn : nullptr, static_cast<const unsigned char*>(s->header) + dn * 64,
+                                    d_compact, d_ovf_idx, d_ovf_rows, ovf_cap, stream)) return rc;
+        SG_CUDA(cudaMemcpyAsync(h_compact, d_compact, SG_EV_COMPACT_HEADER_BYTES + rest * sizeof(sg_ev_compact_obs),
+                                cudaMemcpyDeviceToHost, st));
+        if (ovf_cap > 0) {      // small (cap x 2n floats): copied every step so that the host function needs no CUDA call
+            SG_CUDA(cudaMemcpyAsync(x->h_ovf_idx, d_ovf_idx, sizeof(int32_t) * ovf_cap, cudaMemcpyDeviceToHost, st));
+            SG_CUDA(cudaMemcpyAsync(x->h_ovf_rows, d_ovf_rows, sizeof(float) * 2 * n * (size_t)ovf_cap, cudaMemcpyDeviceToHost, st));
+        }
+        ExpandJob* j = new ExpandJob{*x, h_compact, (int64_t)rest, m->n_stations, m->moer_steps, ovf_cap};
+        j->x.h_obs += dn * obs_dim; j->x.h_reward += dn; j->x.h_done += dn;
+        if (j->x.h_status) j->x.h_status += dn;
+        if (j->x.h_prev_active) j->x.h_prev_active += dn;
+        SG_CUDA(cudaLaunchHostFunc(st, expand_job, j));
+    } else {
+        SG_CUDA(cudaMemsetAsync(d_compact, 0, SG_EV_COMPACT_HEADER_BYTES, st));
+        SG_CUDA(cudaMemcpyAsync(h_compact, d_compact, SG_EV_COMPACT_HEADER_BYTES, cudaMemcpyDeviceToHost, st));
+    }
+    if (dn > 0) {               // (queued behind the records so that the expansion starts while these rows still travel)
+        SG_CUDA(cudaMemcpyAsync(x->h_obs, d_obs, dn * obs_dim * 4, cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaMemcpyAsync(x->h_reward, d_reward, dn * 8, cudaMemcpyDeviceToHost, st));
+        SG_CUDA(cudaMemcpyAsync(x->h_done, d_done, dn, cudaMemcpyDeviceToHost, st));
+        if (x->h_status && d_status) SG_CUDA(cudaMemcpyAsync(x->h_status, d_status, dn, cudaMemcpyDeviceToHost, st));
+    }
+    return 0;
+}
+
 int sg_ev_expand_obs(const void* h_compact, int64_t num_envs, int32_t n_stations, int32_t moer_steps,
                      const float* h_moer, int32_t n_moer_days, uint64_t* h_prev_active, int32_t incremental,
                      const int32_t* h_ovf_idx, const float* h_ovf_rows, int32_t n_ovf,

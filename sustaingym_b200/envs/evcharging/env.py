@@ -47,9 +47,9 @@ class BatchedEVChargingEnv:
     VIOLATION_FACTOR = A_PERS_TO_KWH * VIOLATION_WEIGHT
     CARBON_COST_FACTOR = A_PERS_TO_KWH * (CO2_COST_PER_METRIC_TON / 1000)
 
-    HOST_PATH_NOTE = ("BatchedEVChargingEnv.step_async(pinned host actions) / step_wait(): sg_ev_step_host_compact_async "
-                      "(H2D actions -> step -> pack 120-byte records -> D2H) + sg_ev_expand_obs (host thread pool rebuilds "
-                      "the dense [B,146] f32 observation, bit-identical to a dense copy); two env batches in flight")
+    HOST_PATH_NOTE = ("BatchedEVChargingEnv.step_async(pinned host actions) / step_wait(): sg_ev_step_host_compact_stream "
+                      "(H2D actions -> step -> pack 120-byte records -> D2H -> stream-ordered host function: a thread pool "
+                      "rebuilds the dense [B,146] f32 observation, bit-identical to a dense copy)")
 
     @property
     def h2d_bytes_per_step(self) -> int:
@@ -58,7 +58,9 @@ class BatchedEVChargingEnv:
     @property
     def d2h_bytes_per_step(self) -> int:
         if self.host_obs == "compact":
-            return _lib.SG_EV_COMPACT_HEADER_BYTES + self.num_envs * _lib.SG_EV_COMPACT_RECORD_BYTES
+            dn = self.host_dense_envs
+            return (_lib.SG_EV_COMPACT_HEADER_BYTES + (self.num_envs - dn) * _lib.SG_EV_COMPACT_RECORD_BYTES
+                    + dn * (self.obs_dim * 4 + 8 + 1 + 1))
         return self.num_envs * (self.obs_dim * 4 + 8 + 1)
 
     def __init__(self, data_generator: AbstractTraceGenerator, num_envs: int = 1,
@@ -94,6 +96,13 @@ class BatchedEVChargingEnv:
         # host expansion mode: False = every row rewritten with streaming stores (default: no read-for-ownership of the
         # 38 MB observation batch); True = only the entries that changed, with ordinary stores (cache-resident batches)
         self.host_incremental = os.environ.get("SG_HOST_INCREMENTAL", "0") == "1"
+        # compact host path: the first host_dense_envs envs can cross PCIe as dense rows (DMA) while the others travel
+        # as records expanded by the host threads.  Measured on the B200 box (profiles/r2/e2e_notes.md): any split
+        # gives the same ~0.6 ms per 65 536-env step — the host memory system (~115 GB/s of total traffic: actions
+        # read by the DMA engine, observations written, records written and read) is the limit, not PCIe or the
+        # cores — so the default is 0 (all records: least PCIe traffic, result buffers need no pinning)
+        frac = float(os.environ.get("SG_HOST_DENSE_FRACTION", "0.0"))
+        self.host_dense_envs = int(round(min(max(frac, 0.0), 1.0) * num_envs)) if host_obs == "compact" else 0
 
         # ---- spaces (env.py:143-150, 171-172; wrappers.py:36-41 for the discrete variant) ---------
         k = moer_forecast_steps
@@ -198,7 +207,7 @@ class BatchedEVChargingEnv:
         # host staging for the host-buffer path.  Pinned where the DMA engines touch it: the actions always, the
         # results only on the dense path — on the compact path they are written by the expansion threads, and
         # ordinary (first-touch, NUMA-local) memory is ~2.5x faster for them than cudaHostAlloc memory (measured)
-        pin = (lambda t: t.pin_memory()) if host_obs == "dense" else (lambda t: t)
+        pin = (lambda t: t.pin_memory()) if (host_obs == "dense" or self.host_dense_envs > 0) else (lambda t: t)
         self._h_action = torch.zeros(B, n, dtype=self._action_dtype).pin_memory()
         self._h_obs = pin(torch.zeros(B, self.obs_dim, dtype=torch.float32))
         self._h_reward = pin(torch.zeros(B, dtype=torch.float64))
@@ -212,6 +221,7 @@ class BatchedEVChargingEnv:
         self._compact = None
         self._host_obs_valid = False          # _h_obs holds the expansion of the previous host-path step
         self._pending = None                  # "compact" / "dense": what step_async enqueued
+        self.host_timing = {"sync": 0.0, "expand": 0.0, "steps": 0}
 
     # ------------------------------------------------------------------------------------------
     def __repr__(self) -> str:
@@ -293,7 +303,7 @@ class BatchedEVChargingEnv:
                         self._h_done.data_ptr(), self._d_action.data_ptr(), self.obs.data_ptr(),
                         self.reward.data_ptr(), self.done.data_ptr(), self.status.data_ptr(),
                         _lib.ptr(self.stats), self.work.data_ptr(), self._stream()), "sg_ev_step_host")
-                self.kernel_launches += 2 if self.project_action_in_env else 1
+                self.kernel_launches += 1
             if host_np:
                 done = self._h_done.numpy().astype(bool)
                 return (self._h_obs.numpy().copy(), self._h_reward.numpy().copy(), done,
@@ -343,8 +353,13 @@ class BatchedEVChargingEnv:
                 "h_rows": torch.zeros(cap, 2 * n, dtype=torch.float32).pin_memory(),
                 "prev": torch.zeros(B, dtype=torch.int64),
                 "moer": np.ascontiguousarray(self.data_generator.moer, dtype=np.float32),
-                "h_status": torch.zeros(B, dtype=torch.uint8),
+                "h_status": torch.zeros(B, dtype=torch.uint8).pin_memory(),
             }
+            c = self._compact
+            c["x"] = _lib.EVHostExpand(
+                c["moer"].ctypes.data, c["moer"].shape[0], 0, c["prev"].data_ptr(), c["h_idx"].data_ptr(),
+                c["h_rows"].data_ptr(), self._h_obs.data_ptr(), self._h_reward.data_ptr(), self._h_done.data_ptr(),
+                c["h_status"].data_ptr(), self.host_threads, 0)
         return self._compact
 
     def _enqueue_host(self, h_act: torch.Tensor, stream: int) -> None:
@@ -356,39 +371,37 @@ class BatchedEVChargingEnv:
         with torch.cuda.device(self.device):
             if self.host_obs == "compact":
                 c = self._ensure_compact()
-                _lib.check(self.lib.sg_ev_step_host_compact_async(
+                x = c["x"]
+                x.incremental = int(self._host_obs_valid and self.host_incremental)
+                _lib.check(self.lib.sg_ev_step_host_compact_stream(
                     *args, c["h"].data_ptr(), *dev_out, c["d"].data_ptr(), c["d_idx"].data_ptr(),
-                    c["d_rows"].data_ptr(), c["cap"], _lib.ptr(self.final_obs), stream), "sg_ev_step_host_compact_async")
+                    c["d_rows"].data_ptr(), c["cap"], _lib.ptr(self.final_obs), C.byref(x), self.host_dense_envs, stream),
+                    "sg_ev_step_host_compact_stream")
+                self._host_obs_valid = True       # (the expansion is stream-ordered: the next one may build on it)
                 self.kernel_launches += 1
             else:
                 _lib.check(self.lib.sg_ev_step_host_async(
                     *args, self._h_obs.data_ptr(), self._h_reward.data_ptr(), self._h_done.data_ptr(), *dev_out,
                     stream), "sg_ev_step_host_async")
         self._pending = self.host_obs
-        self.kernel_launches += 2 if self.project_action_in_env else 1
+        self.kernel_launches += 1
 
     def _finish_host(self, stream: "torch.cuda.Stream"):
+        import time
+        t0 = time.perf_counter()
         stream.synchronize()
+        t1 = time.perf_counter()
         B = self.num_envs
         if self._pending == "compact":
+            # the expansion ran on the stream (host function); only a step whose overflow area was too small for the
+            # envs with more than 16 active sessions needs the dense observation
             c = self._compact
-            n_ovf = int(c["h"][:4].view(torch.int32)[0])
-            dense_fallback = n_ovf > c["cap"]
-            n_rows = 0 if dense_fallback else n_ovf
-            if n_rows:                                   # rare: rows of the envs with more than 16 active sessions
-                c["h_idx"][:n_rows].copy_(c["d_idx"][:n_rows]); c["h_rows"][:n_rows].copy_(c["d_rows"][:n_rows])
-                torch.cuda.current_stream(self.device).synchronize()
-            _lib.check(self.lib.sg_ev_expand_obs(
-                c["h"].data_ptr(), B, self.num_stations, self.moer_forecast_steps, c["moer"].ctypes.data,
-                c["moer"].shape[0], c["prev"].data_ptr(), int(self._host_obs_valid and self.host_incremental),
-                c["h_idx"].data_ptr(),
-                c["h_rows"].data_ptr(), n_rows, self._h_obs.data_ptr(), self._h_reward.data_ptr(),
-                self._h_done.data_ptr(), c["h_status"].data_ptr(), self.host_threads), "sg_ev_expand_obs")
-            if dense_fallback:
+            if int(c["h"][:4].view(torch.int32)[0]) > c["cap"]:
                 self._h_obs.copy_(self.obs)
                 torch.cuda.current_stream(self.device).synchronize()
-            self._host_obs_valid = True
         self._pending = None
+        ht = self.host_timing                 # where the host-path time goes (seconds, cumulative)
+        ht["sync"] += t1 - t0; ht["expand"] += time.perf_counter() - t1; ht["steps"] += 1
         # zero-copy results: no torch CPU op (and none of its OpenMP threads) on the per-step path
         return (self._h_obs, self._h_reward, self._h_done.view(torch.bool), self._h_trunc, self._infos())
 
@@ -423,7 +436,7 @@ class BatchedEVChargingEnv:
                 max(self.discrete_bins, 0), self.obs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
                 self.pilots.data_ptr(), _lib.ptr(self.final_obs), self.status.data_ptr(), _lib.ptr(self.stats),
                 self.work.data_ptr(), self._stream()), "sg_ev_step")
-        self.kernel_launches += 2 if self.project_action_in_env else 1
+        self.kernel_launches += 1
         self._host_obs_valid = False          # the next host-path step rewrites every observation row
 
     def export_state(self):

@@ -67,6 +67,55 @@ class _Base:
 _NO_INFO: dict = {}       # shared by every env that has nothing to report this step (treat as read-only)
 
 
+class LazyInfos:
+    """The ``infos`` sequence of a vector step without per-env allocation: ``infos[i]`` is the shared empty dict unless
+    env i finished this step, in which case the dict (``terminal_observation``, ``TimeLimit.truncated``) is built —
+    and the terminal observations fetched from the device — on first access.  Behaves like the list SB3 expects
+    (``len``, indexing, iteration); with 65 536 envs ending their day on the same step, eager construction costs
+    ~0.3 s of Python per episode end."""
+
+    def __init__(self, n: int):
+        self._n = n
+        self._done_idx = None
+        self._fetch = None
+        self._rows = None
+        self._fmt_one = None
+        self._cache: dict = {}
+        self._pos = None
+
+    def _set(self, done_idx, fetch, fmt_one):
+        self._done_idx, self._fetch, self._fmt_one, self._rows, self._pos = done_idx, fetch, fmt_one, None, None
+        self._cache = {}
+
+    def _clear(self):
+        if self._done_idx is not None:
+            self._set(None, None, None)
+
+    def __len__(self):
+        return self._n
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(self._n))]
+        if i < 0:
+            i += self._n
+        if self._done_idx is None:
+            return _NO_INFO
+        if self._pos is None:
+            self._pos = {int(b): j for j, b in enumerate(self._done_idx)}
+        j = self._pos.get(int(i))
+        if j is None:
+            return _NO_INFO
+        if i not in self._cache:
+            if self._rows is None:
+                self._rows = self._fetch()
+            self._cache[i] = {"terminal_observation": self._fmt_one(self._rows[j]), "TimeLimit.truncated": False}
+        return self._cache[i]
+
+    def __iter__(self):
+        return (self[i] for i in range(self._n))
+
+
 class SB3VecEnv(_Base):
     """stable_baselines3.common.vec_env.VecEnv protocol.
 
@@ -85,7 +134,7 @@ class SB3VecEnv(_Base):
         self._actions = None
         self._copy = copy
         self._fast = bool(getattr(env, "auto_reset", False)) and hasattr(env, "step_async") and hasattr(env, "final_obs")
-        self._infos = [_NO_INFO] * self.num_envs
+        self._infos = LazyInfos(self.num_envs) if self._fast else [_NO_INFO] * self.num_envs
         self._dirty = ()
 
     def seed(self, seed=None):
@@ -112,22 +161,25 @@ class SB3VecEnv(_Base):
 
     def step_wait(self):
         infos = self._infos
-        for i in self._dirty:                              # entries filled by the previous step
-            infos[i] = _NO_INFO
-        self._dirty = ()
         if self._fast:
+            infos._clear()
             obs, rew, term, trunc, _ = self.env.step_wait()
             obs, done = obs.numpy(), term.numpy()
             if done.any():                                 # the kernel already reset them: obs holds the reset observation
                 idx = np.nonzero(done)[0]
-                import torch
-                terminal = self.env.final_obs[torch.from_numpy(idx).to(self.env.device)].cpu().numpy()
-                for j, i in enumerate(idx):
-                    infos[i] = {"terminal_observation": self._fmt_one(terminal[j]), "TimeLimit.truncated": False}
-                self._dirty = idx
+                env = self.env
+                final = env.final_obs.clone()              # (device copy: the next step may overwrite final_obs)
+
+                def fetch(idx=idx, final=final, env=env):
+                    import torch
+                    return final[torch.from_numpy(idx).to(env.device)].cpu().numpy()
+                infos._set(idx, fetch, self._fmt_one)
                 self._episode += 1
             rew = rew.numpy().astype(np.float32)
             return self._fmt(obs), rew, (done.copy() if self._copy else done), infos
+        for i in self._dirty:                              # entries filled by the previous step
+            infos[i] = _NO_INFO
+        self._dirty = ()
         obs, rew, term, trunc, _ = self.env.step(self._actions)
         obs = np.asarray(obs)
         done = np.asarray(term) | np.asarray(trunc)

@@ -191,14 +191,16 @@ def test_single_env_gymnasium_view(native_lib):
         np.testing.assert_array_equal(obs_a[k], obs_b[k])
 
 
-@pytest.mark.parametrize("mean,cap", [(30.0, None), (110.0, None), (110.0, 3)])
-def test_compact_host_path_is_bit_identical(native_lib, mean, cap):
+@pytest.mark.parametrize("mean,cap,dense", [(30.0, None, 0), (110.0, None, 0), (110.0, 3, 0), (110.0, None, 97)])
+def test_compact_host_path_is_bit_identical(native_lib, mean, cap, dense, monkeypatch):
     """Host-buffer path through 120-byte records + host expansion (sg_ev_step_host_compact_async, sg_ev_expand_obs)
     against the dense device->host copy: observations, rewards, done flags bit for bit, through an auto-reset;
     mean = 110 sessions/day puts more than 16 active sessions into many envs (overflow rows), cap = 3 forces the
     dense fallback of a step whose overflow area is too small."""
     B = 300
+    monkeypatch.setenv("SG_HOST_DENSE_FRACTION", str(dense / B))      # dense = 97: the first 97 envs travel as dense rows
     gen, env_c, _, _ = make(4, mean, 8, B, True, auto_reset=True, host_obs="compact", host_threads=3)
+    assert env_c.host_dense_envs == dense
     _, env_d, _, _ = make(4, mean, 8, B, True, auto_reset=True, host_obs="dense")
     env_c.reset(seed=0); env_d.reset(seed=0)
     if cap is not None:
