@@ -295,12 +295,12 @@ class RealTraceGenerator(ArrayTraceGenerator):
             df = df[df["claimed"]]
         index = {sid: i for i, sid in enumerate(net.station_ids)}
         df = df[df["station_id"].isin(index)]
-        first = pd.Timestamp(begin, tz="America/Los_Angeles")
-        n_days = (pd.Timestamp(end, tz="America/Los_Angeles") - first).days + 1
+        first = pd.Timestamp(begin)                    # calendar dates (naive): a period may span a DST change
+        n_days = (pd.Timestamp(end) - first).days + 1
         days = [[] for _ in range(n_days)]
         step = self.TIME_STEP_DURATION
         for r in df.itertuples(index=False):
-            d = (r.arrival.normalize() - first).days
+            d = (r.arrival.tz_localize(None).normalize() - first).days
             if not (0 <= d < n_days):
                 continue
             if max(r.departure, r.estimated_departure).day != r.arrival.day:      # :312-315
