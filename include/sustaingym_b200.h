@@ -341,8 +341,9 @@ int sg_ev_project(const sg_ev_model* m, int64_t num_envs, const float* action,
                   const float* demands, double* x_out, uint8_t* status, int32_t* iters,
                   void* stream);
 
-/* MultiAgentEVChargingEnv observation fan-out (sustaingym/envs/evcharging/multiagent_env.py:102-148):
- * out[b, i, :] = past_obs[b, :] with entries i (demand) and n+i (est. departure) taken from cur_obs.
+/* MultiAgentEVChargingEnv observation fan-out as documented (sustaingym/envs/evcharging/multiagent_env.py:102-148):
+ * out[b, i, :] = cur_obs[b, :] with the demand / est. departure entries of the OTHER stations (e < 2n, e != i, n+i)
+ * taken from past_obs.
  * cur_obs/past_obs: [B, obs_dim]; out: [B, n, obs_dim]. */
 int sg_ev_agent_obs(const float* cur_obs, const float* past_obs, int64_t num_envs, int32_t n_stations,
                     int32_t obs_dim, float* out, void* stream);

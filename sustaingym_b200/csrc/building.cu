@@ -111,8 +111,11 @@ __device__ __forceinline__ Weather4 load_weather(const double* w, int e) {
 
 // N > 0: compile-time zone count, everything in registers, rows staged through shared memory.
 // N == 0: generic fallback (n <= 128), per-thread arrays in local memory, direct global rows.
-template <int N, bool DISCRETE>
-__global__ void __launch_bounds__(kTile)
+#ifndef SG_BLD_STEP_MINB
+#define SG_BLD_STEP_MINB 4   // resident 128-thread CTAs per SM the single-step instance is compiled for (see kTileStep)
+#endif
+template <int N, bool DISCRETE, int TILE>
+__global__ void __launch_bounds__(TILE, TILE >= 128 ? SG_BLD_STEP_MINB : 1)
 building_step_kernel(const sg_building_model m, const long long B, const int steps,
                      const void* __restrict__ action_v, float* __restrict__ state,
                      int32_t* __restrict__ epoch_g, int32_t* __restrict__ runs_g,
@@ -126,19 +129,19 @@ building_step_kernel(const sg_building_model m, const long long B, const int ste
     double* sBD = sA + n * n;                                      // [n*(n+4)]
     double* sTarget = sBD + n * row;                               // [n]
     double* sAc = sTarget + n;                                     // [n]
-    double* sStat = sAc + n;                                       // [11 * 4]
-    float* tile = reinterpret_cast<float*>(sStat + 44);            // [kTile*row]   (N > 0 only)
-    // action tile follows: f32 [kTile*n] or i64 [kTile*n]
-    unsigned char* act_tile_raw = reinterpret_cast<unsigned char*>(tile + (N > 0 ? kTile * row : 0));
+    double* sStat = sAc + n;                                       // [11 * 8]
+    float* tile = reinterpret_cast<float*>(sStat + 88);            // [TILE*row]   (N > 0 only)
+    // action tile follows: f32 [TILE*n] or i64 [TILE*n]
+    unsigned char* act_tile_raw = reinterpret_cast<unsigned char*>(tile + (N > 0 ? TILE * row : 0));
     act_tile_raw = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(act_tile_raw) + 15) & ~uintptr_t(15));
 
     const int tid = threadIdx.x;
-    for (int i = tid; i < n * n; i += kTile) sA[i] = m.A_d[i];
-    for (int i = tid; i < n * row; i += kTile) sBD[i] = m.BD_d[i];
-    for (int i = tid; i < n; i += kTile) { sTarget[i] = m.target[i]; sAc[i] = m.ac_map[i]; }
+    for (int i = tid; i < n * n; i += TILE) sA[i] = m.A_d[i];
+    for (int i = tid; i < n * row; i += TILE) sBD[i] = m.BD_d[i];
+    for (int i = tid; i < n; i += TILE) { sTarget[i] = m.target[i]; sAc[i] = m.ac_map[i]; }
 
-    const long long b0 = (long long)blockIdx.x * kTile;
-    const int nvalid = (int)min((long long)kTile, B - b0);
+    const long long b0 = (long long)blockIdx.x * TILE;
+    const int nvalid = (int)min((long long)TILE, B - b0);
     const long long b = b0 + tid;
     const bool valid = tid < nvalid;
 
@@ -146,7 +149,7 @@ building_step_kernel(const sg_building_model m, const long long B, const int ste
     int e = 0, r = 0;
     if constexpr (N > 0) {
         const float* g = state + b0 * row;
-        for (int i = tid; i < nvalid * row; i += kTile) tile[i] = g[i];
+        for (int i = tid; i < nvalid * row; i += TILE) tile[i] = g[i];
     }
     __syncthreads();
     if (valid) {
@@ -164,16 +167,16 @@ building_step_kernel(const sg_building_model m, const long long B, const int ste
 
     // action tile ring (N > 0): slot (s % kRing) holds step s; every call commits one group (maybe empty)
     constexpr int esz = DISCRETE ? 8 : 4;
-    const size_t act_tile_bytes = ((size_t)kTile * n * esz + 15) & ~(size_t)15;
+    const size_t act_tile_bytes = ((size_t)TILE * n * esz + 15) & ~(size_t)15;
     auto stage_actions = [&](const int sp) {
         if (sp < steps) {
             const char* g = reinterpret_cast<const char*>(action_v) + ((long long)sp * B + b0) * n * esz;
             unsigned char* t = act_tile_raw + (size_t)(sp % kRing) * act_tile_bytes;
             const int nbytes = nvalid * n * esz;
             if ((nbytes & 15) == 0 && (reinterpret_cast<uintptr_t>(g) & 15u) == 0) {
-                for (int i = tid * 16; i < nbytes; i += kTile * 16) cp_async_16(t + i, g + i);
+                for (int i = tid * 16; i < nbytes; i += TILE * 16) cp_async_16(t + i, g + i);
             } else {
-                for (int i = tid * 4; i < nbytes; i += kTile * 4) cp_async_4(t + i, g + i);
+                for (int i = tid * 4; i < nbytes; i += TILE * 4) cp_async_4(t + i, g + i);
             }
         }
         cp_async_commit();
@@ -186,7 +189,8 @@ building_step_kernel(const sg_building_model m, const long long B, const int ste
     Weather4 w_cur = {0, 0, 0, 0}, w_nxt = {0, 0, 0, 0};
     if (valid) {
         w_cur = load_weather(m.weather, e);
-        w_nxt = load_weather(m.weather, (e + 1) % m.T);
+        // (a single step needs the next row only for an auto-reset at the end of the episode)
+        if (steps > 1 || r + 1 >= m.episode_len) w_nxt = load_weather(m.weather, (e + 1) % m.T);
     }
 
 #ifdef SG_BLD_TRACE2
@@ -236,7 +240,7 @@ building_step_kernel(const sg_building_model m, const long long B, const int ste
             // ---- exogenous inputs + occupancy heat: env.py:244-263 --------------------------
             const Weather4 w = w_cur;
             w_cur = w_nxt;
-            {   // row the step after next will read
+            if (s + 1 < steps) {   // row the step after next will read
                 w_nxt = load_weather(m.weather, (e + 2) % m.T);
             }
             const float avg_temp = __fdiv_rn(numpy_sum_f32<MAXN>(x, n), (float)n);
@@ -315,11 +319,11 @@ building_step_kernel(const sg_building_model m, const long long B, const int ste
                 __syncthreads();
                 if (obs_out != nullptr) {
                     float* g = obs_out + ((long long)s * B + b0) * row;
-                    for (int i = tid; i < nvalid * row; i += kTile) g[i] = tile[i];
+                    for (int i = tid; i < nvalid * row; i += TILE) g[i] = tile[i];
                 }
                 if (last) {
                     float* g = state + b0 * row;
-                    for (int i = tid; i < nvalid * row; i += kTile) g[i] = tile[i];
+                    for (int i = tid; i < nvalid * row; i += TILE) g[i] = tile[i];
                 }
             } else if (valid) {
                 if (obs_out != nullptr) {
@@ -798,21 +802,35 @@ int launch_building_mma(const sg_building_model* m, long long B, int steps, cons
     return launch_status("building_mma_kernel");
 }
 
-template <int N, bool DISCRETE>
-int launch_building(const sg_building_model* m, long long B, int steps, const void* action, float* state,
-                    int32_t* epoch, int32_t* runs, float* obs_out, double* reward, uint8_t* done,
-                    int flags, double* stats, cudaStream_t st) {
+// Fused rollouts run one warp per CTA (tiles advance independently through the steps: measured +9 % over 128 threads);
+// a single step() has no step loop to decouple, only per-CTA set-up (model -> shared memory, barriers) to amortise: 128
+// envs per CTA (262 144 envs: 31.7 us with 8 192 one-warp CTAs).  Same code, same arithmetic.
+constexpr int kTileStep = 128;
+
+template <int N, bool DISCRETE, int TILE>
+int launch_building_tile(const sg_building_model* m, long long B, int steps, const void* action, float* state,
+                         int32_t* epoch, int32_t* runs, float* obs_out, double* reward, uint8_t* done,
+                         int flags, double* stats, cudaStream_t st) {
     const int n = m->n, row = n + 4;
-    size_t smem = sizeof(double) * (n * n + n * row + 2 * n + 44);
-    if (N > 0) smem += sizeof(float) * kTile * row + 16 + (size_t)kRing * ((((DISCRETE ? 8 : 4) * (size_t)kTile * n) + 15) & ~(size_t)15);
-    auto kern = building_step_kernel<N, DISCRETE>;
+    size_t smem = sizeof(double) * (n * n + n * row + 2 * n + 88);
+    if (N > 0) smem += sizeof(float) * TILE * row + 16 + (size_t)kRing * ((((DISCRETE ? 8 : 4) * (size_t)TILE * n) + 15) & ~(size_t)15);
+    auto kern = building_step_kernel<N, DISCRETE, TILE>;
     if (smem > 48 * 1024) {
         cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) { set_error("building: %zu B of shared memory unavailable", smem); return 2; }
     }
-    const unsigned grid = (unsigned)((B + kTile - 1) / kTile);
-    kern<<<grid, kTile, smem, st>>>(*m, B, steps, action, state, epoch, runs, obs_out, reward, done, flags, stats);
+    const unsigned grid = (unsigned)((B + TILE - 1) / TILE);
+    kern<<<grid, TILE, smem, st>>>(*m, B, steps, action, state, epoch, runs, obs_out, reward, done, flags, stats);
     return launch_status("building_step_kernel");
+}
+
+template <int N, bool DISCRETE>
+int launch_building(const sg_building_model* m, long long B, int steps, const void* action, float* state,
+                    int32_t* epoch, int32_t* runs, float* obs_out, double* reward, uint8_t* done,
+                    int flags, double* stats, cudaStream_t st) {
+    if (N > 0 && steps == 1 && B >= 4 * kTileStep)
+        return launch_building_tile<N, DISCRETE, kTileStep>(m, B, steps, action, state, epoch, runs, obs_out, reward, done, flags, stats, st);
+    return launch_building_tile<N, DISCRETE, kTile>(m, B, steps, action, state, epoch, runs, obs_out, reward, done, flags, stats, st);
 }
 
 int dispatch_building(const sg_building_model* m, long long B, int steps, const void* action, float* state,

@@ -1931,9 +1931,10 @@ ev_project_kernel(const sg_ev_model m, const long long B, const float* __restric
 }
 
 
-// Per-agent observations of MultiAgentEVChargingEnv (multiagent_env.py:102-148): agent i sees the
-// aggregate observation of `periods_delay` steps ago, except its own station's est_departure and
-// demand entries, which are current.  out[b, i, :] for all 54 agents.
+// Per-agent observations of MultiAgentEVChargingEnv as DOCUMENTED (multiagent_env.py:102-148): agent i sees the other
+// stations' est_departure and demand entries of `periods_delay` steps ago; its own station's entries, the MOER
+// fields and the timestep are current.  out[b, i, :] for all 54 agents.  (What the reference actually returns is
+// the current observation for everybody — its deque aliases the live arrays; see envs/evcharging/multiagent_env.py.)
 __global__ void ev_agent_obs_kernel(const float* __restrict__ cur, const float* __restrict__ past, const long long B,
                                     const int n, const int obs_dim, float* __restrict__ out) {
     const long long total = B * n * obs_dim;
@@ -1943,7 +1944,7 @@ __global__ void ev_agent_obs_kernel(const float* __restrict__ cur, const float* 
         const long long bi = idx / obs_dim;
         const int i = (int)(bi % n);
         const long long b = bi / n;
-        const bool own = (e == i) || (e == n + i);
+        const bool own = (e == i) || (e == n + i) || e >= 2 * n;     // only demands / est_departures are delayed (:134-139)
         out[idx] = own ? cur[b * obs_dim + e] : past[b * obs_dim + e];
     }
 }

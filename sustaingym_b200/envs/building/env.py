@@ -170,7 +170,7 @@ class BatchedBuildingEnv:
                 self.epoch.data_ptr(), self.runs.data_ptr(), self.reward.data_ptr(), self.done.data_ptr(),
                 self._flags, _lib.ptr(self.stats), self._stream()), "sg_building_step")
         self.kernel_launches += 1
-        d = self.done.bool()
+        d = self.done.view(torch.bool)                    # zero-copy (no conversion kernel on the step path)
         return self.state, self.reward, d, d, {}          # terminated == truncated == done (env.py:312)
 
     def rollout(self, actions: torch.Tensor, keep_obs: bool = True):

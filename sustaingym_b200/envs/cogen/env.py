@@ -157,6 +157,7 @@ class BatchedCogenEnv:
         self.reward = z(B, dtype=torch.float64)
         self.agent_reward = z(B, 4, dtype=torch.float64)
         self.done = z(B, dtype=torch.uint8)
+        self._trunc = z(B, dtype=torch.bool)              # truncated is always False (cogen/env.py:384)
         self.scratch = z(_lib.cogen_scratch_floats(B), dtype=torch.float32)
         self.Y = z(B, 29, dtype=torch.float32) if keep_outputs else None
         self.stats = z(_lib.SG_STATS_LEN, dtype=torch.float64) if collect_stats else None
@@ -246,7 +247,7 @@ class BatchedCogenEnv:
             d = self.done.cpu().numpy().astype(bool)
             return self.obs.cpu().numpy(), self.reward.cpu().numpy(), d, np.zeros(B, bool), \
                 {"agent_rewards": self.agent_reward.cpu().numpy()}
-        return self.obs, self.reward, self.done.bool(), torch.zeros_like(self.done, dtype=torch.bool), info
+        return self.obs, self.reward, self.done.view(torch.bool), self._trunc, info
 
     def close(self) -> None:
         pass

@@ -71,6 +71,7 @@ class BatchedElectricityMarketEnv:
         self.obs = z(B, self.obs_dim, dtype=torch.float32)
         self.reward = z(B, dtype=torch.float64)
         self.done = z(B, dtype=torch.uint8)
+        self._trunc = z(B, dtype=torch.bool)
         self.info = z(B, 3, dtype=torch.float64)
         self.stats = z(_lib.SG_STATS_LEN, dtype=torch.float64) if collect_stats else None
         if self.stats is not None:
@@ -119,7 +120,7 @@ class BatchedElectricityMarketEnv:
             d = self.done.cpu().numpy().astype(bool)
             return self.obs.cpu().numpy(), self.reward.cpu().numpy(), d, np.zeros(B, bool), \
                 {k_: v.cpu().numpy() for k_, v in info.items()}
-        return self.obs, self.reward, self.done.bool(), torch.zeros_like(self.done, dtype=torch.bool), info
+        return self.obs, self.reward, self.done.view(torch.bool), self._trunc, info
 
     def capture_graph(self, actions):
         """One ``step(actions)`` (CUDA tensor, read in place) as a CUDA graph; see ``envs/_graph.py``."""

@@ -196,6 +196,7 @@ class BatchedEVChargingEnv:
         self.final_obs = z(B, self.obs_dim, dtype=torch.float32) if auto_reset else None
         self.reward = z(B, dtype=torch.float64)
         self.done = z(B, dtype=torch.uint8)
+        self._d_trunc = z(B, dtype=torch.bool)               # truncated is always False (env.py:291)
         self.status = z(B, dtype=torch.uint8)
         self.pilots = z(B, n, dtype=torch.uint8)
         self.work = z(B + _lib.SG_EV_WORK_HEADER_INTS, dtype=torch.int32)   # tile scheduler + work list of the exact projection
@@ -309,12 +310,12 @@ class BatchedEVChargingEnv:
                 return (self._h_obs.numpy().copy(), self._h_reward.numpy().copy(), done,
                         np.zeros(B, bool), self._infos())
             # torch host path: views of the pinned result buffers (valid until the next step)
-            return self._h_obs, self._h_reward, self._h_done.bool(), torch.zeros(B, dtype=torch.bool), self._infos()
+            return self._h_obs, self._h_reward, self._h_done.view(torch.bool), self._h_trunc, self._infos()
         if actions.device != self.device or actions.dtype != self._action_dtype or tuple(actions.shape) != (B, n):
             raise ValueError(f"actions must be a {self._action_dtype} tensor of shape {(B, n)} on {self.device}")
         actions = actions.contiguous()
         self.launch_step(actions)
-        return self.obs, self.reward, self.done.bool(), torch.zeros_like(self.done, dtype=torch.bool), self._infos()
+        return self.obs, self.reward, self.done.view(torch.bool), self._d_trunc, self._infos()
 
     def step_async(self, actions: torch.Tensor) -> None:
         """SB3 ``VecEnv.step_async``: enqueue H2D(actions) -> step -> D2H(obs, reward, done) on this env's

@@ -5,6 +5,13 @@ gets the flattened aggregate observation; with ``periods_delay > 0`` an agent se
 stations' ``est_departures``/``demands`` as they were ``periods_delay`` steps ago and its own as
 they are now (:102-148); the reward is the global reward divided by the number of agents (:184).
 
+``delay_semantics``.  The reference does NOT deliver that delay: ``EVChargingEnv._get_observation`` returns the same
+dict of arrays every step and mutates them in place (env.py:157-163, 383-394); ``MultiAgentEVChargingEnv`` stores
+that dict object in its deque (multiagent_env.py:122-123, 130-131), so the "delayed" entries it reads back alias the
+current arrays and every agent receives the CURRENT aggregate observation whatever ``periods_delay`` is.
+``delay_semantics="reference"`` (default) reproduces that observable behaviour; ``"documented"`` implements what the
+docstring describes (others' ``est_departures`` / ``demands`` delayed, own entries, MOER fields and timestep current).
+
 ``BatchedMultiAgentEVChargingEnv`` keeps the delay ring buffer on the device and materialises the
 ``[num_envs, 54, 146]`` per-agent tensor with ``sg_ev_agent_obs`` only when asked;
 ``MultiAgentEVChargingEnv`` is the reference's single-env dict-of-agents interface.
@@ -25,10 +32,13 @@ from .event_generation import AbstractTraceGenerator
 class BatchedMultiAgentEVChargingEnv:
     def __init__(self, data_generator: AbstractTraceGenerator, num_envs: int = 1, periods_delay: int = 0,
                  moer_forecast_steps: int = 36, project_action_in_env: bool = True, discrete_bins: int = -1,
-                 verbose: int = 0, device=None):
+                 verbose: int = 0, device=None, delay_semantics: str = "reference"):
+        if delay_semantics not in ("reference", "documented"):
+            raise ValueError("delay_semantics must be 'reference' (aliasing: no effective delay) or 'documented'")
         self.env = BatchedEVChargingEnv(data_generator, num_envs, moer_forecast_steps, project_action_in_env,
                                         verbose, device, auto_reset=False, discrete_bins=discrete_bins)
         self.periods_delay = periods_delay
+        self.delay_semantics = delay_semantics
         self.num_envs = num_envs
         self.agents = list(self.env.cn.station_ids)
         self.possible_agents = self.agents
@@ -44,7 +54,7 @@ class BatchedMultiAgentEVChargingEnv:
 
     def _push(self, obs: torch.Tensor, init: bool) -> torch.Tensor:
         """Returns the aggregate observation the *other* agents see (delayed), updating the ring."""
-        if self.periods_delay == 0:
+        if self.periods_delay == 0 or self.delay_semantics == "reference":
             return obs
         if init:
             self._ring = [obs.clone() for _ in range(self.periods_delay)]      # multiagent_env.py:119-123
@@ -87,10 +97,12 @@ class MultiAgentEVChargingEnv:
     metadata: dict[str, Any] = {}
 
     def __init__(self, data_generator: AbstractTraceGenerator, periods_delay: int = 0, moer_forecast_steps: int = 36,
-                 project_action_in_env: bool = True, discrete_bins: int = -1, verbose: int = 0, device=None):
+                 project_action_in_env: bool = True, discrete_bins: int = -1, verbose: int = 0, device=None,
+                 delay_semantics: str = "reference"):
         self._b = BatchedMultiAgentEVChargingEnv(data_generator, 1, periods_delay, moer_forecast_steps,
-                                                 project_action_in_env, discrete_bins, verbose, device)
+                                                 project_action_in_env, discrete_bins, verbose, device, delay_semantics)
         self.periods_delay = periods_delay
+        self.delay_semantics = delay_semantics
         self.agents = list(self._b.agents)
         self.possible_agents = list(self._b.agents)
         self.observation_spaces = {a: self._b.flat_observation_space for a in self.agents}
@@ -103,7 +115,7 @@ class MultiAgentEVChargingEnv:
         return len(self.agents)
 
     def _obss(self) -> dict:
-        if self.periods_delay == 0:
+        if self.periods_delay == 0 or self.delay_semantics == "reference":
             flat = self._b.env.obs.cpu().numpy()[0]
             return {a: flat for a in self.agents}
         per = self._b.agent_observations().cpu().numpy()[0]

@@ -34,11 +34,13 @@ def test_ev_multi_agent_api(native_lib):
     parallel_seed_test(lambda: MultiAgentEVChargingEnv(ev_gen(), periods_delay=2))
 
 
-def test_ev_periods_delay_semantics(native_lib):
-    """Own-station entries current, the others delayed by `periods_delay` (multiagent_env.py:102-148)."""
+def test_ev_periods_delay_documented_semantics(native_lib):
+    """delay_semantics="documented": the other stations' demands / est_departures are `periods_delay` steps old, own
+    entries, MOER fields and timestep current (what multiagent_env.py:102-148 describes)."""
     from sustaingym_b200.envs.evcharging.multiagent_env import BatchedMultiAgentEVChargingEnv
     B, delay = 16, 3
-    env = BatchedMultiAgentEVChargingEnv(ev_gen(mean=70.0), B, periods_delay=delay, project_action_in_env=False)
+    env = BatchedMultiAgentEVChargingEnv(ev_gen(mean=70.0), B, periods_delay=delay, project_action_in_env=False,
+                                         delay_semantics="documented")
     env.reset(seed=0)
     hist = [env.env.obs.clone()]
     rng = np.random.default_rng(0)
@@ -47,11 +49,61 @@ def test_ev_periods_delay_semantics(native_lib):
         hist.append(env.env.obs.clone())
         per = env.agent_observations()
         cur, past = hist[-1], hist[max(0, len(hist) - 1 - delay)]
-        exp = past[:, None, :].repeat(1, 54, 1)
+        exp = cur[:, None, :].repeat(1, 54, 1)
+        exp[:, :, :108] = past[:, None, :108]
         idx = torch.arange(54)
         exp[:, idx, idx] = cur[:, idx]
         exp[:, idx, 54 + idx] = cur[:, 54 + idx]
         assert torch.equal(per, exp), t
+
+
+def test_ev_periods_delay_reference_behaviour(native_lib):
+    """Default: what the reference RETURNS.  Its single-agent env hands out one dict whose arrays it mutates in place
+    (env.py:157-163, 383-394) and the multi-agent wrapper keeps that very dict in its deque (multiagent_env.py:119-139),
+    so the 'delayed' arrays alias the current ones.  The wrapper logic is transcribed below around such a dict and
+    driven with our env's observations: every agent gets the current aggregate observation."""
+    from collections import deque
+    from sustaingym_b200.envs.evcharging.multiagent_env import MultiAgentEVChargingEnv
+    delay = 3
+    ma = MultiAgentEVChargingEnv(ev_gen(mean=70.0), periods_delay=delay, project_action_in_env=False)
+    keys = ("demands", "est_departures", "forecasted_moer", "prev_moer", "timestep")          # sorted: flatten order
+    sl = ma._b.env.obs_slices
+    live = {k: np.zeros(sl[k].stop - sl[k].start, np.float32) for k in keys}                     # the env's self._obs
+
+    def env_get_observation(flat):                   # env.py:383-394: fill the SAME arrays, return the SAME dict
+        for k in keys:
+            live[k][:] = flat[sl[k]]
+        return live
+
+    past = deque(maxlen=delay)
+
+    def create_dict_from_obs_agg(obs_agg, init):     # multiagent_env.py:102-148, verbatim logic
+        flatten = lambda o: np.concatenate([o[k] for k in keys])                                 # noqa: E731
+        if init:
+            past.clear()
+            for _ in range(delay):
+                past.append(obs_agg)
+            return {a: flatten(obs_agg) for a in ma.agents}
+        first = past.popleft()
+        past.append(obs_agg)
+        td = {a: obs_agg.copy() for a in ma.agents}
+        for i, a in enumerate(ma.agents):
+            for var in ("est_departures", "demands"):
+                td[a][var] = first[var]
+                td[a][var][i] = obs_agg[var][i]
+        return {a: flatten(td[a]) for a in ma.agents}
+
+    obss, _ = ma.reset(seed=1)
+    ref = create_dict_from_obs_agg(env_get_observation(ma._b.env.obs.cpu().numpy()[0]), init=True)
+    rng = np.random.default_rng(2)
+    n_busy = 0
+    for t in range(80):
+        for a in ma.agents:
+            np.testing.assert_array_equal(obss[a], ref[a])
+        obss, *_ = ma.step({a: rng.uniform(0, 1, 1).astype(np.float32) for a in ma.agents})
+        ref = create_dict_from_obs_agg(env_get_observation(ma._b.env.obs.cpu().numpy()[0]), init=False)
+        n_busy += int((obss[ma.agents[0]][:54] > 0).sum() > 0)
+    assert n_busy > 20                                # the garage was not empty: the comparison is not vacuous
 
 
 def test_building_api(native_lib):
