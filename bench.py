@@ -515,7 +515,7 @@ def main():
     side = torch.cuda.Stream(dev)
     main_stream = torch.cuda.current_stream(dev)
     tick = torch.cuda.Event()
-    stats_buf = torch.zeros(shared_stats.numel() + 2, dtype=torch.float64, device=dev)   # no allocation in the timed region
+    stats_buf = torch.zeros((world + 1) * shared_stats.numel(), dtype=torch.float64, device=dev)   # no allocation in the timed region
     job_stats = [None]
     for _ in range(2):                                      # warms the side stream, the event and the NCCL communicator up
         tick.record(main_stream)
@@ -646,7 +646,7 @@ def main():
                        "l2_policy": f"{N_SETS} env sets stepped round-robin: ~{N_SETS * 85} MB touched between reuses (> 126 MB L2)",
                        "launch": "one CUDA graph per step: ev_step_main_kernel + ev_step_rare_kernel (work list of envs needing the "
                                  "interior-point solver, normally empty)",
-                       "collective": f"all_reduce_stats (SUM+MIN+MAX of 16 doubles) every {STATS_EVERY} steps on a side stream, "
+                       "collective": f"all_reduce_stats (one all-gather of 16 doubles per rank, reduced locally: SUM / MIN / MAX) every {STATS_EVERY} steps on a side stream, "
                                      f"{n_collectives} inside the timed region"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                          "frac": achieved / hbm, "traffic": traffic, "kernel": "ev_step_main_kernel<1>",
