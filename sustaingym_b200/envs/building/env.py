@@ -2,7 +2,8 @@
 
 ``BatchedBuildingEnv(parameters, num_envs)`` takes the same ``parameters`` dict the reference's
 ``BuildingEnv`` takes (``sustaingym/envs/building/env.py:110-203``; produced by the reference's
-``ParameterGenerator``) and advances ``num_envs`` independent copies per kernel launch.
+``ParameterGenerator`` or by its restatement here, ``envs/building/parameters.py`` — or just the name of one of the 16
+prototype buildings, e.g. ``BuildingEnv("OfficeSmall")``) and advances ``num_envs`` independent copies per kernel launch.
 ``BuildingEnv`` is the ``num_envs = 1`` Gymnasium view.  All per-step arithmetic runs in
 ``sg_building_step`` / ``sg_building_rollout`` / ``sg_building_reset``.
 """
@@ -45,6 +46,9 @@ class BatchedBuildingEnv:
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedBuildingEnv needs a CUDA device (no CPU fallback)")
         self.device = dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        if isinstance(parameters, str):     # a prototype-building name: the reference's test set-up (tests/test_building.py:17-19)
+            from .parameters import ParameterGenerator
+            parameters = ParameterGenerator(parameters, "Hot_Dry", "Tucson")
         p = self.parameters = parameters
         self.num_envs = B = int(num_envs)
         self.n = n = int(p["n"])
@@ -201,9 +205,9 @@ class BatchedBuildingEnv:
 class BuildingEnv:
     """The reference's single-env Gymnasium interface (env.py:16-434) on a 1-env batch."""
 
-    def __init__(self, parameters: dict[str, Any], device=None):
+    def __init__(self, parameters: dict[str, Any] | str, device=None):
         self._b = BatchedBuildingEnv(parameters, 1, device)
-        self.parameters = parameters
+        self.parameters = parameters = self._b.parameters
         for k in ("n", "target", "ac_map", "maxpower", "temp_range", "reward_pnorm", "is_continuous_action",
                   "timestep", "episode_len", "length_of_weather", "q_rate", "error_rate", "A_d", "BD_d",
                   "Qlow", "Qhigh", "low", "high"):

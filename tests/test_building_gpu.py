@@ -137,3 +137,25 @@ def test_tensor_core_kernel_matches_thread_per_env_kernel(native_lib, name, B):
     np.testing.assert_allclose(a[4], b[4], rtol=1e-9)
     np.testing.assert_array_equal(a[5], b[5]); np.testing.assert_array_equal(a[6], b[6])
     np.testing.assert_allclose(a[7][:3], b[7][:3], rtol=1e-9)
+
+
+def test_standalone_building_by_name_matches_survey_vectors(native_lib):
+    """``BuildingEnv("RetailStandalone")`` — parameters from the packaged archive through our ParameterGenerator — against
+    the vectors the survey recorded from the unmodified reference (Hot_Dry / Tucson, reset(seed=5)
+    -> epoch 1439, actions = successive default_rng(0).uniform(-1, 1, n) as f32)."""
+    from sustaingym_b200.envs.building.env import BuildingEnv
+    env = BuildingEnv("RetailStandalone")
+    obs, _ = env.reset(seed=5)
+    assert env.epoch == 1439 and env.n == 5
+    rng = np.random.default_rng(0)
+    want = [([21.803447723388672, 21.775115966796875, 19.753095626831055, 19.665117263793945, 29.285329818725586, 11.0,
+              20.899999618530273, 0.0, -0.07856952399015427], -8.008709221225727),
+            ([22.030057907104492, 21.68138313293457, 20.758813858032227, 20.03554916381836, 34.25482940673828, 11.0,
+              20.899999618530273, 0.0, -0.08379818499088287], -12.496131927911641)]
+    for ob_w, r_w in want:
+        ob, r, *_ = env.step(rng.uniform(-1, 1, 5).astype(np.float32))
+        np.testing.assert_allclose(ob, np.array(ob_w, np.float32), rtol=1e-6, atol=1e-6)
+        assert abs(r - r_w) <= 1e-6 * abs(r_w)
+    env6 = BuildingEnv("OfficeSmall")
+    obs, _ = env6.reset(seed=5)
+    np.testing.assert_allclose(obs, np.array([22, 22, 22, 22, 22, 22, 11.0, 20.899999618530273, 0.0, -0.07856951653957367], np.float32), rtol=1e-6)
