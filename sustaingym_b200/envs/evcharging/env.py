@@ -527,6 +527,23 @@ class EVChargingEnv:
                 "reward_breakdown": {"profit": float(bd[0]), "carbon_cost": float(bd[1]),
                                      "excess_charge": float(bd[2])}}
 
+    @property
+    def moer(self) -> np.ndarray:
+        """The current day's MOER table ``[289, 37]`` (column 0: historical value, 1..36: forecasts) — the array the
+        reference keeps in ``env.moer`` after ``reset`` (env.py:317-318) and its offline-optimal controller reads."""
+        return np.asarray(self.data_generator.moer[int(self._b.moer_day[0])], dtype=np.float64)
+
+    @property
+    def _evs(self) -> list:
+        """The current day's charging sessions as records with ``station_id``, ``arrival``, ``departure``,
+        ``estimated_departure`` and ``requested_energy`` (kWh) — the attributes of the acnportal ``EV`` objects the
+        reference holds in ``env._evs`` (env.py:313-316) that its controllers use."""
+        from types import SimpleNamespace
+        ids = self.cn.station_ids
+        return [SimpleNamespace(station_id=ids[st], arrival=int(arr), departure=int(dep), estimated_departure=int(est),
+                                requested_energy=float(kwh))
+                for arr, dep, est, kwh, st in self.data_generator.days[int(self._b.day[0])]]
+
     def reset(self, *, seed: int | None = None, options: dict | None = None):
         if seed is None:
             # the reference's sequential generator simply moves on to the next day (event_generation.py:284-291)

@@ -45,3 +45,26 @@ def test_greedy_single_env_batched_and_oracle_agree(native_lib):
     assert int(benv.status.cpu().numpy().astype(bool).sum()) >= 0
     rnd = RandomAlgorithm(EVChargingEnv(gen, project_action_in_env=False), seed=1).run(1)
     assert len(rnd) == 1 and np.isfinite(rnd["return"][0])
+
+
+def test_mpc_and_offline_optimal_on_the_drop_in_env(native_lib):
+    """The optimisation-based controllers (baselines.py:53-228) through the reference's own call sequence —
+    ``Algorithm(env).run(seeds)`` on the single-env view: OfflineOptimal >= MPC >= Greedy in return on a busy day,
+    neither of the optimisers pays violation cost (their actions satisfy the network constraints), and the offline
+    trajectory is what was played."""
+    from sustaingym_b200.algorithms.evcharging.baselines import GreedyAlgorithm
+    from sustaingym_b200.algorithms.evcharging.optimal import MPC, OfflineOptimal
+    from sustaingym_b200.envs.evcharging.env import EVChargingEnv
+    from sustaingym_b200.envs.evcharging.event_generation import SyntheticTraceGenerator
+    gen = SyntheticTraceGenerator("caltech", num_days=3, mean_sessions=90.0, seed=5)
+    env = EVChargingEnv(gen, project_action_in_env=False)           # the controllers must be feasible on their own
+    assert env.moer.shape == (289, 37) and len(env._evs) == len(gen.days[int(env._b.day[0])])
+    res = {}
+    for name, alg in (("greedy", GreedyAlgorithm(env)), ("mpc", MPC(env, lookahead=12)), ("offline", OfflineOptimal(env))):
+        res[name] = alg.run([1])
+    r = {k: float(v["return"][0]) for k, v in res.items()}
+    bd = {k: v["reward_breakdown"][0] for k, v in res.items()}
+    assert bd["mpc"]["excess_charge"] <= 1e-9 and bd["offline"]["excess_charge"] <= 1e-9
+    assert bd["greedy"]["excess_charge"] > 0                          # the day is busy enough for greedy to overload
+    assert r["offline"] >= r["mpc"] * (1 - 2e-3) >= r["greedy"] * (1 - 2e-3) ** 2, r
+    assert r["offline"] <= float(res["offline"]["max_profit"][0]) + 1e-9
