@@ -221,6 +221,28 @@ class BuildingEnv:
     def epoch(self) -> int:
         return int(self._b.epoch[0])
 
+    # the arrays the reference's BuildingEnv keeps as attributes and its MPC agent reads (env.py:150-160, 186-187;
+    # algorithms/building/mpc_controller.py:33-37, 50-52)
+    @property
+    def B_d(self) -> np.ndarray:
+        return self.BD_d
+
+    @property
+    def out_temp(self) -> np.ndarray:
+        return np.asarray(self.parameters["out_temp"], np.float64)
+
+    @property
+    def ground_temp(self) -> np.ndarray:
+        return np.asarray(self.parameters["ground_temp"], np.float64)
+
+    @property
+    def ghi(self) -> np.ndarray:
+        return np.asarray(self.parameters["ghi"], np.float64)
+
+    @property
+    def metabolism(self) -> np.ndarray:
+        return np.asarray(self.parameters["metabolism"], np.float64)
+
     def _info(self) -> dict:
         return {"zone_temperature": self.state[: self.n].astype(np.float64),
                 "reward_breakdown": self._reward_breakdown}

@@ -159,3 +159,22 @@ def test_standalone_building_by_name_matches_survey_vectors(native_lib):
     env6 = BuildingEnv("OfficeSmall")
     obs, _ = env6.reset(seed=5)
     np.testing.assert_allclose(obs, np.array([22, 22, 22, 22, 22, 22, 11.0, 20.899999618530273, 0.0, -0.07856951653957367], np.float32), rtol=1e-6)
+
+
+def test_mpc_agent_on_the_drop_in_env(native_lib):
+    """mpc_controller.py's call sequence on the drop-in env: ``MPCAgent(env, beta, pnorm, planning_steps=..).predict()``
+    reads env.A_d / B_d / out_temp / ... / state; the state it predicts is the one the kernel produces."""
+    from sustaingym_b200.algorithms.building.mpc_controller import MPCAgent
+    from sustaingym_b200.envs.building.env import BuildingEnv
+    env = BuildingEnv("OfficeSmall")
+    env.reset(seed=5, options={"T_initial": np.array([25.5, 24.0, 26.0, 27.0, 23.5, 25.0])})
+    ag = MPCAgent(env, beta=float(env.parameters["reward_beta"]), pnorm=2, planning_steps=3, gap_tol=1e-6)
+    total = 0.0
+    for _ in range(12):
+        a, pred = ag.predict()
+        obs, r, *_ = env.step(a)
+        np.testing.assert_allclose(obs[:env.n], pred, atol=2e-4)
+        total += r
+    idle = BuildingEnv("OfficeSmall")
+    idle.reset(seed=5, options={"T_initial": np.array([25.5, 24.0, 26.0, 27.0, 23.5, 25.0])})
+    assert total > sum(idle.step(np.zeros(idle.n, np.float32))[1] for _ in range(12))
