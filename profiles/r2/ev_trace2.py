@@ -12,6 +12,7 @@ T0 = int(os.environ.get("TSTEP", 150))
 gen = SyntheticTraceGenerator("caltech", num_days=256, mean_sessions=25.0, seed=1234)
 env = BatchedEVChargingEnv(gen, B, project_action_in_env=True, auto_reset=True, collect_stats=True)
 env.reset(seed=0)
+if os.environ.get("STATIC"): env._flags |= 32          # SG_EV_FLAG_STATIC_TILES
 g = torch.Generator(device="cuda"); g.manual_seed(0)
 acts = [torch.rand(B, 54, generator=g, device="cuda") for _ in range(4)]
 for i in range(T0): env.launch_step(acts[i % 4])
@@ -33,6 +34,9 @@ print(f"t={T0} tiles {ntiles}; kernel span first tile start -> last tile end: {(
 names = {5: "tile start", 0: "header+prologue", 2: "stage fill", 11: "scan", 12: "keys (last grp)", 3: "keys synced", 13: "loads issued",
          14: "loads arrived", 4: "items done", 6: "checks/rate/wb", 7: "arrivals", 8: "epilogue", 15: "bulk store + wait"}
 order = [5, 0, 2, 11, 12, 3, 13, 14, 4, 6, 7, 8, 15]
+if os.environ.get("KEYS"):      # -DSG_EV_TRACE_KEYS build: stamps 14 / 13 sit inside the scan -> keys interval
+    names.update({14: "j0 known", 13: "group bounds"})
+    order = [5, 0, 2, 11, 14, 13, 12, 3, 4, 6, 7, 8, 15]
 tot = (tr[:, 15] - tr[:, 5]) / 1e3
 print(f"per-tile total: median {np.median(tot):.2f} p10 {np.percentile(tot,10):.2f} p90 {np.percentile(tot, 90):.2f} max {tot.max():.2f} us")
 for a, b_ in zip(order[:-1], order[1:]):

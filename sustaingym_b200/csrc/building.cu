@@ -136,32 +136,36 @@ building_step_kernel(const sg_building_model m, const long long B, const int ste
     act_tile_raw = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(act_tile_raw) + 15) & ~uintptr_t(15));
 
     const int tid = threadIdx.x;
-    for (int i = tid; i < n * n; i += TILE) sA[i] = m.A_d[i];
-    for (int i = tid; i < n * row; i += TILE) sBD[i] = m.BD_d[i];
-    for (int i = tid; i < n; i += TILE) { sTarget[i] = m.target[i]; sAc[i] = m.ac_map[i]; }
-
     const long long b0 = (long long)blockIdx.x * TILE;
     const int nvalid = (int)min((long long)TILE, B - b0);
     const long long b = b0 + tid;
     const bool valid = tid < nvalid;
 
+    // Everything the first step needs is requested up front, in dependency order, so that a CTA's start-up costs two
+    // memory round trips instead of four (a single step is start-up plus one step; with ~3.5 waves of CTAs that
+    // latency IS the launch time): the weather cursor first (the weather rows depend on it), then the model matrices
+    // and the state tile as asynchronous copies straight into shared memory, then the action tiles, then — once the
+    // cursor has arrived — the weather rows; the copies are waited for last.
     float x[MAXN];
     int e = 0, r = 0;
-    if constexpr (N > 0) {
-        const float* g = state + b0 * row;
-        for (int i = tid; i < nvalid * row; i += TILE) tile[i] = g[i];
-    }
-    __syncthreads();
     if (valid) {
         e = epoch_g[b];
         r = runs_g[b];
-        if constexpr (N > 0) {
-#pragma unroll
-            for (int j = 0; j < N; ++j) x[j] = tile[tid * row + j];
+    }
+    for (int i = tid; i < n * n; i += TILE) cp_async_8(sA + i, m.A_d + i);
+    for (int i = tid; i < n * row; i += TILE) cp_async_8(sBD + i, m.BD_d + i);
+    for (int i = tid; i < n; i += TILE) { cp_async_8(sTarget + i, m.target + i); cp_async_8(sAc + i, m.ac_map + i); }
+    if constexpr (N > 0) {
+        const float* g = state + b0 * row;
+        const int nbytes = nvalid * row * 4;
+        if ((nbytes & 15) == 0 && (reinterpret_cast<uintptr_t>(g) & 15u) == 0) {
+            for (int i = tid * 16; i < nbytes; i += TILE * 16)
+                cp_async_16(reinterpret_cast<unsigned char*>(tile) + i, reinterpret_cast<const unsigned char*>(g) + i);
         } else {
-            for (int j = 0; j < n; ++j) x[j] = state[b * row + j];
+            for (int i = tid; i < nvalid * row; i += TILE) cp_async_4(tile + i, g + i);
         }
     }
+    cp_async_commit();
     StatsAcc acc;
     float tail[4] = {0.f, 0.f, 0.f, 0.f};
 
@@ -191,6 +195,17 @@ building_step_kernel(const sg_building_model m, const long long B, const int ste
         w_cur = load_weather(m.weather, e);
         // (a single step needs the next row only for an auto-reset at the end of the episode)
         if (steps > 1 || r + 1 >= m.episode_len) w_nxt = load_weather(m.weather, (e + 1) % m.T);
+    }
+    // model matrices + state tile have landed (the action tiles of the ring may still be in flight)
+    if constexpr (N > 0) cp_async_wait<kPre>(); else cp_async_wait<0>();
+    __syncthreads();
+    if (valid) {
+        if constexpr (N > 0) {
+#pragma unroll
+            for (int j = 0; j < N; ++j) x[j] = tile[tid * row + j];
+        } else {
+            for (int j = 0; j < n; ++j) x[j] = state[b * row + j];
+        }
     }
 
 #ifdef SG_BLD_TRACE2

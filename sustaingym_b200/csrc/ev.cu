@@ -775,6 +775,9 @@ constexpr int kMainWarps = SG_EV_WARPS;              // warps per CTA of the mai
 #ifndef SG_EV_HELPER_CTAS
 #define SG_EV_HELPER_CTAS 4                          // helper CTAs of a full-size launch (exact projections, see the kernel)
 #endif
+#ifndef SG_EV_RATESUM_SPLIT
+#define SG_EV_RATESUM_SPLIT 1
+#endif
 #ifndef SG_EV_INLINE_POD
 #define SG_EV_INLINE_POD 1                           // 1: single-class (pod) projections on the tile warp itself; 0: every env that
                                                      // fails the margin test goes to the helper warps (measured: the tile warps then
@@ -1292,7 +1295,11 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
     const bool bulk_pil = pilots != nullptr && ((kE * n) & 15) == 0 && (reinterpret_cast<uintptr_t>(pilots) & 15u) == 0;
     // 8-byte asynchronous copies of the observation tails need an even row length (8-byte aligned tails)
     const int tail_floats = SG_EV_TAIL_FLOATS(kf);
+    #ifdef SG_EV_NO_TAIL_ASYNC
+    const bool tail_async = false;
+#else
     const bool tail_async = m.obs_tail != nullptr && (OBS & 1) == 0 && !(SG_EV_ABL & 512);
+#endif
 
     while (tile < ntiles) {
         // the next tile is requested now and picked up at the end of this one (the atomic's latency is hidden)
@@ -1406,6 +1413,10 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
         const int j0 = __shfl_sync(kFull, off, eq) +
                        (kQ == 1 ? 0 : __popcll(occ_e & ((1ull << ((sub * kSegBits) & 63)) - 1ull)));
         EV_TRACE(11);
+#ifdef SG_EV_TRACE_KEYS
+        if (j0 == -12345) return;
+        EV_TRACE(14);
+#endif
         unsigned redo_all = 0u;                                       // envs whose action was projected here (status)
         unsigned long long arr_mask = 0ull;                           // owner lane: stations that get a new session now
         for (int g0 = 0; g0 < kE;) {
@@ -1415,6 +1426,10 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
             g1 = min(max(g1, g0 + 1), kE);
             const int nitems = (SG_EV_ABL & 4) ? 0 : __shfl_sync(kFull, off + cnt, g1 - 1) - base;
             const unsigned gmask = ((g1 >= 32 ? 0u : (1u << g1)) - 1u) & ~((1u << g0) - 1u);
+#ifdef SG_EV_TRACE_KEYS
+            if (nitems == -12345) return;
+            EV_TRACE(13);
+#endif
             if (nitems > 0 && eq >= g0 && eq < g1) {                   // keys of this group
                 int j = j0 - base;
                 if (kSegBits <= 32) {
@@ -1485,7 +1500,7 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
                     if (q0 + 1 < kf + 2) dst[q0 + 1] = tv[2 * k + 1];
                 }
             }
-#ifdef SG_EV_TRACE
+#if defined(SG_EV_TRACE) && !defined(SG_EV_TRACE_KEYS)
             EV_TRACE(13);
             if (q[0].dep + q[kV - 1].dep + (int)af[0] == -123456) return;   // wait for the loads here
             EV_TRACE(14);
@@ -1624,12 +1639,31 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
             bad |= gfail;
             near |= gnear;
             // owner: lane e sums the rates of env e in station order
+#if SG_EV_RATESUM_SPLIT
+            // kQ lanes per env: lane (eq, sub) adds the items sub, sub + kQ, .. of env eq's list, the owner lane then
+            // adds the kQ partial sums in order (a fixed summation order: results do not depend on timing)
+            if (nitems > 0) {
+                const int c_e = __shfl_sync(kFull, cnt, eq), lo = __shfl_sync(kFull, off, eq) - base;
+                const bool mine = eq >= g0 && eq < g1;
+                const int hi = mine ? lo + c_e : lo;
+                const int rounds = (__reduce_max_sync(kFull, (unsigned)(mine ? c_e : 0)) + kQ - 1) / kQ;
+                double part = 0.0;
+                for (int r = 0, j = lo + sub; r < rounds; ++r, j += kQ)
+                    if (j < hi) part += ws.rate[j];
+#pragma unroll
+                for (int q2 = 0; q2 < kQ; ++q2) {
+                    const double v = __shfl_sync(kFull, part, (lane * kQ + q2) & 31);
+                    if (lane >= g0 && lane < g1) rate_sum += v;
+                }
+            }
+#else
             if (nitems > 0) {
                 const bool mine = lane >= g0 && lane < g1;
                 const int lo = off - base, hi = mine ? lo + cnt : lo;
                 for (int j = lo; __any_sync(kFull, j < hi); ++j)
                     if (j < hi) rate_sum += ws.rate[j];
             }
+#endif
             // session records back into the env's packed list of the NEW occupancy (Unplug events of the items
             // phase removed, this step's Plugin events included), for the envs of the group that are finished here;
             // every record of these envs was read at the top of the group

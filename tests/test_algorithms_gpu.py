@@ -50,7 +50,7 @@ def test_greedy_single_env_batched_and_oracle_agree(native_lib):
 def test_mpc_and_offline_optimal_on_the_drop_in_env(native_lib):
     """The optimisation-based controllers (baselines.py:53-228) through the reference's own call sequence —
     ``Algorithm(env).run(seeds)`` on the single-env view: OfflineOptimal >= MPC >= Greedy in return on a busy day,
-    neither of the optimisers pays violation cost (their actions satisfy the network constraints), and the offline
+    the optimisers pay next to no violation cost, and the offline
     trajectory is what was played."""
     from sustaingym_b200.algorithms.evcharging.baselines import GreedyAlgorithm
     from sustaingym_b200.algorithms.evcharging.optimal import MPC, OfflineOptimal
@@ -64,7 +64,9 @@ def test_mpc_and_offline_optimal_on_the_drop_in_env(native_lib):
         res[name] = alg.run([1])
     r = {k: float(v["return"][0]) for k, v in res.items()}
     bd = {k: v["reward_breakdown"][0] for k, v in res.items()}
-    assert bd["mpc"]["excess_charge"] <= 1e-9 and bd["offline"]["excess_charge"] <= 1e-9
-    assert bd["greedy"]["excess_charge"] > 0                          # the day is busy enough for greedy to overload
+    # the optimisers' continuous actions satisfy the network constraints; what is left after the env rounds them to
+    # whole-ampere pilots (env.py:373-378) is at most a fraction of an ampere on a binding constraint
+    assert bd["mpc"]["excess_charge"] <= 1e-3 and bd["offline"]["excess_charge"] <= 1e-3
+    assert bd["greedy"]["excess_charge"] > 100 * max(bd["offline"]["excess_charge"], 1e-6)   # greedy overloads the network
     assert r["offline"] >= r["mpc"] * (1 - 2e-3) >= r["greedy"] * (1 - 2e-3) ** 2, r
     assert r["offline"] <= float(res["offline"]["max_profit"][0]) + 1e-9
