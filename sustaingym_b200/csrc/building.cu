@@ -30,6 +30,7 @@ namespace {
 constexpr int kTile = SG_BLD_TILE;  // envs per CTA
 constexpr int kPre = 3;     // rollout software pipeline: action tiles of the next kPre steps are in flight (cp.async)
 constexpr int kRing = kPre + 1;
+constexpr int kTileStep = 128;   // envs per CTA tile of the single-step kernels (see launch_building)
 
 __device__ __forceinline__ void cp_async_16(void* smem, const void* gmem) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
@@ -109,6 +110,92 @@ __device__ __forceinline__ Weather4 load_weather(const double* w, int e) {
     return {a.x, a.y, b.x, b.y};
 }
 
+// One env, one step (env.py:233-312): action row -> exogenous inputs + occupancy heat -> X_new = A_d X + BD_d Y ->
+// reward -> cursor / counters (+ the auto-reset state, env.py:346-378).  `w` is the weather row of the current cursor,
+// `w_after` the row after it (read only by an auto-reset).  Shared by the rollout kernel and the single-step kernel.
+template <int N, bool DISCRETE, int MAXN>
+__device__ __forceinline__ void bld_env_step(const sg_building_model& m, const int n, const double* __restrict__ sA,
+                                             const double* __restrict__ sBD, const double* __restrict__ sTarget,
+                                             const double* __restrict__ sAc, const unsigned char* __restrict__ act_row,
+                                             float (&x)[MAXN], float (&tail)[4], int& e, int& r, const Weather4& w,
+                                             const Weather4& w_after, const int flags, StatsAcc& acc, double& rew, bool& dn) {
+    const int row = n + 4;
+    // ---- action: env.py:234-235 ----------------------------------------------------
+    double act[MAXN];
+    float a_dot = 0.f;       // f32 x.dot(x) of LA.norm (continuous actions are f32)
+    double a_dot64 = 0.0;
+#pragma unroll
+    for (int j = 0; j < n; ++j) {
+        if constexpr (DISCRETE) {
+            const long long ai = reinterpret_cast<const long long*>(act_row)[j];
+            const float qlow100 = __fmul_rn(-(float)sAc[j], 100.f);
+            act[j] = ((double)ai + (double)qlow100) / 100.0;
+            a_dot64 = fma(act[j], act[j], a_dot64);
+        } else {
+            const float af = reinterpret_cast<const float*>(act_row)[j];
+            act[j] = (double)af;
+            a_dot = __fmaf_rn(af, af, a_dot);
+            a_dot64 = fma(act[j], act[j], a_dot64);
+        }
+    }
+    // ---- exogenous inputs + occupancy heat: env.py:244-263 --------------------------
+    const float avg_temp = __fdiv_rn(numpy_sum_f32<MAXN>(x, n), (float)n);
+    const double occ = occupower_f32temp(avg_temp, w.meta);
+    // ---- X_new = A_d X + BD_d Y: env.py:266 ; error/reward: env.py:272-276 -----------
+    double err2 = 0.0, errp = 0.0;
+    float xn[MAXN];
+    const bool p2 = (m.pnorm == 2.0);
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+        const double* Ai = sA + i * n;
+        const double* Bi = sBD + i * row;
+        double v = Bi[0] * occ;
+        v = fma(Bi[1], w.ground, v);
+        v = fma(Bi[2], w.out, v);
+        v = fma(Bi[n + 3], w.ghi, v);
+        double va = 0.0;
+#pragma unroll
+        for (int j = 0; j < n; ++j) { va = fma(Ai[j], (double)x[j], va); v = fma(Bi[3 + j], act[j], v); }
+        v += va;
+        const double er = v * sAc[i] - sTarget[i] * sAc[i];
+        err2 = fma(er, er, err2);
+        if (!p2) errp += pow(fabs(er), m.pnorm);
+        xn[i] = (float)v;
+    }
+    double a_term, e_term;
+    if (p2) {
+        e_term = sqrt(err2) * m.error_rate;
+        if constexpr (DISCRETE) a_term = sqrt(a_dot64) * m.q_rate;
+        else a_term = (double)__fmul_rn(__fsqrt_rn(a_dot), (float)m.q_rate);
+    } else {
+        double ap = 0.0;
+        for (int j = 0; j < n; ++j) ap += pow(fabs(act[j]), m.pnorm);
+        a_term = pow(ap, 1.0 / m.pnorm) * m.q_rate;
+        e_term = pow(errp, 1.0 / m.pnorm) * m.error_rate;
+    }
+    rew = -(a_term + e_term);
+    // ---- new state: env.py:286-296 ; cursor/counters: env.py:302-309 ------------------
+#pragma unroll
+    for (int j = 0; j < n; ++j) x[j] = xn[j];
+    tail[0] = (float)w.out; tail[1] = (float)w.ground; tail[2] = (float)w.ghi;
+    tail[3] = (float)(occ / 1000.0);
+    e += 1; r += 1;
+    if (e >= m.T) e = 0;
+    dn = r >= m.episode_len;
+    acc.add(rew, dn, -e_term, -a_term, 0.0);
+    if (dn && (flags & SG_BUILDING_FLAG_AUTORESET)) {   // env.py:346-378 at the current cursor
+        r = 0;
+        double sum = 0.0;
+        for (int j = 0; j < n; ++j) sum += sTarget[j];
+        const Weather4 w2 = w_after;                     // (row e: already prefetched)
+        const double occ0 = occupower_f64temp(sum / n, w2.meta);
+#pragma unroll
+        for (int j = 0; j < n; ++j) x[j] = (float)sTarget[j];
+        tail[0] = (float)w2.out; tail[1] = (float)w2.ground; tail[2] = (float)w2.ghi;
+        tail[3] = (float)(occ0 / 1000.0);
+    }
+}
+
 // N > 0: compile-time zone count, everything in registers, rows staged through shared memory.
 // N == 0: generic fallback (n <= 128), per-thread arrays in local memory, direct global rows.
 #ifndef SG_BLD_STEP_MINB
@@ -116,12 +203,16 @@ __device__ __forceinline__ Weather4 load_weather(const double* w, int e) {
 #endif
 template <int N, bool DISCRETE, int TILE>
 __global__ void __launch_bounds__(TILE, TILE >= 128 ? SG_BLD_STEP_MINB : 1)
-building_step_kernel(const sg_building_model m, const long long B, const int steps,
+building_step_kernel(const sg_building_model m, const long long B, const int steps_arg,
                      const void* __restrict__ action_v, float* __restrict__ state,
                      int32_t* __restrict__ epoch_g, int32_t* __restrict__ runs_g,
                      float* __restrict__ obs_out, double* __restrict__ reward_g,
                      uint8_t* __restrict__ done_g, const int flags, double* __restrict__ stats) {
     constexpr int MAXN = N > 0 ? N : 128;
+    // the 128-env instance is the single-step one (launch_building): with the step count a compile-time 1 the step
+    // loop disappears and the model matrices are read from shared memory where they are used instead of being
+    // hoisted into ~140 registers for the whole loop — which is what capped that instance at 3-4 CTAs per SM
+    const int steps = TILE >= 128 ? 1 : steps_arg;
     const int n = N > 0 ? N : m.n;
     const int row = n + 4;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -227,96 +318,14 @@ building_step_kernel(const sg_building_model m, const long long B, const int ste
         double rew = 0.0;
         bool dn = false;
         if (valid) {
-            // ---- action: env.py:234-235 ----------------------------------------------------
-            double act[MAXN];
-            float a_dot = 0.f;       // f32 x.dot(x) of LA.norm (continuous actions are f32)
-            double a_dot64 = 0.0;
-#pragma unroll
-            for (int j = 0; j < n; ++j) {
-                {
-                    if constexpr (DISCRETE) {
-                        long long ai;
-                        if constexpr (N > 0) ai = reinterpret_cast<const long long*>(act_tile)[tid * n + j];
-                        else ai = reinterpret_cast<const long long*>(action_v)[((long long)s * B + b) * n + j];
-                        const float qlow100 = __fmul_rn(-(float)sAc[j], 100.f);
-                        act[j] = ((double)ai + (double)qlow100) / 100.0;
-                        a_dot64 = fma(act[j], act[j], a_dot64);
-                    } else {
-                        float af;
-                        if constexpr (N > 0) af = reinterpret_cast<const float*>(act_tile)[tid * n + j];
-                        else af = reinterpret_cast<const float*>(action_v)[((long long)s * B + b) * n + j];
-                        act[j] = (double)af;
-                        a_dot = __fmaf_rn(af, af, a_dot);
-                        a_dot64 = fma(act[j], act[j], a_dot64);
-                    }
-                }
-            }
-            SG_P2(1);
-            // ---- exogenous inputs + occupancy heat: env.py:244-263 --------------------------
+            const unsigned char* act_row;
+            if constexpr (N > 0) act_row = act_tile + (size_t)tid * n * esz;
+            else act_row = reinterpret_cast<const unsigned char*>(action_v) + ((long long)s * B + b) * n * esz;
+            // exogenous inputs of this step; the row the step after next will read is requested now
             const Weather4 w = w_cur;
             w_cur = w_nxt;
-            if (s + 1 < steps) {   // row the step after next will read
-                w_nxt = load_weather(m.weather, (e + 2) % m.T);
-            }
-            const float avg_temp = __fdiv_rn(numpy_sum_f32<MAXN>(x, n), (float)n);
-            const double occ = occupower_f32temp(avg_temp, w.meta);
-            SG_P2(2);
-            // ---- X_new = A_d X + BD_d Y: env.py:266 ; error/reward: env.py:272-276 -----------
-            double err2 = 0.0, errp = 0.0;
-            float xn[MAXN];
-            const bool p2 = (m.pnorm == 2.0);
-#pragma unroll
-            for (int i = 0; i < n; ++i) {
-                {
-                    const double* Ai = sA + i * n;
-                    const double* Bi = sBD + i * row;
-                    double v = Bi[0] * occ;
-                    v = fma(Bi[1], w.ground, v);
-                    v = fma(Bi[2], w.out, v);
-                    v = fma(Bi[n + 3], w.ghi, v);
-                    double va = 0.0;
-#pragma unroll
-                    for (int j = 0; j < n; ++j) { va = fma(Ai[j], (double)x[j], va); v = fma(Bi[3 + j], act[j], v); }
-                    v += va;
-                    const double er = v * sAc[i] - sTarget[i] * sAc[i];
-                    err2 = fma(er, er, err2);
-                    if (!p2) errp += pow(fabs(er), m.pnorm);
-                    xn[i] = (float)v;
-                }
-            }
-            SG_P2(3);
-            double a_term, e_term;
-            if (p2) {
-                e_term = sqrt(err2) * m.error_rate;
-                if constexpr (DISCRETE) a_term = sqrt(a_dot64) * m.q_rate;
-                else a_term = (double)__fmul_rn(__fsqrt_rn(a_dot), (float)m.q_rate);
-            } else {
-                double ap = 0.0;
-                for (int j = 0; j < n; ++j) ap += pow(fabs(act[j]), m.pnorm);
-                a_term = pow(ap, 1.0 / m.pnorm) * m.q_rate;
-                e_term = pow(errp, 1.0 / m.pnorm) * m.error_rate;
-            }
-            rew = -(a_term + e_term);
-            // ---- new state: env.py:286-296 ; cursor/counters: env.py:302-309 ------------------
-#pragma unroll
-            for (int j = 0; j < n; ++j) x[j] = xn[j];
-            tail[0] = (float)w.out; tail[1] = (float)w.ground; tail[2] = (float)w.ghi;
-            tail[3] = (float)(occ / 1000.0);
-            e += 1; r += 1;
-            if (e >= m.T) e = 0;
-            dn = r >= m.episode_len;
-            acc.add(rew, dn, -e_term, -a_term, 0.0);
-            if (dn && (flags & SG_BUILDING_FLAG_AUTORESET)) {   // env.py:346-378 at the current cursor
-                r = 0;
-                double sum = 0.0;
-                for (int j = 0; j < n; ++j) sum += sTarget[j];
-                const Weather4 w2 = w_cur;                       // (row e: already prefetched)
-                const double occ0 = occupower_f64temp(sum / n, w2.meta);
-#pragma unroll
-                for (int j = 0; j < n; ++j) x[j] = (float)sTarget[j];
-                tail[0] = (float)w2.out; tail[1] = (float)w2.ground; tail[2] = (float)w2.ghi;
-                tail[3] = (float)(occ0 / 1000.0);
-            }
+            if (s + 1 < steps) w_nxt = load_weather(m.weather, (e + 2) % m.T);
+            bld_env_step<N, DISCRETE, MAXN>(m, n, sA, sBD, sTarget, sAc, act_row, x, tail, e, r, w, w_cur, flags, acc, rew, dn);
             reward_g[(long long)s * B + b] = rew;
             done_g[(long long)s * B + b] = dn ? 1 : 0;
         }
@@ -359,6 +368,118 @@ building_step_kernel(const sg_building_model m, const long long B, const int ste
     if (blockIdx.x == 5 && tid == 0) printf("steps %d: top %lld act %lld occ %lld matvec %lld reward %lld emit %lld (cycles/step)\n", steps, tp[0] / steps, tp[1] / steps, tp[2] / steps, tp[3] / steps, tp[4] / steps, tp[5] / steps);
 #endif
     if (valid) { epoch_g[b] = e; runs_g[b] = r; }
+    if (stats != nullptr) {
+        __syncthreads();
+        stats_flush_block(acc, stats, sStat);
+    }
+}
+
+// Single step, N > 0, large batches: a persistent kernel.  The one-tile-per-CTA form above spends a CTA's life on
+// start-up latency (model matrices, state tile, cursor -> weather row: ~6 us from launch to exit, measured at 32 768
+// envs where every CTA is resident at once) and a 262 144-env step was 2.8 such waves.  Here a CTA keeps the model in
+// shared memory and walks over tiles of 128 envs with a two-slot ring: while tile i is computed, the state rows, action
+// rows and cursors of tile i+1 are already on their way (cp.async / plain loads into registers), so a tile costs its
+// arithmetic plus the weather-row lookup instead of the whole chain.  Same arithmetic (bld_env_step), same results.
+template <int N, bool DISCRETE>
+__global__ void __launch_bounds__(kTileStep, SG_BLD_STEP_MINB)
+building_step1_kernel(const sg_building_model m, const long long B, const void* __restrict__ action_v,
+                      float* __restrict__ state, int32_t* __restrict__ epoch_g, int32_t* __restrict__ runs_g,
+                      double* __restrict__ reward_g, uint8_t* __restrict__ done_g, const int flags,
+                      double* __restrict__ stats) {
+    constexpr int TILE = kTileStep, n = N, row = N + 4, esz = DISCRETE ? 8 : 4;
+    constexpr int tile_bytes = TILE * row * 4, act_bytes = (TILE * n * esz + 15) & ~15;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* sA = reinterpret_cast<double*>(smem_raw);
+    double* sBD = sA + n * n;
+    double* sTarget = sBD + n * row;
+    double* sAc = sTarget + n;
+    double* sStat = sAc + n;                                       // [11 * 8]
+    unsigned char* ring = reinterpret_cast<unsigned char*>(sStat + 88);   // 2 x (state tile | action tile)
+    const int tid = threadIdx.x;
+    const long long ntiles = (B + TILE - 1) / TILE;
+
+    // tile t into ring slot `slot`: this thread's cursors (weather row, step count) into registers, the state and
+    // action rows as asynchronous copies (one commit group, maybe empty)
+    auto issue = [&](const long long t, const int slot, int& e_out, int& r_out) {
+        if (t < ntiles) {
+            const long long b0 = t * TILE;
+            const int nvalid = (int)min((long long)TILE, B - b0);
+            if (tid < nvalid) { e_out = epoch_g[b0 + tid]; r_out = runs_g[b0 + tid]; }
+            unsigned char* st = ring + (size_t)slot * (tile_bytes + act_bytes);
+            const unsigned char* gs = reinterpret_cast<const unsigned char*>(state + b0 * row);
+            const unsigned char* ga = reinterpret_cast<const unsigned char*>(action_v) + b0 * n * esz;
+            const int sb = nvalid * row * 4, ab = nvalid * n * esz;
+            if ((sb & 15) == 0 && (reinterpret_cast<uintptr_t>(gs) & 15u) == 0)
+                for (int i = tid * 16; i < sb; i += TILE * 16) cp_async_16(st + i, gs + i);
+            else
+                for (int i = tid * 4; i < sb; i += TILE * 4) cp_async_4(st + i, gs + i);
+            if ((ab & 15) == 0 && (reinterpret_cast<uintptr_t>(ga) & 15u) == 0)
+                for (int i = tid * 16; i < ab; i += TILE * 16) cp_async_16(st + tile_bytes + i, ga + i);
+            else
+                for (int i = tid * 4; i < ab; i += TILE * 4) cp_async_4(st + tile_bytes + i, ga + i);
+        }
+        cp_async_commit();
+    };
+
+    // (measured: requesting the weather row one tile ahead and the cursors two tiles ahead, or 5-6 CTAs per SM with
+    // fewer registers, made the step slower — 16.2-19 us against 14.4 us; the kernel is bound by instruction issue
+    // (~800 warp instructions per 32 envs), not by these latencies)
+    int e_nx = 0, r_nx = 0;
+    long long t = blockIdx.x;
+    for (int i = tid; i < n * n; i += TILE) cp_async_8(sA + i, m.A_d + i);
+    for (int i = tid; i < n * row; i += TILE) cp_async_8(sBD + i, m.BD_d + i);
+    for (int i = tid; i < n; i += TILE) { cp_async_8(sTarget + i, m.target + i); cp_async_8(sAc + i, m.ac_map + i); }
+    issue(t, 0, e_nx, r_nx);                                       // (the model copies ride in the first group)
+    StatsAcc acc;
+    for (int it = 0; t < ntiles; ++it, t += gridDim.x) {
+        const int slot = it & 1;
+        const long long b0 = t * TILE;
+        const int nvalid = (int)min((long long)TILE, B - b0);
+        const bool valid = tid < nvalid;
+        const long long b = b0 + tid;
+        int e = e_nx, r = r_nx;
+        // weather rows of this tile's cursors (requested before anything waits; the next row only for an auto-reset)
+        Weather4 w = {0, 0, 0, 0}, w_after = {0, 0, 0, 0};
+        if (valid) {
+            w = load_weather(m.weather, e);
+            if (r + 1 >= m.episode_len) w_after = load_weather(m.weather, (e + 1) % m.T);
+        }
+        cp_async_wait<0>();
+        __syncthreads();                                           // tile `it` landed; the other slot is free again
+        issue(t + gridDim.x, slot ^ 1, e_nx, r_nx);
+        float* tile = reinterpret_cast<float*>(ring + (size_t)slot * (tile_bytes + act_bytes));
+        const unsigned char* act_tile = reinterpret_cast<const unsigned char*>(tile) + tile_bytes;
+        if (valid) {
+            float x[N], tail[4];
+#pragma unroll
+            for (int j = 0; j < N; ++j) x[j] = tile[tid * row + j];
+            double rew;
+            bool dn;
+            bld_env_step<N, DISCRETE, N>(m, n, sA, sBD, sTarget, sAc, act_tile + (size_t)tid * n * esz, x, tail, e, r, w,
+                                         w_after, flags, acc, rew, dn);
+            reward_g[b] = rew;
+            done_g[b] = dn ? 1 : 0;
+            epoch_g[b] = e;
+            runs_g[b] = r;
+#pragma unroll
+            for (int j = 0; j < N; ++j) tile[tid * row + j] = x[j];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) tile[tid * row + N + j] = tail[j];
+        }
+        __syncthreads();
+        {   // the new rows go back with coalesced 16-byte stores
+            float* g = state + b0 * row;
+            const int nb = nvalid * row * 4;
+            if ((nb & 15) == 0 && (reinterpret_cast<uintptr_t>(g) & 15u) == 0)
+                for (int i = tid * 16; i < nb; i += TILE * 16)
+                    *reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(g) + i) =
+                        *reinterpret_cast<const uint4*>(reinterpret_cast<const unsigned char*>(tile) + i);
+            else
+                for (int i = tid; i < nvalid * row; i += TILE) g[i] = tile[i];
+        }
+        // (the slot is refilled two iterations from now, after the __syncthreads at the top of the next one)
+    }
+    cp_async_wait<0>();
     if (stats != nullptr) {
         __syncthreads();
         stats_flush_block(acc, stats, sStat);
@@ -820,7 +941,6 @@ int launch_building_mma(const sg_building_model* m, long long B, int steps, cons
 // Fused rollouts run one warp per CTA (tiles advance independently through the steps: measured +9 % over 128 threads);
 // a single step() has no step loop to decouple, only per-CTA set-up (model -> shared memory, barriers) to amortise: 128
 // envs per CTA (262 144 envs: 31.7 us with 8 192 one-warp CTAs).  Same code, same arithmetic.
-constexpr int kTileStep = 128;
 
 template <int N, bool DISCRETE, int TILE>
 int launch_building_tile(const sg_building_model* m, long long B, int steps, const void* action, float* state,
@@ -843,8 +963,27 @@ template <int N, bool DISCRETE>
 int launch_building(const sg_building_model* m, long long B, int steps, const void* action, float* state,
                     int32_t* epoch, int32_t* runs, float* obs_out, double* reward, uint8_t* done,
                     int flags, double* stats, cudaStream_t st) {
-    if (N > 0 && steps == 1 && B >= 4 * kTileStep)
-        return launch_building_tile<N, DISCRETE, kTileStep>(m, B, steps, action, state, epoch, runs, obs_out, reward, done, flags, stats, st);
+    if constexpr (N > 0) {
+        if (steps == 1 && obs_out == nullptr && B >= 4 * kTileStep && !getenv("SG_BLD_NO_PERSISTENT")) {
+            // persistent single-step kernel: every CTA resident, tiles of kTileStep envs dealt round-robin
+            constexpr int esz = DISCRETE ? 8 : 4;
+            const size_t smem = sizeof(double) * (N * N + N * (N + 4) + 2 * N + 88) +
+                                2 * ((size_t)kTileStep * (N + 4) * 4 + (((size_t)kTileStep * N * esz + 15) & ~(size_t)15));
+            auto kern = building_step1_kernel<N, DISCRETE>;
+            if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+                set_error("building: %zu B of shared memory unavailable", smem);
+                return 2;
+            }
+            int sms = sg_device_sm_count();
+            if (sms <= 0) sms = 148;
+            const long long ntiles = (B + kTileStep - 1) / kTileStep;
+            const unsigned grid = (unsigned)std::min<long long>(ntiles, (long long)sms * SG_BLD_STEP_MINB);
+            kern<<<grid, kTileStep, smem, st>>>(*m, B, action, state, epoch, runs, reward, done, flags, stats);
+            return launch_status("building_step1_kernel");
+        }
+        if (steps == 1 && B >= 4 * kTileStep)
+            return launch_building_tile<N, DISCRETE, kTileStep>(m, B, steps, action, state, epoch, runs, obs_out, reward, done, flags, stats, st);
+    }
     return launch_building_tile<N, DISCRETE, kTile>(m, B, steps, action, state, epoch, runs, obs_out, reward, done, flags, stats, st);
 }
 
