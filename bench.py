@@ -11,7 +11,7 @@ pilot rounding -> acnsim period -> observation -> reward).  Reported on ONE JSON
   e2e        the same through the public host API (pinned host actions in, host obs/reward/done out) with the
              H2D copy of the actions and the D2H copy of the results of every step inside the timed region
   roofline   algorithmic bytes per launch (1709 B/env-step) / the step time OF THE SAME TIMED
-             WINDOW as ``value`` (main kernel + the normally empty rare kernel + graph launch), against
+             WINDOW as ``value`` (ONE kernel per step, launched as a CUDA graph), against
              MEASURED_PEAKS.json hbm_gbs
   cpu_baseline  the NumPy oracle port timed on this box's host cores on a bounded sample
   secondary  BASELINE configs 3-5 (Market 65 536; Building n=5 262 144 envs split over the ranks, single step
@@ -644,15 +644,15 @@ def main():
                        "mean_occupied_stations": 0.5 * (occ0 + occ1),
                        "n_projected": st[6], "n_projected_per_step": st[6] / max(args.steps, 1),
                        "l2_policy": f"{N_SETS} env sets stepped round-robin: ~{N_SETS * 85} MB touched between reuses (> 126 MB L2)",
-                       "launch": "one CUDA graph per step: ev_step_main_kernel + ev_step_rare_kernel (work list of envs needing the "
-                                 "interior-point solver, normally empty)",
+                       "launch": "one CUDA graph per step holding ONE kernel, ev_step_main_kernel<1>: tile CTAs + 4 helper CTAs (the helpers "
+                                 "run the interior-point projections the tile warps hand over through a work list)",
                        "collective": f"all_reduce_stats (one all-gather of 16 doubles per rank, reduced locally: SUM / MIN / MAX) every {STATS_EVERY} steps on a side stream, "
                                      f"{n_collectives} inside the timed region"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                          "frac": achieved / hbm, "traffic": traffic, "kernel": "ev_step_main_kernel<1>",
                          "traffic_source": traffic_src,
                          "kernel_ms": ms_step,
-                         "kernel_ms_note": "step time of the timed window itself (main + rare kernel + graph launch), the same window as `value`",
+                         "kernel_ms_note": "step time of the timed window itself (kernel + graph launch), the same window as `value`",
                          "kernel_ms_event_pairs_whole_episode": kern_events_ms,
                          "algorithmic_bytes_per_launch": ALGO_BYTES_PER_ENV_STEP * B,
                          "peak_source": peak_src},

@@ -12,4 +12,7 @@ PROF_STEPS=152 ncu --set full --clock-control none --import-source on -k regex:e
     python profiles/prof_ev.py > gpurun_out/r2_prof_ev_midday.log 2>&1
 PROF_STEPS=14 ncu --set full --clock-control none --import-source on -k regex:ev_step_main -s 12 -c 1 -f -o gpurun_out/r2_prof_ev_night \
     python profiles/prof_ev.py > gpurun_out/r2_prof_ev_night.log 2>&1
-tail -4 gpurun_out/r2_tests.log
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/r2_smoke.log
+ncu --set full --clock-control none --import-source on -k regex:building_step1 -s 30 -c 1 -f -o gpurun_out/r2_prof_building_step1 \
+    python profiles/r2/building_step_probe.py > gpurun_out/r2_prof_building_step1.log 2>&1
+tail -4 gpurun_out/r2_tests.log; tail -2 gpurun_out/r2_smoke.log
