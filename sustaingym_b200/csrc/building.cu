@@ -202,7 +202,9 @@ __device__ __forceinline__ void bld_env_step(const sg_building_model& m, const i
 #define SG_BLD_STEP_MINB 4   // resident 128-thread CTAs per SM the single-step instance is compiled for (see kTileStep)
 #endif
 template <int N, bool DISCRETE, int TILE>
-__global__ void __launch_bounds__(TILE, TILE >= 128 ? SG_BLD_STEP_MINB : 1)
+// (one-warp CTAs of the rollout: 12 per SM = 3 warps per scheduler needs <= 170 registers; left to itself ptxas takes
+// 190, i.e. 2 warps per scheduler and 1.5x the waves of CTAs at 262 144 envs — measured 0.38 against 0.49 of HBM)
+__global__ void __launch_bounds__(TILE, TILE >= 128 ? SG_BLD_STEP_MINB : 12)
 building_step_kernel(const sg_building_model m, const long long B, const int steps_arg,
                      const void* __restrict__ action_v, float* __restrict__ state,
                      int32_t* __restrict__ epoch_g, int32_t* __restrict__ runs_g,
