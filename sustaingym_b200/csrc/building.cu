@@ -287,7 +287,7 @@ building_step_kernel(const sg_building_model m, const long long B, const int ste
     if (valid) {
         w_cur = load_weather(m.weather, e);
         // (a single step needs the next row only for an auto-reset at the end of the episode)
-        if (steps > 1 || r + 1 >= m.episode_len) w_nxt = load_weather(m.weather, (e + 1) % m.T);
+        if (TILE < 128 || r + 1 >= m.episode_len) w_nxt = load_weather(m.weather, (e + 1) % m.T);
     }
     // model matrices + state tile have landed (the action tiles of the ring may still be in flight)
     if constexpr (N > 0) cp_async_wait<kPre>(); else cp_async_wait<0>();
@@ -326,7 +326,9 @@ building_step_kernel(const sg_building_model m, const long long B, const int ste
             // exogenous inputs of this step; the row the step after next will read is requested now
             const Weather4 w = w_cur;
             w_cur = w_nxt;
-            if (s + 1 < steps) w_nxt = load_weather(m.weather, (e + 2) % m.T);
+            // (unconditional in the rollout instance: a test on the step index here costs the rollout 20 % — the load
+            // is no longer scheduled ahead of the step's arithmetic; the row past the last step is read and dropped)
+            if (TILE < 128) w_nxt = load_weather(m.weather, (e + 2) % m.T);
             bld_env_step<N, DISCRETE, MAXN>(m, n, sA, sBD, sTarget, sAc, act_row, x, tail, e, r, w, w_cur, flags, acc, rew, dn);
             reward_g[(long long)s * B + b] = rew;
             done_g[(long long)s * B + b] = dn ? 1 : 0;
