@@ -52,7 +52,7 @@ OBS_DIM = 2 * N_STATIONS + MOER_STEPS + 2
 ALGO_BYTES_PER_ENV_STEP = 1709          # SURVEY.md 8(d), EV n=54 k=36
 N_SETS = 4
 PHASES = (36, 108, 180, 252)            # day phase (t) each env set / CPU quarter is pre-rolled to
-STATS_EVERY = 16                        # steps between two all-reduces of the statistics vector
+STATS_EVERY = int(os.environ.get("SG_BENCH_STATS_EVERY", 16))   # steps between two exchanges of the statistics vector
 POOL_DAYS = 256
 MEAN_SESSIONS = 25.0
 METRIC = "env_steps_per_sec"

@@ -38,7 +38,10 @@ def all_reduce_stats(stats: torch.Tensor, group=None, out: torch.Tensor | None =
         res.copy_(stats)
         return res
     gathered = out[n:(world + 1) * n].view(world, n)
-    dist.all_gather(list(gathered.unbind(0)), stats.contiguous(), group=group)
+    try:        # one contiguous output: no temporaries, no per-rank copy kernels (NCCL; gloo of recent PyTorch too)
+        dist.all_gather_into_tensor(out[n:(world + 1) * n], stats.contiguous(), group=group)
+    except (RuntimeError, NotImplementedError, AttributeError):
+        dist.all_gather(list(gathered.unbind(0)), stats.contiguous(), group=group)
     torch.sum(gathered, dim=0, out=res)
     res[STATS_MIN:STATS_MIN + 1].copy_(gathered[:, STATS_MIN].min().reshape(1))
     res[STATS_MAX:STATS_MAX + 1].copy_(gathered[:, STATS_MAX].max().reshape(1))
