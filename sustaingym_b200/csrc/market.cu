@@ -38,25 +38,39 @@ market_step_kernel(const sg_market_model m, const long long B, const float* __re
                    uint8_t* __restrict__ done, double* __restrict__ info /* [B,3] price, dispatch, energy or NULL */,
                    double* __restrict__ stats) {
     __shared__ MarketShared sh;
+    // A step is one wave of CTAs: its duration is the chain of dependent memory round trips, so every load is requested
+    // as early as its address is known — the env's clock first (the load / MOER rows depend on it), then the fleet
+    // tables, the env's state and bids, then the load / MOER values — and the first barrier comes after all of them.
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = m.k, W = kT + k, G = m.n_gen, obs_dim = 6 + 4 * k;
+    int day = 0, t = kT;
+    if (b < B) { day = day_t[b * 2]; t = day_t[b * 2 + 1]; }
     for (int i = threadIdx.x; i < kMaxGen; i += blockDim.x) {
         sh.cost[i] = i < m.n_gen ? m.gen_cost[i] : 1e300;
         sh.cap[i] = i < m.n_gen ? m.gen_cap[i] : 0.0;
     }
+    double e = 0.0, racc = 0.0, load = 0.0, moer = 0.0;
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const bool stepping = b < B && t < kT;
+    if (stepping) {
+        e = state[b * 4 + 0]; racc = state[b * 4 + 3];
+        for (int i = 0; i < 2 * k; ++i) a[i] = fmaxf(action[b * 2 * k + i], 0.f);
+        load = m.load[(long long)day * W + t]; moer = m.moer[(long long)day * W + t];
+    }
     __syncthreads();
-    if (threadIdx.x == 0) { double c = 0; for (int i = 0; i < kMaxGen; ++i) { c += sh.cap[i]; sh.cum[i] = c; } }
+    // cumulative capacities: thread i adds cap[0..i] in index order (the rounding of a sequential running sum, computed
+    // by 64 threads side by side instead of one thread walking the array between two barriers)
+    if (threadIdx.x < kMaxGen) {
+        double c = 0;
+        for (int i = 0; i <= (int)threadIdx.x; ++i) c += sh.cap[i];
+        sh.cum[threadIdx.x] = c;
+    }
     __syncthreads();
-    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     StatsAcc acc;
     if (b < B) {
-        const int k = m.k, W = kT + k, G = m.n_gen, obs_dim = 6 + 4 * k;
-        const int day = day_t[b * 2], t = day_t[b * 2 + 1];
         if (t >= kT) { reward[b] = 0.0; done[b] = 1; }
         else {
-            double e = state[b * 4 + 0], racc = state[b * 4 + 3];
-            float a[8];
-            for (int i = 0; i < 2 * k; ++i) a[i] = fmaxf(action[b * 2 * k + i], 0.f);
             const double a_c = (double)a[0], a_d = (double)a[k];
-            const double load = m.load[(long long)day * W + t], moer = m.moer[(long long)day * W + t];
             const double q_d = fmax(fmin(m.p_max, e * m.eta_d / kTau), 0.0);
             const double q_c = fmax(fmin(m.p_max, (m.e_max - e) / (m.eta_c * kTau)), 0.0);
             double cheap_d = 0.0, cheap_c = 0.0;
