@@ -1,5 +1,5 @@
 """Small invocations of the three big kernels for compute-sanitizer (racecheck / memcheck), SURVEY.md section 5.
-usage: python profiles/r2/sanitize_targets.py ev|building|cogen"""
+usage: python profiles/r2/sanitize_targets.py ev|building|building_step|market|cogen"""
 import os
 import sys
 
@@ -37,6 +37,31 @@ elif which == "building":
     env.step(acts[0])
     torch.cuda.synchronize()
     print("building ok (building_mma_kernel, n =", params["n"], ")")
+elif which == "building_step":
+    # building_step1_kernel<5>: persistent CTAs over a two-slot tile ring — capped to 2 CTAs' worth of tiles per CTA and a
+    # ragged last tile; plus the one-tile-per-CTA rollout kernel (cp.async start-up, action ring)
+    from helpers import building_fixtures, load_building_fixture
+    from sustaingym_b200.envs.building.env import BatchedBuildingEnv
+    g_, params = load_building_fixture([p for p in building_fixtures() if "retail_s5" in p][0])
+    B = 148 * 4 * 128 * 2 + 77                          # every CTA walks over >= 2 tiles, the last tile is partial
+    env = BatchedBuildingEnv(dict(params, episode_len=3), B, auto_reset=True, collect_stats=True)
+    env.reset(epochs=np.arange(B) % 1000)
+    a = torch.rand(B, params["n"], device="cuda") * 2 - 1
+    for t in range(4):
+        env.step(a)
+    small = BatchedBuildingEnv(dict(params, episode_len=3), 200, auto_reset=True)
+    small.reset(epochs=np.arange(200))
+    small.rollout(torch.rand(5, 200, params["n"], device="cuda") * 2 - 1, keep_obs=True)
+    torch.cuda.synchronize()
+    print("building_step ok (building_step1_kernel + building_step_kernel, n =", params["n"], ")", float(env.stats[0]), "steps")
+elif which == "market":
+    from sustaingym_b200.envs.electricitymarket.env import BatchedElectricityMarketEnv
+    env = BatchedElectricityMarketEnv(1000)
+    env.reset(seed=0)
+    for t in range(4):
+        env.step(torch.rand(1000, 2, device="cuda") * 100)
+    torch.cuda.synchronize()
+    print("market ok")
 elif which == "cogen":
     from sustaingym_b200.envs.cogen.env import BatchedCogenEnv
     env = BatchedCogenEnv(256, forecast_horizon=12)
