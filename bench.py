@@ -528,11 +528,15 @@ def main():
         with torch.cuda.stream(side):
             job_stats[0] = all_reduce_stats(shared_stats, out=stats_buf)
         main_stream.wait_stream(side)
-    ctx.barrier()
+    # (NVML is initialised BEFORE the barrier: it takes tens of milliseconds on an 8-GPU box and a different time on every
+    # rank; after the barrier that skew would sit inside the timed region of every rank that has to wait for the slowest
+    # one at the first exchange — at --steps 20 on 8 GPUs it was 18 ms of a 1 ms region)
     sampler = ClockSampler(physical_gpu_index(local_rank))
-    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n_collectives = 0
+    torch.cuda.synchronize(dev)
+    ctx.barrier()
+    sampler.start()
     e0.record()
     for i in range(args.steps):
         graphs[(args.warmup + i) % N_SETS].replay()
