@@ -555,7 +555,7 @@ def main():
     ms_total = ctx.max_over_ranks(e0.elapsed_time(e1))
     ms_step = ms_total / args.steps
     value = world * B * args.steps / (ms_total * 1e-3)
-    launches = 2 * args.steps
+    launches = args.steps                       # one ev_step_main_kernel<1> per step (per rank)
     occ1 = occupancy()
     st = job_stats[0].cpu().numpy()
     achieved = ALGO_BYTES_PER_ENV_STEP * B / (ms_step * 1e-3) / 1e9
