@@ -28,6 +28,7 @@
 //
 // Bound: HBM.  Algorithmic bytes per env-step: SURVEY.md 8d (1709 B at n=54, k=36).
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -1195,12 +1196,19 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
                     const int flags, const int bins, float* __restrict__ obs, double* __restrict__ reward,
                     uint8_t* __restrict__ done, uint8_t* __restrict__ pilots, float* __restrict__ final_obs,
                     uint8_t* __restrict__ status, double* __restrict__ stats, int32_t* __restrict__ work,
-                    const int n_helpers) {
+                    const int n_helpers, const long long t_full, const int tail_envs) {
     __shared__ EvTables sh;
     __shared__ WarpShared wsm[kMainWarps];
     extern __shared__ __align__(128) unsigned char stage_raw[];       // per warp: kE observation rows | kE pilot rows
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long ntiles = (B + kE - 1) / kE;
+    // Tiling (chosen by sg_ev_step): the first t_full tiles hold kE envs, the envs left after them are cut into tiles
+    // of tail_envs <= kE envs.  A tile costs a warp ~10 us of dependent latency plus ~0.25 us per env, so when the
+    // last round of kE-env tiles would occupy only part of the warps, the same envs spread over ALL warps in small
+    // tiles end the launch earlier.
+    const long long tail_first = t_full * kE;                       // first env of the small tiles
+    const long long ntiles = t_full + (B > tail_first ? (B - tail_first + tail_envs - 1) / tail_envs : 0);
+    auto tile_b0 = [&](const long long t) { return t < t_full ? t * kE : tail_first + (t - t_full) * tail_envs; };
+    auto tile_cap = [&](const long long t) { return t < t_full ? kE : tail_envs; };
     const long long wstride = (long long)((int)gridDim.x - n_helpers) * kMainWarps;   // tile warps of the launch
     if (MODE != 0 && (int)blockIdx.x < n_helpers) {
         // ---------------- helper CTAs: the envs the tile warps could not finish (exact projection needed) --------
@@ -1272,7 +1280,7 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
     // the first tile's env headers are requested before the table copy
     EnvHeader* __restrict__ headers = reinterpret_cast<EnvHeader*>(s.header);
     EnvHeader hd = empty_header();
-    if (tile < ntiles && tile * kE + lane < B && lane < kE) hd = ld_header(headers + tile * kE + lane);
+    if (tile < ntiles && tile_b0(tile) + lane < B && lane < tile_cap(tile)) hd = ld_header(headers + tile_b0(tile) + lane);
     bool first_tile = true;
     load_tables(m.tables, sh);
     WarpShared& ws = wsm[warp];
@@ -1309,8 +1317,8 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
 #ifdef SG_EV_TRACE
         if (g_trace != nullptr && lane == 0) { unsigned sm; asm volatile("mov.u32 %0, %%smid;" : "=r"(sm)); g_trace[tile * 16 + 1] = sm; }
 #endif
-        const long long b0 = tile * kE;
-        const int nv = (int)min((long long)kE, B - b0);
+        const long long b0 = tile_b0(tile);
+        const int nv = (int)min((long long)tile_cap(tile), B - b0);
         const long long b = b0 + lane;
         const bool env = lane < nv;                    // owner lanes
         if (!first_tile) {
@@ -1686,8 +1694,8 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
         // action rows into L2 while this tile finishes (checks, arrivals, epilogue, write-out).  The lists are packed, so
         // the first two lines of an env's block hold its first 6-8 sessions — all of them for a typical garage.
         const long long tile_next = sched != nullptr ? wstride + (long long)__shfl_sync(kFull, next_ticket, 0) : tile + wstride;
-        if (tile_next < ntiles && (tile_next + 1) * kE <= B && !(SG_EV_ABL & 1024)) {
-            const long long bn = tile_next * kE;
+        if (tile_next < ntiles && tile_b0(tile_next) + kE <= B && !(SG_EV_ABL & 1024)) {
+            const long long bn = tile_b0(tile_next);
             const unsigned char* hp = reinterpret_cast<const unsigned char*>(headers + bn) + lane * 128;
             if (lane < (kE * 64 + 127) / 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(hp));
             const int eper = lane / (32 / kE), part = lane % (32 / kE);            // 32 / kE lines per env
@@ -1793,13 +1801,19 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
         if (tail_async) asm volatile("cp.async.wait_all;" ::: "memory");  // the tails have landed in the staged rows
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // staged rows -> visible to the bulk-copy engine
         __syncwarp();
-        const bool whole = nv == kE && live_mask == kOwnerMask && ar_mask == 0u;
+        // every env of the tile live and none at the end of its day: the tile's rows go out as ONE bulk copy — also for
+        // a short tile, if its byte range is 16-byte aligned and a multiple of 16 bytes (even env counts)
+        const unsigned nv_mask = nv >= 32 ? 0xffffffffu : ((1u << nv) - 1u);
+        const bool whole = nv > 0 && live_mask == nv_mask && ar_mask == 0u;
+        const bool rows_ok = (reinterpret_cast<uintptr_t>(obs) & 15u) == 0 && (((long long)nv * OBS) & 3) == 0 && ((b0 * OBS) & 3) == 0;
+        const bool pil_ok = pilots != nullptr && (reinterpret_cast<uintptr_t>(pilots) & 15u) == 0 && ((nv * n) & 15) == 0 && ((b0 * n) & 15) == 0;
+        (void)bulk_rows; (void)bulk_pil;
         if (SG_EV_ABL & 256) {                          // (ablation: no observation / pilot rows written)
         } else
-        if (whole && bulk_rows) {
+        if (whole && rows_ok) {
             if (lane == 0)
                 asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(obs + b0 * OBS),
-                             "r"((unsigned)__cvta_generic_to_shared(srows)), "r"(kE * OBS * 4) : "memory");
+                             "r"((unsigned)__cvta_generic_to_shared(srows)), "r"(nv * OBS * 4) : "memory");
         } else {
             for (int r = 0; r < nv; ++r) {
                 if (!((live_mask >> r) & 1u)) continue;
@@ -1816,10 +1830,10 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
             }
         }
         if (pilots != nullptr && !(SG_EV_ABL & 256)) {
-            if (whole && bulk_pil) {
+            if (whole && pil_ok) {
                 if (lane == 0)
                     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(pilots + b0 * n),
-                                 "r"((unsigned)__cvta_generic_to_shared(spil)), "r"(kE * n) : "memory");
+                                 "r"((unsigned)__cvta_generic_to_shared(spil)), "r"(nv * n) : "memory");
             } else {
                 for (int r = 0; r < nv; ++r)
                     if ((live_mask >> r) & 1u)
@@ -2062,7 +2076,7 @@ int sg_ev_step(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, con
     // one warp per kE-env tile; SG_EV_MINB resident CTAs per SM, larger batches loop (persistent).  With the
     // projection on, the first n_helpers CTAs of the grid are helpers (exact projection of the envs the tile warps
     // hand over, see the kernel); they come out of the same residency budget so that every CTA is resident at once
-    const long long ntiles = (num_envs + sg::kE - 1) / sg::kE;
+    long long ntiles = (num_envs + sg::kE - 1) / sg::kE;
     const long long want = (ntiles + sg::kMainWarps - 1) / sg::kMainWarps;
     const long long resident = (long long)sms * SG_EV_MINB;
     int n_helpers = 0;
@@ -2074,6 +2088,27 @@ int sg_ev_step(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, con
         const long v = atol(cap);
         if (v >= 1) grid = (unsigned)std::min<long long>(grid, v);
     }
+    // Tiling.  W tile warps take the kE-env tiles in rounds; when the last round would be less than 3/4 full, its envs
+    // are cut into tiles of 8 instead if those fit one round (8 envs: observation AND pilot rows of a tile stay 16-byte
+    // aligned multiples of 16 bytes, so they still leave as bulk copies).  Measured at 65 536 envs (3 520 + 576 tiles on
+    // 1 760 warps): 50.9 us uniform, 49.8 us with the last 9 216 envs in 8-env tiles, 51.3 us in 6-env tiles (pilot rows
+    // by plain stores), 55.0 / 59.1 us with 8- / 12-env tiles throughout (profiles/r2/tiling_probe.sh).
+    long long t_full = ntiles;
+    int tail_envs = sg::kE;
+    {
+        const long long W = (long long)grid * sg::kMainWarps, full = num_envs / sg::kE;
+        const long long rounds = (ntiles + W - 1) / W, last = ntiles - (rounds - 1) * W;
+        if (rounds >= 2 && 4 * last < 3 * W && (rounds - 1) * W <= full) {
+            t_full = (rounds - 1) * W;
+            const long long rem = num_envs - t_full * sg::kE;
+            tail_envs = (int)std::min<long long>(sg::kE, 8 * ((rem + 8 * W - 1) / (8 * W)));
+            if (tail_envs >= sg::kE) t_full = ntiles;
+        }
+        if (const char* ov = getenv("SG_EV_TILING")) {            // "t_full,tail_envs" (diagnostic override)
+            long long a = 0; int c = 0;
+            if (sscanf(ov, "%lld,%d", &a, &c) == 2 && a >= 0 && a * sg::kE <= num_envs && c >= 1 && c <= sg::kE) { t_full = a; tail_envs = c; }
+        }
+    }
     grid += (unsigned)n_helpers;
     // staging rows in dynamic shared memory: per warp kE observation rows + kE pilot rows
     const int OBS = 2 * m->n_stations + m->moer_steps + 2;
@@ -2082,12 +2117,12 @@ int sg_ev_step(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs, con
         auto kern = sg::ev_step_main_kernel<1>;
         SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         kern<<<grid, sg::kMainThreads, dyn, st>>>(*m, *s, num_envs, action, flags, discrete_bins, obs, reward, done, pilots,
-                                                  final_obs, status, stats, work, n_helpers);
+                                                  final_obs, status, stats, work, n_helpers, t_full, tail_envs);
     } else {
         auto kern = sg::ev_step_main_kernel<0>;
         SG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
         kern<<<grid, sg::kMainThreads, dyn, st>>>(*m, *s, num_envs, action, flags, discrete_bins, obs, reward, done, pilots,
-                                                  final_obs, status, stats, work, 0);
+                                                  final_obs, status, stats, work, 0, t_full, tail_envs);
     }
     return sg::launch_status("ev_step_main_kernel");
 }

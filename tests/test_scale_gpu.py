@@ -131,6 +131,34 @@ def test_ev_capped_grid_is_bitwise_identical(native_lib, capped_grid):
     assert torch.equal(d_a, d_b) and torch.equal(k_a, k_b)
 
 
+@pytest.mark.parametrize("tiling", ["0,8", "0,6", "3,2", "5,10", "1,16", "0,1"])
+def test_ev_short_tiles_are_bitwise_identical(native_lib, capped_grid, tiling, monkeypatch):
+    """The launcher cuts the envs of a thin last round into short tiles (sg_ev_step: tiling).  Any tiling — forced here
+    through SG_EV_TILING = "full 16-env tiles, envs per tile after them", with bulk and plain-store write-outs, odd
+    sizes, a ragged end — writes exactly what the uniform tiling writes, through an end of day with auto-reset."""
+    from sustaingym_b200.envs.evcharging.env import BatchedEVChargingEnv
+    from sustaingym_b200.envs.evcharging.event_generation import SyntheticTraceGenerator
+    B = 333
+    gen = SyntheticTraceGenerator("caltech", num_days=8, mean_sessions=80.0, seed=4)
+    envs = [BatchedEVChargingEnv(gen, B, project_action_in_env=True, auto_reset=True) for _ in range(2)]
+    for e in envs:
+        e.reset(seed=3)
+        e.t[:] = 240                                  # busy afternoon -> end of day -> next morning
+    capped_grid(2)
+    acts = [torch.rand(B, 54, device="cuda") for _ in range(4)]
+    for t in range(70):
+        monkeypatch.delenv("SG_EV_TILING", raising=False)
+        o0, r0, d0, _, _ = envs[0].step(acts[t % 4])
+        monkeypatch.setenv("SG_EV_TILING", tiling)
+        o1, r1, d1, _, _ = envs[1].step(acts[t % 4])
+        assert torch.equal(o0, o1) and torch.equal(r0, r1) and torch.equal(d0, d1), t
+        assert torch.equal(envs[0].pilots, envs[1].pilots) and torch.equal(envs[0].status, envs[1].status), t
+    monkeypatch.delenv("SG_EV_TILING", raising=False)
+    assert torch.equal(envs[0].header, envs[1].header) and torch.equal(envs[0].final_obs, envs[1].final_obs)
+    d_a, k_a = envs[0].export_state(); d_b, k_b = envs[1].export_state()
+    assert torch.equal(d_a, d_b) and torch.equal(k_a, k_b)
+
+
 @pytest.mark.parametrize("B,mean,project", [(257, 70.0, True), (200, 80.0, True), (257, 70.0, False)])
 def test_ev_oracle_parity_with_many_tiles_per_warp(native_lib, capped_grid, B, mean, project):
     """The 288-step oracle comparison of test_ev_gpu.py with ONE CTA: 4 warps share 13-17 tiles of 16 envs."""
