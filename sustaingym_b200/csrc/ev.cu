@@ -10,17 +10,17 @@
 //   _get_reward                   env.py:431-464
 //   DiscreteActionWrapper.action  sustaingym/envs/wrappers.py:43-45
 //
-// One kernel launch per step (ev_step_main_kernel, documented at its definition): a warp owns a tile
-// of 32 consecutive envs, the observation/pilot rows of the tile are written with coalesced vector
-// stores by the whole warp, and one thread advances one env by walking only its OCCUPIED stations
-// (64-bit occupancy mask + 32-byte session records, double-buffered).  The network constraints
-// depend on the schedule only through <= 8 per-class sums, kept per thread.
+// One kernel launch per step (ev_step_main_kernel, documented at its definition).  Tile CTAs: a warp owns a tile of
+// 16 consecutive envs (8 in a thin last round), lists the OCCUPIED stations of the tile (64-bit occupancy masks), and
+// works one (env, station) item per lane on packed per-env lists of 32-byte session records; the observation / pilot
+// rows of the tile are assembled in shared memory and leave as one bulk (TMA) copy each.  The network constraints
+// depend on the schedule only through <= 8 per-class sums, kept per env in shared memory.
 //
-// The projection has a fast path (box-clipped action already satisfies the network: it IS the
-// projection), decided per thread with an f32 margin test, and a slow path run warp-cooperatively
-// inside the same kernel for the rare envs that need it: exact test, exact single-class (pod)
-// solve, else a primal-dual interior point on the QCQP whose Newton systems are reduced to
-// n_classes x n_classes + n_constraints x n_constraints Cholesky factorisations.
+// The projection has a fast path (the box-clipped action already satisfies the network: it IS the projection),
+// certified per env with integer screens and an f32 margin test, an exact single-class (pod) solve run by the tile
+// warp itself, and — for the few envs that need it — a primal-dual interior point on the QCQP (Newton systems reduced
+// to n_classes x n_classes + n_constraints x n_constraints Cholesky factorisations) run by helper CTAs of the same
+// launch, which take those envs from a work list while the tile warps go on.
 //
 // All divisions by constants use the FMA-corrected reciprocal (Markstein) which reproduces the
 // IEEE quotient the reference's Python arithmetic produces (checked on 2e7 samples per constant,
@@ -1071,7 +1071,7 @@ __device__ __noinline__ bool fallback_env(const EvTables& sh, WarpShared& ws, co
 // (checks): a thread-serial version of this took 12-17 us on one lane and, with ~60 such envs per 65 536-env step,
 // set the end of the launch.  Returns 0: the clipped action is feasible (exact test), nothing to do; 1: projected,
 // x_i = clip(a_i - ws.nu[class_i], 0, u_i); 2: a coupled constraint is (or became) violated -> interior point
-// (rare kernel).
+// (helper warps).
 __device__ __forceinline__ int pod_solve(const EvTables& sh, WarpShared& ws, const int lo, const int hi, const int J,
                                          const unsigned suspects, const int lane) {
     // exact class sums of the clipped action: lane c < kMC sums class c over the items (broadcast reads)
@@ -1172,9 +1172,8 @@ __device__ __forceinline__ int pod_solve(const EvTables& sh, WarpShared& ws, con
 //            rounded schedule); an env that is not certainly feasible is left to fallback_env;
 //   arrivals Plugin events with timestamp <= t+1 from the day's arrival-sorted list;
 //   epilogue reward, cumulative breakdown, clock, mask, statistics.
-// The kernel contains no function call: envs that need the exact projection are appended to a work
-// list and finished by ev_step_rare_kernel (second launch of the step), so the rare path's register
-// and stack needs (interior-point solver) do not burden this kernel.
+// Envs that need the interior-point solver are appended to a work list and finished by the helper CTAs of the same
+// launch (fallback_env), so that path's register and stack needs do not sit on the tile warps' critical path.
 // =================================================================================================
 #ifdef SG_EV_TRACE
 __device__ unsigned long long* g_trace = nullptr;     // [ntiles][16] phase timestamps (diagnostic builds only)
@@ -1590,7 +1589,7 @@ ev_step_main_kernel(const sg_ev_model m, const sg_ev_state s, const long long B,
             pair_checks();
             // ---- envs whose clipped action is not certainly feasible (rare): the exact test and the exact
             // single-class (pod) projection run here, one env at a time on the whole warp; envs that need the
-            // interior-point solver go to the work list of ev_step_rare_kernel (gfail)
+            // interior-point solver go to the helper warps' work list (gfail)
             unsigned gfail = 0u;
             if (!SG_EV_INLINE_POD) {
                 gfail = MODE != 0 ? gbad : 0u;        // every env that is not certainly feasible goes to the helper warps
