@@ -1148,28 +1148,33 @@ __device__ __forceinline__ int pod_solve(const EvTables& sh, WarpShared& ws, con
 }
 
 // =================================================================================================
-// Main kernel: one launch = one step() of all envs.  A warp owns a tile of kE consecutive envs; lane
+// Main kernel: one launch = one step() of all envs.  A warp owns a tile of kE consecutive envs (tiles are
+// dealt by a global ticket counter; a thin last round is cut into 8-env tiles, see sg_ev_step); lane
 // e < kE keeps env e's scalars ("owner"), and the phases that have more parallelism than envs are
 // spread over all 32 lanes:
 //
 //   stage    the tile's observation rows and pilot rows (both contiguous in global memory) are
 //            assembled in shared memory: zero-filled with 16-byte stores (an empty station reads 0
-//            and, with the projection on, has pilot 0), the MOER row + timestep tail copied by kQ
-//            lanes per env; with the projection off the pilot rows are computed densely with their
-//            class sums.  At the end of the tile ONE bulk asynchronous copy (cp.async.bulk, the TMA
-//            engine) per array writes the finished rows to global memory: full aligned sectors, each
-//            byte written once, no store instructions on the SM;
+//            and, with the projection on, has pilot 0), the MOER row + timestep tail copied
+//            asynchronously (cp.async) from the observation-tail table; with the projection off the
+//            pilot rows are computed densely with their class sums.  At the end of the tile ONE bulk
+//            asynchronous copy (cp.async.bulk, the TMA engine) per array writes the finished rows to
+//            global memory: full aligned sectors, each byte written once, no store instructions on
+//            the SM; its completion is waited for only when the staging rows are needed again;
 //   items    the occupied stations of the tile's envs (bits of the per-env 64-bit masks) are
 //            enumerated into one work list and processed one (env, station) item per lane, so lanes
 //            stay balanced whatever the per-env occupancy: one 32-byte session record (single
-//            256-bit load) + one action value in, battery arithmetic (branch-free, exact), the record
-//            goes to the other state copy, the two observation entries and the pilot byte are
-//            patched into the staged rows, class sums of the clipped action / pilots are
-//            accumulated with shared-memory atomics, the rate goes to a list in shared memory;
-//   owner    lane e sums the rates of env e in station order (deterministic f64 sum);
-//   check    one (env, constraint) pair per lane: class sums of the clipped action against the
-//            network constraints in f32 with a margin (and the same for the excess current of the
-//            rounded schedule); an env that is not certainly feasible is left to fallback_env;
+//            256-bit load, position = rank of the station among the env's occupied ones) + one
+//            action value in, battery arithmetic (branch-free, exact), the two observation entries
+//            and the pilot byte patched into the staged rows, class sums of the clipped action /
+//            pilots accumulated with shared-memory integer atomics, the rate to a list in shared
+//            memory; the records go back into the env's packed list of the NEW occupancy once the
+//            checks have passed;
+//   rates    kQ lanes per env add the env's rates in a fixed order (deterministic f64 sum);
+//   check    owner lane e tests its env: integer screens on the class sums first, the coupled
+//            constraints in f32 with a margin only when the total current could violate one (and the
+//            same for the excess current of the rounded schedule); an env that is not certainly
+//            feasible gets the exact pod projection here (pod_solve) or goes to the helper warps;
 //   arrivals Plugin events with timestamp <= t+1 from the day's arrival-sorted list;
 //   epilogue reward, cumulative breakdown, clock, mask, statistics.
 // Envs that need the interior-point solver are appended to a work list and finished by the helper CTAs of the same
