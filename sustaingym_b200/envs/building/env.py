@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 from ... import _lib, spaces
+from .._state import StateDictMixin, nvtx_method
 
 OCCU_COEF_LINEAR = 7.139322   # env.py:99
 DISCRETE_LENGTH = 100         # env.py:102
@@ -39,7 +40,9 @@ def seed_to_epoch(seed: int, episode_len: int, time_res: int, length_of_weather:
     return min(int((seed / num_days_normalizer) * length_of_weather), length_of_weather - 1)
 
 
-class BatchedBuildingEnv:
+class BatchedBuildingEnv(StateDictMixin):
+
+    _STATE_TENSORS = ('state', 'epoch', 'runs', 'reward', 'done', 'stats')          # checkpointed by state_dict() (envs/_state.py)
     def __init__(self, parameters: dict[str, Any], num_envs: int = 1, device=None, auto_reset: bool = False,
                  collect_stats: bool = False, tensor_cores: bool = True):
         self.lib = _lib.load()
@@ -118,6 +121,7 @@ class BatchedBuildingEnv:
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
+    @nvtx_method("sg:building.reset")
     def reset(self, *, seed=None, options: dict | None = None, epochs: np.ndarray | None = None,
               mask: np.ndarray | torch.Tensor | None = None):
         """env.py:314-386.  ``seed``: int (env i gets ``seed + i``), array of per-env seeds, or None
@@ -152,6 +156,7 @@ class BatchedBuildingEnv:
         self.kernel_launches += 1
         return self.state, {}
 
+    @nvtx_method("sg:building.step")
     def step(self, actions):
         """env.py:205-312 for every env. CUDA tensor in -> CUDA tensors out (async); NumPy in -> NumPy out."""
         B, n = self.num_envs, self.n
@@ -177,6 +182,7 @@ class BatchedBuildingEnv:
         d = self.done.view(torch.bool)                    # zero-copy (no conversion kernel on the step path)
         return self.state, self.reward, d, d, {}          # terminated == truncated == done (env.py:312)
 
+    @nvtx_method("sg:building.rollout")
     def rollout(self, actions: torch.Tensor, keep_obs: bool = True):
         """``T`` fused steps in one launch. ``actions``: [T, B, n]. Returns (obs [T,B,n+4] or None,
         reward [T,B], done [T,B])."""

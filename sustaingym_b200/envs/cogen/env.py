@@ -16,6 +16,7 @@ import numpy as np
 import torch
 
 from ... import _lib, spaces
+from .._state import StateDictMixin, nvtx_method
 from ...data.cogen_ambients import AMBIENT_COLS, real_ambients, synthetic_ambients  # noqa: F401
 
 PLANT_NPZ = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))),
@@ -104,9 +105,11 @@ def action_row_to_dict(row: np.ndarray) -> dict:
     return out
 
 
-class BatchedCogenEnv:
+class BatchedCogenEnv(StateDictMixin):
     """Constructor mirrors cogen/env.py:75-82.  ``ambients`` ([days, 96, 7]) overrides the table; by default it
     is the reference's own xlsx-derived table for ``renewables_magnitude`` (packaged, ``data/cogen_ambients.py``)."""
+
+    _STATE_TENSORS = ('prev_action', 'day_t', 'obs', 'reward', 'agent_reward', 'done', 'Y', 'stats')          # checkpointed by state_dict() (envs/_state.py)
 
     def __init__(self, num_envs: int = 1, ambients: np.ndarray | None = None, renewables_magnitude: float = 0.,
                  ramp_penalty: float = 2., supply_imbalance_penalty: float = 1000,
@@ -189,6 +192,7 @@ class BatchedCogenEnv:
         self.kernel_launches += 2
         return Y
 
+    @nvtx_method("sg:cogen.reset")
     def reset(self, *, seed=None, options=None, days: np.ndarray | None = None, init_actions: np.ndarray | None = None,
               mask: np.ndarray | torch.Tensor | None = None):
         """cogen/env.py:186-230. ``seed``: int (env i gets seed+i) or per-env array -> day = seed % n_days
@@ -223,6 +227,7 @@ class BatchedCogenEnv:
         self.kernel_launches += 1
         return self.obs, {}
 
+    @nvtx_method("sg:cogen.step")
     def step(self, actions, noise: torch.Tensor | None = None):
         """cogen/env.py:355-387. ``actions``: [B,15] f32 CUDA tensor (or NumPy -> NumPy out).  ``noise``:
         optional [B,k,7] f64 standard-normal draws (scaled here by forecast_noise_std); when the env

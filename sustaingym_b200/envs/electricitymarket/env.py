@@ -8,6 +8,7 @@ import numpy as np
 import torch
 
 from ... import _lib, spaces
+from .._state import StateDictMixin, nvtx_method
 
 T_STEPS = 288
 
@@ -34,7 +35,9 @@ def synthetic_load_moer(n_days: int, k: int = 1, seed: int = 0):
     return load, moer
 
 
-class BatchedElectricityMarketEnv:
+class BatchedElectricityMarketEnv(StateDictMixin):
+
+    _STATE_TENSORS = ('state', 'day_t', 'prev_action', 'obs', 'reward', 'done', 'info', 'stats')          # checkpointed by state_dict() (envs/_state.py)
     def __init__(self, num_envs: int = 1, load: np.ndarray | None = None, moer: np.ndarray | None = None,
                  gen_cost: np.ndarray | None = None, gen_cap: np.ndarray | None = None, k: int = 1,
                  use_intermediate_rewards: bool = True, e_max: float = 80.0, e_init: float = 40.0,
@@ -81,6 +84,7 @@ class BatchedElectricityMarketEnv:
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
+    @nvtx_method("sg:market.reset")
     def reset(self, *, seed=None, options=None, days: np.ndarray | None = None, mask=None):
         B = self.num_envs
         if days is None:
@@ -105,6 +109,7 @@ class BatchedElectricityMarketEnv:
         self.kernel_launches += 1
         return self.obs, {}
 
+    @nvtx_method("sg:market.step")
     def step(self, actions):
         B = self.num_envs
         host = isinstance(actions, np.ndarray)

@@ -17,13 +17,14 @@ import numpy as np
 import torch
 
 from ... import _lib, spaces
+from .._state import StateDictMixin, nvtx_method
 from .event_generation import AbstractTraceGenerator
 from .network import ChargingNetworkSpec
 
 OBS_KEYS = ("demands", "est_departures", "forecasted_moer", "prev_moer", "timestep")  # sorted (flatten order)
 
 
-class BatchedEVChargingEnv:
+class BatchedEVChargingEnv(StateDictMixin):
     """See module docstring.  Mirrors the constructor of the reference (env.py:116-119) plus
     ``num_envs``/``device``/``auto_reset``.
 
@@ -31,6 +32,15 @@ class BatchedEVChargingEnv:
     (``demands | est_departures | forecasted_moer | prev_moer | timestep``); ``obs_dict()`` gives
     the Dict view (slices of the same storage).
     """
+
+    _STATE_TENSORS = ('slots', 'header', 'obs', 'final_obs', 'reward', 'done', 'status', 'pilots', 'stats')          # checkpointed by state_dict() (envs/_state.py)
+
+    def load_state_dict(self, sd: dict) -> None:
+        StateDictMixin.load_state_dict(self, sd)
+        self.work.zero_()                              # scheduler / work-list scratch: at rest between steps
+        if self._compact is not None:                  # incremental host expansion: forget what the host rows held
+            self._compact["prev"].fill_((1 << self.num_stations) - 1)
+
 
     # env.py:99-114
     TIMESTEP_DURATION = 5
@@ -243,6 +253,7 @@ class BatchedEVChargingEnv:
         obs = self.obs if obs is None else obs
         return {k: obs[..., s] for k, s in self.obs_slices.items()}
 
+    @nvtx_method("sg:ev.reset")
     def reset(self, *, seed: int | np.ndarray | None = None, options: dict | None = None,
               mask: torch.Tensor | np.ndarray | None = None):
         """env.py:293-338 for every env (or those in ``mask``).  ``seed`` may be one int (env i gets
@@ -274,6 +285,7 @@ class BatchedEVChargingEnv:
         self._host_obs_valid = False
         return self.obs, self._infos()
 
+    @nvtx_method("sg:ev.step")
     def step(self, actions):
         """env.py:229-291 for every env.  ``actions``: ``[num_envs, n]`` CUDA tensor (device path,
         returns CUDA tensors, asynchronous) or NumPy array (host path: pinned H2D copy, step, D2H
