@@ -761,7 +761,7 @@ __device__ __forceinline__ int slot_rank(const unsigned long long occ, const int
 #define SG_EV_MINB 3     // resident CTAs per SM the kernel is compiled for (3 x 128 threads -> <= 168 registers, no spills)
 #endif
 #ifndef SG_EV_KV
-#define SG_EV_KV 3
+#define SG_EV_KV 2
 #endif
 #ifndef SG_EV_ABL
 #define SG_EV_ABL 0      // timing ablations (diagnostic builds only; results are wrong when non-zero)
