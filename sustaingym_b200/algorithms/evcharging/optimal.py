@@ -209,3 +209,28 @@ class OfflineOptimal(BaseAlgorithm):
             action = np.zeros(self.env.num_stations)
         self.timestep += 1
         return action
+
+
+def mpc_policy(batched_env, lookahead: int = 12, workers: int | None = None):
+    """MPC as a device policy for ``run_batched``: the batched observation goes to the host once per step, one linear
+    program per env is solved there (a thread pool: HiGHS releases the GIL), the actions come back as one ``[B, n]`` CUDA
+    tensor.  All envs still advance with ONE kernel launch per step; the controller, not the env, is the cost."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    from types import SimpleNamespace
+
+    import torch
+    consts = SimpleNamespace(ACTION_SCALE_FACTOR=batched_env.ACTION_SCALE_FACTOR, PROFIT_FACTOR=batched_env.PROFIT_FACTOR,
+                             CARBON_COST_FACTOR=batched_env.CARBON_COST_FACTOR, A_PERS_TO_KWH=batched_env.A_PERS_TO_KWH)
+    view = SimpleNamespace(action_space=SimpleNamespace(low=np.zeros(batched_env.num_stations)),
+                           moer_forecast_steps=batched_env.moer_forecast_steps, _b=consts, cn=batched_env.cn,
+                           num_stations=batched_env.num_stations)
+    B = batched_env.num_envs
+    ctrls = [MPC(view, lookahead) for _ in range(B)]
+    pool = ThreadPoolExecutor(max_workers=workers or min(B, os.cpu_count() or 1))
+
+    def policy(obs: dict):
+        host = {k: v.detach().cpu().numpy() for k, v in obs.items()}
+        acts = list(pool.map(lambda i: ctrls[i].get_action({k: host[k][i] for k in host}), range(B)))
+        return torch.from_numpy(np.asarray(acts, dtype=np.float32)).to(batched_env.device)
+    return policy

@@ -70,3 +70,18 @@ def test_mpc_and_offline_optimal_on_the_drop_in_env(native_lib):
     assert bd["greedy"]["excess_charge"] > 100 * max(bd["offline"]["excess_charge"], 1e-6)   # greedy overloads the network
     assert r["offline"] >= r["mpc"] * (1 - 2e-3) >= r["greedy"] * (1 - 2e-3) ** 2, r
     assert r["offline"] <= float(res["offline"]["max_profit"][0]) + 1e-9
+
+
+def test_mpc_as_a_batched_policy(native_lib):
+    """``run_batched`` with MPC (one LP per env on the host, one kernel launch per step for all envs) returns what MPC
+    returns on the single-env view for the same seeds."""
+    from sustaingym_b200.algorithms.base import run_batched
+    from sustaingym_b200.algorithms.evcharging.optimal import MPC, mpc_policy
+    from sustaingym_b200.envs.evcharging.env import BatchedEVChargingEnv, EVChargingEnv
+    from sustaingym_b200.envs.evcharging.event_generation import SyntheticTraceGenerator
+    gen = SyntheticTraceGenerator("caltech", num_days=4, mean_sessions=40.0, seed=8)
+    seeds = [0, 1, 2]
+    benv = BatchedEVChargingEnv(gen, len(seeds), project_action_in_env=True, auto_reset=False)
+    batched = run_batched(benv, mpc_policy(benv, lookahead=6), seeds)
+    single = MPC(EVChargingEnv(gen, project_action_in_env=True), lookahead=6).run(seeds)
+    np.testing.assert_allclose(batched["return"], single["return"], rtol=1e-9)
