@@ -226,3 +226,48 @@ def test_compact_host_path_is_bit_identical(native_lib, mean, cap, dense, monkey
     assert torch.equal(env_c.obs, env_d.obs)
     if mean > 100:
         assert n_over > 100               # the overflow rows were really used
+
+
+def edge_case_days():
+    """Hand-made days around the boundaries of the event model."""
+    full = [(2, 280, 270, 60.0, i) for i in range(54)]                     # every station occupied all day long
+    back_to_back = []
+    for i in range(0, 54, 3):                                               # a departure and an arrival in the same period,
+        t = 0                                                               # session after session on the same station
+        while t + 9 < 287:
+            back_to_back.append((t, t + 9, min(t + 9 + (i % 5) - 2, 287), 3.0 + i % 7, i))
+            t += 9
+    odd = [(0, 287, 287, 100.0, 0), (1, 287, 287, 150.0, 1),              # first / last periods, energy above the 100 kWh cap
+           (5, 5, 6, 10.0, 2), (7, 8, 8, 0.0005, 3),                      # zero-length session; fully charged on arrival
+           (10, 200, 12, 0.2, 4), (10, 200, 11, 90.0, 5),                 # estimated departure long passed; tiny / huge demand
+           (285, 287, 287, 20.0, 6), (286, 287, 287, 20.0, 7), (287, 287, 287, 5.0, 8)]   # arrivals in the last periods
+    pods = [(3, 250, 240, 40.0, i) for i in range(10, 26)] + [(100, 180, 170, 8.0, i) for i in range(26, 54)]   # both pods full
+    return [[], full, back_to_back, odd, pods]
+
+
+@pytest.mark.parametrize("project", [False, True])
+def test_edge_case_days(native_lib, project):
+    """Empty day, 54 of 54 stations occupied (one env fills a whole item group; every pod and winding constraint binds),
+    sessions chained on one station, zero-length / instantly full / over-cap sessions, events in the first and last
+    periods — kernel vs oracle over the whole day, several envs per day (different actions)."""
+    from sustaingym_b200.envs.evcharging.env import BatchedEVChargingEnv
+    from sustaingym_b200.envs.evcharging.event_generation import ArrayTraceGenerator, synthetic_moer
+    days = edge_case_days()
+    gen = ArrayTraceGenerator(days, synthetic_moer(len(days), 3))
+    B = 40
+    env = BatchedEVChargingEnv(gen, B, project_action_in_env=project)
+    net = O.caltech_acn()
+    # (the generator caps the requested energy at 100 kWh when it packs the sessions, event_generation.py:169-170; the
+    # oracle takes sessions that are capped already)
+    sess = [[O.Session(a, dp, e, min(kwh, 100.0), st) for a, dp, e, kwh, st in d] for d in gen.days]
+    orc = O.EVOracle(net, sess, gen.moer.astype(np.float64), B, moer_forecast_steps=36, project_action_in_env=project)
+
+    def actions(rng, t):
+        a = rng.uniform(0, 1, (B, 54)).astype(np.float32)
+        a[::4] = 1.0                                   # a quarter of the envs always ask for everything
+        a[1::8] = 0.0                                  # ... and some for nothing
+        return a
+    clean, n_exact, n_slow = run_parity(env, orc, net, gen, B, 288, 0, actions, project)
+    assert clean.mean() > 0.9
+    if project:
+        assert n_slow > 1000                           # the interior-point path ran (full garage, everything asked for)
