@@ -72,7 +72,9 @@ int sg_building_reset(const sg_building_model* m, int64_t num_envs,
                       void* stream);
 
 /* One step() of B independent envs.  `state` is the previous observation and is overwritten
- * with the new one (the reference's state IS its f32 observation, env.py:286-296). */
+ * with the new one (the reference's state IS its f32 observation, env.py:286-296).
+ * (n in {3, 5, 6, 10} and num_envs >= 512: a persistent kernel walks over 128-env tiles; the environment variable
+ * SG_BLD_NO_PERSISTENT selects the one-tile-per-CTA kernel instead — same results, for comparison.) */
 int sg_building_step(const sg_building_model* m, int64_t num_envs,
                      const void* action /* [device] [B,n] f32 or i64 */,
                      float* state /* [device] [B,n+4] in/out */,
@@ -221,6 +223,9 @@ int sg_ev_reset(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs,
  * With m->project != 0 the box-clipped action is tested against the network constraints per env (it
  * is then the exact projection); the few envs that violate them are finished by helper CTAs of the
  * same launch (exact single-class solve, else interior point) and report SG_EV_STATUS_PROJECTED.
+ * Diagnostic environment variables (results never depend on them): SG_EV_MAX_CTAS=<n> caps the tile CTAs of the
+ * launch; SG_EV_TILING="<full tiles>,<envs per tile after them>" overrides how the batch is cut into warp tiles
+ * (default: 16-env tiles, the envs of a thin last round in 8-env tiles).
  */
 int sg_ev_step(const sg_ev_model* m, const sg_ev_state* s, int64_t num_envs,
                const void* action, int32_t flags, int32_t discrete_bins,
